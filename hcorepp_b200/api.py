@@ -1,0 +1,375 @@
+"""Host-side mirror of the reference's operator interface for the TLR-GEMM path, on top of the C ABI.
+
+Same names, argument meaning and error behaviour as the reference (file:line relative to the ecrc/hcorepp tree):
+  RunContext              include/hcorepp/kernels/cuda/RunContext.hpp:15-53
+  CompressionParameters   include/hcorepp/operators/helpers/CompressionParameters.hpp:44-46
+  DenseTile               include/hcorepp/operators/concrete/Dense.hpp:56-91
+  CompressedTile          include/hcorepp/operators/concrete/Compressed.hpp:67-151
+  HCore.Gemm              include/hcorepp/api/HCore.hpp:41-46   (src/api/HCore.cpp:22-344)
+  TileMatrix              include/hcorepp/helpers/TileMatrix.hpp:22-189
+  tile_matrix_multiplication   examples/matrix_multiplication/omp_main.cpp:70-154
+
+PyTorch is used for device memory and streams only (plumbing); all arithmetic happens in libhcore_b200.so.
+Nothing here imports oracle/ and there is no CPU path: every call ends in a CUDA kernel or raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import lib, check, hcb_tile, hcb_compress_params, TILE_DENSE, TILE_COMPRESSED
+
+MAX_RANK_RATIO = 3  # include/hcorepp/operators/concrete/Compressed.hpp:14
+
+_PFX = {torch.float64: "d", torch.float32: "s"}
+_CT = {torch.float64: C.c_double, torch.float32: C.c_float}
+_NP2T = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}
+
+
+def _fn(name, dtype):
+    return getattr(lib, f"hcb_{_PFX[dtype]}{name}")
+
+
+class RunContext:
+    """CUDA run context: device + the stream every kernel is enqueued on (torch's current stream)."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        if not torch.cuda.is_available():
+            # let the library report it: there is no CPU fallback
+            check(lib.hcb_ctx_create(device, C.byref(h)))
+        torch.cuda.set_device(device)
+        self.device = torch.device("cuda", device)
+        self.torch_stream = torch.cuda.current_stream(device)
+        check(lib.hcb_ctx_create_on_stream(device, C.c_void_p(self.torch_stream.cuda_stream), C.byref(h)))
+        self.h = h
+
+    def Sync(self):
+        check(lib.hcb_ctx_sync(self.h))
+
+    def SupportsOMP(self) -> bool:
+        return False
+
+    def reserve_workspace(self, nbytes: int):
+        check(lib.hcb_ctx_reserve_workspace(self.h, nbytes))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib.hcb_ctx_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+@dataclass
+class CompressionParameters:
+    accuracy: float = 1e-4
+    use_trmm: bool = False
+    use_ungqr: bool = True
+    truncated_svd: bool = False
+    fixed_rank: int = 0
+    svd: int = 1  # LAPACK_GESDD in the reference; the device path is one-sided Jacobi either way
+
+    def c(self) -> hcb_compress_params:
+        return hcb_compress_params(self.accuracy, int(self.use_trmm), int(self.use_ungqr), int(self.truncated_svd),
+                                   int(self.fixed_rank), int(self.svd), 0)
+
+
+def _to_device_colmajor(a, ctx: RunContext) -> torch.Tensor:
+    """m x n array -> device tensor of shape (n, m), C-contiguous == column-major m x n with ld = m."""
+    if isinstance(a, torch.Tensor):
+        t = a.detach().to(ctx.device)
+        return t.t().contiguous()
+    a = np.asarray(a)
+    return torch.from_numpy(np.ascontiguousarray(a.T)).to(ctx.device)
+
+
+class DenseTile:
+    """DenseTile(m, n, data, ld, ColMajor, ctx) -- one device buffer, column-major."""
+
+    def __init__(self, data, ctx: RunContext):
+        self.ctx = ctx
+        self.t = _to_device_colmajor(data, ctx)  # (n, m)
+        self.n, self.m = self.t.shape
+        self.dtype = self.t.dtype
+
+    dense = True
+
+    def isDense(self):
+        return True
+
+    def isCompressed(self):
+        return False
+
+    def GetNumOfRows(self):
+        return self.m
+
+    def GetNumOfCols(self):
+        return self.n
+
+    def desc(self) -> hcb_tile:
+        return hcb_tile(TILE_DENSE, self.m, self.n, self.m, 0, 0, None, self.t.data_ptr())
+
+    def to_numpy(self) -> np.ndarray:
+        return np.asfortranarray(self.t.t().cpu().numpy())
+
+    to_dense = to_numpy
+
+
+class CompressedTile:
+    """U (m x rank, ld m) at offset 0, V (rank x n, ld rank) at offset m*max_rank; the rank lives on the device."""
+
+    dense = False
+
+    def __init__(self, m, n, max_rank, dtype, ctx: RunContext, buf=None, rank=None, rank_bound=0):
+        self.ctx, self.m, self.n, self.max_rank, self.dtype = ctx, int(m), int(n), int(max_rank), dtype
+        self.rank_bound = int(rank_bound)
+        self.buf = buf if buf is not None else torch.zeros(self.m * self.max_rank + self.max_rank * self.n,
+                                                          dtype=dtype, device=ctx.device)
+        self.rank = rank if rank is not None else torch.ones(1, dtype=torch.int32, device=ctx.device)
+
+    # -- constructors mirroring Compressed.hpp:67-151
+    @classmethod
+    def from_uv(cls, U, V, ctx: RunContext, max_rank=None):
+        """CompressedTile(m, n, U, V, ld, rank, ...): maxRank = rank unless given (Compressed.cpp:28)."""
+        U, V = np.asarray(U), np.asarray(V)
+        m, rk = U.shape
+        n = V.shape[1]
+        assert V.shape[0] == rk
+        t = cls(m, n, max_rank or max(rk, 1), _NP2T[U.dtype], ctx)
+        if rk > 0:
+            t.buf[: m * rk] = torch.from_numpy(np.ascontiguousarray(U.T).reshape(-1)).to(ctx.device)
+            t.buf[m * t.max_rank: m * t.max_rank + rk * n] = torch.from_numpy(
+                np.ascontiguousarray(V.astype(U.dtype).T).reshape(-1)).to(ctx.device)
+        t.rank.fill_(rk)
+        return t
+
+    @classmethod
+    def compress(cls, dense, params: CompressionParameters, ctx: RunContext):
+        """Compressing constructor (Compressed.cpp:75-146): maxRank = max(min(m,n)/3, 1)."""
+        d = DenseTile(dense, ctx)
+        t = cls(d.m, d.n, max(min(d.m, d.n) // MAX_RANK_RATIO, 1), d.dtype, ctx)
+        ptrs = (C.c_void_p * 1)(d.t.data_ptr())
+        descs = (hcb_tile * 1)(t.desc())
+        prm = params.c()
+        check(_fn("compress_batched", d.dtype)(ctx.h, 1, ptrs, d.m, descs, C.byref(prm), None))
+        ctx.Sync()
+        return t
+
+    def isDense(self):
+        return False
+
+    def isCompressed(self):
+        return True
+
+    def GetNumOfRows(self):
+        return self.m
+
+    def GetNumOfCols(self):
+        return self.n
+
+    def GetTileRank(self) -> int:
+        """Host getter: refreshes from the device-resident rank (synchronises, like RunContext::Sync())."""
+        return int(self.rank.item())
+
+    def GetULeadingDim(self):
+        return self.m
+
+    def GetVLeadingDim(self):
+        return self.GetTileRank()
+
+    def desc(self) -> hcb_tile:
+        return hcb_tile(TILE_COMPRESSED, self.m, self.n, 0, self.max_rank, self.rank_bound, self.rank.data_ptr(),
+                        self.buf.data_ptr())
+
+    def factors(self):
+        rk = self.GetTileRank()
+        U = self.buf[: self.m * rk].reshape(rk, self.m).t()
+        V = self.buf[self.m * self.max_rank: self.m * self.max_rank + rk * self.n].reshape(self.n, rk).t()
+        return U, V
+
+    def GetUMatrix(self) -> np.ndarray:
+        return np.asfortranarray(self.factors()[0].cpu().numpy())
+
+    def GetVMatrix(self) -> np.ndarray:
+        return np.asfortranarray(self.factors()[1].cpu().numpy())
+
+    def to_dense(self) -> np.ndarray:
+        U, V = self.factors()
+        return np.asfortranarray((U @ V).cpu().numpy())
+
+
+def gemm_batched(alpha, A, opA, B, opB, beta, Cs, ctx: RunContext, params: CompressionParameters | None = None,
+                 info: torch.Tensor | None = None):
+    """One fused launch sequence for many tile triples: C[t] = alpha*op(A[t])*op(B[t]) + beta*C[t] (+ recompression)."""
+    n = len(Cs)
+    assert len(A) == n and len(B) == n
+    params = params or CompressionParameters(1e-9)
+    dtype = Cs[0].dtype
+    da = (hcb_tile * n)(*[t.desc() for t in A])
+    db = (hcb_tile * n)(*[t.desc() for t in B])
+    dc = (hcb_tile * n)(*[t.desc() for t in Cs])
+    prm = params.c()
+    ct = _CT[dtype]
+    check(_fn("tlr_gemm_batched", dtype)(ctx.h, n, da, int(bool(opA)), db, int(bool(opB)), dc, ct(alpha), ct(beta),
+                                         C.byref(prm), None if info is None else info.data_ptr()))
+
+
+class HCore:
+    """hcorepp::api::HCore<T> -- static tile routines (only Gemm is on the hot path)."""
+
+    @staticmethod
+    def Gemm(alpha, A, opA, B, opB, beta, Ct, ctx: RunContext, params: CompressionParameters | None = None):
+        """HCore<T>::Gemm(alpha, A, opA, B, opB, beta, C, context, flops, memoryUnit, params) (HCore.hpp:41-46).
+
+        Dense*Dense -> Compressed leaves C full rank (U = alpha*A*B + beta*C, V = I; HCore.cpp:272-299): like the
+        reference (DataHolder::Resize) the tile buffer is re-allocated when its capacity is too small."""
+        if (A.dense and B.dense and not Ct.dense) and Ct.max_rank < min(Ct.m, Ct.n):
+            rk = Ct.GetTileRank()
+            U, V = Ct.factors()
+            newcap = min(Ct.m, Ct.n)
+            buf = torch.zeros(Ct.m * newcap + newcap * Ct.n, dtype=Ct.dtype, device=ctx.device)
+            buf[: Ct.m * rk] = U.t().reshape(-1)
+            buf[Ct.m * newcap: Ct.m * newcap + rk * Ct.n] = V.t().reshape(-1)
+            Ct.buf, Ct.max_rank = buf, newcap
+        gemm_batched(alpha, [A], opA, [B], opB, beta, [Ct], ctx, params)
+
+
+class TileMatrix:
+    """helpers::TileMatrix<T>: an mt x nt grid of tiles in ONE pooled device buffer (+ a device rank table and a
+    pre-built descriptor array), so that a whole k-step is a single batched call with no per-tile host work."""
+
+    def __init__(self, mt, nt, tm, tn, dtype, ctx: RunContext, compressed=True, max_rank=None, rank_bound=0):
+        self.mt, self.nt, self.tm, self.tn, self.dtype, self.ctx = mt, nt, tm, tn, dtype, ctx
+        self.compressed = compressed
+        self.max_rank = (max_rank or max(min(tm, tn) // MAX_RANK_RATIO, 1)) if compressed else 0
+        self.rank_bound = rank_bound
+        self.tile_elems = (tm * self.max_rank + self.max_rank * tn) if compressed else tm * tn
+        self.buf = torch.zeros(mt * nt * self.tile_elems, dtype=dtype, device=ctx.device)
+        self.ranks = torch.ones(mt * nt, dtype=torch.int32, device=ctx.device)
+        self._build_descs()
+
+    def _build_descs(self):
+        n = self.mt * self.nt
+        esz = self.buf.element_size()
+        base, rbase = self.buf.data_ptr(), self.ranks.data_ptr()
+        self.descs = (hcb_tile * n)()
+        for lin in range(n):  # column-major grid: lin = j + i*mt  (TileMatrix.hpp:78-80)
+            d = self.descs[lin]
+            d.type = TILE_COMPRESSED if self.compressed else TILE_DENSE
+            d.m, d.n, d.ld = self.tm, self.tn, self.tm
+            d.max_rank, d.rank_bound = self.max_rank, self.rank_bound
+            d.d_rank = rbase + 4 * lin if self.compressed else None
+            d.d_data = base + esz * self.tile_elems * lin
+
+    def set_rank_bound(self, bound: int):
+        self.rank_bound = int(bound)
+        for d in self.descs:
+            d.rank_bound = self.rank_bound
+
+    def lin(self, row, col):
+        return row + col * self.mt
+
+    def tile_buf(self, row, col):
+        o = self.lin(row, col) * self.tile_elems
+        return self.buf[o: o + self.tile_elems]
+
+    def GetTile(self, row, col):
+        """Tile<T>* GetTile(row, col) -- a view object sharing the pooled storage."""
+        lin = self.lin(row, col)
+        if self.compressed:
+            return CompressedTile(self.tm, self.tn, self.max_rank, self.dtype, self.ctx, buf=self.tile_buf(row, col),
+                                  rank=self.ranks[lin: lin + 1], rank_bound=self.rank_bound)
+        t = DenseTile.__new__(DenseTile)
+        t.ctx, t.t, t.m, t.n, t.dtype = self.ctx, self.tile_buf(row, col).view(self.tn, self.tm), self.tm, self.tn, self.dtype
+        return t
+
+    # -- constructors (TileMatrix.hpp:40-41, 62-63)
+    @classmethod
+    def from_dense(cls, raw, tm, tn, ctx: RunContext, params: CompressionParameters | None = None):
+        """TileMatrix(RawMatrix, rowTile, colTile[, params], ctx): dense tiles, or compressed (one SVD per tile,
+        here ONE batched device call instead of the reference's serial loop, TileMatrix.cpp:150-171)."""
+        raw_t = raw if isinstance(raw, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(raw))
+        raw_t = raw_t.to(ctx.device)
+        M, N = raw_t.shape
+        assert M % tm == 0 and N % tn == 0, "ragged edge tiles: build them tile by tile with CompressedTile/DenseTile"
+        mt, nt = M // tm, N // tn
+        dtype = raw_t.dtype
+        # (mt, tm, nt, tn) -> (nt, mt, tn, tm): tile (j,i) column-major at lin = j + i*mt
+        tiles = raw_t.view(mt, tm, nt, tn).permute(2, 0, 3, 1).contiguous()
+        if params is None:
+            tmx = cls(mt, nt, tm, tn, dtype, ctx, compressed=False)
+            tmx.buf.copy_(tiles.reshape(-1))
+            return tmx
+        tmx = cls(mt, nt, tm, tn, dtype, ctx, compressed=True)
+        n = mt * nt
+        esz = tiles.element_size()
+        ptrs = (C.c_void_p * n)(*[tiles.data_ptr() + esz * tm * tn * lin for lin in range(n)])
+        prm = params.c()
+        check(_fn("compress_batched", dtype)(ctx.h, n, ptrs, tm, tmx.descs, C.byref(prm), None))
+        ctx.Sync()
+        return tmx
+
+    @classmethod
+    def zeros_compressed(cls, mt, nt, tm, tn, dtype, ctx: RunContext, rank_bound=0):
+        """What the compressing constructor gives for an all-zero matrix (the drivers' C0, omp_main.cpp:243,355):
+        rank-1 tiles whose product is zero, maxRank = min(tm,tn)/3."""
+        return cls(mt, nt, tm, tn, dtype, ctx, compressed=True, rank_bound=rank_bound)
+
+    def reset_to_zero(self):
+        """Back to the drivers' C0: rank-1 tiles whose product is zero (only the live column/row is cleared)."""
+        assert self.compressed
+        v = self.buf.view(self.mt * self.nt, self.tile_elems)
+        v[:, : self.tm].zero_()
+        v[:, self.tm * self.max_rank: self.tm * self.max_rank + self.tn].zero_()
+        self.ranks.fill_(1)
+
+    def load_factors(self, U: torch.Tensor, V: torch.Tensor, rank: int):
+        """Fill every tile from compact factor stacks: U (ntiles, rank, tm) [= column-major tm x rank], V (ntiles, tn,
+        rank) [= column-major rank x tn], tile order lin = row + col*mt. Device-to-device or pinned-host-to-device."""
+        v = self.buf.view(self.mt * self.nt, self.tile_elems)
+        v[:, : self.tm * rank].copy_(U.reshape(self.mt * self.nt, -1), non_blocking=True)
+        v[:, self.tm * self.max_rank: self.tm * self.max_rank + rank * self.tn].copy_(
+            V.reshape(self.mt * self.nt, -1), non_blocking=True)
+        self.ranks.fill_(rank)
+
+    def rank_table(self) -> np.ndarray:
+        return self.ranks.cpu().numpy().reshape(self.nt, self.mt).T.copy()
+
+    def ToRawMatrix(self) -> np.ndarray:
+        """RawMatrix ToRawMatrix(ctx) (TileMatrix.cpp:187-252): U*V per tile, assembled on the host."""
+        out = np.zeros((self.mt * self.tm, self.nt * self.tn), dtype=np.float64 if self.dtype == torch.float64 else np.float32)
+        for i in range(self.nt):
+            for j in range(self.mt):
+                out[j * self.tm:(j + 1) * self.tm, i * self.tn:(i + 1) * self.tn] = self.GetTile(j, i).to_dense()
+        return out
+
+    def GetMemoryFootprint(self) -> int:
+        """bytes actually holding data (TileMatrix.cpp:176-184)."""
+        esz = self.buf.element_size()
+        if not self.compressed:
+            return self.mt * self.nt * self.tm * self.tn * esz
+        return int(self.ranks.sum().item()) * (self.tm + self.tn) * esz
+
+
+def tile_matrix_multiplication(A: TileMatrix, B: TileMatrix, Cm: TileMatrix, alpha, beta, ctx: RunContext,
+                               params: CompressionParameters, owned=None, info: torch.Tensor | None = None,
+                               k_range=None):
+    """for i, j: for k: HCore::Gemm(A(j,k), B(k,i), C(j,i)) (omp_main.cpp:112-126) -- all owned (j,i) of one k in one
+    batched call, k sequential.  `owned`: optional list of linear C indices (j + i*mt) this rank owns."""
+    assert A.nt == B.mt and A.mt == Cm.mt and B.nt == Cm.nt
+    ct = _CT[Cm.dtype]
+    prm = params.c()
+    if owned is None:
+        o_ptr, n_owned = None, 0
+    else:
+        n_owned = len(owned)
+        o_ptr = (C.c_int64 * n_owned)(*owned)
+    k0, k1 = k_range if k_range is not None else (0, A.nt)
+    check(_fn("tlr_matmul", Cm.dtype)(ctx.h, Cm.mt, Cm.nt, A.nt, A.descs, B.descs, Cm.descs, o_ptr, n_owned, k0, k1,
+                                      ct(alpha), ct(beta), C.byref(prm), None if info is None else info.data_ptr()))

@@ -1,0 +1,880 @@
+// hcb_capi.cu -- the C ABI of libhcore_b200.so (declared in include/hcore_b200.h) and the host-side orchestration
+// of the fused batched TLR-GEMM flow.  Host code here only builds descriptors and enqueues kernels: there is no
+// CPU arithmetic path and no fallback -- without a CUDA device every compute entry point returns HCB_ENODEVICE.
+#include "common.cuh"
+#include "kernels_blas.cuh"
+#include "kernels_qr.cuh"
+#include "kernels_svd.cuh"
+#include "kernels_tlr.cuh"
+
+#include <algorithm>
+#include <type_traits>
+
+namespace hcb {
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+int ensure_ws(hcb_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->ws_bytes) return HCB_OK;
+    // grow-only arena: growing synchronises (in-flight kernels may still use the old arena) -- callers reserve up
+    // front (hcb_ctx_reserve_workspace) so that steady-state calls never get here.
+    HCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->ws) HCB_CUDA(cudaFree(ctx->ws));
+    ctx->ws = nullptr;
+    ctx->ws_bytes = 0;
+    const size_t want = align_up(bytes + bytes / 8, 1 << 20);
+    cudaError_t e = cudaMalloc(&ctx->ws, want);
+    if (e != cudaSuccess) return fail(HCB_ENOMEM, std::string("workspace cudaMalloc: ") + cudaGetErrorString(e));
+    ctx->ws_bytes = want;
+    return HCB_OK;
+}
+
+int ring_upload(hcb_ctx *ctx, const void *host, size_t bytes, void **d_out) {
+    ParamRing &r = ctx->ring;
+    const size_t need = align_up(bytes, 256);
+    if (need > r.cap) {
+        HCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (r.h) HCB_CUDA(cudaFreeHost(r.h));
+        if (r.d) HCB_CUDA(cudaFree(r.d));
+        r.cap = align_up(std::max(need * 4, (size_t) 1 << 20), 4096);
+        r.off = 0;
+        HCB_CUDA(cudaMallocHost((void **) &r.h, r.cap));
+        HCB_CUDA(cudaMalloc((void **) &r.d, r.cap));
+    }
+    if (r.off + need > r.cap) {
+        // wrap: earlier slots may still be in flight -> wait for the stream once per lap
+        HCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        r.off = 0;
+    }
+    std::memcpy(r.h + r.off, host, bytes);
+    HCB_CUDA(cudaMemcpyAsync(r.d + r.off, r.h + r.off, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *d_out = r.d + r.off;
+    r.off += need;
+    return HCB_OK;
+}
+
+struct PhaseScope {  // records begin/end events around one phase when timing is enabled
+    hcb_ctx *ctx;
+    cudaEvent_t end = nullptr;
+    PhaseScope(hcb_ctx *c, int phase) : ctx(c) {
+        if (!c->timing) return;
+        auto get = [&]() {
+            if (c->ev_used == c->ev_pool.size()) {
+                cudaEvent_t e;
+                cudaEventCreate(&e);
+                c->ev_pool.push_back(e);
+            }
+            return c->ev_pool[c->ev_used++];
+        };
+        cudaEvent_t beg = get();
+        end = get();
+        cudaEventRecord(beg, c->stream);
+        c->phase_recs.push_back({phase, beg, end});
+    }
+    ~PhaseScope() {
+        if (end) cudaEventRecord(end, ctx->stream);
+    }
+};
+
+static int check_ctx(hcb_ctx *ctx) {
+    if (!ctx) return fail(HCB_EINVAL, "null context");
+    HCB_CUDA(cudaSetDevice(ctx->device));
+    return HCB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// launch helpers (device-resident problem arrays)
+// ---------------------------------------------------------------------------------------------------------------
+template<typename T>
+int launch_gemm(hcb_ctx *ctx, const GemmProb<T> *d_probs, int n_probs, int m_bound, int n_bound) {
+    if (n_probs <= 0 || m_bound <= 0 || n_bound <= 0) return HCB_OK;
+    for (int off = 0; off < n_probs; off += 65535) {
+        const int cnt = std::min(65535, n_probs - off);
+        if (m_bound <= 32 && n_bound <= 32) {
+            dim3 grid(1, cnt);
+            k_gemm_batched<T, 32, 32, 16><<<grid, 256, 0, ctx->stream>>>(d_probs + off);
+        } else {
+            dim3 grid(std::max(1, cdiv(m_bound, 64) * cdiv(n_bound, 64)), cnt);
+            k_gemm_batched<T, 64, 64, 16><<<grid, 256, 0, ctx->stream>>>(d_probs + off);
+        }
+        HCB_LAUNCH_CHECK("k_gemm_batched");
+    }
+    return HCB_OK;
+}
+
+template<typename T>
+int launch_copy(hcb_ctx *ctx, const CopyProb<T> *d_probs, int n_probs, int rows_bound, int cols_bound) {
+    if (n_probs <= 0 || rows_bound <= 0 || cols_bound <= 0) return HCB_OK;
+    for (int off = 0; off < n_probs; off += 65535) {
+        const int cnt = std::min(65535, n_probs - off);
+        dim3 grid(std::max(1, std::min(1024, cdiv(rows_bound, 32) * cdiv(cols_bound, 32))), cnt);
+        k_copy_batched<T><<<grid, dim3(32, 8), 0, ctx->stream>>>(d_probs + off);
+        HCB_LAUNCH_CHECK("k_copy_batched");
+    }
+    return HCB_OK;
+}
+
+template<typename T>
+int launch_qr(hcb_ctx *ctx, const QrProb<T> *d_probs, int n_probs) {
+    if (n_probs <= 0) return HCB_OK;
+    k_geqrf_batched<T><<<n_probs, 512, 0, ctx->stream>>>(d_probs);
+    HCB_LAUNCH_CHECK("k_geqrf_batched");
+    return HCB_OK;
+}
+
+template<typename T>
+int launch_refl(hcb_ctx *ctx, const ReflProb<T> *d_probs, int n_probs, int nvec_bound) {
+    if (n_probs <= 0 || nvec_bound <= 0) return HCB_OK;
+    for (int off = 0; off < n_probs; off += 65535) {
+        const int cnt = std::min(65535, n_probs - off);
+        dim3 grid(std::max(1, cdiv(nvec_bound, 8)), cnt);
+        k_apply_reflectors<T><<<grid, 256, 0, ctx->stream>>>(d_probs + off);
+        HCB_LAUNCH_CHECK("k_apply_reflectors");
+    }
+    return HCB_OK;
+}
+
+template<typename T>
+int launch_svd(hcb_ctx *ctx, const SvdProb<T> *d_probs, int n_probs, int a_bound, int b_bound) {
+    if (n_probs <= 0) return HCB_OK;
+    // shared memory: enough for the whole bound-sized problem, capped at the opt-in limit; the kernel decides per
+    // problem (from its true a, b) whether it fits, and otherwise works in global memory with sigma in smem.
+    size_t want = ((size_t) a_bound * b_bound + (size_t) b_bound * b_bound + (size_t) b_bound) * sizeof(T);
+    const size_t cap = ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0;
+    if (want > cap) want = cap / 16 * 16;
+    if ((size_t) std::max(b_bound, 1) * sizeof(T) > want) return fail(HCB_EUNSUPPORTED, "svd: problem too large");
+    want = align_up(want, 16);
+    HCB_CUDA(cudaFuncSetAttribute(k_jacobi_svd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) want));
+    k_jacobi_svd<T><<<n_probs, 512, want, ctx->stream>>>(d_probs, (int) (want / sizeof(T)), 40);
+    HCB_LAUNCH_CHECK("k_jacobi_svd");
+    return HCB_OK;
+}
+
+// single host-side problem -> device (through the pinned ring) -> batched kernel with a batch of one
+template<typename P>
+int upload_one(hcb_ctx *ctx, const P &prob, const P **d_out) {
+    void *d = nullptr;
+    HCB_TRY(ring_upload(ctx, &prob, sizeof(P), &d));
+    *d_out = reinterpret_cast<const P *>(d);
+    return HCB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (2) fine-grained kernel table
+// ---------------------------------------------------------------------------------------------------------------
+template<typename T>
+int t_gemm(hcb_ctx *ctx, int ta, int tb, int64_t m, int64_t n, int64_t k, T alpha, const T *A, int64_t lda, const T *B,
+           int64_t ldb, T beta, T *C, int64_t ldc) {
+    HCB_TRY(check_ctx(ctx));
+    if (m < 0 || n < 0 || k < 0) return fail(HCB_EINVAL, "gemm: negative dimension");
+    if (m == 0 || n == 0) return HCB_OK;
+    GemmProb<T> g{A, B, C, (int) m, (int) n, (int) k, (int) lda, (int) ldb, (int) ldc, ta ? 1 : 0, tb ? 1 : 0, alpha, beta};
+    const GemmProb<T> *d;
+    HCB_TRY(upload_one(ctx, g, &d));
+    return launch_gemm<T>(ctx, d, 1, (int) m, (int) n);
+}
+
+template<typename T>
+int t_copy(hcb_ctx *ctx, const T *src, int lds, T *dst, int ldd, int rows, int cols, int trans, T scale) {
+    if (rows <= 0 || cols <= 0) return HCB_OK;
+    CopyProb<T> c{src, dst, rows, cols, lds, ldd, trans, scale};
+    const CopyProb<T> *d;
+    HCB_TRY(upload_one(ctx, c, &d));
+    return launch_copy<T>(ctx, d, 1, rows, cols);
+}
+
+template<typename T>
+int t_multiply_by_alpha(hcb_ctx *ctx, T *arr, int64_t rows, int64_t cols, int64_t m, int64_t rank, T alpha) {
+    HCB_TRY(check_ctx(ctx));
+    const size_t count = (size_t) rows * cols;
+    if (count == 0) return HCB_OK;
+    k_scale_flat<T><<<cdiv(count, 256), 256, 0, ctx->stream>>>(arr, (size_t) m * rank, count, alpha);
+    HCB_LAUNCH_CHECK("k_scale_flat");
+    return HCB_OK;
+}
+
+template<typename T>
+int t_process_v(hcb_ctx *ctx, int64_t n, int64_t crank, int ungqr, int64_t vm, T beta, const T *CV, int64_t ldcv, T *V,
+                int64_t arank, const T *B, int cholesky) {
+    HCB_TRY(check_ctx(ctx));
+    (void) ungqr;  // conj is the identity for real T (Definitions.hpp:10-13 instantiates float/double only)
+    if (cholesky) {
+        // omp/kernels.cpp:35-55: V (ld ldcv) = beta*CV, Vptr (ld arank) = B -- plain scaled copies
+        HCB_TRY(t_copy<T>(ctx, CV, (int) ldcv, V, (int) ldcv, (int) crank, (int) n, 0, beta));
+        return t_copy<T>(ctx, B, (int) arank, V + n * crank, (int) arank, (int) arank, (int) n, 0, T(1));
+    }
+    // omp/kernels.cpp:57-77: V[j + i*vm] = beta*CV[i + j*ldcv] ; Vptr[j + i*vm] = B[i + j*arank]
+    HCB_TRY(t_copy<T>(ctx, CV, (int) ldcv, V, (int) vm, (int) n, (int) crank, 1, beta));
+    return t_copy<T>(ctx, B, (int) arank, V + n * crank, (int) vm, (int) n, (int) arank, 1, T(1));
+}
+
+template<typename T>
+int t_new_rank_device(hcb_ctx *ctx, int truncated, const T *sigma, int64_t size_s, T acc, int32_t *d_rank) {
+    HCB_TRY(check_ctx(ctx));
+    k_new_rank<T><<<1, 32, 0, ctx->stream>>>(sigma, (int) size_s, acc, truncated, d_rank);
+    HCB_LAUNCH_CHECK("k_new_rank");
+    return HCB_OK;
+}
+
+template<typename T>
+int t_new_rank(hcb_ctx *ctx, int truncated, const T *sigma, int64_t size_s, T acc, int64_t *host_rank) {
+    HCB_TRY(check_ctx(ctx));
+    HCB_TRY(ensure_ws(ctx, 256));
+    int32_t *d = reinterpret_cast<int32_t *>(ctx->ws);
+    HCB_TRY(t_new_rank_device<T>(ctx, truncated, sigma, size_s, acc, d));
+    int32_t h = 0;
+    HCB_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    HCB_CUDA(cudaStreamSynchronize(ctx->stream));  // host-visible rank: the reference syncs here too
+    *host_rank = h;
+    return HCB_OK;
+}
+
+template<typename T>
+int t_uvptr(hcb_ctx *ctx, int64_t rank, int64_t vm, T *UV, const T *Vnew) {
+    HCB_TRY(check_ctx(ctx));  // UV (rank x vm, ld rank) = Vnew (vm x rank, ld vm)^T
+    return t_copy<T>(ctx, Vnew, (int) vm, UV, (int) rank, (int) rank, (int) vm, 1, T(1));
+}
+
+template<typename T>
+int t_vtnew(hcb_ctx *ctx, int64_t rk, int ungqr, int64_t min_vm_vn, const T *sigma, T *VT, int64_t size_s, int64_t vm) {
+    HCB_TRY(check_ctx(ctx));
+    const int cols = (int) (ungqr ? min_vm_vn : vm);
+    if (rk <= 0 || cols <= 0) return HCB_OK;
+    dim3 block(32, 8), grid(cdiv(rk, 32), cdiv(cols, 8));
+    k_scale_rows<T><<<grid, block, 0, ctx->stream>>>(VT, (int) size_s, (int) rk, cols, sigma);
+    HCB_LAUNCH_CHECK("k_scale_rows");
+    return HCB_OK;
+}
+
+template<typename T>
+int t_fill_identity(hcb_ctx *ctx, int64_t n, T *A) {
+    HCB_TRY(check_ctx(ctx));
+    if (n <= 0) return HCB_OK;
+    k_fill_diag<T><<<cdiv(n, 256), 256, 0, ctx->stream>>>(A, (int) n, (int) n, T(1));
+    HCB_LAUNCH_CHECK("k_fill_diag");
+    return HCB_OK;
+}
+
+template<typename T>
+int t_lacpy(hcb_ctx *ctx, int type, int64_t m, int64_t n, const T *A, int64_t lda, T *B, int64_t ldb) {
+    HCB_TRY(check_ctx(ctx));
+    if (m <= 0 || n <= 0) return HCB_OK;
+    dim3 block(32, 8), grid(cdiv(m, 32), cdiv(n, 8));
+    k_lacpy<T><<<grid, block, 0, ctx->stream>>>((char) type, (int) m, (int) n, A, (int) lda, B, (int) ldb);
+    HCB_LAUNCH_CHECK("k_lacpy");
+    return HCB_OK;
+}
+
+template<typename T>
+int t_laset(hcb_ctx *ctx, int type, int64_t m, int64_t n, T off, T diag, T *A, int64_t lda) {
+    HCB_TRY(check_ctx(ctx));
+    if (m <= 0 || n <= 0) return HCB_OK;
+    dim3 block(32, 8), grid(cdiv(m, 32), cdiv(n, 8));
+    k_laset<T><<<grid, block, 0, ctx->stream>>>((char) type, (int) m, (int) n, off, diag, A, (int) lda);
+    HCB_LAUNCH_CHECK("k_laset");
+    return HCB_OK;
+}
+
+template<typename T>
+int t_geqrf(hcb_ctx *ctx, int64_t m, int64_t n, T *A, int64_t lda, T *tau) {
+    HCB_TRY(check_ctx(ctx));
+    if (m <= 0 || n <= 0) return HCB_OK;
+    QrProb<T> q{A, tau, (int) m, (int) n, (int) lda};
+    const QrProb<T> *d;
+    HCB_TRY(upload_one(ctx, q, &d));
+    return launch_qr<T>(ctx, d, 1);
+}
+
+template<typename T>
+int t_unmqr(hcb_ctx *ctx, int side, int trans, int64_t m, int64_t n, int64_t k, const T *A, int64_t lda, const T *tau,
+            T *C, int64_t ldc) {
+    HCB_TRY(check_ctx(ctx));
+    if (m <= 0 || n <= 0 || k <= 0) return HCB_OK;
+    const bool right = (side == 1 || side == 'R');
+    const bool tr = (trans != 0 && trans != 'N');
+    // Q = H_0 ... H_{k-1}.  Left: Q C applies H_{k-1} first, Q^T C applies H_0 first.
+    //                        Right: C Q applies H_0 first, C Q^T applies H_{k-1} first.
+    const int forward = right ? (tr ? 0 : 1) : (tr ? 1 : 0);
+    ReflProb<T> r{A, tau, C, (int) (right ? n : m), (int) k, (int) lda, (int) m, (int) n, (int) ldc, right ? 1 : 0,
+                  forward, nullptr};
+    const ReflProb<T> *d;
+    HCB_TRY(upload_one(ctx, r, &d));
+    return launch_refl<T>(ctx, d, 1, (int) (right ? m : n));
+}
+
+template<typename T>
+int t_ungqr(hcb_ctx *ctx, int64_t m, int64_t n, int64_t k, T *A, int64_t lda, const T *tau) {
+    HCB_TRY(check_ctx(ctx));
+    if (m <= 0 || n <= 0) return HCB_OK;
+    // explicit Q (m x n) = H_0..H_{k-1} [I;0]: keep the reflectors in scratch, overwrite A with [I;0], apply.
+    const size_t bytes = align_up((size_t) m * k * sizeof(T), 256);
+    HCB_TRY(ensure_ws(ctx, bytes));
+    T *Vw = reinterpret_cast<T *>(ctx->ws);
+    HCB_TRY(t_copy<T>(ctx, A, (int) lda, Vw, (int) m, (int) m, (int) k, 0, T(1)));
+    HCB_TRY(t_laset<T>(ctx, 'G', m, n, T(0), T(1), A, lda));
+    ReflProb<T> r{Vw, tau, A, (int) m, (int) k, (int) m, (int) m, (int) n, (int) lda, 0, 0, nullptr};
+    const ReflProb<T> *d;
+    HCB_TRY(upload_one(ctx, r, &d));
+    return launch_refl<T>(ctx, d, 1, (int) n);
+}
+
+template<typename T>
+int t_svd(hcb_ctx *ctx, int64_t m, int64_t n, T *A, int64_t lda, T *S, T *U, int64_t ldu, T *VT, int64_t ldvt) {
+    HCB_TRY(check_ctx(ctx));
+    if (m <= 0 || n <= 0) return HCB_OK;
+    const int a = (int) std::max(m, n), b = (int) std::min(m, n);
+    const bool transposed = m < n;
+    // scratch: M (a*b) | J (b*b) | Us (a*b) | Vs (b*b)
+    const size_t eM = (size_t) a * b, eJ = (size_t) b * b;
+    HCB_TRY(ensure_ws(ctx, (2 * eM + 2 * eJ) * sizeof(T) + 1024));
+    T *M = reinterpret_cast<T *>(ctx->ws), *J = M + eM, *Us = J + eJ, *Vs = Us + eM;
+    HCB_TRY(t_copy<T>(ctx, A, (int) lda, M, a, a, b, transposed ? 1 : 0, T(1)));
+    SvdProb<T> sp{M, J, Us, Vs, S, nullptr, a, b, a, a, b};
+    const SvdProb<T> *d;
+    HCB_TRY(upload_one(ctx, sp, &d));
+    HCB_TRY(launch_svd<T>(ctx, d, 1, a, b));
+    if (!transposed) {  // A = Us S Vs^T : U = Us (m x n), VT = Vs^T (n x n)
+        HCB_TRY(t_copy<T>(ctx, Us, a, U, (int) ldu, (int) m, b, 0, T(1)));
+        return t_copy<T>(ctx, Vs, b, VT, (int) ldvt, b, (int) n, 1, T(1));
+    }
+    // A^T = Us S Vs^T -> A = Vs S Us^T : U = Vs (m x m), VT = Us^T (m x n)
+    HCB_TRY(t_copy<T>(ctx, Vs, b, U, (int) ldu, (int) m, b, 0, T(1)));
+    return t_copy<T>(ctx, Us, a, VT, (int) ldvt, b, (int) n, 1, T(1));
+}
+
+template<typename T>
+int t_trmm(hcb_ctx *ctx, int side, int uplo, int trans, int diag, int64_t m, int64_t n, T alpha, const T *A, int64_t lda,
+           T *B, int64_t ldb) {
+    HCB_TRY(check_ctx(ctx));
+    if (m <= 0 || n <= 0) return HCB_OK;
+    // B := alpha op(tri(A)) B (Left) or alpha B op(tri(A)) (Right): expand the triangle, GEMM into scratch, copy back.
+    const bool right = (side == 'R' || side == 1);
+    const int na = (int) (right ? n : m);
+    const size_t eD = (size_t) na * na, eO = (size_t) m * n;
+    HCB_TRY(ensure_ws(ctx, (eD + eO) * sizeof(T) + 1024));
+    T *D = reinterpret_cast<T *>(ctx->ws), *O = D + eD;
+    dim3 block(32, 8), grid(cdiv(na, 32), cdiv(na, 8));
+    k_expand_tri<T><<<grid, block, 0, ctx->stream>>>((char) uplo, (char) diag, na, A, (int) lda, D);
+    HCB_LAUNCH_CHECK("k_expand_tri");
+    const int tr = (trans != 0 && trans != 'N') ? 1 : 0;
+    GemmProb<T> g = right ? GemmProb<T>{B, D, O, (int) m, (int) n, na, (int) ldb, na, (int) m, 0, tr, alpha, T(0)}
+                          : GemmProb<T>{D, B, O, (int) m, (int) n, na, na, (int) ldb, (int) m, tr, 0, alpha, T(0)};
+    const GemmProb<T> *d;
+    HCB_TRY(upload_one(ctx, g, &d));
+    HCB_TRY(launch_gemm<T>(ctx, d, 1, (int) m, (int) n));
+    return t_copy<T>(ctx, O, (int) m, B, (int) ldb, (int) m, (int) n, 0, T(1));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (3) fused batched TLR GEMM
+// ---------------------------------------------------------------------------------------------------------------
+struct BatchShape {
+    int m = 0, n = 0, k = 0;           // maxima over the batch
+    int kA = 0, kB = 0, kC = 0, maxrankC = 0;  // rank bounds
+    int mix = 0;
+};
+
+static inline int bound_of(const hcb_tile &t) {
+    if (t.type != HCB_TILE_COMPRESSED) return 0;
+    return t.rank_bound > 0 ? std::min(t.rank_bound, t.max_rank) : t.max_rank;
+}
+
+template<typename T>
+struct Layout {
+    size_t slab = 0, o_w1 = 0, o_w2 = 0, o_uw = 0, o_vw = 0, o_tauu = 0, o_tauv = 0, o_m = 0, o_j = 0, o_us = 0,
+           o_vs = 0, o_sig = 0, o_vn = 0;
+    int r_b = 0, pq_b = 0;
+};
+
+template<typename T>
+Layout<T> make_layout(const BatchShape &s) {
+    Layout<T> L;
+    size_t off = 0;
+    auto take = [&](size_t elems) { size_t o = off; off += align_up(std::max<size_t>(elems, 1), 32); return o; };
+    size_t w1 = 0, w2 = 0;
+    switch (s.mix) {
+        case CCC: w1 = (size_t) s.kA * s.kB; break;
+        case CCD: w1 = (size_t) s.kA * s.kB; w2 = (size_t) s.kA * s.n; break;
+        case CDD: w1 = (size_t) s.kA * s.n; break;
+        case DCD: w1 = (size_t) s.m * s.kB; break;
+        case DDC: w1 = (size_t) s.m * s.n; break;
+        default: break;
+    }
+    L.o_w1 = take(w1);
+    L.o_w2 = take(w2);
+    const bool recomp = (s.mix == CCC || s.mix == CDC || s.mix == DCC);
+    if (recomp) {
+        const int kp = (s.mix == DCC) ? s.kB : s.kA;
+        L.r_b = s.kC + kp;
+        const int p_b = std::min(s.m, L.r_b), q_b = std::min(s.n, L.r_b);
+        L.pq_b = std::max(p_b, q_b);
+        const size_t sq = (size_t) L.pq_b * L.pq_b;
+        L.o_uw = take((size_t) s.m * L.r_b);
+        L.o_vw = take((size_t) s.n * L.r_b);
+        L.o_tauu = take(L.r_b);
+        L.o_tauv = take(L.r_b);
+        L.o_m = take(sq);
+        L.o_j = take(sq);
+        L.o_us = take(sq);
+        L.o_vs = take(sq);
+        L.o_sig = take(L.pq_b);
+        L.o_vn = take((size_t) s.n * std::min(L.pq_b, std::max(s.maxrankC, 1)));
+    }
+    L.slab = off;
+    return L;
+}
+
+template<typename T>
+struct DescArrays {  // device arrays living at the front of the scratch arena
+    size_t bytes = 0;
+    size_t o_g1, o_g2, o_g3, o_cp, o_qr, o_rf, o_svd, o_rc, o_rk, o_tiles;
+    explicit DescArrays(int n) {
+        size_t off = 0;
+        auto take = [&](size_t b) { size_t o = off; off += align_up(b, 256); return o; };
+        o_g1 = take(sizeof(GemmProb<T>) * n);
+        o_g2 = take(sizeof(GemmProb<T>) * n);
+        o_g3 = take(sizeof(GemmProb<T>) * n);
+        o_cp = take(sizeof(CopyProb<T>) * 4 * n);
+        o_qr = take(sizeof(QrProb<T>) * 2 * n);
+        o_rf = take(sizeof(ReflProb<T>) * 2 * n);
+        o_svd = take(sizeof(SvdProb<T>) * n);
+        o_rc = take(sizeof(RecompProb<T>) * n);
+        o_rk = take(sizeof(int) * n);
+        o_tiles = take(sizeof(hcb_tile) * 3 * n);
+        bytes = off;
+    }
+};
+
+static int classify(const hcb_tile *A, const hcb_tile *B, const hcb_tile *C, int64_t n, int opA, int opB, BatchShape &s) {
+    if (n <= 0) return HCB_OK;
+    const int ta = A[0].type, tb = B[0].type, tc = C[0].type;
+    s.mix = (ta == HCB_TILE_COMPRESSED ? 4 : 0) | (tb == HCB_TILE_COMPRESSED ? 2 : 0) | (tc == HCB_TILE_COMPRESSED ? 1 : 0);
+    for (int64_t t = 0; t < n; ++t) {
+        if (A[t].type != ta || B[t].type != tb || C[t].type != tc)
+            return fail(HCB_EINVAL, "tlr_gemm_batched: the batch must be homogeneous in its Dense/Compressed mix");
+        const int am = opA ? A[t].n : A[t].m, ak = opA ? A[t].m : A[t].n;
+        const int bk = opB ? B[t].n : B[t].m, bn = opB ? B[t].m : B[t].n;
+        if (am != C[t].m || bn != C[t].n || ak != bk)
+            return fail(HCB_EINVAL, "tlr_gemm_batched: op(A) op(B) does not conform with C");
+        for (const hcb_tile *x : {&A[t], &B[t], &C[t]}) {
+            if (!x->d_data) return fail(HCB_EINVAL, "tlr_gemm_batched: null tile buffer");
+            if (x->type == HCB_TILE_COMPRESSED && (!x->d_rank || x->max_rank < 1))
+                return fail(HCB_EINVAL, "tlr_gemm_batched: compressed tile needs d_rank and max_rank >= 1");
+            if (x->type == HCB_TILE_DENSE && x->ld < x->m) return fail(HCB_EINVAL, "tlr_gemm_batched: dense ld < m");
+        }
+        if (s.mix == DDC && C[t].max_rank < std::min(C[t].m, C[t].n))
+            return fail(HCB_EINVAL, "tlr_gemm_batched: Dense*Dense -> Compressed makes C full rank "
+                                    "(HCore.cpp:291-298): max_rank must be >= min(m, n)");
+        s.m = std::max(s.m, C[t].m);
+        s.n = std::max(s.n, C[t].n);
+        s.k = std::max(s.k, ak);
+        s.kA = std::max(s.kA, bound_of(A[t]));
+        s.kB = std::max(s.kB, bound_of(B[t]));
+        s.kC = std::max(s.kC, bound_of(C[t]));
+        s.maxrankC = std::max(s.maxrankC, C[t].max_rank);
+    }
+    return HCB_OK;
+}
+
+template<typename T>
+int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, const hcb_tile *B, int opB,
+                       const hcb_tile *C, T alpha, T beta, const hcb_compress_params *prm, int32_t *d_info) {
+    HCB_TRY(check_ctx(ctx));
+    if (n64 <= 0) return HCB_OK;
+    if (!A || !B || !C || !prm) return fail(HCB_EINVAL, "tlr_gemm_batched: null argument");
+    if (n64 > (1 << 24)) return fail(HCB_EINVAL, "tlr_gemm_batched: batch too large");
+    const int n = (int) n64;
+    BatchShape s;
+    HCB_TRY(classify(A, B, C, n, opA, opB, s));
+    const Layout<T> L = make_layout<T>(s);
+    const DescArrays<T> D(n);
+    const size_t total = D.bytes + L.slab * sizeof(T) * (size_t) n + 256;
+    HCB_TRY(ensure_ws(ctx, total));
+    char *base = reinterpret_cast<char *>(ctx->ws);
+
+    // descriptors: host arrays -> pinned ring -> device
+    std::vector<hcb_tile> packed(3 * (size_t) n);
+    std::copy(A, A + n, packed.begin());
+    std::copy(B, B + n, packed.begin() + n);
+    std::copy(C, C + n, packed.begin() + 2 * (size_t) n);
+    hcb_tile *d_tiles = reinterpret_cast<hcb_tile *>(base + D.o_tiles);
+    {
+        void *staged = nullptr;
+        HCB_TRY(ring_upload(ctx, packed.data(), packed.size() * sizeof(hcb_tile), &staged));
+        HCB_CUDA(cudaMemcpyAsync(d_tiles, staged, packed.size() * sizeof(hcb_tile), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+
+    SetupArgs<T> sa;
+    sa.A = d_tiles; sa.B = d_tiles + n; sa.C = d_tiles + 2 * (size_t) n;
+    sa.n_tiles = n; sa.mix = s.mix; sa.opA = opA ? 1 : 0; sa.opB = opB ? 1 : 0;
+    sa.alpha = alpha; sa.beta = beta;
+    sa.ws = reinterpret_cast<T *>(base + align_up(D.bytes, 256));
+    sa.slab = L.slab; sa.o_w1 = L.o_w1; sa.o_w2 = L.o_w2; sa.o_uw = L.o_uw; sa.o_vw = L.o_vw;
+    sa.o_tauu = L.o_tauu; sa.o_tauv = L.o_tauv; sa.o_m = L.o_m; sa.o_j = L.o_j; sa.o_us = L.o_us; sa.o_vs = L.o_vs;
+    sa.o_sig = L.o_sig; sa.o_vn = L.o_vn;
+    sa.kA_b = s.kA; sa.kB_b = s.kB; sa.kC_b = s.kC; sa.r_b = L.r_b;
+    sa.rk_new = reinterpret_cast<int *>(base + D.o_rk);
+    sa.info = d_info;
+    sa.g1 = reinterpret_cast<GemmProb<T> *>(base + D.o_g1);
+    sa.g2 = reinterpret_cast<GemmProb<T> *>(base + D.o_g2);
+    sa.g3 = reinterpret_cast<GemmProb<T> *>(base + D.o_g3);
+    sa.cp = reinterpret_cast<CopyProb<T> *>(base + D.o_cp);
+    sa.qr = reinterpret_cast<QrProb<T> *>(base + D.o_qr);
+    sa.rf = reinterpret_cast<ReflProb<T> *>(base + D.o_rf);
+    sa.svd = reinterpret_cast<SvdProb<T> *>(base + D.o_svd);
+    sa.rc = reinterpret_cast<RecompProb<T> *>(base + D.o_rc);
+    {
+        PhaseScope ph(ctx, 0);
+        k_setup_tlr<T><<<cdiv(n, 128), 128, 0, ctx->stream>>>(sa);
+        HCB_LAUNCH_CHECK("k_setup_tlr");
+    }
+
+    // contraction phases (grids sized from rank BOUNDS; kernels read the true shapes from the descriptors)
+    const int kmaxAB = std::max(s.kA, s.kB);
+    int g1m = s.m, g1n = s.n, g2m = s.m, g2n = s.n;
+    switch (s.mix) {
+        case CCC: g1m = s.kA; g1n = s.kB; g2m = s.n; g2n = s.kA; break;
+        case CCD: g1m = s.kA; g1n = s.kB; g2m = s.kA; g2n = s.n; break;
+        case CDD: g1m = s.kA; g1n = s.n; break;
+        case DCD: g1m = s.m; g1n = s.kB; break;
+        case CDC: g1m = s.n; g1n = s.kA; break;
+        case DCC: g1m = s.m; g1n = s.kB; break;
+        default: break;
+    }
+    (void) kmaxAB;
+    {
+        PhaseScope ph(ctx, 1);
+        HCB_TRY(launch_gemm<T>(ctx, sa.g1, n, g1m, g1n));
+        if (s.mix == CCC || s.mix == CCD || s.mix == CDD || s.mix == DCD || s.mix == DDC)
+            HCB_TRY(launch_gemm<T>(ctx, sa.g2, n, g2m, g2n));
+        if (s.mix == CCD) HCB_TRY(launch_gemm<T>(ctx, sa.g3, n, s.m, s.n));
+    }
+
+    if (s.mix == DDC) {
+        dim3 grid(std::max(1, std::min(256, cdiv((long long) s.m * s.n, 256))), n);
+        k_ddc_finalize<T><<<grid, 256, 0, ctx->stream>>>(sa.C, sa.ws, L.slab, L.o_w1, d_info);
+        HCB_LAUNCH_CHECK("k_ddc_finalize");
+        return HCB_OK;
+    }
+    if (!(s.mix == CCC || s.mix == CDC || s.mix == DCC)) return HCB_OK;  // dense C: done
+
+    // recompression (Compressed.cpp:332-682)
+    {
+        PhaseScope ph(ctx, 2);
+        HCB_TRY(launch_copy<T>(ctx, sa.cp, 4 * n, std::max(s.m, s.n), std::max(L.r_b, 1)));
+    }
+    {
+        PhaseScope ph(ctx, 3);
+        HCB_TRY(launch_qr<T>(ctx, sa.qr, 2 * n));
+    }
+    {
+        PhaseScope ph(ctx, 4);
+        dim3 grid(std::max(1, std::min(64, cdiv((long long) L.pq_b * L.pq_b, 256))), n);
+        k_core_build<T><<<grid, 256, 0, ctx->stream>>>(sa.rc);
+        HCB_LAUNCH_CHECK("k_core_build");
+        HCB_TRY(launch_svd<T>(ctx, sa.svd, n, L.pq_b, L.pq_b));
+        k_truncate<T><<<n, 256, 0, ctx->stream>>>(sa.rc, (T) prm->accuracy, prm->truncated_svd, (int) prm->fixed_rank);
+        HCB_LAUNCH_CHECK("k_truncate");
+    }
+    const int rk_bound = std::max(1, std::min(L.pq_b, s.maxrankC));
+    {
+        PhaseScope ph(ctx, 5);
+        HCB_TRY(launch_refl<T>(ctx, sa.rf, 2 * n, rk_bound));
+    }
+    {
+        PhaseScope ph(ctx, 6);
+        dim3 grid(std::max(1, std::min(256, cdiv(rk_bound, 32) * cdiv(s.n, 32))), n);
+        k_finalize<T><<<grid, dim3(32, 8), 0, ctx->stream>>>(sa.rc);
+        HCB_LAUNCH_CHECK("k_finalize");
+    }
+    return HCB_OK;
+}
+
+template<typename T>
+int t_tlr_matmul(hcb_ctx *ctx, int64_t mt, int64_t nt, int64_t kt, const hcb_tile *A, const hcb_tile *B,
+                 const hcb_tile *C, const int64_t *owned, int64_t n_owned, int64_t k_begin, int64_t k_end, T alpha,
+                 T beta, const hcb_compress_params *prm, int32_t *d_info) {
+    HCB_TRY(check_ctx(ctx));
+    if (mt <= 0 || nt <= 0 || kt <= 0) return HCB_OK;
+    if (k_begin < 0 || k_end > kt || k_begin > k_end) return fail(HCB_EINVAL, "tlr_matmul: bad k range");
+    const int64_t total = owned ? n_owned : mt * nt;
+    if (total <= 0) return HCB_OK;
+    std::vector<hcb_tile> a(total), b(total), c(total);
+    for (int64_t k = k_begin; k < k_end; ++k) {  // the k-sum of one C tile is sequential (each step recompresses)
+        for (int64_t q = 0; q < total; ++q) {
+            const int64_t lin = owned ? owned[q] : q;
+            if (lin < 0 || lin >= mt * nt) return fail(HCB_EINVAL, "tlr_matmul: owned index out of range");
+            const int64_t j = lin % mt, i = lin / mt;
+            a[q] = A[j + k * mt];
+            b[q] = B[k + i * kt];
+            c[q] = C[lin];
+        }
+        HCB_TRY(t_tlr_gemm_batched<T>(ctx, total, a.data(), 0, b.data(), 0, c.data(), alpha, beta, prm, d_info));
+    }
+    return HCB_OK;
+}
+
+template<typename T>
+int t_compress_batched(hcb_ctx *ctx, int64_t n64, const T *const *dense, int64_t ld, const hcb_tile *out,
+                       const hcb_compress_params *prm, int32_t *d_info) {
+    HCB_TRY(check_ctx(ctx));
+    if (n64 <= 0) return HCB_OK;
+    if (!dense || !out || !prm) return fail(HCB_EINVAL, "compress_batched: null argument");
+    (void) d_info;
+    int m = 0, n = 0;
+    for (int64_t t = 0; t < n64; ++t) {
+        if (out[t].type != HCB_TILE_COMPRESSED || !out[t].d_rank || !out[t].d_data || !dense[t])
+            return fail(HCB_EINVAL, "compress_batched: bad output tile");
+        m = std::max(m, out[t].m);
+        n = std::max(n, out[t].n);
+    }
+    const int a = std::max(m, n), b = std::min(m, n);
+    const size_t eM = align_up((size_t) a * b, 32), eJ = align_up((size_t) b * b, 32), eS = align_up((size_t) b, 32);
+    const size_t slab = 2 * eM + 2 * eJ + eS;
+    // chunk the batch so that the scratch stays below ~8 GiB
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n64, (int64_t) (((size_t) 8 << 30) / (slab * sizeof(T)))));
+    for (int64_t c0 = 0; c0 < n64; c0 += chunk) {
+        const int cnt = (int) std::min<int64_t>(chunk, n64 - c0);
+        const size_t desc = align_up(sizeof(CopyProb<T>) * cnt, 256) + align_up(sizeof(SvdProb<T>) * cnt, 256) +
+                            align_up(sizeof(CompressProb<T>) * cnt, 256);
+        HCB_TRY(ensure_ws(ctx, desc + slab * sizeof(T) * cnt + 256));
+        char *base = reinterpret_cast<char *>(ctx->ws);
+        CopyProb<T> *d_cp = reinterpret_cast<CopyProb<T> *>(base);
+        SvdProb<T> *d_sv = reinterpret_cast<SvdProb<T> *>(base + align_up(sizeof(CopyProb<T>) * cnt, 256));
+        CompressProb<T> *d_fp = reinterpret_cast<CompressProb<T> *>(reinterpret_cast<char *>(d_sv) +
+                                                                    align_up(sizeof(SvdProb<T>) * cnt, 256));
+        T *ws = reinterpret_cast<T *>(base + align_up(desc, 256));
+        std::vector<CopyProb<T>> cp(cnt);
+        std::vector<SvdProb<T>> sv(cnt);
+        std::vector<CompressProb<T>> fp(cnt);
+        for (int t = 0; t < cnt; ++t) {
+            const hcb_tile &o = out[c0 + t];
+            const int tm = o.m, tn = o.n, ta = std::max(tm, tn), tb = std::min(tm, tn);
+            const bool tr = tm < tn;
+            T *M = ws + (size_t) t * slab, *J = M + eM, *Us = J + eJ, *Vs = Us + eM, *sg = Vs + eJ;
+            cp[t] = CopyProb<T>{dense[c0 + t], M, ta, tb, (int) ld, ta, tr ? 1 : 0, T(1)};
+            sv[t] = SvdProb<T>{M, J, Us, Vs, sg, nullptr, ta, tb, ta, ta, tb};
+            T *U = reinterpret_cast<T *>(o.d_data), *V = U + (size_t) tm * o.max_rank;
+            // m >= n: A = Us S Vs^T (Uf = Us m x s, Vf = Vs n x s); m < n: A^T = Us S Vs^T -> Uf = Vs, Vf = Us
+            fp[t] = tr ? CompressProb<T>{Vs, Us, sg, U, V, o.d_rank, nullptr, tm, tn, tb, tb, ta, o.max_rank}
+                       : CompressProb<T>{Us, Vs, sg, U, V, o.d_rank, nullptr, tm, tn, tb, ta, tb, o.max_rank};
+        }
+        void *st = nullptr;
+        HCB_TRY(ring_upload(ctx, cp.data(), sizeof(CopyProb<T>) * cnt, &st));
+        HCB_CUDA(cudaMemcpyAsync(d_cp, st, sizeof(CopyProb<T>) * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
+        HCB_TRY(ring_upload(ctx, sv.data(), sizeof(SvdProb<T>) * cnt, &st));
+        HCB_CUDA(cudaMemcpyAsync(d_sv, st, sizeof(SvdProb<T>) * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
+        HCB_TRY(ring_upload(ctx, fp.data(), sizeof(CompressProb<T>) * cnt, &st));
+        HCB_CUDA(cudaMemcpyAsync(d_fp, st, sizeof(CompressProb<T>) * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
+        HCB_TRY(launch_copy<T>(ctx, d_cp, cnt, a, b));
+        HCB_TRY(launch_svd<T>(ctx, d_sv, cnt, a, b));
+        k_compress_finalize<T><<<cnt, 256, 0, ctx->stream>>>(d_fp, (T) prm->accuracy, prm->truncated_svd,
+                                                              (int) prm->fixed_rank);
+        HCB_LAUNCH_CHECK("k_compress_finalize");
+        if (c0 + chunk < n64) HCB_CUDA(cudaStreamSynchronize(ctx->stream));  // scratch is reused by the next chunk
+    }
+    return HCB_OK;
+}
+
+template<typename T>
+size_t t_workspace(int64_t n_tiles, int64_t m, int64_t n, int64_t k, int64_t r_bound) {
+    BatchShape s;
+    s.m = (int) m; s.n = (int) n; s.k = (int) k; s.mix = CCC;
+    s.kA = s.kB = (int) ((r_bound + 1) / 2);
+    s.kC = (int) (r_bound - s.kA);
+    s.maxrankC = (int) std::max<int64_t>(1, std::min(m, n) / 3);
+    const Layout<T> L = make_layout<T>(s);
+    const DescArrays<T> D((int) n_tiles);
+    return D.bytes + L.slab * sizeof(T) * (size_t) n_tiles + 512;
+}
+
+}  // namespace hcb
+
+// =================================================================================================================
+// extern "C"
+// =================================================================================================================
+using namespace hcb;
+
+extern "C" {
+
+const char *hcb_last_error(void) { return g_last_error.c_str(); }
+const char *hcb_version(void) { return "hcore_b200 0.1 (sm_100a; batched TLR GEMM + recompression; no CPU fallback)"; }
+uint64_t hcb_launch_count(void) { return g_launches.load(); }
+void hcb_launch_count_reset(void) { g_launches.store(0); }
+
+static int ctx_init(int device, cudaStream_t stream, bool own, hcb_ctx **out) {
+    if (!out) return fail(HCB_EINVAL, "null out pointer");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(HCB_ENODEVICE, std::string("no CUDA device (") + cudaGetErrorString(e) +
+                                       "): libhcore_b200 has no CPU fallback");
+    if (device < 0 || device >= count) return fail(HCB_EINVAL, "device index out of range");
+    HCB_CUDA(cudaSetDevice(device));
+    hcb_ctx *c = new hcb_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    HCB_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    if (own) {
+        HCB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    } else {
+        c->stream = stream;
+    }
+    *out = c;
+    return HCB_OK;
+}
+
+int hcb_ctx_create(int device, hcb_ctx **out) { return ctx_init(device, nullptr, true, out); }
+int hcb_ctx_create_on_stream(int device, void *s, hcb_ctx **out) { return ctx_init(device, (cudaStream_t) s, false, out); }
+
+int hcb_ctx_destroy(hcb_ctx *c) {
+    if (!c) return HCB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->ws) cudaFree(c->ws);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->ring.h) cudaFreeHost(c->ring.h);
+    if (c->ring.d) cudaFree(c->ring.d);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return HCB_OK;
+}
+
+int hcb_ctx_phase_timing(hcb_ctx *c, int enable) {
+    HCB_TRY(check_ctx(c));
+    c->timing = enable != 0;
+    return HCB_OK;
+}
+int hcb_ctx_phase_times(hcb_ctx *c, double *ms, uint64_t *launches) {
+    HCB_TRY(check_ctx(c));
+    HCB_CUDA(cudaStreamSynchronize(c->stream));
+    for (auto &r : c->phase_recs) {
+        float t = 0.f;
+        HCB_CUDA(cudaEventElapsedTime(&t, r.beg, r.end));
+        if (ms) ms[r.phase] += t;
+        if (launches) launches[r.phase] += 1;
+    }
+    c->phase_recs.clear();
+    c->ev_used = 0;
+    return HCB_OK;
+}
+const char *hcb_phase_name(int phase) {
+    static const char *names[HCB_N_PHASES] = {"setup", "contraction", "stack", "panel_qr", "core_svd", "apply_q", "finalize"};
+    return (phase >= 0 && phase < HCB_N_PHASES) ? names[phase] : "?";
+}
+
+int hcb_ctx_sync(hcb_ctx *c) {
+    HCB_TRY(check_ctx(c));
+    HCB_CUDA(cudaStreamSynchronize(c->stream));
+    return HCB_OK;
+}
+void *hcb_ctx_stream(hcb_ctx *c) { return c ? (void *) c->stream : nullptr; }
+int hcb_ctx_device(hcb_ctx *c) { return c ? c->device : -1; }
+int hcb_ctx_sm_count(hcb_ctx *c) { return c ? c->sm_count : 0; }
+int hcb_ctx_reserve_workspace(hcb_ctx *c, size_t bytes) {
+    HCB_TRY(check_ctx(c));
+    return ensure_ws(c, bytes);
+}
+size_t hcb_ctx_workspace_bytes(hcb_ctx *c) { return c ? c->ws_bytes : 0; }
+
+int hcb_malloc(hcb_ctx *c, size_t bytes, void **d_out) {
+    HCB_TRY(check_ctx(c));
+    if (!d_out) return fail(HCB_EINVAL, "null out pointer");
+    cudaError_t e = cudaMalloc(d_out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(HCB_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return HCB_OK;
+}
+int hcb_free(hcb_ctx *c, void *p) {
+    HCB_TRY(check_ctx(c));
+    if (p) HCB_CUDA(cudaFree(p));
+    return HCB_OK;
+}
+int hcb_memcpy(hcb_ctx *c, void *dst, const void *src, size_t bytes, int kind) {
+    HCB_TRY(check_ctx(c));
+    static const cudaMemcpyKind kinds[5] = {cudaMemcpyHostToDevice, cudaMemcpyDeviceToDevice, cudaMemcpyDeviceToHost,
+                                            cudaMemcpyHostToHost, cudaMemcpyDefault};
+    if (kind < 0 || kind > 4) return fail(HCB_EINVAL, "memcpy: bad kind");
+    if (bytes) HCB_CUDA(cudaMemcpyAsync(dst, src, bytes, kinds[kind], c->stream));
+    return HCB_OK;
+}
+int hcb_memset(hcb_ctx *c, void *dst, int value, size_t bytes) {
+    HCB_TRY(check_ctx(c));
+    if (bytes) HCB_CUDA(cudaMemsetAsync(dst, value, bytes, c->stream));
+    return HCB_OK;
+}
+
+#define HCB_DEFINE_KERNEL_TABLE(P, T)                                                                                 \
+    int hcb_##P##gemm(hcb_ctx *c, int ta, int tb, int64_t m, int64_t n, int64_t k, T alpha, const T *A, int64_t lda,   \
+                      const T *B, int64_t ldb, T beta, T *C, int64_t ldc) {                                           \
+        return t_gemm<T>(c, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);                                   \
+    }                                                                                                                 \
+    int hcb_##P##multiply_by_alpha(hcb_ctx *c, T *arr, int64_t rows, int64_t cols, int64_t m, int64_t rank, T alpha) { \
+        return t_multiply_by_alpha<T>(c, arr, rows, cols, m, rank, alpha);                                           \
+    }                                                                                                                 \
+    int hcb_##P##process_v(hcb_ctx *c, int64_t n, int64_t crank, int ungqr, int64_t vm, T beta, const T *CV,          \
+                           int64_t ldcv, T *V, int64_t arank, const T *B, int cholesky) {                             \
+        return t_process_v<T>(c, n, crank, ungqr, vm, beta, CV, ldcv, V, arank, B, cholesky);                        \
+    }                                                                                                                 \
+    int hcb_##P##new_rank(hcb_ctx *c, int trunc, const T *sig, int64_t size_s, T acc, int64_t *host_rank) {            \
+        return t_new_rank<T>(c, trunc, sig, size_s, acc, host_rank);                                                 \
+    }                                                                                                                 \
+    int hcb_##P##new_rank_device(hcb_ctx *c, int trunc, const T *sig, int64_t size_s, T acc, int32_t *d_rank) {        \
+        return t_new_rank_device<T>(c, trunc, sig, size_s, acc, d_rank);                                             \
+    }                                                                                                                 \
+    int hcb_##P##uvptr(hcb_ctx *c, int64_t rank, int64_t vm, T *UV, const T *Vnew) {                                   \
+        return t_uvptr<T>(c, rank, vm, UV, Vnew);                                                                    \
+    }                                                                                                                 \
+    int hcb_##P##vtnew(hcb_ctx *c, int64_t rk, int ungqr, int64_t mn, const T *sig, T *VT, int64_t size_s,             \
+                       int64_t vm) {                                                                                  \
+        return t_vtnew<T>(c, rk, ungqr, mn, sig, VT, size_s, vm);                                                    \
+    }                                                                                                                 \
+    int hcb_##P##uvptr_conj(hcb_ctx *c, int64_t, int64_t, T *) { return check_ctx(c); }                                \
+    int hcb_##P##fill_identity(hcb_ctx *c, int64_t n, T *A) { return t_fill_identity<T>(c, n, A); }                    \
+    int hcb_##P##lacpy(hcb_ctx *c, int type, int64_t m, int64_t n, const T *A, int64_t lda, T *B, int64_t ldb) {       \
+        return t_lacpy<T>(c, type, m, n, A, lda, B, ldb);                                                            \
+    }                                                                                                                 \
+    int hcb_##P##laset(hcb_ctx *c, int type, int64_t m, int64_t n, T off, T diag, T *A, int64_t lda) {                 \
+        return t_laset<T>(c, type, m, n, off, diag, A, lda);                                                         \
+    }                                                                                                                 \
+    int hcb_##P##geqrf(hcb_ctx *c, int64_t m, int64_t n, T *A, int64_t lda, T *tau) {                                  \
+        return t_geqrf<T>(c, m, n, A, lda, tau);                                                                     \
+    }                                                                                                                 \
+    int hcb_##P##ungqr(hcb_ctx *c, int64_t m, int64_t n, int64_t k, T *A, int64_t lda, const T *tau) {                 \
+        return t_ungqr<T>(c, m, n, k, A, lda, tau);                                                                  \
+    }                                                                                                                 \
+    int hcb_##P##unmqr(hcb_ctx *c, int side, int trans, int64_t m, int64_t n, int64_t k, const T *A, int64_t lda,      \
+                       const T *tau, T *C, int64_t ldc) {                                                             \
+        return t_unmqr<T>(c, side, trans, m, n, k, A, lda, tau, C, ldc);                                             \
+    }                                                                                                                 \
+    int hcb_##P##svd(hcb_ctx *c, int64_t m, int64_t n, T *A, int64_t lda, T *S, T *U, int64_t ldu, T *VT,              \
+                     int64_t ldvt) {                                                                                  \
+        return t_svd<T>(c, m, n, A, lda, S, U, ldu, VT, ldvt);                                                       \
+    }                                                                                                                 \
+    int hcb_##P##trmm(hcb_ctx *c, int side, int uplo, int trans, int diag, int64_t m, int64_t n, T alpha, const T *A,  \
+                      int64_t lda, T *B, int64_t ldb) {                                                               \
+        return t_trmm<T>(c, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb);                                   \
+    }                                                                                                                 \
+    int hcb_##P##tlr_gemm_batched(hcb_ctx *c, int64_t n, const hcb_tile *A, int opA, const hcb_tile *B, int opB,       \
+                                  const hcb_tile *C, T alpha, T beta, const hcb_compress_params *p, int32_t *info) {  \
+        return t_tlr_gemm_batched<T>(c, n, A, opA, B, opB, C, alpha, beta, p, info);                                 \
+    }                                                                                                                 \
+    int hcb_##P##compress_batched(hcb_ctx *c, int64_t n, const T *const *dense, int64_t ld, const hcb_tile *out,       \
+                                  const hcb_compress_params *p, int32_t *info) {                                      \
+        return t_compress_batched<T>(c, n, dense, ld, out, p, info);                                                 \
+    }                                                                                                                 \
+    int hcb_##P##tlr_matmul(hcb_ctx *c, int64_t mt, int64_t nt, int64_t kt, const hcb_tile *A, const hcb_tile *B,      \
+                            const hcb_tile *C, const int64_t *owned, int64_t n_owned, int64_t k_begin,                \
+                            int64_t k_end, T alpha, T beta, const hcb_compress_params *p, int32_t *info) {            \
+        return t_tlr_matmul<T>(c, mt, nt, kt, A, B, C, owned, n_owned, k_begin, k_end, alpha, beta, p, info);        \
+    }                                                                                                                 \
+    size_t hcb_##P##tlr_gemm_workspace(int64_t n_tiles, int64_t m, int64_t n, int64_t k, int64_t r_bound) {            \
+        return t_workspace<T>(n_tiles, m, n, k, r_bound);                                                            \
+    }
+
+HCB_DEFINE_KERNEL_TABLE(d, double)
+HCB_DEFINE_KERNEL_TABLE(s, float)
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// kernels_qr.cuh -- batched Householder QR and reflector application (general path: any m, n, ld).
+//
+// Replaces cusolverDnXgeqrf / cusolverDn{S,D}orgqr / cusolverDnDormqr as called per tile by the reference
+// (src/kernels/cuda/CudaKernels.cu:534-561, 962-1017, 732-768).  Output layout and sign convention are LAPACK's
+// (dgeqr2/dlarfg: beta = -sign(alpha)*||x||, tau = (beta-alpha)/beta, v(0) = 1 implicit), so R and the reflectors
+// match the reference's known answers (tests/kernels/TestKernels.cpp:470-511).
+#pragma once
+#include "common.cuh"
+
+namespace hcb {
+
+// One CTA per panel. Per column j: (1) CTA-wide norm of A[j+1:, j]; (2) thread 0 forms beta/tau; (3) v scaled in
+// place; (4) every warp owns a set of trailing columns and applies H_j = I - tau v v^T to each of them with one
+// fused pass (dot product, warp-shuffle reduction, rank-1 update); column reads are fully coalesced.
+template<typename T>
+__global__ void __launch_bounds__(512) k_geqrf_batched(const QrProb<T> *__restrict__ probs) {
+    const QrProb<T> p = probs[blockIdx.x];
+    const int m = p.m, n = p.n, lda = p.lda;
+    const int kmax = m < n ? m : n;
+    if (kmax <= 0) return;
+    __shared__ T red[33];
+    __shared__ T s_tau, s_scale;
+    T *A = p.A;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
+
+    for (int j = 0; j < kmax; ++j) {
+        T *col = A + (size_t) j * lda;
+        // (1) ||A[j+1:m, j]||^2
+        T ss = T(0);
+        for (int i = j + 1 + tid; i < m; i += nthr) { const T x = col[i]; ss = fma(x, x, ss); }
+        ss = block_sum(ss, red);
+        // (2) Householder scalars
+        if (tid == 0) {
+            const T alpha = col[j];
+            if (ss == T(0)) {
+                s_tau = T(0);  // H = I (dlarfg: xnorm == 0)
+                s_scale = T(0);
+            } else {
+                const T nrm = t_sqrt(fma(alpha, alpha, ss));
+                const T beta = alpha >= T(0) ? -nrm : nrm;
+                s_tau = (beta - alpha) / beta;
+                s_scale = T(1) / (alpha - beta);
+                col[j] = beta;
+            }
+            p.tau[j] = s_tau;
+        }
+        __syncthreads();
+        const T tau = s_tau, scale = s_scale;
+        if (tau != T(0)) {
+            // (3) v = x / (alpha - beta)
+            for (int i = j + 1 + tid; i < m; i += nthr) col[i] *= scale;
+            __syncthreads();
+            // (4) trailing update, one warp per column
+            for (int c = j + 1 + w; c < n; c += nw) {
+                T *cc = A + (size_t) c * lda;
+                T dot = T(0);
+                for (int i = j + 1 + lane; i < m; i += 32) dot = fma(col[i], cc[i], dot);
+                dot = warp_sum(dot);
+                dot += cc[j];  // v(0) = 1
+                const T t = tau * dot;
+                __syncwarp();  // every lane has read cc[j] before lane 0 overwrites it
+                if (lane == 0) cc[j] -= t;
+                for (int i = j + 1 + lane; i < m; i += 32) cc[i] = fma(-t, col[i], cc[i]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Apply k Householder reflectors (LAPACK layout) to C.
+//   side_right == 0 : C := H.. C   -- every column of C is independent -> one warp per column
+//   side_right == 1 : C := C H..   -- every row    of C is independent -> one warp per row
+// forward == 1 applies H_0 first (Q^T C, or C Q); forward == 0 applies H_{k-1} first (Q C, or C Q^T).
+// grid = (vector_blocks, n_problems); a warp loops over its vectors, no CTA-level synchronisation is needed.
+template<typename T>
+__global__ void __launch_bounds__(256) k_apply_reflectors(const ReflProb<T> *__restrict__ probs) {
+    const ReflProb<T> p = probs[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    int nvec = p.side_right ? p.mc : p.nc;
+    if (p.nc_dev) nvec = *p.nc_dev;
+    const int len = p.mv;  // reflector length == length of each transformed vector
+    const size_t estride = p.side_right ? (size_t) p.ldc : 1;  // element stride inside one vector
+    const size_t vstride = p.side_right ? 1 : (size_t) p.ldc;  // stride between vectors
+    for (int vec = warp_global; vec < nvec; vec += warps_total) {
+        T *x = p.C + (size_t) vec * vstride;
+        for (int jj = 0; jj < p.k; ++jj) {
+            const int j = p.forward ? jj : p.k - 1 - jj;
+            const T tau = p.tau[j];
+            if (tau == T(0)) continue;
+            const T *v = p.V + (size_t) j * p.ldv;
+            T dot = T(0);
+            for (int i = j + 1 + lane; i < len; i += 32) dot = fma(v[i], x[(size_t) i * estride], dot);
+            dot = warp_sum(dot);
+            dot += x[(size_t) j * estride];
+            const T t = tau * dot;
+            __syncwarp();
+            if (lane == 0) x[(size_t) j * estride] -= t;
+            for (int i = j + 1 + lane; i < len; i += 32) x[(size_t) i * estride] = fma(-t, v[i], x[(size_t) i * estride]);
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace hcb

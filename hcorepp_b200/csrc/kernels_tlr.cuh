@@ -1,0 +1,319 @@
+// kernels_tlr.cuh -- the fused, batched TLR-GEMM flow: device-side problem setup + the recompression glue kernels.
+//
+// Mirrors, for a whole batch of (A,B,C) tile triples at once and with all ranks resident on the device,
+//   HCore<T>::Gemm              src/api/HCore.cpp:22-344       (operand-mix decision table, temp products)
+//   CompressedTile<T>::Gemm     src/operators/concrete/Compressed.cpp:208-694 (stack, QR x2, core SVD, truncate, rebuild)
+// The reference runs ~20 launches + 5 cuSOLVER calls + 1 host sync PER TILE; here one launch per phase covers the batch.
+#pragma once
+#include "common.cuh"
+#include "kernels_blas.cuh"
+
+namespace hcb {
+
+enum Mix { DDD = 0, DDC = 1, DCD = 2, DCC = 3, CDD = 4, CDC = 5, CCD = 6, CCC = 7 };
+
+template<typename T>
+struct RecompProb {
+    T *UW, *VW;        // QR'd stacks: UW m x r (ld m), VW n x r (ld n)
+    T *tauU, *tauV;
+    T *M;              // core (p x q) or its transpose, stored a x b (ld a), a >= b
+    T *Us, *Vs, *sigma;  // Jacobi outputs: Us a x b (ld a), Vs b x b (ld b)
+    T *CU, *CV;        // output tile factors (CU ld m; CV ld = new rank)
+    T *VN;             // n x rank scratch (ld n): V factor before the final transpose
+    int *rank_ptr;     // C tile's device-resident rank
+    int *rk_new;       // scratch: rank chosen by the truncation rule
+    int *info;
+    int m, n, r, p, q, a, b, transposed, max_rank, active;
+};
+
+template<typename T>
+struct SetupArgs {
+    const hcb_tile *A, *B, *C;  // device copies of the descriptor arrays
+    int n_tiles, mix, opA, opB;
+    T alpha, beta;
+    // per-tile scratch (element offsets inside one tile's slab) and slab stride
+    T *ws;
+    size_t slab, o_w1, o_w2, o_uw, o_vw, o_tauu, o_tauv, o_m, o_j, o_us, o_vs, o_sig, o_vn;
+    int kA_b, kB_b, kC_b, r_b;  // rank bounds the scratch was sized for
+    int *rk_new;                // n_tiles ints
+    int *info;                  // n_tiles ints (may be null)
+    GemmProb<T> *g1, *g2, *g3;
+    CopyProb<T> *cp;            // 4 per tile
+    QrProb<T> *qr;              // 2 per tile
+    ReflProb<T> *rf;            // 2 per tile
+    SvdProb<T> *svd;
+    RecompProb<T> *rc;
+};
+
+template<typename T>
+__device__ __forceinline__ GemmProb<T> mk_gemm(const T *A, int lda, int ta, const T *B, int ldb, int tb, T *C, int ldc,
+                                               int m, int n, int k, T alpha, T beta) {
+    GemmProb<T> g;
+    g.A = A; g.B = B; g.C = C; g.m = m; g.n = n; g.k = k; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+    g.ta = ta; g.tb = tb; g.alpha = alpha; g.beta = beta;
+    return g;
+}
+
+template<typename T>
+__device__ __forceinline__ CopyProb<T> mk_copy(const T *src, int lds, T *dst, int ldd, int rows, int cols, int trans,
+                                               T scale) {
+    CopyProb<T> c;
+    c.src = src; c.dst = dst; c.rows = rows; c.cols = cols; c.lds = lds; c.ldd = ldd; c.trans = trans; c.scale = scale;
+    return c;
+}
+
+// One thread per tile triple: reads the (device-resident) ranks and writes every problem descriptor of the step.
+// Operand factors (HCore.cpp:57-110): a compressed operand X = XU * XV contributes, under op,
+//   left factor  L (rows x kx) = op ? XV^T : XU        right factor R (kx x cols) = op ? XU^T : XV.
+template<typename T>
+__global__ void k_setup_tlr(SetupArgs<T> s) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= s.n_tiles) return;
+    const hcb_tile A = s.A[t], B = s.B[t], C = s.C[t];
+    const int m = C.m, n = C.n;
+    const int kdim = s.opA ? A.m : A.n;  // inner dimension of op(A) op(B)
+    const bool ac = A.type == HCB_TILE_COMPRESSED, bc = B.type == HCB_TILE_COMPRESSED, cc = C.type == HCB_TILE_COMPRESSED;
+    const int ka = ac ? *A.d_rank : 0, kb = bc ? *B.d_rank : 0, kc = cc ? *C.d_rank : 0;
+    T *slab = s.ws + (size_t) t * s.slab;
+    GemmProb<T> g1 = mk_gemm<T>(nullptr, 1, 0, nullptr, 1, 0, nullptr, 1, 0, 0, 0, T(0), T(0)), g2 = g1, g3 = g1;
+    CopyProb<T> c0 = mk_copy<T>(nullptr, 1, nullptr, 1, 0, 0, 0, T(0)), c1 = c0, c2 = c0, c3 = c0;
+    QrProb<T> q0{nullptr, nullptr, 0, 0, 1}, q1 = q0;
+    ReflProb<T> r0{nullptr, nullptr, nullptr, 0, 0, 1, 0, 0, 1, 0, 0, nullptr}, r1 = r0;
+    SvdProb<T> sv{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 1, 1, 1};
+    RecompProb<T> rc;
+    memset(&rc, 0, sizeof(rc));
+    int bad = 0;
+    if ((ac && (ka > s.kA_b || ka < 0)) || (bc && (kb > s.kB_b || kb < 0)) || (cc && (kc > s.kC_b || kc < 0))) bad = 1;
+
+    // operand views
+    const T *Ad = (const T *) A.d_data, *Bd = (const T *) B.d_data;
+    T *Cd = (T *) C.d_data;
+    // dense: (ptr, ld, trans) ; compressed: left factor AL (m x ka), right factor AR (ka x kdim)
+    const T *AU = Ad, *AV = Ad + (size_t) A.m * A.max_rank;
+    const T *BU = Bd, *BV = Bd + (size_t) B.m * B.max_rank;
+    const T *ALp = s.opA ? AV : AU; const int ALld = s.opA ? ka : A.m, ALt = s.opA;
+    const T *ARp = s.opA ? AU : AV; const int ARld = s.opA ? A.m : ka, ARt = s.opA;
+    const T *BLp = s.opB ? BV : BU; const int BLld = s.opB ? kb : B.m, BLt = s.opB;
+    const T *BRp = s.opB ? BU : BV; const int BRld = s.opB ? B.m : kb, BRt = s.opB;
+    T *CU = Cd, *CV = Cd + (size_t) C.m * C.max_rank;
+    T *W1 = slab + s.o_w1, *W2 = slab + s.o_w2, *UW = slab + s.o_uw, *VW = slab + s.o_vw;
+    const T one = T(1), zero = T(0);
+    int kp = 0;  // rank of the product term entering the recompression
+
+    if (!bad) {
+        switch (s.mix) {
+            case DDD:  // HCore.cpp:300-313 -> DenseTile::Gemm (Dense.cpp:46-108)
+                g1 = mk_gemm<T>(Ad, A.ld, s.opA, Bd, B.ld, s.opB, Cd, C.ld, m, n, kdim, s.alpha, s.beta);
+                break;
+            case CDD:  // T = AR*op(B) (ka x n) ; C = alpha*AL*T + beta*C  (HCore.cpp:246-258)
+                g1 = mk_gemm<T>(ARp, ARld, ARt, Bd, B.ld, s.opB, W1, ka, ka, n, kdim, one, zero);
+                g2 = mk_gemm<T>(ALp, ALld, ALt, W1, ka, 0, Cd, C.ld, m, n, ka, s.alpha, s.beta);
+                break;
+            case DCD:  // T = op(A)*BL (m x kb) ; C = alpha*T*BR + beta*C  (HCore.cpp:234-245)
+                g1 = mk_gemm<T>(Ad, A.ld, s.opA, BLp, BLld, BLt, W1, m, m, kb, kdim, one, zero);
+                g2 = mk_gemm<T>(W1, m, 0, BRp, BRld, BRt, Cd, C.ld, m, n, kb, s.alpha, s.beta);
+                break;
+            case CCD:  // T1 = AR*BL ; T2 = T1*BR ; C = alpha*AL*T2 + beta*C  (HCore.cpp:221-232)
+                g1 = mk_gemm<T>(ARp, ARld, ARt, BLp, BLld, BLt, W1, ka, ka, kb, kdim, one, zero);
+                g2 = mk_gemm<T>(W1, ka, 0, BRp, BRld, BRt, W2, ka, ka, n, kb, one, zero);
+                g3 = mk_gemm<T>(ALp, ALld, ALt, W2, ka, 0, Cd, C.ld, m, n, ka, s.alpha, s.beta);
+                break;
+            case DDC:  // T = alpha*op(A)*op(B) ; T += beta*CU*CV ; C := (U = T, V = I)  (HCore.cpp:272-299)
+                g1 = mk_gemm<T>(Ad, A.ld, s.opA, Bd, B.ld, s.opB, W1, m, m, n, kdim, s.alpha, zero);
+                g2 = mk_gemm<T>(CU, m, 0, CV, kc, 0, W1, m, m, n, kc, s.beta, one);
+                break;
+            case CDC:  // U_AB = AL (m x ka) ; V_AB^T = op(B)^T * AR^T (n x ka)
+                kp = ka;
+                c1 = mk_copy<T>(ALp, ALld, UW + (size_t) m * kc, m, m, ka, ALt, s.alpha);
+                g1 = mk_gemm<T>(Bd, B.ld, !s.opB, ARp, ARld, !ARt, VW + (size_t) n * kc, n, n, ka, kdim, one, zero);
+                break;
+            case DCC:  // U_AB = alpha*op(A)*BL (m x kb) ; V_AB^T = BR^T (n x kb)
+                kp = kb;
+                g1 = mk_gemm<T>(Ad, A.ld, s.opA, BLp, BLld, BLt, UW + (size_t) m * kc, m, m, kb, kdim, s.alpha, zero);
+                c1 = mk_copy<T>(BRp, BRld, VW + (size_t) n * kc, n, n, kb, !BRt, one);
+                break;
+            case CCC:  // T1 = AR*BL (ka x kb) ; V_AB^T = BR^T * T1^T (n x ka) ; U_AB = AL  (HCore.cpp:221-232,300-313)
+                kp = ka;
+                g1 = mk_gemm<T>(ARp, ARld, ARt, BLp, BLld, BLt, W1, ka, ka, kb, kdim, one, zero);
+                g2 = mk_gemm<T>(BRp, BRld, !BRt, W1, ka, 1, VW + (size_t) n * kc, n, n, ka, kb, one, zero);
+                c1 = mk_copy<T>(ALp, ALld, UW + (size_t) m * kc, m, m, ka, ALt, s.alpha);
+                break;
+        }
+        if (cc && s.mix != DDC) {
+            // stacks (Compressed.cpp:332-349, 378-379): UW = [CU | alpha*U_AB], VW = [beta*CV^T | V_AB^T]
+            const int r = kc + kp;
+            if (r > s.r_b) {
+                bad = 1;
+            } else {
+                c0 = mk_copy<T>(CU, m, UW, m, m, kc, 0, one);
+                c2 = mk_copy<T>(CV, kc, VW, n, n, kc, 1, s.beta);
+                const int p = m < r ? m : r, q = n < r ? n : r;
+                q0 = QrProb<T>{UW, slab + s.o_tauu, m, r, m};
+                q1 = QrProb<T>{VW, slab + s.o_tauv, n, r, n};
+                rc.UW = UW; rc.VW = VW; rc.tauU = slab + s.o_tauu; rc.tauV = slab + s.o_tauv;
+                rc.M = slab + s.o_m; rc.Us = slab + s.o_us; rc.Vs = slab + s.o_vs; rc.sigma = slab + s.o_sig;
+                rc.CU = CU; rc.CV = CV; rc.VN = slab + s.o_vn; rc.rank_ptr = C.d_rank; rc.rk_new = s.rk_new + t;
+                rc.info = s.info ? s.info + t : nullptr;
+                rc.m = m; rc.n = n; rc.r = r; rc.p = p; rc.q = q; rc.max_rank = C.max_rank; rc.active = 1;
+                rc.transposed = p < q;
+                rc.a = rc.transposed ? q : p;
+                rc.b = rc.transposed ? p : q;
+                sv = SvdProb<T>{rc.M, slab + s.o_j, rc.Us, rc.Vs, rc.sigma, rc.info, rc.a, rc.b, rc.a, rc.a, rc.b};
+                // rebuild (Compressed.cpp:551-560, 611-628): CU = Q_U [Unew;0], VN = Q_V [Vfac;0], rank read on device
+                r0 = ReflProb<T>{UW, rc.tauU, CU, m, p, m, m, 0, m, 0, 0, rc.rk_new};
+                r1 = ReflProb<T>{VW, rc.tauV, rc.VN, n, q, n, n, 0, n, 0, 0, rc.rk_new};
+            }
+        }
+    }
+    if (bad) {
+        g1.m = g2.m = g3.m = 0;
+        c0.rows = c1.rows = c2.rows = c3.rows = 0;
+        q0.m = q1.m = 0;
+        r0.k = r1.k = 0; r0.nc = r1.nc = 0; r0.nc_dev = r1.nc_dev = nullptr;
+        sv.a = sv.b = 0;
+        rc.active = 0;
+        if (s.info) s.info[t] = 4;  // rank exceeded the bound the scratch was sized for: tile left untouched
+    } else if (s.info) {
+        s.info[t] = 0;
+    }
+    s.g1[t] = g1; s.g2[t] = g2; s.g3[t] = g3;
+    s.cp[4 * t + 0] = c0; s.cp[4 * t + 1] = c1; s.cp[4 * t + 2] = c2; s.cp[4 * t + 3] = c3;
+    s.qr[2 * t + 0] = q0; s.qr[2 * t + 1] = q1;
+    s.rf[2 * t + 0] = r0; s.rf[2 * t + 1] = r1;
+    s.svd[t] = sv;
+    s.rc[t] = rc;
+}
+
+// core = RU * RV^T with RU = triu(UW[:p, :r]), RV = triu(VW[:q, :r]) (Compressed.cpp:363-370, 442-461), written as
+// M (a x b, ld a): core itself when p >= q, its transpose otherwise.  grid = (chunks, n_tiles)
+template<typename T>
+__global__ void __launch_bounds__(256) k_core_build(const RecompProb<T> *__restrict__ probs) {
+    const RecompProb<T> p = probs[blockIdx.y];
+    if (!p.active) return;
+    const int total = p.p * p.q;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int i = idx % p.p, j = idx / p.p;
+        T acc = T(0);
+        for (int l = (i > j ? i : j); l < p.r; ++l)
+            acc = fma(p.UW[(size_t) i + (size_t) l * p.m], p.VW[(size_t) j + (size_t) l * p.n], acc);
+        if (p.transposed) p.M[(size_t) j + (size_t) i * p.a] = acc;
+        else p.M[(size_t) i + (size_t) j * p.a] = acc;
+    }
+}
+
+// Rank truncation on the device (Compressed.cpp:509-527 + omp/kernels.cpp:82-104) and scatter of the truncated
+// core factors: CU[:, :rk] = [Ufac ; 0] (m x rk), VN[:, :rk] = [Vfac * diag(sigma) ; 0] (n x rk).  One CTA per tile.
+template<typename T>
+__global__ void __launch_bounds__(256) k_truncate(const RecompProb<T> *__restrict__ probs, T accuracy, int truncated,
+                                                  int fixed_rank) {
+    const RecompProb<T> p = probs[blockIdx.x];
+    if (!p.active) return;
+    __shared__ int s_rk;
+    if (threadIdx.x == 0) {
+        int rk;
+        if (fixed_rank > 0) rk = fixed_rank < p.r ? fixed_rank : p.r;
+        else rk = new_rank_rule(p.sigma, p.b, accuracy, truncated);
+        if (rk > p.b) rk = p.b;  // only b = min(m, n, r) singular triplets exist
+        if (rk < 1) rk = 1;
+        if (rk > p.max_rank) {
+            rk = p.max_rank;
+            if (p.info) atomicOr(p.info, 2);
+        }
+        s_rk = rk;
+        *p.rk_new = rk;
+    }
+    __syncthreads();
+    const int rk = s_rk;
+    // not transposed: core = Us S Vs^T  -> Ufac = Us (p x b), Vfac = Vs (q x b)
+    // transposed    : core^T = Us S Vs^T -> core = Vs S Us^T -> Ufac = Vs (p x b, b == p), Vfac = Us (q x b, a == q)
+    const T *Uf = p.transposed ? p.Vs : p.Us;
+    const int ldUf = p.transposed ? p.b : p.a;
+    const T *Vf = p.transposed ? p.Us : p.Vs;
+    const int ldVf = p.transposed ? p.a : p.b;
+    for (int idx = threadIdx.x; idx < p.m * rk; idx += blockDim.x) {
+        const int i = idx % p.m, c = idx / p.m;
+        p.CU[(size_t) i + (size_t) c * p.m] = (i < p.p) ? Uf[(size_t) i + (size_t) c * ldUf] : T(0);
+    }
+    for (int idx = threadIdx.x; idx < p.n * rk; idx += blockDim.x) {
+        const int i = idx % p.n, c = idx / p.n;
+        p.VN[(size_t) i + (size_t) c * p.n] = (i < p.q) ? p.sigma[c] * Vf[(size_t) i + (size_t) c * ldVf] : T(0);
+    }
+}
+
+// CV (rk x n, ld rk) = VN^T (CalculateUVptr, omp/kernels.cpp:106-114) and commit the new rank (Compressed.cpp:656-662).
+// grid = (tile_chunks, n_tiles), block = (32, 8)
+template<typename T>
+__global__ void __launch_bounds__(256) k_finalize(const RecompProb<T> *__restrict__ probs) {
+    const RecompProb<T> p = probs[blockIdx.y];
+    if (!p.active) return;
+    __shared__ T tile[32][33];
+    const int rk = *p.rk_new;
+    const int tr = (rk + 31) / 32, tc = (p.n + 31) / 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int t = blockIdx.x; t < tr * tc; t += gridDim.x) {
+        const int r0 = (t % tr) * 32, c0 = (t / tr) * 32;  // r: rank index, c: column of the tile (row of VN)
+        for (int j = ty; j < 32; j += 8) {
+            const int c = c0 + tx, r = r0 + j;
+            tile[j][tx] = (r < rk && c < p.n) ? p.VN[(size_t) c + (size_t) r * p.n] : T(0);
+        }
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8) {
+            const int r = r0 + tx, c = c0 + j;
+            if (r < rk && c < p.n) p.CV[(size_t) r + (size_t) c * rk] = tile[tx][j];
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && tx == 0 && ty == 0) *p.rank_ptr = rk;
+}
+
+// DDC epilogue (HCore.cpp:291-298 -> CompressedTile::ReadjustTile, Compressed.cpp:696-734): U = T (m x rank),
+// V = identity (rank x n, ld rank), rank = min(m, n).  grid = (chunks, n_tiles)
+template<typename T>
+__global__ void __launch_bounds__(256) k_ddc_finalize(const hcb_tile *__restrict__ Ctiles, const T *__restrict__ ws,
+                                                      size_t slab, size_t o_w1, const int *__restrict__ info) {
+    const hcb_tile C = Ctiles[blockIdx.y];
+    if (info && info[blockIdx.y] != 0) return;
+    const int m = C.m, n = C.n, rank = m < n ? m : n;
+    const T *W = ws + (size_t) blockIdx.y * slab + o_w1;
+    T *CU = (T *) C.d_data, *CV = CU + (size_t) m * C.max_rank;
+    const int gstride = gridDim.x * blockDim.x, g0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int idx = g0; idx < m * rank; idx += gstride) CU[idx] = W[idx];
+    for (int idx = g0; idx < rank * n; idx += gstride) CV[idx] = (idx % rank == idx / rank) ? T(1) : T(0);
+    if (g0 == 0) *C.d_rank = rank;
+}
+
+// Initial compression epilogue (Compressed.cpp:103-135): rank rule, U = Uf[:, :rk], V = diag(sigma) Vf[:, :rk]^T.
+template<typename T>
+struct CompressProb {
+    const T *Uf; const T *Vf; const T *sigma;  // Uf: m x s (ld ldu), Vf: n x s (ld ldv)
+    T *U; T *V; int *rank_ptr; int *info;
+    int m, n, s, ldu, ldv, max_rank;
+};
+
+template<typename T>
+__global__ void __launch_bounds__(256) k_compress_finalize(const CompressProb<T> *__restrict__ probs, T accuracy,
+                                                           int truncated, int fixed_rank) {
+    const CompressProb<T> p = probs[blockIdx.x];
+    __shared__ int s_rk;
+    if (threadIdx.x == 0) {
+        int rk;
+        if (fixed_rank > 0) rk = fixed_rank < p.s ? fixed_rank : p.s;
+        else rk = new_rank_rule(p.sigma, p.s, accuracy, truncated);
+        if (rk < 1) rk = 1;
+        if (rk > p.max_rank) rk = p.max_rank;  // Compressed.cpp:117-119 (silent clamp)
+        s_rk = rk;
+        *p.rank_ptr = rk;
+    }
+    __syncthreads();
+    const int rk = s_rk;
+    for (int idx = threadIdx.x; idx < p.m * rk; idx += blockDim.x) {
+        const int i = idx % p.m, c = idx / p.m;
+        p.U[(size_t) i + (size_t) c * p.m] = p.Uf[(size_t) i + (size_t) c * p.ldu];
+    }
+    for (int idx = threadIdx.x; idx < rk * p.n; idx += blockDim.x) {
+        const int c = idx % rk, j = idx / rk;
+        p.V[(size_t) c + (size_t) j * rk] = p.sigma[c] * p.Vf[(size_t) j + (size_t) c * p.ldv];
+    }
+}
+
+}  // namespace hcb

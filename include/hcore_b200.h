@@ -1,0 +1,149 @@
+/*
+ * hcore_b200.h -- C ABI of libhcore_b200.so: the B200-native (sm_100a) replacement for the reference's device
+ * backend on the TLR-GEMM hot path.
+ *
+ * What it replaces (file:line relative to the ecrc/hcorepp reference tree):
+ *   - the kernel table   hcorepp::kernels::HCoreKernels<T>      include/hcorepp/kernels/kernels.hpp:27-129,
+ *     as implemented for CUDA by src/kernels/cuda/kernels.cpp + src/kernels/cuda/CudaKernels.cu
+ *     (cuBLAS via BLAS++ queue, cuSOLVER, element-wise SIMT kernels);
+ *   - hcorepp::memory::{AllocateArray,DestroyArray,Memcpy,Memset}  include/hcorepp/kernels/cuda/memory.hpp:15-43;
+ *   - hcorepp::kernels::RunContext (CUDA)                          include/hcorepp/kernels/cuda/RunContext.hpp:15-53;
+ *   - and, as ONE fused batched call, the whole per-tile flow
+ *       HCore<T>::Gemm (src/api/HCore.cpp:22-344) -> CompressedTile<T>::Gemm (src/operators/concrete/Compressed.cpp:208-694)
+ *     for many (A,B,C) tile triples per launch with ranks kept on the device (no per-tile host sync, which the
+ *     reference pays in CudaKernels.cu:656-697), plus the compressing constructor (Compressed.cpp:75-146).
+ *
+ * Conventions: plain C, no exceptions, every function returns 0 on success or an HCB_E* code
+ * (hcb_last_error() gives the text).  All matrices are column-major.  Pointers named d_* are DEVICE pointers.
+ * Everything is enqueued on the context's stream; nothing synchronises unless documented.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with HCB_ENODEVICE.
+ */
+#ifndef HCORE_B200_H
+#define HCORE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HCB_OK 0
+#define HCB_EINVAL 1    /* bad argument */
+#define HCB_ECUDA 2     /* CUDA runtime error (text in hcb_last_error) */
+#define HCB_ENODEVICE 3 /* no CUDA device: there is no CPU fallback */
+#define HCB_ENOMEM 4
+#define HCB_EUNSUPPORTED 5
+
+typedef struct hcb_ctx hcb_ctx;
+
+/* ---- context / memory : RunContext + hcorepp::memory (cuda/RunContext.hpp:15-53, cuda/memory.hpp:15-43) -------- */
+int hcb_ctx_create(int device, hcb_ctx **out);                       /* owns a new non-blocking stream */
+int hcb_ctx_create_on_stream(int device, void *cuda_stream, hcb_ctx **out); /* borrows the caller's stream */
+int hcb_ctx_destroy(hcb_ctx *ctx);
+int hcb_ctx_sync(hcb_ctx *ctx);                                      /* RunContext::Sync() */
+void *hcb_ctx_stream(hcb_ctx *ctx);                                  /* RunContext::GetStream() */
+int hcb_ctx_device(hcb_ctx *ctx);
+int hcb_ctx_sm_count(hcb_ctx *ctx);
+/* grow-only scratch arena (replaces MemoryUnit pool, pool/MemoryHandler.hpp:21-157); never memset per call */
+int hcb_ctx_reserve_workspace(hcb_ctx *ctx, size_t bytes);
+size_t hcb_ctx_workspace_bytes(hcb_ctx *ctx);
+int hcb_malloc(hcb_ctx *ctx, size_t bytes, void **d_out);            /* memory::AllocateArray */
+int hcb_free(hcb_ctx *ctx, void *d_ptr);                             /* memory::DestroyArray */
+/* kind: 0 H2D, 1 D2D, 2 D2H, 3 H2H, 4 automatic (memory::MemoryTransfer, memory.hpp:22-44); async on the stream */
+int hcb_memcpy(hcb_ctx *ctx, void *dst, const void *src, size_t bytes, int kind);
+int hcb_memset(hcb_ctx *ctx, void *d_dst, int value, size_t bytes);  /* memory::Memset */
+/* Per-phase device timing of the fused batched path, measured with CUDA events recorded on the context's stream
+ * (the stream the kernels are launched on). Phases: 0 setup, 1 contraction GEMMs, 2 stack assembly, 3 panel QR,
+ * 4 core build + Jacobi SVD + truncation, 5 apply-Q rebuild, 6 finalize.  hcb_ctx_phase_times synchronises, adds the
+ * elapsed milliseconds / launch counts since the last call into ms[7] / launches[7] and clears the records. */
+#define HCB_N_PHASES 7
+int hcb_ctx_phase_timing(hcb_ctx *ctx, int enable);
+int hcb_ctx_phase_times(hcb_ctx *ctx, double *ms, uint64_t *launches);
+const char *hcb_phase_name(int phase);
+const char *hcb_last_error(void);
+const char *hcb_version(void);
+/* number of kernel launches issued by this library since the last reset (bench.py's gpu_launches claim) */
+uint64_t hcb_launch_count(void);
+void hcb_launch_count_reset(void);
+
+/* ---- compression parameters : operators::CompressionParameters (CompressionParameters.hpp:44-46) -------------- */
+typedef struct hcb_compress_params {
+    double accuracy;      /* default 1e-4 */
+    int32_t use_trmm;     /* accepted; the fused path always forms RU*RV^T (same product) */
+    int32_t use_ungqr;    /* accepted; Q is always applied implicitly (same product) */
+    int32_t truncated_svd;/* 1: threshold relative to sigma_0 (omp/kernels.cpp:87-95) */
+    int64_t fixed_rank;   /* 0 = truncate by accuracy */
+    int32_t svd_type;     /* 0 GESVD / 1 GESDD in the reference; one-sided Jacobi here either way */
+    int32_t reserved;
+} hcb_compress_params;
+
+/* ---- tiles : operators::TileMetadata + data buffer (Tile.hpp:30-52) ------------------------------------------ */
+#define HCB_TILE_DENSE 0
+#define HCB_TILE_COMPRESSED 1
+typedef struct hcb_tile {
+    int32_t type;       /* HCB_TILE_DENSE | HCB_TILE_COMPRESSED */
+    int32_t m, n;       /* rows, cols */
+    int32_t ld;         /* dense: leading dimension; compressed: ignored (ldU = m, ldV = rank, Compressed.cpp:29-34) */
+    int32_t max_rank;   /* compressed: capacity; V starts at d_data + m*max_rank (Compressed.cpp:180-185) */
+    int32_t rank_bound; /* host-known upper bound on *d_rank used to size grids/scratch (0 -> max_rank) */
+    int32_t *d_rank;    /* compressed: DEVICE int32 holding the current rank (the device owns rank truth) */
+    void *d_data;       /* DEVICE buffer: dense m x n (ld) or [U (m x max_rank) | V (max_rank x n)] */
+} hcb_tile;
+
+/* ---- (2) fine-grained kernel table : one symbol per HCoreKernels<T> entry (kernels.hpp:27-129) --------------- */
+/* trans: 0 NoTrans, 1 Trans.  type for lacpy/laset: 'G','U','L' (common::MatrixType).  side 'L'/'R'. */
+#define HCB_DECLARE_KERNEL_TABLE(P, T)                                                                                  \
+    int hcb_##P##gemm(hcb_ctx *, int transA, int transB, int64_t m, int64_t n, int64_t k, T alpha, const T *dA,           \
+                      int64_t lda, const T *dB, int64_t ldb, T beta, T *dC, int64_t ldc);  /* kernels.hpp:27-29 */      \
+    int hcb_##P##multiply_by_alpha(hcb_ctx *, T *dArr, int64_t rows, int64_t cols, int64_t m, int64_t rank, T alpha);   \
+    int hcb_##P##process_v(hcb_ctx *, int64_t n, int64_t crank, int ungqr, int64_t vm, T beta, const T *dCV,            \
+                           int64_t ldcv, T *dV, int64_t arank, const T *dB, int cholesky);  /* kernels.hpp:36-38 */     \
+    int hcb_##P##new_rank(hcb_ctx *, int truncated, const T *dSigma, int64_t size_s, T accuracy,                       \
+                          int64_t *host_rank); /* SYNCS (host result, like CudaKernels.cu:656-697) */                  \
+    int hcb_##P##new_rank_device(hcb_ctx *, int truncated, const T *dSigma, int64_t size_s, T accuracy,                \
+                                 int32_t *d_rank); /* async variant: rank stays on the device */                       \
+    int hcb_##P##uvptr(hcb_ctx *, int64_t rank, int64_t vm, T *dUV, const T *dVnew);       /* CalculateUVptr */        \
+    int hcb_##P##vtnew(hcb_ctx *, int64_t rk, int ungqr, int64_t min_vm_vn, const T *dSigma, T *dVT, int64_t size_s,   \
+                       int64_t vm);                                                        /* CalculateVTnew */        \
+    int hcb_##P##uvptr_conj(hcb_ctx *, int64_t rank, int64_t vm, T *dUV);                  /* no-op for real T */      \
+    int hcb_##P##fill_identity(hcb_ctx *, int64_t n, T *dA);                               /* FillIdentityMatrix */    \
+    int hcb_##P##lacpy(hcb_ctx *, int type, int64_t m, int64_t n, const T *dA, int64_t lda, T *dB, int64_t ldb);        \
+    int hcb_##P##laset(hcb_ctx *, int type, int64_t m, int64_t n, T offdiag, T diag, T *dA, int64_t lda);               \
+    int hcb_##P##geqrf(hcb_ctx *, int64_t m, int64_t n, T *dA, int64_t lda, T *dTau);      /* LAPACK layout */         \
+    int hcb_##P##ungqr(hcb_ctx *, int64_t m, int64_t n, int64_t k, T *dA, int64_t lda, const T *dTau);                  \
+    int hcb_##P##unmqr(hcb_ctx *, int side, int trans, int64_t m, int64_t n, int64_t k, const T *dA, int64_t lda,       \
+                       const T *dTau, T *dC, int64_t ldc);                                                             \
+    int hcb_##P##svd(hcb_ctx *, int64_t m, int64_t n, T *dA, int64_t lda, T *dS, T *dU, int64_t ldu, T *dVT,            \
+                     int64_t ldvt); /* SomeVec/SomeVec; dA destroyed */                                                \
+    int hcb_##P##trmm(hcb_ctx *, int side, int uplo, int trans, int diag, int64_t m, int64_t n, T alpha, const T *dA,   \
+                      int64_t lda, T *dB, int64_t ldb);                                                                \
+    /* ---- (3) fused batched fast path -------------------------------------------------------------------------- */  \
+    /* C[t] = alpha*op(A[t])*op(B[t]) + beta*C[t] for t < n_tiles, all eight Dense/Compressed operand mixes of      */  \
+    /* HCore<T>::Gemm (HCore.cpp:36-313; the batch must be mix-homogeneous), recompression included, ranks on the   */  \
+    /* device.  A,B,C are HOST arrays of descriptors.  d_info (device int32[n_tiles], may be NULL): 0 ok,           */  \
+    /* 1 Jacobi not converged, 2 rank clipped to max_rank.  Asynchronous.                                           */  \
+    int hcb_##P##tlr_gemm_batched(hcb_ctx *, int64_t n_tiles, const hcb_tile *A, int opA, const hcb_tile *B, int opB,   \
+                                  const hcb_tile *C, T alpha, T beta, const hcb_compress_params *p, int32_t *d_info);   \
+    /* Compressing constructor, batched (Compressed.cpp:75-146): dense tile t (m x n, ld) -> out[t] (U, V, *d_rank) */  \
+    int hcb_##P##compress_batched(hcb_ctx *, int64_t n_tiles, const T *const *dense_ptrs_host, int64_t ld,              \
+                                  const hcb_tile *out, const hcb_compress_params *p, int32_t *d_info);                 \
+    /* Multi-tile driver (examples/matrix_multiplication/omp_main.cpp:112-126) on one GPU:                           */  \
+    /* for k: C(j,i) += A(j,k)*B(k,i) for all owned (j,i) in ONE batched call per k.  Grids are column-major         */  \
+    /* arrays of descriptors: A[j + k*mt], B[k + i*kt], C[j + i*mt]; owned == NULL means all C tiles, else a list of */  \
+    /* n_owned linear C indices (2D block-cyclic ownership is decided by the caller). Only k in [k_begin, k_end)   */  \
+    /* is accumulated (0, kt for the whole product).                                                                */  \
+    int hcb_##P##tlr_matmul(hcb_ctx *, int64_t mt, int64_t nt, int64_t kt, const hcb_tile *A, const hcb_tile *B,        \
+                            const hcb_tile *C, const int64_t *owned, int64_t n_owned, int64_t k_begin, int64_t k_end,   \
+                            T alpha, T beta, const hcb_compress_params *p, int32_t *d_info);                                            \
+    /* scratch bytes the fused path needs for a batch of n_tiles (m x n) tiles with rank bound r = kc+ka            */  \
+    /* (replaces HCore<T>::CalculateMemoryPoolSize, HCore.cpp:417-480)                                              */  \
+    size_t hcb_##P##tlr_gemm_workspace(int64_t n_tiles, int64_t m, int64_t n, int64_t k, int64_t r_bound);
+
+HCB_DECLARE_KERNEL_TABLE(d, double)
+HCB_DECLARE_KERNEL_TABLE(s, float)
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HCORE_B200_H */

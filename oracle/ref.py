@@ -48,6 +48,8 @@ def _declare(L):
         f("tile_dense").argtypes = [i64, i64, vp, i64]
         f("tile_uv").restype = vp
         f("tile_uv").argtypes = [i64, i64, vp, vp, i64]
+        f("tile_uv_cap").restype = vp
+        f("tile_uv_cap").argtypes = [i64, i64, vp, vp, i64, i64]
         f("tile_compress").restype = vp
         f("tile_compress").argtypes = [i64, i64, vp, i64, C.c_double, C.c_int, C.c_int, C.c_int, i64, C.c_int]
         f("tile_info").argtypes = [vp, vp]
@@ -129,6 +131,13 @@ class RefTile:
         V = fcol(V, U.dtype)
         assert U.shape[1] == V.shape[0]
         return cls(fn("tile_uv", U.dtype)(U.shape[0], V.shape[1], ptr(U), ptr(V), U.shape[1]), U.dtype)
+
+    @classmethod
+    def from_uv_cap(cls, U, V, max_rank):
+        """Same state as a compress-constructed tile (capacity max_rank, V ld = rank) without running the SVD."""
+        U = fcol(U)
+        V = fcol(V, U.dtype)
+        return cls(fn("tile_uv_cap", U.dtype)(U.shape[0], V.shape[1], ptr(U), ptr(V), U.shape[1], max_rank), U.dtype)
 
     @classmethod
     def compress(cls, a, p: Params):

@@ -56,6 +56,19 @@ void *tile_uv(int64_t m, int64_t n, const T *U, const T *V, int64_t rank) {
                                  ctx());
 }
 
+// A tile in exactly the state the compressing constructor leaves it in (capacity max_rank, current rank `rank`,
+// V stored with ld = rank at offset m*max_rank; Compressed.cpp:83-87,132-141) without paying for an SVD: build it at
+// full capacity through the (m, n, UV, ld, rank) constructor and shrink the rank with the public ReadjustTileRank().
+template<typename T>
+void *tile_uv_cap(int64_t m, int64_t n, const T *U, const T *V, int64_t rank, int64_t max_rank) {
+    std::vector<T> uv((size_t) (m + n) * max_rank, T(0));
+    std::memcpy(uv.data(), U, sizeof(T) * m * rank);
+    std::memcpy(uv.data() + (size_t) m * max_rank, V, sizeof(T) * rank * n);
+    auto *t = new CompressedTile<T>(m, n, uv.data(), m, max_rank, blas::Layout::ColMajor, ctx());
+    t->ReadjustTileRank(rank, ctx());
+    return t;
+}
+
 template<typename T>
 void *tile_compress(int64_t m, int64_t n, const T *data, int64_t ld, const CompressionParameters &p) {
     return new CompressedTile<T>(m, n, const_cast<T *>(data), ld, p, blas::Layout::ColMajor, ctx());
@@ -164,6 +177,10 @@ void latms_law(int64_t m, int64_t n, int64_t tile_size, int64_t *seed, T *out, i
     }                                                                                                                \
     extern "C" void *hcref_##P##tile_uv(int64_t m, int64_t n, const T *U, const T *V, int64_t rank) {                \
         return tile_uv<T>(m, n, U, V, rank);                                                                         \
+    }                                                                                                                \
+    extern "C" void *hcref_##P##tile_uv_cap(int64_t m, int64_t n, const T *U, const T *V, int64_t rank,              \
+                                            int64_t max_rank) {                                                      \
+        return tile_uv_cap<T>(m, n, U, V, rank, max_rank);                                                           \
     }                                                                                                                \
     extern "C" void *hcref_##P##tile_compress(int64_t m, int64_t n, const T *d, int64_t ld, double acc,              \
                                               int use_trmm, int use_ungqr, int trunc, int64_t fixed_rank,            \

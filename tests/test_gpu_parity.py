@@ -1,0 +1,449 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything goes through the C ABI of libhcore_b200.so
+(directly, or via the thin hcorepp_b200.api mirror) and is compared with the oracle (oracle/tlr_oracle.py), the
+reference's own known-answer vectors, and fixtures produced by running the reference (tests/golden/).
+
+Tolerances (BASELINE.json north_star): ||C_gpu - C_ref||_F / ||C_ref||_F <= 10 * accuracy on reconstructed products,
+output ranks within +/-1 of the reference; element-wise index/copy kernels are compared exactly.
+/root/reference is NOT used here (it does not exist on the GPU box).
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import tlr_oracle as O  # noqa: E402  (checker only)
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+VEC = json.load(open(os.path.join(GOLDEN, "reference_vectors.json")))
+K = VEC["kernels"]
+DT = [np.float64, np.float32]
+TT = {np.float64: torch.float64, np.float32: torch.float32}
+F = lambda x, dt=np.float64: np.asfortranarray(np.array(x, dtype=dt))
+
+
+@pytest.fixture(scope="module")
+def hc():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import hcorepp_b200 as h
+    return h
+
+
+@pytest.fixture(scope="module")
+def ctx(hc):
+    return hc.RunContext(0)
+
+
+def dev(a):
+    """numpy (any shape, interpreted column-major via Fortran flattening) -> flat device tensor."""
+    a = np.asarray(a)
+    return torch.from_numpy(np.ascontiguousarray(a.reshape(-1, order="F"))).cuda()
+
+
+def host(t, shape):
+    return t.cpu().numpy().reshape(shape, order="F")
+
+
+def fn(name, dt):
+    from hcorepp_b200 import _capi
+    return getattr(_capi.lib, f"hcb_{'d' if dt == np.float64 else 's'}{name}")
+
+
+def ok(rc):
+    from hcorepp_b200 import _capi
+    _capi.check(rc)
+
+
+def ct(dt):
+    return C.c_double if dt == np.float64 else C.c_float
+
+
+def relerr(a, b):
+    return np.linalg.norm(np.asarray(a, np.float64) - np.asarray(b, np.float64)) / max(np.linalg.norm(np.asarray(b, np.float64)), 1e-300)
+
+
+def approx(a, b, tol=1e-2):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.all(np.abs(a - b) <= tol * np.maximum(np.abs(a), np.abs(b)) + 1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ kernel table
+@pytest.mark.parametrize("dt", DT)
+def test_kernel_table_known_answers(ctx, dt):
+    c = ct(dt)
+    g = K["gemm"]
+    A, B, C0 = dev(F(g["A"], dt)), dev(F(g["B"], dt)), dev(F(g["C0"], dt))
+    ok(fn("gemm", dt)(ctx.h, 0, 0, 3, 5, 4, c(1), A.data_ptr(), 3, B.data_ptr(), 4, c(1), C0.data_ptr(), 3))
+    assert np.array_equal(host(C0, (3, 5)), F(g["C"], dt))
+
+    g = K["multiply_by_alpha"]
+    a = dev(np.array(g["flat_in"], dtype=dt))
+    ok(fn("multiply_by_alpha", dt)(ctx.h, a.data_ptr(), g["rows"], g["cols"], g["m"], g["rank"], c(g["alpha"])))
+    assert np.array_equal(a.cpu().numpy(), np.array(g["flat_out"], dtype=dt))
+
+    g = K["process_v"]
+    cv, b, v = dev(np.array(g["cv_flat"], dtype=dt)), dev(np.array(g["b_flat"], dtype=dt)), dev(np.zeros(10, dtype=dt))
+    ok(fn("process_v", dt)(ctx.h, g["n"], g["crank"], 0, g["vm"], c(g["beta"]), cv.data_ptr(), g["ldcv"], v.data_ptr(),
+                           g["arank"], b.data_ptr(), 0))
+    assert np.array_equal(v.cpu().numpy(), np.array(g["v_flat"], dtype=dt))
+
+    for key in ("new_rank_abs", "new_rank_rel"):
+        g = K[key]
+        s = dev(np.array(g["sigma"], dtype=dt))
+        r = C.c_int64(0)
+        ok(fn("new_rank", dt)(ctx.h, int(g["truncated"]), s.data_ptr(), len(g["sigma"]), c(g["accuracy"]), C.byref(r)))
+        assert r.value == g["rank"]
+        dr = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ok(fn("new_rank_device", dt)(ctx.h, int(g["truncated"]), s.data_ptr(), len(g["sigma"]), c(g["accuracy"]), dr.data_ptr()))
+        assert int(dr.item()) == g["rank"]
+
+    g = K["uvptr"]
+    vn, uv = dev(np.array(g["vnew_flat"], dtype=dt)), dev(np.zeros(6, dtype=dt))
+    ok(fn("uvptr", dt)(ctx.h, g["rank"], g["vm"], uv.data_ptr(), vn.data_ptr()))
+    assert np.array_equal(uv.cpu().numpy(), np.array(g["uv_flat"], dtype=dt))
+
+    for key in ("vtnew_noungqr", "vtnew_ungqr"):
+        g = K[key]
+        vt, s = dev(np.array(g["vt_flat"], dtype=dt)), dev(np.array(g["sigma"], dtype=dt))
+        ok(fn("vtnew", dt)(ctx.h, g["rk"], int(g["ungqr"]), min(g["vm"], g["vn"]), s.data_ptr(), vt.data_ptr(), g["size_s"], g["vm"]))
+        assert np.array_equal(vt.cpu().numpy(), np.array(g["out_flat"], dtype=dt))
+
+    a = dev(np.zeros(9, dtype=dt))
+    ok(fn("fill_identity", dt)(ctx.h, 3, a.data_ptr()))
+    assert np.array_equal(host(a, (3, 3)), np.eye(3, dtype=dt))
+
+    g = K["lacpy"]
+    for kind in "GUL":
+        a, b = dev(np.array(g["a_flat"], dtype=dt)), dev(np.zeros(16, dtype=dt))
+        ok(fn("lacpy", dt)(ctx.h, ord(kind), 4, 4, a.data_ptr(), 4, b.data_ptr(), 4))
+        assert np.array_equal(b.cpu().numpy(), np.array(g[kind], dtype=dt))
+    g = K["laset"]
+    for kind in "GUL":
+        a = dev(np.zeros(16, dtype=dt))
+        ok(fn("laset", dt)(ctx.h, ord(kind), 4, 4, c(g["offdiag"]), c(g["diag"]), a.data_ptr(), 4))
+        assert np.array_equal(a.cpu().numpy(), np.array(g[kind], dtype=dt))
+
+    for key in ("trmm", "trmm_unit"):
+        g = K[key]
+        a, b = dev(np.array(g["a_flat"], dtype=dt)), dev(np.array(g["b_flat"], dtype=dt))
+        ok(fn("trmm", dt)(ctx.h, ord(g["side"]), ord(g["uplo"]), ord(g["trans"]), ord(g["diag"]), 4, 4, c(g["alpha"]),
+                          a.data_ptr(), 4, b.data_ptr(), 4))
+        assert approx(b.cpu().numpy(), g["out_flat"], g["tol_rel"])
+
+    g = K["geqrf"]
+    a, tau = dev(np.array(g["a_flat"], dtype=dt)), dev(np.zeros(2, dtype=dt))
+    ok(fn("geqrf", dt)(ctx.h, g["m"], g["n"], a.data_ptr(), g["m"], tau.data_ptr()))
+    assert approx(a.cpu().numpy(), g["qr_flat"], g["tol_rel"]) and approx(tau.cpu().numpy(), g["tau"], g["tol_rel"])
+
+    A = F(K["svd"]["A"], dt)
+    a, s, u, vt = dev(A), dev(np.zeros(3, dt)), dev(np.zeros(9, dt)), dev(np.zeros(9, dt))
+    ok(fn("svd", dt)(ctx.h, 3, 3, a.data_ptr(), 3, s.data_ptr(), u.data_ptr(), 3, vt.data_ptr(), 3))
+    U, S, VT = host(u, (3, 3)), s.cpu().numpy(), host(vt, (3, 3))
+    assert approx((U * S) @ VT, A)
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("shape", [(40, 7), (300, 45), (1024, 71), (5, 9), (33, 33), (1, 1)])
+def test_geqrf_ungqr_unmqr_vs_lapack(ctx, dt, shape):
+    m, n = shape
+    rng = np.random.default_rng(m * 1000 + n)
+    A = np.asfortranarray(rng.standard_normal((m, n)).astype(dt))
+    k = min(m, n)
+    a, tau = dev(A), dev(np.zeros(k, dt))
+    ok(fn("geqrf", dt)(ctx.h, m, n, a.data_ptr(), m, tau.data_ptr()))
+    qr_g, tau_g = host(a, (m, n)), tau.cpu().numpy()
+    qr_o, tau_o = O.k_geqrf(A)
+    tol = 1e-11 if dt == np.float64 else 2e-4
+    assert relerr(np.triu(qr_g), np.triu(qr_o)) < tol          # R, including LAPACK's sign convention
+    assert relerr(qr_g, qr_o) < tol and relerr(tau_g, tau_o) < tol
+    if m >= n:
+        q = dev(qr_g)
+        ok(fn("ungqr", dt)(ctx.h, m, n, n, q.data_ptr(), m, tau.data_ptr()))
+        Q = host(q, (m, n))
+        assert relerr(Q, O.k_ungqr(m, n, n, qr_o, tau_o)) < tol
+        assert relerr(Q.T @ Q, np.eye(n)) < tol
+        assert relerr(Q @ np.triu(qr_g[:n, :]), A) < tol
+    # unmqr, all four (side, trans) combinations against LAPACK
+    ncols = 6
+    for side, trans in (("L", "N"), ("L", "T"), ("R", "N"), ("R", "T")):
+        Cm = np.asfortranarray(rng.standard_normal((m, ncols) if side == "L" else (ncols, m)).astype(dt))
+        cdev = dev(Cm)
+        ok(fn("unmqr", dt)(ctx.h, 0 if side == "L" else 1, 0 if trans == "N" else 1, Cm.shape[0], Cm.shape[1], k,
+                           a.data_ptr(), m, tau.data_ptr(), cdev.data_ptr(), Cm.shape[0]))
+        want = O.k_unmqr(side, trans, qr_o[:, :k], tau_o, Cm)
+        assert relerr(host(cdev, Cm.shape), want) < tol, (side, trans)
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("shape", [(9, 9), (71, 71), (130, 130), (64, 20), (20, 64), (7, 1), (1, 5), (200, 200)])
+def test_svd_vs_lapack(ctx, dt, shape):
+    m, n = shape
+    rng = np.random.default_rng(m * 7 + n)
+    k = min(m, n)
+    # graded spectrum, like the recompression cores: singular values from 1 down to ~eps
+    A = rng.standard_normal((m, k)) @ np.diag(np.logspace(0, -14 if dt == np.float64 else -6, k)) @ rng.standard_normal((k, n))
+    A = np.asfortranarray(A.astype(dt))
+    a, s, u, vt = dev(A), dev(np.zeros(k, dt)), dev(np.zeros(m * k, dt)), dev(np.zeros(k * n, dt))
+    ok(fn("svd", dt)(ctx.h, m, n, a.data_ptr(), m, s.data_ptr(), u.data_ptr(), m, vt.data_ptr(), k))
+    U, S, VT = host(u, (m, k)), s.cpu().numpy(), host(vt, (k, n))
+    _, s_ref, _ = O.k_svd(A)
+    eps = np.finfo(dt).eps
+    assert np.all(np.diff(S) <= 0)                                            # sorted
+    assert np.max(np.abs(S - s_ref)) <= 50 * eps * s_ref[0]                   # absolute agreement with gesdd
+    assert relerr((U * S) @ VT, A) < 200 * eps                                # reconstructs A
+    big = S > 1e3 * eps * S[0]
+    assert np.max(np.abs(U[:, big].T @ U[:, big] - np.eye(big.sum()))) < 1e3 * eps
+    assert np.max(np.abs(VT[big] @ VT[big].T - np.eye(big.sum()))) < 1e3 * eps
+
+
+# ------------------------------------------------------------------------------------------------ tile level
+def mk_tile(hc, ctx, kind, D, U, V, dt, max_rank=None):
+    if kind == "D":
+        return hc.DenseTile(np.asarray(D, dtype=dt), ctx)
+    return hc.CompressedTile.from_uv(np.asarray(U, dtype=dt), np.asarray(V, dtype=dt), ctx, max_rank=max_rank)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_compressed_tile_gemm_known_answer(hc, ctx, dt):
+    g = VEC["compressed_tile_gemm"]  # tests/operators/TestCompressedTile.cpp:124-260 (C rank 2 zeros += A*B, DDC-free path)
+    A, B = F(g["A"], dt), F(g["B"], dt)
+    # CompressedTile::Gemm(alpha, A-as-U_AB, B-as-V_AB): exactly a DCC-shaped call with BU = I: use A dense, B = (I, B)
+    Ct = hc.CompressedTile.from_uv(np.zeros((3, 2), dt), np.zeros((2, 2), dt), ctx)
+    Bt = hc.CompressedTile.from_uv(np.eye(3, dtype=dt), B, ctx)
+    hc.HCore.Gemm(1.0, hc.DenseTile(A, ctx), False, Bt, False, 1.0, Ct, ctx, hc.CompressionParameters(float(np.finfo(dt).eps)))
+    assert approx(Ct.to_dense(), g["C"], g["tol_rel"])
+    assert Ct.GetTileRank() == 2
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("case", VEC["hcore_gemm"]["cases"], ids=lambda c: c["name"])
+def test_hcore_gemm_known_answers(hc, ctx, case, dt):
+    def tile(name):
+        if name in case:
+            return hc.DenseTile(F(case[name], dt), ctx)
+        return hc.CompressedTile.from_uv(F(case[name + "U"], dt), F(case[name + "V"], dt), ctx)
+    A, B = tile("A"), tile("B")
+    m, n = A.m, B.n
+    if case["C0"] == "zeros":
+        Ct = hc.DenseTile(np.zeros((m, n), dt), ctx)
+    else:
+        r = case["c_rank"]
+        Ct = hc.CompressedTile.from_uv(np.zeros((m, r), dt), np.zeros((r, n), dt), ctx)
+    p = hc.CompressionParameters(float(np.finfo(dt).eps)) if case.get("acc") == "eps" else hc.CompressionParameters()
+    hc.HCore.Gemm(case["alpha"], A, False, B, False, case["beta"], Ct, ctx, p)
+    assert approx(Ct.to_dense(), case["C"], VEC["hcore_gemm"]["tol_rel"])
+
+
+MIXES = ["DDD", "DDC", "DCD", "DCC", "CDD", "CDC", "CCD", "CCC"]
+
+
+@pytest.mark.parametrize("dt,name", [(np.float64, "f64"), (np.float32, "f32")])
+@pytest.mark.parametrize("mix", MIXES)
+def test_mixes_vs_reference_fixture(hc, ctx, mix, dt, name):
+    """tests/api/AdvancedGemmTest.cpp inputs; outputs of the reference itself (tests/golden/ref_mixes_*.npz)."""
+    z = np.load(os.path.join(GOLDEN, f"ref_mixes_{name}.npz"))
+    acc = float(z["acc"])
+    a = mk_tile(hc, ctx, mix[0], z["A"], z["AU"], z["AV"], dt)
+    b = mk_tile(hc, ctx, mix[1], z["B"], z["BU"], z["BV"], dt)
+    c = mk_tile(hc, ctx, mix[2], z["C"], z["CU"], z["CV"], dt)
+    hc.HCore.Gemm(float(z["alpha"]), a, False, b, False, float(z["beta"]), c, ctx, hc.CompressionParameters(acc))
+    out, ref_out = c.to_dense(), z[f"{mix}_out"]
+    assert relerr(out, ref_out) <= 10 * acc
+    if mix[2] == "C":
+        assert abs(c.GetTileRank() - int(z[f"{mix}_rank"])) <= 1
+    if mix in ("DDD", "DCD", "CDD", "CCD"):  # pure contractions: rounding-level agreement
+        assert relerr(out, ref_out) <= (1e-13 if dt == np.float64 else 1e-5)
+    # the reference's own acceptance bound (AdvancedGemmTest.cpp:245-256)
+    A, B, C0 = z["A"].astype(np.float64), z["B"].astype(np.float64), z["C"].astype(np.float64)
+    ninf = lambda M: np.abs(M).sum(axis=1).max()
+    cref = float(z["alpha"]) * A @ B + float(z["beta"]) * C0
+    if mix != "DDC":
+        bound = np.sqrt(A.shape[1] + 2) * abs(float(z["alpha"])) * ninf(A) * ninf(B) + 2 * abs(float(z["beta"])) * ninf(C0)
+        err_ref = ninf(ref_out - cref) / bound
+        assert ninf(out - cref) / bound < max(3 * acc, 1.5 * err_ref)
+
+
+def test_multitile_vs_reference_fixture(hc, ctx):
+    z = np.load(os.path.join(GOLDEN, "ref_multitile_f64.npz"))
+    T, nb, acc = int(z["T"]), int(z["nb"]), float(z["acc"])
+    dt = np.float64
+
+    def grid(name):
+        tm = hc.TileMatrix(T, T, nb, nb, torch.float64, ctx, compressed=True)
+        for j in range(T):
+            for i in range(T):
+                U, V = z[f"{name}_U_{j}_{i}"], z[f"{name}_V_{j}_{i}"]
+                t = tm.GetTile(j, i)
+                rk = U.shape[1]
+                t.buf[: nb * rk] = torch.from_numpy(np.ascontiguousarray(U.T).reshape(-1)).cuda()
+                t.buf[nb * tm.max_rank: nb * tm.max_rank + rk * nb] = torch.from_numpy(np.ascontiguousarray(V.T).reshape(-1)).cuda()
+                t.rank.fill_(rk)
+        return tm
+    A, B, Cm = grid("A"), grid("B"), grid("C0")
+    info = torch.zeros(T * T, dtype=torch.int32, device="cuda")
+    hc.tile_matrix_multiplication(A, B, Cm, 1.0, 1.0, ctx, hc.CompressionParameters(acc), info=info)
+    ctx.Sync()
+    assert int(info.max().item()) in (0, 2)  # 2 = clipped at maxRank, which the reference does silently too
+    assert np.max(np.abs(Cm.rank_table() - z["C_ranks"])) <= 1
+    assert relerr(Cm.ToRawMatrix(), z["C_dense"]) <= 10 * acc
+
+
+@pytest.mark.parametrize("dt,name", [(np.float64, "f64"), (np.float32, "f32")])
+def test_compress_vs_reference_fixture(hc, ctx, dt, name):
+    z = np.load(os.path.join(GOLDEN, f"ref_compress_{name}.npz"))
+    acc = float(z["acc"])
+    t = hc.CompressedTile.compress(z["A"], hc.CompressionParameters(acc), ctx)
+    assert t.max_rank == int(z["max_rank"])
+    assert abs(t.GetTileRank() - int(z["rank"])) <= 1
+    assert relerr(t.to_dense(), z["U"] @ z["V"]) <= 10 * acc
+    U = t.GetUMatrix().astype(np.float64)
+    assert np.max(np.abs(U.T @ U - np.eye(U.shape[1]))) < (1e-10 if dt == np.float64 else 1e-3)  # U orthonormal, S in V
+
+
+# ------------------------------------------------------------------------------------------------ live vs the oracle
+def oracle_tile(kind, D, UV, dt):
+    return O.DenseTile(np.asfortranarray(D.astype(dt))) if kind == "D" else O.CompressedTile.from_uv(UV[0].astype(dt), UV[1].astype(dt))
+
+
+def lowrank(rng, m, n, k, dt, decay=0.5):
+    U, _ = np.linalg.qr(rng.standard_normal((m, k)))
+    V, _ = np.linalg.qr(rng.standard_normal((n, k)))
+    s = decay ** np.arange(k)
+    return U.astype(dt), (s[:, None] * V.T).astype(dt)
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("dims", [(96, 80, 112), (3, 2, 3), (17, 33, 5), (256, 256, 256), (1, 1, 1), (130, 64, 31)])
+def test_all_mixes_ragged_vs_oracle(hc, ctx, dims, dt):
+    m, n, k = dims
+    rng = np.random.default_rng(m + 10 * n + 100 * k)
+    acc = 1e-6 if dt == np.float64 else 1e-3
+    ka, kb, kc = max(1, min(m, k) // 3), max(1, min(k, n) // 3), max(1, min(m, n) // 4)
+    AUV, BUV, CUV = lowrank(rng, m, k, ka, dt), lowrank(rng, k, n, kb, dt), lowrank(rng, m, n, kc, dt)
+    Ad, Bd, Cd = AUV[0] @ AUV[1], BUV[0] @ BUV[1], CUV[0] @ CUV[1]
+    cap = max(1, min(m, n))  # generous capacity so that truncation, not clipping, decides the rank
+    for mix in MIXES:
+        a = mk_tile(hc, ctx, mix[0], Ad, *AUV, dt)
+        b = mk_tile(hc, ctx, mix[1], Bd, *BUV, dt)
+        c = mk_tile(hc, ctx, mix[2], Cd, *CUV, dt, max_rank=cap)
+        oa, ob = oracle_tile(mix[0], Ad, AUV, dt), oracle_tile(mix[1], Bd, BUV, dt)
+        oc = oracle_tile(mix[2], Cd, CUV, dt)
+        if mix[2] == "C":
+            oc.max_rank = cap
+        hc.HCore.Gemm(1.5, a, False, b, False, -0.5, c, ctx, hc.CompressionParameters(acc))
+        O.hcore_gemm(dt(1.5), oa, False, ob, False, dt(-0.5), oc, O.CompressionParameters(acc))
+        ref = oc.to_dense()
+        scale = max(np.linalg.norm(ref), 1e-30)
+        assert np.linalg.norm(c.to_dense().astype(np.float64) - ref) <= 10 * acc * max(scale, 1.0), mix
+        if mix[2] == "C" and mix != "DDC":
+            assert abs(c.GetTileRank() - oc.rank) <= 1, (mix, c.GetTileRank(), oc.rank)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_transposed_operands_dense_output(hc, ctx, dt):
+    """op = Trans on dense and compressed operands with a dense C (Dense.cpp:46-108 handles ops; HCore.cpp:73-81,101-109)."""
+    rng = np.random.default_rng(5)
+    m, n, k = 70, 50, 90
+    AUV, BUV = lowrank(rng, k, m, 9, dt), lowrank(rng, n, k, 7, dt)  # stored transposed: A is k x m, B is n x k
+    Ad, Bd = AUV[0] @ AUV[1], BUV[0] @ BUV[1]
+    C0 = rng.standard_normal((m, n)).astype(dt)
+    want = 2.0 * Ad.T.astype(np.float64) @ Bd.T + 0.5 * C0
+    for mix in ("DDD", "CDD", "DCD", "CCD"):
+        a = mk_tile(hc, ctx, mix[0], Ad, *AUV, dt)
+        b = mk_tile(hc, ctx, mix[1], Bd, *BUV, dt)
+        c = hc.DenseTile(C0, ctx)
+        hc.HCore.Gemm(2.0, a, True, b, True, 0.5, c, ctx)
+        assert relerr(c.to_dense(), want) < (1e-12 if dt == np.float64 else 1e-4), mix
+
+
+def test_rank_truncation_straddling_accuracy(hc, ctx):
+    """Singular values placed just above / below the absolute threshold: ranks must agree with the oracle +/-1."""
+    rng = np.random.default_rng(11)
+    nb, acc = 128, 1e-6
+    U, _ = np.linalg.qr(rng.standard_normal((nb, 12)))
+    V, _ = np.linalg.qr(rng.standard_normal((nb, 12)))
+    s = np.array([1, .5, .1, 1e-2, 1e-3, 1e-4, 1e-5, 2e-6, 1.2e-6, 0.9e-6, 5e-7, 1e-8])
+    A = (U * s) @ V.T
+    t = hc.CompressedTile.compress(A, hc.CompressionParameters(acc), ctx)
+    o = O.CompressedTile.compress(A, O.CompressionParameters(acc))
+    assert abs(t.GetTileRank() - o.rank) <= 1 and o.rank == 9
+    # fixed-rank mode (Compressed.cpp:103-109, 510-515)
+    t = hc.CompressedTile.compress(A, hc.CompressionParameters(acc, fixed_rank=5), ctx)
+    assert t.GetTileRank() == 5
+    # relative threshold (truncatedSvd, omp/kernels.cpp:87-95)
+    t = hc.CompressedTile.compress(A * 100, hc.CompressionParameters(acc, truncated_svd=True), ctx)
+    o = O.CompressedTile.compress(A * 100, O.CompressionParameters(acc, truncated_svd=True))
+    assert abs(t.GetTileRank() - o.rank) <= 1
+
+
+def test_batched_equals_one_by_one_and_info(hc, ctx):
+    """One batched call over many triples == the same triples one at a time; rank-bound violations are reported."""
+    rng = np.random.default_rng(3)
+    nb, n = 64, 9
+    mk = lambda k: lowrank(rng, nb, nb, k, np.float64)
+    As, Bs, C1, C2 = [], [], [], []
+    for t in range(n):
+        As.append(hc.CompressedTile.from_uv(*mk(5 + t % 3), ctx))
+        Bs.append(hc.CompressedTile.from_uv(*mk(4 + t % 2), ctx))
+        cu, cv = mk(3)
+        C1.append(hc.CompressedTile.from_uv(cu, cv, ctx, max_rank=21))
+        C2.append(hc.CompressedTile.from_uv(cu, cv, ctx, max_rank=21))
+    p = hc.CompressionParameters(1e-8)
+    info = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    hc.gemm_batched(1.0, As, False, Bs, False, 1.0, C1, ctx, p, info=info)
+    for t in range(n):
+        hc.HCore.Gemm(1.0, As[t], False, Bs[t], False, 1.0, C2[t], ctx, p)
+    ctx.Sync()
+    assert int(info.abs().max().item()) == 0
+    for t in range(n):
+        assert C1[t].GetTileRank() == C2[t].GetTileRank()
+        assert relerr(C1[t].to_dense(), C2[t].to_dense()) < 1e-12
+    # a rank bound that is too small must be detected on the device and leave the tile untouched
+    before = C1[0].to_dense()
+    As[0].rank_bound = 2
+    info1 = torch.zeros(1, dtype=torch.int32, device="cuda")
+    hc.gemm_batched(1.0, As[:1], False, Bs[:1], False, 1.0, C1[:1], ctx, p, info=info1)
+    ctx.Sync()
+    assert int(info1.item()) == 4 and np.array_equal(C1[0].to_dense(), before)
+
+
+def test_full_size_tile_properties(hc, ctx):
+    """BASELINE config sizes (nb = 1024, ranks 44, acc 1e-8): size-independent properties of one k-sweep --
+    U orthonormal, product within 10*acc of the dense result, rank trace non-decreasing then stable, idempotent
+    recompression (adding a zero-rank-1 update does not change the product)."""
+    torch.manual_seed(0)
+    nb, k, acc, kt = 1024, 44, 1e-8, 3
+    s = torch.from_numpy(O.latms_spectrum(nb, np.float64)[:k].copy()).cuda()
+
+    def synth():
+        qu, _ = torch.linalg.qr(torch.randn(nb, k, dtype=torch.float64, device="cuda"))
+        qv, _ = torch.linalg.qr(torch.randn(nb, k, dtype=torch.float64, device="cuda"))
+        return qu, s[:, None] * qv.t()
+    p = hc.CompressionParameters(acc)
+    Ct = hc.CompressedTile(nb, nb, nb // 3, torch.float64, ctx)
+    dense = torch.zeros(nb, nb, dtype=torch.float64, device="cuda")
+    ranks = []
+    for _ in range(kt):
+        (au, av), (bu, bv) = synth(), synth()
+        A = hc.CompressedTile.from_uv(au.cpu().numpy(), av.cpu().numpy(), ctx, max_rank=nb // 3)
+        B = hc.CompressedTile.from_uv(bu.cpu().numpy(), bv.cpu().numpy(), ctx, max_rank=nb // 3)
+        hc.HCore.Gemm(1.0, A, False, B, False, 1.0, Ct, ctx, p)
+        dense += (au @ av) @ (bu @ bv)
+        ranks.append(Ct.GetTileRank())
+    U, V = Ct.factors()
+    err = (torch.linalg.norm(U @ V - dense) / torch.linalg.norm(dense)).item()
+    assert err <= 10 * acc
+    orth = torch.linalg.norm(U.t() @ U - torch.eye(U.shape[1], dtype=torch.float64, device="cuda")).item()
+    assert orth < 1e-10
+    assert ranks[0] <= ranks[1] + 1 and all(1 <= r <= nb // 3 for r in ranks)
+    before = (U @ V).clone()
+    Z = hc.CompressedTile(nb, nb, nb // 3, torch.float64, ctx)  # rank-1 zero tile
+    hc.HCore.Gemm(1.0, Z, False, Z, False, 1.0, Ct, ctx, p)
+    U2, V2 = Ct.factors()
+    assert (torch.linalg.norm(U2 @ V2 - before) / torch.linalg.norm(before)).item() <= 10 * acc
+    assert abs(Ct.GetTileRank() - ranks[-1]) <= 1
