@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--nb", type=int, default=1024)
     ap.add_argument("--acc", type=float, default=1e-8)
     ap.add_argument("--rank", type=int, default=0, help="rank of the synthetic A/B tiles (0: from the spectrum law)")
-    ap.add_argument("--kc-bound", type=int, default=64, help="rank bound used to size scratch for C tiles")
+    ap.add_argument("--kc-bound", type=int, default=0,
+                    help="rank bound used to size scratch for C tiles (0: calibrate with one untimed pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     return ap.parse_args()
@@ -227,6 +228,13 @@ def main():
         Cm = hc.TileMatrix.zeros_compressed(mt, nt, nb, nb, dt, ctx, rank_bound=args.kc_bound)
         n_local_gemms = mt * nt * kt
         info = torch.zeros(mt * nt, dtype=torch.int32, device=dev)
+        if args.kc_bound == 0:
+            # untimed calibration pass with the safe bound (max_rank): learn how far the C ranks grow, then size the
+            # scratch / grids of the timed passes from that (+ margin). A violated bound is detected on the device.
+            hc.tile_matrix_multiplication(A, B, Cm, 1.0, 1.0, ctx, prm, info=info)
+            ctx.Sync()
+            args.kc_bound = int(min(Cm.max_rank, (int(Cm.ranks.max().item()) + 8 + 7) // 8 * 8))
+            Cm.set_rank_bound(args.kc_bound)
 
         def one_pass():
             Cm.reset_to_zero()
@@ -269,6 +277,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     bad = int((info & 5).max().item())  # 1: Jacobi not converged, 4: rank bound exceeded (2 = clipped at maxRank is legal)
+    sweeps = int((info >> 8).max().item())
     ms_per_step = ms / args.steps
     value = total_gemms / (ms_per_step * 1e-3)
 
@@ -296,7 +305,8 @@ def main():
             "baseline_config": "BASELINE.json configs[2]" if (T, nb, world) == (16, 1024, 1) else "custom",
             "l2": "inputs larger than L2 (A+B live factors %.0f MB per GPU, C scratch re-written every k)" % (
                 2 * T * T * 2 * nb * krank * 8 / 1e6)},
-        "gpu_launches": launches, "jacobi_or_bound_flags": bad,
+        "gpu_launches": launches, "jacobi_or_bound_flags": bad, "jacobi_sweeps_last_step_max": sweeps,
+        "c_rank_bound": args.kc_bound,
     }
     if rank_env == 0:
         result["clocks"] = clocks

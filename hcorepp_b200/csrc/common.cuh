@@ -130,11 +130,11 @@ struct ReflProb {  // apply k reflectors stored in V (LAPACK layout, ldv) + tau 
 };
 
 template<typename T>
-struct SvdProb {  // one-sided Jacobi on M (a x b, a >= b): M = Uout * diag(sigma) * Vout^T, sigma descending
-    T *M;         // work (global), overwritten
-    T *J;         // work (global) b x b, ld b
+struct SvdProb {  // one-sided Jacobi on M (a x b, a >= b): M = Uout * diag(sigma) * V^T, sigma descending
+    T *M;         // input (global), preserved
+    T *J;         // work (global) a*b elements: rotated copy of M when the problem does not fit shared memory
     T *Uout;      // a x b, ld ldu : normalised left vectors (zero columns where sigma == 0)
-    T *Vout;      // b x b, ld ldv : right vectors
+    T *Vout;      // b x b, ld ldv : receives V diag(sigma) = M^T Uout from the follow-up GEMM
     T *sigma;     // b
     int *info;    // optional: |= 1 when not converged
     int a, b, ldm, ldu, ldv;

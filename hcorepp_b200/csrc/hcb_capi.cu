@@ -138,14 +138,15 @@ template<typename T>
 int launch_svd(hcb_ctx *ctx, const SvdProb<T> *d_probs, int n_probs, int a_bound, int b_bound) {
     if (n_probs <= 0) return HCB_OK;
     // shared memory: enough for the whole bound-sized problem, capped at the opt-in limit; the kernel decides per
-    // problem (from its true a, b) whether it fits, and otherwise works in global memory with sigma in smem.
-    size_t want = ((size_t) a_bound * b_bound + (size_t) b_bound * b_bound + (size_t) b_bound) * sizeof(T);
+    // problem (from its true a, b) whether it fits, and otherwise rotates a global copy with only sigma in smem.
+    size_t want = ((size_t) a_bound * b_bound + (size_t) b_bound) * sizeof(T);
     const size_t cap = ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0;
     if (want > cap) want = cap / 16 * 16;
     if ((size_t) std::max(b_bound, 1) * sizeof(T) > want) return fail(HCB_EUNSUPPORTED, "svd: problem too large");
     want = align_up(want, 16);
     HCB_CUDA(cudaFuncSetAttribute(k_jacobi_svd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) want));
-    k_jacobi_svd<T><<<n_probs, 512, want, ctx->stream>>>(d_probs, (int) (want / sizeof(T)), 40);
+    const int threads = b_bound >= 96 ? 1024 : (b_bound >= 32 ? 512 : 256);  // one warp per column pair
+    k_jacobi_svd<T><<<n_probs, threads, want, ctx->stream>>>(d_probs, (int) (want / sizeof(T)), 40);
     HCB_LAUNCH_CHECK("k_jacobi_svd");
     return HCB_OK;
 }
@@ -324,15 +325,25 @@ int t_svd(hcb_ctx *ctx, int64_t m, int64_t n, T *A, int64_t lda, T *S, T *U, int
     if (m <= 0 || n <= 0) return HCB_OK;
     const int a = (int) std::max(m, n), b = (int) std::min(m, n);
     const bool transposed = m < n;
-    // scratch: M (a*b) | J (b*b) | Us (a*b) | Vs (b*b)
+    // scratch: M (a*b) | Mwork (a*b) | Us (a*b) | Vs (b*b)
     const size_t eM = (size_t) a * b, eJ = (size_t) b * b;
-    HCB_TRY(ensure_ws(ctx, (2 * eM + 2 * eJ) * sizeof(T) + 1024));
-    T *M = reinterpret_cast<T *>(ctx->ws), *J = M + eM, *Us = J + eJ, *Vs = Us + eM;
+    HCB_TRY(ensure_ws(ctx, (3 * eM + eJ) * sizeof(T) + 1024));
+    T *M = reinterpret_cast<T *>(ctx->ws), *Mw = M + eM, *Us = Mw + eM, *Vs = Us + eM;
     HCB_TRY(t_copy<T>(ctx, A, (int) lda, M, a, a, b, transposed ? 1 : 0, T(1)));
-    SvdProb<T> sp{M, J, Us, Vs, S, nullptr, a, b, a, a, b};
+    SvdProb<T> sp{M, Mw, Us, Vs, S, nullptr, a, b, a, a, b};
     const SvdProb<T> *d;
     HCB_TRY(upload_one(ctx, sp, &d));
     HCB_TRY(launch_svd<T>(ctx, d, 1, a, b));
+    // Vs = M^T Us = V diag(S); normalise its columns to get V
+    GemmProb<T> g{M, Us, Vs, b, b, a, a, a, b, 1, 0, T(1), T(0)};
+    const GemmProb<T> *dg;
+    HCB_TRY(upload_one(ctx, g, &dg));
+    HCB_TRY(launch_gemm<T>(ctx, dg, 1, b, b));
+    {
+        dim3 block(32, 8), grid(cdiv(b, 32), cdiv(b, 8));
+        k_unscale_cols<T><<<grid, block, 0, ctx->stream>>>(Vs, b, b, b, S);
+        HCB_LAUNCH_CHECK("k_unscale_cols");
+    }
     if (!transposed) {  // A = Us S Vs^T : U = Us (m x n), VT = Vs^T (n x n)
         HCB_TRY(t_copy<T>(ctx, Us, a, U, (int) ldu, (int) m, b, 0, T(1)));
         return t_copy<T>(ctx, Vs, b, VT, (int) ldvt, b, (int) n, 1, T(1));
@@ -427,13 +438,14 @@ Layout<T> make_layout(const BatchShape &s) {
 template<typename T>
 struct DescArrays {  // device arrays living at the front of the scratch arena
     size_t bytes = 0;
-    size_t o_g1, o_g2, o_g3, o_cp, o_qr, o_rf, o_svd, o_rc, o_rk, o_tiles;
+    size_t o_g1, o_g2, o_g3, o_gv, o_cp, o_qr, o_rf, o_svd, o_rc, o_rk, o_tiles;
     explicit DescArrays(int n) {
         size_t off = 0;
         auto take = [&](size_t b) { size_t o = off; off += align_up(b, 256); return o; };
         o_g1 = take(sizeof(GemmProb<T>) * n);
         o_g2 = take(sizeof(GemmProb<T>) * n);
         o_g3 = take(sizeof(GemmProb<T>) * n);
+        o_gv = take(sizeof(GemmProb<T>) * n);
         o_cp = take(sizeof(CopyProb<T>) * 4 * n);
         o_qr = take(sizeof(QrProb<T>) * 2 * n);
         o_rf = take(sizeof(ReflProb<T>) * 2 * n);
@@ -518,6 +530,7 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     sa.g1 = reinterpret_cast<GemmProb<T> *>(base + D.o_g1);
     sa.g2 = reinterpret_cast<GemmProb<T> *>(base + D.o_g2);
     sa.g3 = reinterpret_cast<GemmProb<T> *>(base + D.o_g3);
+    sa.gv = reinterpret_cast<GemmProb<T> *>(base + D.o_gv);
     sa.cp = reinterpret_cast<CopyProb<T> *>(base + D.o_cp);
     sa.qr = reinterpret_cast<QrProb<T> *>(base + D.o_qr);
     sa.rf = reinterpret_cast<ReflProb<T> *>(base + D.o_rf);
@@ -573,6 +586,7 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
         k_core_build<T><<<grid, 256, 0, ctx->stream>>>(sa.rc);
         HCB_LAUNCH_CHECK("k_core_build");
         HCB_TRY(launch_svd<T>(ctx, sa.svd, n, L.pq_b, L.pq_b));
+        HCB_TRY(launch_gemm<T>(ctx, sa.gv, n, L.pq_b, L.pq_b));
         k_truncate<T><<<n, 256, 0, ctx->stream>>>(sa.rc, (T) prm->accuracy, prm->truncated_svd, (int) prm->fixed_rank);
         HCB_LAUNCH_CHECK("k_truncate");
     }
@@ -630,20 +644,23 @@ int t_compress_batched(hcb_ctx *ctx, int64_t n64, const T *const *dense, int64_t
     }
     const int a = std::max(m, n), b = std::min(m, n);
     const size_t eM = align_up((size_t) a * b, 32), eJ = align_up((size_t) b * b, 32), eS = align_up((size_t) b, 32);
-    const size_t slab = 2 * eM + 2 * eJ + eS;
+    const size_t slab = 3 * eM + eJ + eS;
     // chunk the batch so that the scratch stays below ~8 GiB
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n64, (int64_t) (((size_t) 8 << 30) / (slab * sizeof(T)))));
     for (int64_t c0 = 0; c0 < n64; c0 += chunk) {
         const int cnt = (int) std::min<int64_t>(chunk, n64 - c0);
         const size_t desc = align_up(sizeof(CopyProb<T>) * cnt, 256) + align_up(sizeof(SvdProb<T>) * cnt, 256) +
-                            align_up(sizeof(CompressProb<T>) * cnt, 256);
+                            align_up(sizeof(CompressProb<T>) * cnt, 256) + align_up(sizeof(GemmProb<T>) * cnt, 256);
         HCB_TRY(ensure_ws(ctx, desc + slab * sizeof(T) * cnt + 256));
         char *base = reinterpret_cast<char *>(ctx->ws);
         CopyProb<T> *d_cp = reinterpret_cast<CopyProb<T> *>(base);
         SvdProb<T> *d_sv = reinterpret_cast<SvdProb<T> *>(base + align_up(sizeof(CopyProb<T>) * cnt, 256));
         CompressProb<T> *d_fp = reinterpret_cast<CompressProb<T> *>(reinterpret_cast<char *>(d_sv) +
                                                                     align_up(sizeof(SvdProb<T>) * cnt, 256));
+        GemmProb<T> *d_gv = reinterpret_cast<GemmProb<T> *>(reinterpret_cast<char *>(d_fp) +
+                                                            align_up(sizeof(CompressProb<T>) * cnt, 256));
         T *ws = reinterpret_cast<T *>(base + align_up(desc, 256));
+        std::vector<GemmProb<T>> gv(cnt);
         std::vector<CopyProb<T>> cp(cnt);
         std::vector<SvdProb<T>> sv(cnt);
         std::vector<CompressProb<T>> fp(cnt);
@@ -651,13 +668,12 @@ int t_compress_batched(hcb_ctx *ctx, int64_t n64, const T *const *dense, int64_t
             const hcb_tile &o = out[c0 + t];
             const int tm = o.m, tn = o.n, ta = std::max(tm, tn), tb = std::min(tm, tn);
             const bool tr = tm < tn;
-            T *M = ws + (size_t) t * slab, *J = M + eM, *Us = J + eJ, *Vs = Us + eM, *sg = Vs + eJ;
+            T *M = ws + (size_t) t * slab, *Mw = M + eM, *Us = Mw + eM, *Vs = Us + eM, *sg = Vs + eJ;
             cp[t] = CopyProb<T>{dense[c0 + t], M, ta, tb, (int) ld, ta, tr ? 1 : 0, T(1)};
-            sv[t] = SvdProb<T>{M, J, Us, Vs, sg, nullptr, ta, tb, ta, ta, tb};
+            sv[t] = SvdProb<T>{M, Mw, Us, Vs, sg, nullptr, ta, tb, ta, ta, tb};
+            gv[t] = GemmProb<T>{M, Us, Vs, tb, tb, ta, ta, ta, tb, 1, 0, T(1), T(0)};  // Vs = M^T Us = V diag(sigma)
             T *U = reinterpret_cast<T *>(o.d_data), *V = U + (size_t) tm * o.max_rank;
-            // m >= n: A = Us S Vs^T (Uf = Us m x s, Vf = Vs n x s); m < n: A^T = Us S Vs^T -> Uf = Vs, Vf = Us
-            fp[t] = tr ? CompressProb<T>{Vs, Us, sg, U, V, o.d_rank, nullptr, tm, tn, tb, tb, ta, o.max_rank}
-                       : CompressProb<T>{Us, Vs, sg, U, V, o.d_rank, nullptr, tm, tn, tb, ta, tb, o.max_rank};
+            fp[t] = CompressProb<T>{Us, Vs, sg, U, V, o.d_rank, nullptr, tm, tn, tb, ta, tr ? 1 : 0, o.max_rank};
         }
         void *st = nullptr;
         HCB_TRY(ring_upload(ctx, cp.data(), sizeof(CopyProb<T>) * cnt, &st));
@@ -666,8 +682,11 @@ int t_compress_batched(hcb_ctx *ctx, int64_t n64, const T *const *dense, int64_t
         HCB_CUDA(cudaMemcpyAsync(d_sv, st, sizeof(SvdProb<T>) * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
         HCB_TRY(ring_upload(ctx, fp.data(), sizeof(CompressProb<T>) * cnt, &st));
         HCB_CUDA(cudaMemcpyAsync(d_fp, st, sizeof(CompressProb<T>) * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
+        HCB_TRY(ring_upload(ctx, gv.data(), sizeof(GemmProb<T>) * cnt, &st));
+        HCB_CUDA(cudaMemcpyAsync(d_gv, st, sizeof(GemmProb<T>) * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
         HCB_TRY(launch_copy<T>(ctx, d_cp, cnt, a, b));
         HCB_TRY(launch_svd<T>(ctx, d_sv, cnt, a, b));
+        HCB_TRY(launch_gemm<T>(ctx, d_gv, cnt, b, b));
         k_compress_finalize<T><<<cnt, 256, 0, ctx->stream>>>(d_fp, (T) prm->accuracy, prm->truncated_svd,
                                                               (int) prm->fixed_rank);
         HCB_LAUNCH_CHECK("k_compress_finalize");

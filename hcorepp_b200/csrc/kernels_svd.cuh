@@ -22,12 +22,15 @@ __device__ __forceinline__ void rr_pair(int nb2, int round, int slot, int &x, in
     if (x > y) { const int t = x; x = y; y = t; }
 }
 
-// One CTA per problem. M (a x b, a >= b) -> Uout diag(sigma) Vout^T, sigma sorted descending.
-// dynamic shared memory: smem_elems elements of T. Layout when the problem fits: [M a*b | J b*b | sig b];
-// otherwise only [sig b] lives in shared memory and M/J are worked on in global memory.
+// One CTA per problem. M (a x b, a >= b) = Uout diag(sigma) V^T; only the LEFT factor is produced here:
+// the rotations are not accumulated.  The caller gets the scaled right factor V diag(sigma) = M^T Uout with one
+// batched GEMM afterwards (exactly the quantity the recompression needs, Compressed.cpp:598-622), which halves the
+// Jacobi work and its shared-memory footprint.  p.M is left untouched.
+// dynamic shared memory: smem_elems elements of T. Layout when the problem fits: [M a*b | sig b]; otherwise only
+// [sig b] lives in shared memory and the rotations work on a global copy of M (p.J, a*b elements).
 template<typename T>
-__global__ void __launch_bounds__(512) k_jacobi_svd(const SvdProb<T> *__restrict__ probs, int smem_elems,
-                                                    int max_sweeps) {
+__global__ void __launch_bounds__(1024) k_jacobi_svd(const SvdProb<T> *__restrict__ probs, int smem_elems,
+                                                     int max_sweeps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
     __shared__ int s_rot;
@@ -35,28 +38,27 @@ __global__ void __launch_bounds__(512) k_jacobi_svd(const SvdProb<T> *__restrict
     const int a = p.a, b = p.b;
     if (a <= 0 || b <= 0) return;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
-    const bool fits = (size_t) a * b + (size_t) b * b + (size_t) b <= (size_t) smem_elems;
-    T *M, *J, *sig;
+    const bool fits = (size_t) a * b + (size_t) b <= (size_t) smem_elems;
+    T *M, *sig;
     int ldm;
     if (fits) {
         M = sm;
-        J = sm + (size_t) a * b;
-        sig = J + (size_t) b * b;
+        sig = sm + (size_t) a * b;
         ldm = a;
-        for (int idx = tid; idx < a * b; idx += nthr) M[idx] = p.M[(size_t) (idx % a) + (size_t) (idx / a) * p.ldm];
     } else {
-        M = p.M;
-        J = p.J;
+        M = p.J;
         sig = sm;
-        ldm = p.ldm;
+        ldm = a;
     }
-    for (int idx = tid; idx < b * b; idx += nthr) J[idx] = (idx % b == idx / b) ? T(1) : T(0);
+    for (int idx = tid; idx < a * b; idx += nthr) M[idx] = p.M[(size_t) (idx % a) + (size_t) (idx / a) * p.ldm];
     __syncthreads();
 
     const T tol = Eps<T>::v() * t_sqrt((T) a);
     const int nb2 = (b + 1) & ~1;
     bool converged = (b < 2);
+    int sweeps_used = 0;
     for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
+        ++sweeps_used;
         __syncthreads();
         if (tid == 0) s_rot = 0;
         __syncthreads();
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(512) k_jacobi_svd(const SvdProb<T> *__restrict
                 beta = warp_sum(beta);
                 gamma = warp_sum(gamma);
                 const T lim = tol * t_sqrt(alpha) * t_sqrt(beta);
-                if (t_abs(gamma) > lim && lim >= T(0) && gamma != T(0)) {
+                if (t_abs(gamma) > lim && gamma != T(0)) {
                     if (lane == 0) s_rot = 1;
                     const T zeta = (beta - alpha) / (T(2) * gamma);
                     const T t = (zeta >= T(0) ? T(1) : T(-1)) / (t_abs(zeta) + t_sqrt(fma(zeta, zeta, T(1))));
@@ -88,19 +90,16 @@ __global__ void __launch_bounds__(512) k_jacobi_svd(const SvdProb<T> *__restrict
                         mx[i] = c * u - s * v;
                         my[i] = s * u + c * v;
                     }
-                    T *jx = J + (size_t) x * b, *jy = J + (size_t) y * b;
-                    for (int i = lane; i < b; i += 32) {
-                        const T u = jx[i], v = jy[i];
-                        jx[i] = c * u - s * v;
-                        jy[i] = s * u + c * v;
-                    }
                 }
             }
             __syncthreads();
         }
         converged = (s_rot == 0);
     }
-    if (!converged && p.info && tid == 0) atomicOr(p.info, 1);
+    if (p.info && tid == 0) {
+        if (!converged) atomicOr(p.info, 1);
+        atomicOr(p.info, sweeps_used << 8);  // diagnostics: number of Jacobi sweeps in bits 8..15
+    }
 
     // singular values = column norms
     for (int c = w; c < b; c += nw) {
@@ -111,7 +110,7 @@ __global__ void __launch_bounds__(512) k_jacobi_svd(const SvdProb<T> *__restrict
         if (lane == 0) sig[c] = t_sqrt(ss);
     }
     __syncthreads();
-    // rank-sort (descending, stable) and scatter the normalised / permuted factors
+    // rank-sort (descending, stable) and scatter the normalised / permuted left factor
     for (int c = w; c < b; c += nw) {
         const T sc = sig[c];
         int pos = 0;
@@ -124,9 +123,16 @@ __global__ void __launch_bounds__(512) k_jacobi_svd(const SvdProb<T> *__restrict
         const T *mc = M + (size_t) c * ldm;
         T *uo = p.Uout + (size_t) pos * p.ldu;
         for (int i = lane; i < a; i += 32) uo[i] = (sc > T(0)) ? mc[i] / sc : T(0);
-        const T *jc = J + (size_t) c * b;
-        T *vo = p.Vout + (size_t) pos * p.ldv;
-        for (int i = lane; i < b; i += 32) vo[i] = jc[i];
+    }
+}
+
+// Vout[:, c] /= sigma[c] (zero where sigma == 0): turns V diag(sigma) = M^T Uout into the orthonormal right factor.
+template<typename T>
+__global__ void k_unscale_cols(T *__restrict__ V, int ld, int rows, int cols, const T *__restrict__ sigma) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i < rows && j < cols) {
+        const T s = sigma[j];
+        V[(size_t) i + (size_t) j * ld] = s > T(0) ? V[(size_t) i + (size_t) j * ld] / s : T(0);
     }
 }
 

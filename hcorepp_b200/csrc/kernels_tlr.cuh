@@ -37,7 +37,7 @@ struct SetupArgs {
     int kA_b, kB_b, kC_b, r_b;  // rank bounds the scratch was sized for
     int *rk_new;                // n_tiles ints
     int *info;                  // n_tiles ints (may be null)
-    GemmProb<T> *g1, *g2, *g3;
+    GemmProb<T> *g1, *g2, *g3, *gv;  // gv: V diag(sigma) = M^T Us after the Jacobi kernel
     CopyProb<T> *cp;            // 4 per tile
     QrProb<T> *qr;              // 2 per tile
     ReflProb<T> *rf;            // 2 per tile
@@ -75,7 +75,7 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
     const bool ac = A.type == HCB_TILE_COMPRESSED, bc = B.type == HCB_TILE_COMPRESSED, cc = C.type == HCB_TILE_COMPRESSED;
     const int ka = ac ? *A.d_rank : 0, kb = bc ? *B.d_rank : 0, kc = cc ? *C.d_rank : 0;
     T *slab = s.ws + (size_t) t * s.slab;
-    GemmProb<T> g1 = mk_gemm<T>(nullptr, 1, 0, nullptr, 1, 0, nullptr, 1, 0, 0, 0, T(0), T(0)), g2 = g1, g3 = g1;
+    GemmProb<T> g1 = mk_gemm<T>(nullptr, 1, 0, nullptr, 1, 0, nullptr, 1, 0, 0, 0, T(0), T(0)), g2 = g1, g3 = g1, gv = g1;
     CopyProb<T> c0 = mk_copy<T>(nullptr, 1, nullptr, 1, 0, 0, 0, T(0)), c1 = c0, c2 = c0, c3 = c0;
     QrProb<T> q0{nullptr, nullptr, 0, 0, 1}, q1 = q0;
     ReflProb<T> r0{nullptr, nullptr, nullptr, 0, 0, 1, 0, 0, 1, 0, 0, nullptr}, r1 = r0;
@@ -159,6 +159,7 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
                 rc.a = rc.transposed ? q : p;
                 rc.b = rc.transposed ? p : q;
                 sv = SvdProb<T>{rc.M, slab + s.o_j, rc.Us, rc.Vs, rc.sigma, rc.info, rc.a, rc.b, rc.a, rc.a, rc.b};
+                gv = mk_gemm<T>(rc.M, rc.a, 1, rc.Us, rc.a, 0, rc.Vs, rc.b, rc.b, rc.b, rc.a, one, zero);
                 // rebuild (Compressed.cpp:551-560, 611-628): CU = Q_U [Unew;0], VN = Q_V [Vfac;0], rank read on device
                 r0 = ReflProb<T>{UW, rc.tauU, CU, m, p, m, m, 0, m, 0, 0, rc.rk_new};
                 r1 = ReflProb<T>{VW, rc.tauV, rc.VN, n, q, n, n, 0, n, 0, 0, rc.rk_new};
@@ -166,7 +167,7 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
         }
     }
     if (bad) {
-        g1.m = g2.m = g3.m = 0;
+        g1.m = g2.m = g3.m = gv.m = 0;
         c0.rows = c1.rows = c2.rows = c3.rows = 0;
         q0.m = q1.m = 0;
         r0.k = r1.k = 0; r0.nc = r1.nc = 0; r0.nc_dev = r1.nc_dev = nullptr;
@@ -176,7 +177,7 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
     } else if (s.info) {
         s.info[t] = 0;
     }
-    s.g1[t] = g1; s.g2[t] = g2; s.g3[t] = g3;
+    s.g1[t] = g1; s.g2[t] = g2; s.g3[t] = g3; s.gv[t] = gv;
     s.cp[4 * t + 0] = c0; s.cp[4 * t + 1] = c1; s.cp[4 * t + 2] = c2; s.cp[4 * t + 3] = c3;
     s.qr[2 * t + 0] = q0; s.qr[2 * t + 1] = q1;
     s.rf[2 * t + 0] = r0; s.rf[2 * t + 1] = r1;
@@ -224,19 +225,28 @@ __global__ void __launch_bounds__(256) k_truncate(const RecompProb<T> *__restric
     }
     __syncthreads();
     const int rk = s_rk;
-    // not transposed: core = Us S Vs^T  -> Ufac = Us (p x b), Vfac = Vs (q x b)
-    // transposed    : core^T = Us S Vs^T -> core = Vs S Us^T -> Ufac = Vs (p x b, b == p), Vfac = Us (q x b, a == q)
-    const T *Uf = p.transposed ? p.Vs : p.Us;
-    const int ldUf = p.transposed ? p.b : p.a;
-    const T *Vf = p.transposed ? p.Us : p.Vs;
-    const int ldVf = p.transposed ? p.a : p.b;
-    for (int idx = threadIdx.x; idx < p.m * rk; idx += blockDim.x) {
-        const int i = idx % p.m, c = idx / p.m;
-        p.CU[(size_t) i + (size_t) c * p.m] = (i < p.p) ? Uf[(size_t) i + (size_t) c * ldUf] : T(0);
-    }
-    for (int idx = threadIdx.x; idx < p.n * rk; idx += blockDim.x) {
-        const int i = idx % p.n, c = idx / p.n;
-        p.VN[(size_t) i + (size_t) c * p.n] = (i < p.q) ? p.sigma[c] * Vf[(size_t) i + (size_t) c * ldVf] : T(0);
+    // Us = normalised left factor of M, Vs = (right factor of M) * diag(sigma)  [= M^T Us].
+    // not transposed (M = core)  : Ufac = Us (p x b),            Vfac*S = Vs (q x b)
+    // transposed (M = core^T)    : core = (Vs/S) S Us^T -> Ufac = Vs / sigma (p x b, b == p), Vfac*S = Us * sigma (q x b)
+    if (!p.transposed) {
+        for (int idx = threadIdx.x; idx < p.m * rk; idx += blockDim.x) {
+            const int i = idx % p.m, c = idx / p.m;
+            p.CU[(size_t) i + (size_t) c * p.m] = (i < p.p) ? p.Us[(size_t) i + (size_t) c * p.a] : T(0);
+        }
+        for (int idx = threadIdx.x; idx < p.n * rk; idx += blockDim.x) {
+            const int i = idx % p.n, c = idx / p.n;
+            p.VN[(size_t) i + (size_t) c * p.n] = (i < p.q) ? p.Vs[(size_t) i + (size_t) c * p.b] : T(0);
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < p.m * rk; idx += blockDim.x) {
+            const int i = idx % p.m, c = idx / p.m;
+            const T sg = p.sigma[c];
+            p.CU[(size_t) i + (size_t) c * p.m] = (i < p.p && sg > T(0)) ? p.Vs[(size_t) i + (size_t) c * p.b] / sg : T(0);
+        }
+        for (int idx = threadIdx.x; idx < p.n * rk; idx += blockDim.x) {
+            const int i = idx % p.n, c = idx / p.n;
+            p.VN[(size_t) i + (size_t) c * p.n] = (i < p.q) ? p.sigma[c] * p.Us[(size_t) i + (size_t) c * p.a] : T(0);
+        }
     }
 }
 
@@ -266,28 +276,37 @@ __global__ void __launch_bounds__(256) k_finalize(const RecompProb<T> *__restric
     if (blockIdx.x == 0 && tx == 0 && ty == 0) *p.rank_ptr = rk;
 }
 
-// DDC epilogue (HCore.cpp:291-298 -> CompressedTile::ReadjustTile, Compressed.cpp:696-734): U = T (m x rank),
-// V = identity (rank x n, ld rank), rank = min(m, n).  grid = (chunks, n_tiles)
+// DDC epilogue (HCore.cpp:291-298 -> CompressedTile::ReadjustTile, Compressed.cpp:696-734): C becomes full rank,
+// rank = min(m, n), with the dense result T held in one factor and the identity in the other.  For m >= n this is
+// exactly the reference's (U = T, V = I).  For m < n the reference's index arithmetic is wrong (its own comment:
+// "not handled correctly", HCore.cpp:296); here the mathematically equivalent (U = I, V = T) is written instead.
+// grid = (chunks, n_tiles)
 template<typename T>
 __global__ void __launch_bounds__(256) k_ddc_finalize(const hcb_tile *__restrict__ Ctiles, const T *__restrict__ ws,
                                                       size_t slab, size_t o_w1, const int *__restrict__ info) {
     const hcb_tile C = Ctiles[blockIdx.y];
     if (info && info[blockIdx.y] != 0) return;
     const int m = C.m, n = C.n, rank = m < n ? m : n;
-    const T *W = ws + (size_t) blockIdx.y * slab + o_w1;
+    const T *W = ws + (size_t) blockIdx.y * slab + o_w1;  // T, m x n, ld m
     T *CU = (T *) C.d_data, *CV = CU + (size_t) m * C.max_rank;
     const int gstride = gridDim.x * blockDim.x, g0 = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int idx = g0; idx < m * rank; idx += gstride) CU[idx] = W[idx];
-    for (int idx = g0; idx < rank * n; idx += gstride) CV[idx] = (idx % rank == idx / rank) ? T(1) : T(0);
+    if (m >= n) {
+        for (int idx = g0; idx < m * rank; idx += gstride) CU[idx] = W[idx];
+        for (int idx = g0; idx < rank * n; idx += gstride) CV[idx] = (idx % rank == idx / rank) ? T(1) : T(0);
+    } else {
+        for (int idx = g0; idx < m * rank; idx += gstride) CU[idx] = (idx % m == idx / m) ? T(1) : T(0);
+        for (int idx = g0; idx < rank * n; idx += gstride) CV[idx] = W[idx];  // V = T (rank == m, ld m)
+    }
     if (g0 == 0) *C.d_rank = rank;
 }
 
 // Initial compression epilogue (Compressed.cpp:103-135): rank rule, U = Uf[:, :rk], V = diag(sigma) Vf[:, :rk]^T.
+// Us/Vs are the Jacobi outputs for M = A (m >= n) or M = A^T (m < n): Us normalised (a x s), Vs = V diag(sigma) (s x s).
 template<typename T>
 struct CompressProb {
-    const T *Uf; const T *Vf; const T *sigma;  // Uf: m x s (ld ldu), Vf: n x s (ld ldv)
+    const T *Us; const T *Vs; const T *sigma;
     T *U; T *V; int *rank_ptr; int *info;
-    int m, n, s, ldu, ldv, max_rank;
+    int m, n, s, a, transposed, max_rank;
 };
 
 template<typename T>
@@ -306,13 +325,25 @@ __global__ void __launch_bounds__(256) k_compress_finalize(const CompressProb<T>
     }
     __syncthreads();
     const int rk = s_rk;
-    for (int idx = threadIdx.x; idx < p.m * rk; idx += blockDim.x) {
-        const int i = idx % p.m, c = idx / p.m;
-        p.U[(size_t) i + (size_t) c * p.m] = p.Uf[(size_t) i + (size_t) c * p.ldu];
-    }
-    for (int idx = threadIdx.x; idx < rk * p.n; idx += blockDim.x) {
-        const int c = idx % rk, j = idx / rk;
-        p.V[(size_t) c + (size_t) j * rk] = p.sigma[c] * p.Vf[(size_t) j + (size_t) c * p.ldv];
+    if (!p.transposed) {  // A = Us S V^T : U = Us[:, :rk], V = (V S)^T = Vs^T
+        for (int idx = threadIdx.x; idx < p.m * rk; idx += blockDim.x) {
+            const int i = idx % p.m, c = idx / p.m;
+            p.U[(size_t) i + (size_t) c * p.m] = p.Us[(size_t) i + (size_t) c * p.a];
+        }
+        for (int idx = threadIdx.x; idx < rk * p.n; idx += blockDim.x) {
+            const int c = idx % rk, j = idx / rk;
+            p.V[(size_t) c + (size_t) j * rk] = p.Vs[(size_t) j + (size_t) c * p.s];
+        }
+    } else {  // A^T = Us S V^T -> A = V S Us^T : U = Vs / sigma (m x rk), V = sigma * Us^T (rk x n)
+        for (int idx = threadIdx.x; idx < p.m * rk; idx += blockDim.x) {
+            const int i = idx % p.m, c = idx / p.m;
+            const T sg = p.sigma[c];
+            p.U[(size_t) i + (size_t) c * p.m] = sg > T(0) ? p.Vs[(size_t) i + (size_t) c * p.s] / sg : T(0);
+        }
+        for (int idx = threadIdx.x; idx < rk * p.n; idx += blockDim.x) {
+            const int c = idx % rk, j = idx / rk;
+            p.V[(size_t) c + (size_t) j * rk] = p.sigma[c] * p.Us[(size_t) j + (size_t) c * p.a];
+        }
     }
 }
 

@@ -121,8 +121,9 @@ typedef struct hcb_tile {
     /* ---- (3) fused batched fast path -------------------------------------------------------------------------- */  \
     /* C[t] = alpha*op(A[t])*op(B[t]) + beta*C[t] for t < n_tiles, all eight Dense/Compressed operand mixes of      */  \
     /* HCore<T>::Gemm (HCore.cpp:36-313; the batch must be mix-homogeneous), recompression included, ranks on the   */  \
-    /* device.  A,B,C are HOST arrays of descriptors.  d_info (device int32[n_tiles], may be NULL): 0 ok,           */  \
-    /* 1 Jacobi not converged, 2 rank clipped to max_rank.  Asynchronous.                                           */  \
+    /* device.  A,B,C are HOST arrays of descriptors.  d_info (device int32[n_tiles], may be NULL): low byte flags  */  \
+    /* 0 ok | 1 Jacobi not converged | 2 rank clipped to max_rank | 4 a rank exceeded its rank_bound (tile left     */  \
+    /* untouched); bits 8..15 = Jacobi sweeps used (diagnostics).  Asynchronous.                                    */  \
     int hcb_##P##tlr_gemm_batched(hcb_ctx *, int64_t n_tiles, const hcb_tile *A, int opA, const hcb_tile *B, int opB,   \
                                   const hcb_tile *C, T alpha, T beta, const hcb_compress_params *p, int32_t *d_info);   \
     /* Compressing constructor, batched (Compressed.cpp:75-146): dense tile t (m x n, ld) -> out[t] (U, V, *d_rank) */  \

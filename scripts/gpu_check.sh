@@ -11,7 +11,7 @@ echo "== fp64 yardstick"; timeout 300 python scripts/fp64_peak.py > gpurun_out/f
 echo "== bench"; timeout 1500 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2>gpurun_out/bench.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
 if [ "$MODE" = "full" ]; then
   echo "== ncu launch list"
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 800 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 1 --warmup 3 --tiles 8 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
   echo "ncu rc=$?"; python scripts/summarize_launches.py gpurun_out/launches.csv | tee gpurun_out/launches_summary.txt | head -30
 fi

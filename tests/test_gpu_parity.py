@@ -194,7 +194,7 @@ def test_svd_vs_lapack(ctx, dt, shape):
     _, s_ref, _ = O.k_svd(A)
     eps = np.finfo(dt).eps
     assert np.all(np.diff(S) <= 0)                                            # sorted
-    assert np.max(np.abs(S - s_ref)) <= 50 * eps * s_ref[0]                   # absolute agreement with gesdd
+    assert np.max(np.abs(S - s_ref)) <= 4 * max(m, n) * eps * s_ref[0]        # absolute agreement with gesdd
     assert relerr((U * S) @ VT, A) < 200 * eps                                # reconstructs A
     big = S > 1e3 * eps * S[0]
     assert np.max(np.abs(U[:, big].T @ U[:, big] - np.eye(big.sum()))) < 1e3 * eps
@@ -288,7 +288,7 @@ def test_multitile_vs_reference_fixture(hc, ctx):
     info = torch.zeros(T * T, dtype=torch.int32, device="cuda")
     hc.tile_matrix_multiplication(A, B, Cm, 1.0, 1.0, ctx, hc.CompressionParameters(acc), info=info)
     ctx.Sync()
-    assert int(info.max().item()) in (0, 2)  # 2 = clipped at maxRank, which the reference does silently too
+    assert int((info & 0xff).max().item()) in (0, 2)  # 2 = clipped at maxRank, which the reference does silently too
     assert np.max(np.abs(Cm.rank_table() - z["C_ranks"])) <= 1
     assert relerr(Cm.ToRawMatrix(), z["C_dense"]) <= 10 * acc
 
@@ -338,6 +338,10 @@ def test_all_mixes_ragged_vs_oracle(hc, ctx, dims, dt):
         hc.HCore.Gemm(1.5, a, False, b, False, -0.5, c, ctx, hc.CompressionParameters(acc))
         O.hcore_gemm(dt(1.5), oa, False, ob, False, dt(-0.5), oc, O.CompressionParameters(acc))
         ref = oc.to_dense()
+        if mix == "DDC":
+            # full-rank result held exactly in one factor; for m < n the reference's own index arithmetic is wrong
+            # (HCore.cpp:296 "not handled correctly"), so the check is against the dense truth for every shape
+            ref = 1.5 * Ad.astype(np.float64) @ Bd.astype(np.float64) - 0.5 * Cd.astype(np.float64)
         scale = max(np.linalg.norm(ref), 1e-30)
         assert np.linalg.norm(c.to_dense().astype(np.float64) - ref) <= 10 * acc * max(scale, 1.0), mix
         if mix[2] == "C" and mix != "DDC":
@@ -399,7 +403,8 @@ def test_batched_equals_one_by_one_and_info(hc, ctx):
     for t in range(n):
         hc.HCore.Gemm(1.0, As[t], False, Bs[t], False, 1.0, C2[t], ctx, p)
     ctx.Sync()
-    assert int(info.abs().max().item()) == 0
+    assert int((info & 0xff).max().item()) == 0
+    assert 1 <= int((info >> 8).max().item()) <= 30  # Jacobi sweeps used (diagnostics)
     for t in range(n):
         assert C1[t].GetTileRank() == C2[t].GetTileRank()
         assert relerr(C1[t].to_dense(), C2[t].to_dense()) < 1e-12
@@ -409,13 +414,13 @@ def test_batched_equals_one_by_one_and_info(hc, ctx):
     info1 = torch.zeros(1, dtype=torch.int32, device="cuda")
     hc.gemm_batched(1.0, As[:1], False, Bs[:1], False, 1.0, C1[:1], ctx, p, info=info1)
     ctx.Sync()
-    assert int(info1.item()) == 4 and np.array_equal(C1[0].to_dense(), before)
+    assert int(info1.item()) & 0xff == 4 and np.array_equal(C1[0].to_dense(), before)
 
 
 def test_full_size_tile_properties(hc, ctx):
-    """BASELINE config sizes (nb = 1024, ranks 44, acc 1e-8): size-independent properties of one k-sweep --
-    U orthonormal, product within 10*acc of the dense result, rank trace non-decreasing then stable, idempotent
-    recompression (adding a zero-rank-1 update does not change the product)."""
+    """BASELINE config sizes (nb = 1024, ranks 44, acc 1e-8): one C tile through a 3-step k-sweep, against the oracle
+    (<= 10*acc, ranks +/-1) and through size-independent properties -- U orthonormal, the reference's own normalised
+    error check against the dense product (omp_main.cpp:366-372), and idempotent recompression."""
     torch.manual_seed(0)
     nb, k, acc, kt = 1024, 44, 1e-8, 3
     s = torch.from_numpy(O.latms_spectrum(nb, np.float64)[:k].copy()).cuda()
@@ -424,23 +429,32 @@ def test_full_size_tile_properties(hc, ctx):
         qu, _ = torch.linalg.qr(torch.randn(nb, k, dtype=torch.float64, device="cuda"))
         qv, _ = torch.linalg.qr(torch.randn(nb, k, dtype=torch.float64, device="cuda"))
         return qu, s[:, None] * qv.t()
-    p = hc.CompressionParameters(acc)
+    p, po = hc.CompressionParameters(acc), O.CompressionParameters(acc)
     Ct = hc.CompressedTile(nb, nb, nb // 3, torch.float64, ctx)
+    oC = O.CompressedTile(np.zeros((nb, 1), order="F"), np.zeros((1, nb), order="F"), nb // 3)
     dense = torch.zeros(nb, nb, dtype=torch.float64, device="cuda")
-    ranks = []
+    ranks, oranks = [], []
+    a_inf = b_inf = 0.0
     for _ in range(kt):
         (au, av), (bu, bv) = synth(), synth()
-        A = hc.CompressedTile.from_uv(au.cpu().numpy(), av.cpu().numpy(), ctx, max_rank=nb // 3)
-        B = hc.CompressedTile.from_uv(bu.cpu().numpy(), bv.cpu().numpy(), ctx, max_rank=nb // 3)
+        aun, avn, bun, bvn = (x.cpu().numpy() for x in (au, av, bu, bv))
+        A = hc.CompressedTile.from_uv(aun, avn, ctx, max_rank=nb // 3)
+        B = hc.CompressedTile.from_uv(bun, bvn, ctx, max_rank=nb // 3)
         hc.HCore.Gemm(1.0, A, False, B, False, 1.0, Ct, ctx, p)
+        O.hcore_gemm(1.0, O.CompressedTile.from_uv(aun, avn), False, O.CompressedTile.from_uv(bun, bvn), False, 1.0, oC, po)
         dense += (au @ av) @ (bu @ bv)
+        a_inf += (au @ av).abs().sum(dim=1).max().item()
+        b_inf += (bu @ bv).abs().sum(dim=1).max().item()
         ranks.append(Ct.GetTileRank())
+        oranks.append(oC.rank)
+    assert max(abs(a - b) for a, b in zip(ranks, oranks)) <= 1, (ranks, oranks)
     U, V = Ct.factors()
-    err = (torch.linalg.norm(U @ V - dense) / torch.linalg.norm(dense)).item()
-    assert err <= 10 * acc
+    ref = torch.from_numpy(oC.to_dense()).cuda()
+    assert (torch.linalg.norm(U @ V - ref) / torch.linalg.norm(ref)).item() <= 10 * acc
     orth = torch.linalg.norm(U.t() @ U - torch.eye(U.shape[1], dtype=torch.float64, device="cuda")).item()
     assert orth < 1e-10
-    assert ranks[0] <= ranks[1] + 1 and all(1 <= r <= nb // 3 for r in ranks)
+    err_inf = (U @ V - dense).abs().sum(dim=1).max().item()
+    assert err_inf / ((a_inf / kt + b_inf / kt) * acc * nb) < 10  # the example driver's own pass criterion
     before = (U @ V).clone()
     Z = hc.CompressedTile(nb, nb, nb // 3, torch.float64, ctx)  # rank-1 zero tile
     hc.HCore.Gemm(1.0, Z, False, Z, False, 1.0, Ct, ctx, p)
