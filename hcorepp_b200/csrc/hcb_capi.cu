@@ -93,6 +93,9 @@ int launch_gemm(hcb_ctx *ctx, const GemmProb<T> *d_probs, int n_probs, int m_bou
         if (m_bound <= 32 && n_bound <= 32) {
             dim3 grid(1, cnt);
             k_gemm_batched<T, 32, 32, 16><<<grid, 256, 0, ctx->stream>>>(d_probs + off);
+        } else if (m_bound <= 32) {
+            dim3 grid(std::max(1, cdiv(n_bound, 64)), cnt);
+            k_gemm_batched<T, 32, 64, 16><<<grid, 256, 0, ctx->stream>>>(d_probs + off);
         } else {
             dim3 grid(std::max(1, cdiv(m_bound, 64) * cdiv(n_bound, 64)), cnt);
             k_gemm_batched<T, 64, 64, 16><<<grid, 256, 0, ctx->stream>>>(d_probs + off);
@@ -393,8 +396,8 @@ static inline int bound_of(const hcb_tile &t) {
 template<typename T>
 struct Layout {
     size_t slab = 0, o_w1 = 0, o_w2 = 0, o_uw = 0, o_vw = 0, o_tauu = 0, o_tauv = 0, o_m = 0, o_j = 0, o_us = 0,
-           o_vs = 0, o_sig = 0, o_vn = 0;
-    int r_b = 0, pq_b = 0;
+           o_vs = 0, o_sig = 0, o_vn = 0, o_vcu = 0, o_vcv = 0, o_tbu = 0, o_tbv = 0, o_wbu = 0, o_wbv = 0;
+    int r_b = 0, pq_b = 0, wcols = 0, nblk = 0;
 };
 
 template<typename T>
@@ -430,6 +433,15 @@ Layout<T> make_layout(const BatchShape &s) {
         L.o_vs = take(sq);
         L.o_sig = take(L.pq_b);
         L.o_vn = take((size_t) s.n * std::min(L.pq_b, std::max(s.maxrankC, 1)));
+        // blocked QR: clean reflector panels, T blocks, GEMM temporaries
+        L.nblk = cdiv(L.pq_b, NBQ);
+        L.wcols = std::max(L.r_b, std::max(s.maxrankC, 1));
+        L.o_vcu = take((size_t) s.m * L.r_b);
+        L.o_vcv = take((size_t) s.n * L.r_b);
+        L.o_tbu = take((size_t) NBQ * NBQ * L.nblk);
+        L.o_tbv = take((size_t) NBQ * NBQ * L.nblk);
+        L.o_wbu = take((size_t) 2 * NBQ * L.wcols);
+        L.o_wbv = take((size_t) 2 * NBQ * L.wcols);
     }
     L.slab = off;
     return L;
@@ -439,7 +451,8 @@ template<typename T>
 struct DescArrays {  // device arrays living at the front of the scratch arena
     size_t bytes = 0;
     size_t o_g1, o_g2, o_g3, o_gv, o_cp, o_qr, o_rf, o_svd, o_rc, o_rk, o_tiles;
-    explicit DescArrays(int n) {
+    size_t o_bqr = 0, o_blf = 0, o_bgw = 0, o_bgw2 = 0, o_bgup = 0, o_agw = 0, o_agw2 = 0, o_agup = 0;
+    explicit DescArrays(int n, int nblk = 0) {
         size_t off = 0;
         auto take = [&](size_t b) { size_t o = off; off += align_up(b, 256); return o; };
         o_g1 = take(sizeof(GemmProb<T>) * n);
@@ -453,6 +466,17 @@ struct DescArrays {  // device arrays living at the front of the scratch arena
         o_rc = take(sizeof(RecompProb<T>) * n);
         o_rk = take(sizeof(int) * n);
         o_tiles = take(sizeof(hcb_tile) * 3 * n);
+        if (nblk > 0) {
+            const size_t nb = (size_t) nblk * 2 * n;
+            o_bqr = take(sizeof(QrProb<T>) * nb);
+            o_blf = take(sizeof(LarftProb<T>) * nb);
+            o_bgw = take(sizeof(GemmProb<T>) * nb);
+            o_bgw2 = take(sizeof(GemmProb<T>) * nb);
+            o_bgup = take(sizeof(GemmProb<T>) * nb);
+            o_agw = take(sizeof(GemmProb<T>) * nb);
+            o_agw2 = take(sizeof(GemmProb<T>) * nb);
+            o_agup = take(sizeof(GemmProb<T>) * nb);
+        }
         bytes = off;
     }
 };
@@ -499,7 +523,8 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     BatchShape s;
     HCB_TRY(classify(A, B, C, n, opA, opB, s));
     const Layout<T> L = make_layout<T>(s);
-    const DescArrays<T> D(n);
+    const bool blocked = L.r_b > 2 * NBQ;  // compact-WY path once the stacked rank spans more than two blocks
+    const DescArrays<T> D(n, blocked ? L.nblk : 0);
     const size_t total = D.bytes + L.slab * sizeof(T) * (size_t) n + 256;
     HCB_TRY(ensure_ws(ctx, total));
     char *base = reinterpret_cast<char *>(ctx->ws);
@@ -524,6 +549,8 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     sa.slab = L.slab; sa.o_w1 = L.o_w1; sa.o_w2 = L.o_w2; sa.o_uw = L.o_uw; sa.o_vw = L.o_vw;
     sa.o_tauu = L.o_tauu; sa.o_tauv = L.o_tauv; sa.o_m = L.o_m; sa.o_j = L.o_j; sa.o_us = L.o_us; sa.o_vs = L.o_vs;
     sa.o_sig = L.o_sig; sa.o_vn = L.o_vn;
+    sa.o_vcu = L.o_vcu; sa.o_vcv = L.o_vcv; sa.o_tbu = L.o_tbu; sa.o_tbv = L.o_tbv; sa.o_wbu = L.o_wbu; sa.o_wbv = L.o_wbv;
+    sa.wcols = L.wcols;
     sa.kA_b = s.kA; sa.kB_b = s.kB; sa.kC_b = s.kC; sa.r_b = L.r_b;
     sa.rk_new = reinterpret_cast<int *>(base + D.o_rk);
     sa.info = d_info;
@@ -576,9 +603,32 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
         PhaseScope ph(ctx, 2);
         HCB_TRY(launch_copy<T>(ctx, sa.cp, 4 * n, std::max(s.m, s.n), std::max(L.r_b, 1)));
     }
-    {
+    const int npan = 2 * n, nbt = L.nblk * npan;
+    if (!blocked) {
         PhaseScope ph(ctx, 3);
         HCB_TRY(launch_qr<T>(ctx, sa.qr, 2 * n));
+    } else {
+        // blocked Householder QR: per NBQ-column block -- panel factorisation, T_b + clean V_b, then the trailing
+        // update A2 -= V_b T_b^T (V_b^T A2) as three batched GEMMs
+        PhaseScope ph(ctx, 3);
+        QrBlockArrays<T> qa{reinterpret_cast<QrProb<T> *>(base + D.o_bqr), reinterpret_cast<LarftProb<T> *>(base + D.o_blf),
+                            reinterpret_cast<GemmProb<T> *>(base + D.o_bgw), reinterpret_cast<GemmProb<T> *>(base + D.o_bgw2),
+                            reinterpret_cast<GemmProb<T> *>(base + D.o_bgup), L.nblk, npan};
+        k_setup_qr_blocks<T><<<cdiv(nbt, 128), 128, 0, ctx->stream>>>(sa.rc, qa);
+        HCB_LAUNCH_CHECK("k_setup_qr_blocks");
+        const int mx = std::max(s.m, s.n);
+        for (int b = 0; b < L.nblk; ++b) {
+            const size_t o = (size_t) b * npan;
+            HCB_TRY(launch_qr<T>(ctx, qa.qr + o, npan));
+            k_larft_extract<T><<<npan, 256, 0, ctx->stream>>>(qa.lf + o);
+            HCB_LAUNCH_CHECK("k_larft_extract");
+            const int nt_b = L.r_b - (b + 1) * NBQ;
+            if (nt_b > 0) {
+                HCB_TRY(launch_gemm<T>(ctx, qa.gw + o, npan, NBQ, nt_b));
+                HCB_TRY(launch_gemm<T>(ctx, qa.gw2 + o, npan, NBQ, nt_b));
+                HCB_TRY(launch_gemm<T>(ctx, qa.gup + o, npan, mx - b * NBQ, nt_b));
+            }
+        }
     }
     {
         PhaseScope ph(ctx, 4);
@@ -591,9 +641,23 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
         HCB_LAUNCH_CHECK("k_truncate");
     }
     const int rk_bound = std::max(1, std::min(L.pq_b, s.maxrankC));
-    {
+    if (!blocked) {
         PhaseScope ph(ctx, 5);
         HCB_TRY(launch_refl<T>(ctx, sa.rf, 2 * n, rk_bound));
+    } else {
+        // blocked rebuild C := Q [X;0]: blocks last-to-first, three batched GEMMs per block, rank read on the device
+        PhaseScope ph(ctx, 5);
+        ApplyBlockArrays<T> aa{reinterpret_cast<GemmProb<T> *>(base + D.o_agw), reinterpret_cast<GemmProb<T> *>(base + D.o_agw2),
+                               reinterpret_cast<GemmProb<T> *>(base + D.o_agup), L.nblk, npan};
+        k_setup_apply_blocks<T><<<cdiv(nbt, 128), 128, 0, ctx->stream>>>(sa.rc, aa);
+        HCB_LAUNCH_CHECK("k_setup_apply_blocks");
+        const int mx = std::max(s.m, s.n);
+        for (int b = L.nblk - 1; b >= 0; --b) {
+            const size_t o = (size_t) b * npan;
+            HCB_TRY(launch_gemm<T>(ctx, aa.gw + o, npan, NBQ, rk_bound));
+            HCB_TRY(launch_gemm<T>(ctx, aa.gw2 + o, npan, NBQ, rk_bound));
+            HCB_TRY(launch_gemm<T>(ctx, aa.gup + o, npan, mx - b * NBQ, rk_bound));
+        }
     }
     {
         PhaseScope ph(ctx, 6);
@@ -703,7 +767,7 @@ size_t t_workspace(int64_t n_tiles, int64_t m, int64_t n, int64_t k, int64_t r_b
     s.kC = (int) (r_bound - s.kA);
     s.maxrankC = (int) std::max<int64_t>(1, std::min(m, n) / 3);
     const Layout<T> L = make_layout<T>(s);
-    const DescArrays<T> D((int) n_tiles);
+    const DescArrays<T> D((int) n_tiles, L.nblk);
     return D.bytes + L.slab * sizeof(T) * (size_t) n_tiles + 512;
 }
 

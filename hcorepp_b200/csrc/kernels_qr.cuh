@@ -103,4 +103,67 @@ __global__ void __launch_bounds__(256) k_apply_reflectors(const ReflProb<T> *__r
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Blocked (compact-WY) machinery: Q_b = H_j0 .. H_j0+jb-1 = I - V_b T_b V_b^T (LAPACK dlarft, forward/columnwise).
+// The panel factorisation of each NBQ-column block stays level-2 (k_geqrf_batched on the sub-panel); everything else
+// -- trailing update in the QR, and the whole rebuild Q*[X;0] -- becomes batched GEMMs (k_gemm_batched) with
+// device-resident descriptors, which is where the flops are once the stacked rank r = kc + ka reaches the hundreds.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int NBQ = 32;  // reflector block size
+
+template<typename T>
+struct LarftProb {
+    const T *A;    // first element of the block inside the factored panel: &A[j0 + j0*lda]
+    const T *tau;  // &tau[j0]
+    T *Vc;         // &Vc[j0 + j0*ldvc]: receives the clean unit-lower-trapezoidal copy of the block's reflectors
+    T *Tm;         // NBQ x NBQ (ld NBQ): receives T_b (upper triangular, zeros below)
+    int lda, ldvc, rows, jb;  // rows = m - j0 ; jb = reflectors in this block (0: nothing to do)
+};
+
+// One CTA (256 threads) per block: (1) Vc = unit-lower-trapezoid(V_b); (2) G = Vc^T Vc (strict upper part);
+// (3) T by the dlarft recurrence: T(i,i) = tau_i, T(0:i,i) = -tau_i * T(0:i,0:i) * G(0:i,i).
+template<typename T>
+__global__ void __launch_bounds__(256) k_larft_extract(const LarftProb<T> *__restrict__ probs) {
+    const LarftProb<T> p = probs[blockIdx.x];
+    const int jb = p.jb, rows = p.rows;
+    if (jb <= 0 || rows <= 0) return;
+    __shared__ T G[NBQ][NBQ + 1];
+    __shared__ T Ts[NBQ][NBQ + 1];
+    __shared__ T tcol[NBQ];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+    for (int c = 0; c < jb; ++c) {
+        const T *src = p.A + (size_t) c * p.lda;
+        T *dst = p.Vc + (size_t) c * p.ldvc;
+        for (int i = tid; i < rows; i += blockDim.x) dst[i] = (i < c) ? T(0) : (i == c ? T(1) : src[i]);
+    }
+    for (int idx = tid; idx < NBQ * NBQ; idx += blockDim.x) Ts[idx / NBQ][idx % NBQ] = T(0);
+    __syncthreads();
+    for (int pr = w; pr < jb * jb; pr += nw) {
+        const int i = pr / jb, j = pr % jb;
+        if (i >= j) continue;
+        const T *vi = p.Vc + (size_t) i * p.ldvc, *vj = p.Vc + (size_t) j * p.ldvc;
+        T d = T(0);
+        for (int r = j + lane; r < rows; r += 32) d = fma(vi[r], vj[r], d);  // vj is zero above row j
+        d = warp_sum(d);
+        if (lane == 0) G[i][j] = d;
+    }
+    __syncthreads();
+    if (w == 0) {
+        for (int i = 0; i < jb; ++i) {
+            const T ti = p.tau[i];
+            if (lane < i) tcol[lane] = -ti * G[lane][i];
+            __syncwarp();
+            T acc = T(0);
+            if (lane < i)
+                for (int c = lane; c < i; ++c) acc = fma(Ts[lane][c], tcol[c], acc);
+            __syncwarp();
+            if (lane < i) Ts[lane][i] = acc;
+            if (lane == i) Ts[i][i] = ti;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < NBQ * NBQ; idx += blockDim.x) p.Tm[idx] = Ts[idx % NBQ][idx / NBQ];  // column-major
+}
+
 }  // namespace hcb

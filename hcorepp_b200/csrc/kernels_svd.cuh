@@ -22,12 +22,44 @@ __device__ __forceinline__ void rr_pair(int nb2, int round, int slot, int &x, in
     if (x > y) { const int t = x; x = y; y = t; }
 }
 
+// One Jacobi rotation of the column pair (mx, my) of length a, done by one warp. Returns true if it rotated.
+template<typename T>
+__device__ __forceinline__ bool jacobi_rotate(T *__restrict__ mx, T *__restrict__ my, int a, int lane, T tol) {
+    T alpha = T(0), beta = T(0), gamma = T(0);
+    for (int i = lane; i < a; i += 32) {
+        const T u = mx[i], v = my[i];
+        alpha = fma(u, u, alpha);
+        beta = fma(v, v, beta);
+        gamma = fma(u, v, gamma);
+    }
+    alpha = warp_sum(alpha);
+    beta = warp_sum(beta);
+    gamma = warp_sum(gamma);
+    const T lim = tol * t_sqrt(alpha) * t_sqrt(beta);
+    if (!(t_abs(gamma) > lim) || gamma == T(0)) return false;
+    const T zeta = (beta - alpha) / (T(2) * gamma);
+    const T t = (zeta >= T(0) ? T(1) : T(-1)) / (t_abs(zeta) + t_sqrt(fma(zeta, zeta, T(1))));
+    const T c = T(1) / t_sqrt(fma(t, t, T(1)));
+    const T s = c * t;
+    for (int i = lane; i < a; i += 32) {
+        const T u = mx[i], v = my[i];
+        mx[i] = fma(-s, v, c * u);
+        my[i] = fma(s, u, c * v);
+    }
+    return true;
+}
+
 // One CTA per problem. M (a x b, a >= b) = Uout diag(sigma) V^T; only the LEFT factor is produced here:
 // the rotations are not accumulated.  The caller gets the scaled right factor V diag(sigma) = M^T Uout with one
 // batched GEMM afterwards (exactly the quantity the recompression needs, Compressed.cpp:598-622), which halves the
 // Jacobi work and its shared-memory footprint.  p.M is left untouched.
-// dynamic shared memory: smem_elems elements of T. Layout when the problem fits: [M a*b | sig b]; otherwise only
-// [sig b] lives in shared memory and the rotations work on a global copy of M (p.J, a*b elements).
+//
+// Three regimes, chosen per problem from its true size (dynamic shared memory = smem_elems elements of T):
+//   (A) a*b + b fits            : the whole matrix lives in shared memory, plain cyclic (round-robin) one-sided Jacobi;
+//   (B) two column blocks fit   : BLOCK one-sided Jacobi -- the rotated copy of M lives in global memory (p.J, L2
+//                                 resident), pairs of w-column blocks are staged in shared memory, all w*w cross pairs
+//                                 (and, once per sweep, the pairs inside each block) are rotated there, blocks go back;
+//   (C) otherwise               : rotations directly on the global copy (slow, correctness-only fallback).
 template<typename T>
 __global__ void __launch_bounds__(1024) k_jacobi_svd(const SvdProb<T> *__restrict__ probs, int smem_elems,
                                                      int max_sweeps) {
@@ -39,67 +71,110 @@ __global__ void __launch_bounds__(1024) k_jacobi_svd(const SvdProb<T> *__restric
     if (a <= 0 || b <= 0) return;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
     const bool fits = (size_t) a * b + (size_t) b <= (size_t) smem_elems;
+    int bw = 0;  // block width of regime (B)
+    if (!fits) {
+        bw = 32;
+        while (bw >= 2 && (size_t) 2 * a * bw + (size_t) b > (size_t) smem_elems) bw >>= 1;
+        if (bw < 2) bw = 0;
+    }
     T *M, *sig;
-    int ldm;
+    const int ldm = a;
     if (fits) {
         M = sm;
         sig = sm + (size_t) a * b;
-        ldm = a;
     } else {
         M = p.J;
-        sig = sm;
-        ldm = a;
+        sig = sm + (size_t) 2 * a * bw;
     }
     for (int idx = tid; idx < a * b; idx += nthr) M[idx] = p.M[(size_t) (idx % a) + (size_t) (idx / a) * p.ldm];
     __syncthreads();
 
     const T tol = Eps<T>::v() * t_sqrt((T) a);
-    const int nb2 = (b + 1) & ~1;
     bool converged = (b < 2);
     int sweeps_used = 0;
-    for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
-        ++sweeps_used;
-        __syncthreads();
-        if (tid == 0) s_rot = 0;
-        __syncthreads();
-        for (int round = 0; round < nb2 - 1; ++round) {
-            for (int slot = w; slot < nb2 / 2; slot += nw) {
-                int x, y;
-                rr_pair(nb2, round, slot, x, y);
-                if (y >= b) continue;  // dummy player (odd b)
-                T *mx = M + (size_t) x * ldm, *my = M + (size_t) y * ldm;
-                T alpha = T(0), beta = T(0), gamma = T(0);
-                for (int i = lane; i < a; i += 32) {
-                    const T u = mx[i], v = my[i];
-                    alpha = fma(u, u, alpha);
-                    beta = fma(v, v, beta);
-                    gamma = fma(u, v, gamma);
+    if (fits || bw == 0) {
+        // ---- regimes (A) and (C): cyclic one-sided Jacobi over all column pairs, one warp per pair
+        const int nb2 = (b + 1) & ~1;
+        for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
+            ++sweeps_used;
+            __syncthreads();
+            if (tid == 0) s_rot = 0;
+            __syncthreads();
+            for (int round = 0; round < nb2 - 1; ++round) {
+                for (int slot = w; slot < nb2 / 2; slot += nw) {
+                    int x, y;
+                    rr_pair(nb2, round, slot, x, y);
+                    if (y >= b) continue;  // dummy player (odd b)
+                    if (jacobi_rotate(M + (size_t) x * ldm, M + (size_t) y * ldm, a, lane, tol) && lane == 0) s_rot = 1;
                 }
-                alpha = warp_sum(alpha);
-                beta = warp_sum(beta);
-                gamma = warp_sum(gamma);
-                const T lim = tol * t_sqrt(alpha) * t_sqrt(beta);
-                if (t_abs(gamma) > lim && gamma != T(0)) {
-                    if (lane == 0) s_rot = 1;
-                    const T zeta = (beta - alpha) / (T(2) * gamma);
-                    const T t = (zeta >= T(0) ? T(1) : T(-1)) / (t_abs(zeta) + t_sqrt(fma(zeta, zeta, T(1))));
-                    const T c = T(1) / t_sqrt(fma(t, t, T(1)));
-                    const T s = c * t;
-                    for (int i = lane; i < a; i += 32) {
-                        const T u = mx[i], v = my[i];
-                        mx[i] = c * u - s * v;
-                        my[i] = s * u + c * v;
+                __syncthreads();
+            }
+            converged = (s_rot == 0);
+        }
+    } else {
+        // ---- regime (B): block one-sided Jacobi
+        T *BA = sm, *BB = sm + (size_t) a * bw;
+        const int nblk = (b + bw - 1) / bw, nblk2 = (nblk + 1) & ~1;
+        for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
+            ++sweeps_used;
+            __syncthreads();
+            if (tid == 0) s_rot = 0;
+            __syncthreads();
+            for (int bround = 0; bround < (nblk2 > 1 ? nblk2 - 1 : 1); ++bround) {
+                for (int bslot = 0; bslot < nblk2 / 2; ++bslot) {
+                    int bi, bj;
+                    if (nblk2 > 1) rr_pair(nblk2, bround, bslot, bi, bj);
+                    else { bi = 0; bj = 1; }
+                    if (bi >= nblk) continue;
+                    const bool have_j = bj < nblk;
+                    const int ci0 = bi * bw, cj0 = bj * bw;
+                    const int wi = min(bw, b - ci0), wj = have_j ? min(bw, b - cj0) : 0;
+                    // stage the two column blocks
+                    for (int idx = tid; idx < a * wi; idx += nthr) BA[idx] = M[(size_t) ci0 * ldm + idx];
+                    for (int idx = tid; idx < a * wj; idx += nthr) BB[idx] = M[(size_t) cj0 * ldm + idx];
+                    __syncthreads();
+                    if (bround == 0) {
+                        // once per sweep every block meets exactly one partner in round 0: rotate ALL pairs of the
+                        // union (inside-block pairs included); BA and BB are contiguous, so the union is one array
+                        const int nu = wi + wj, nu2 = (nu + 1) & ~1;
+                        T *UB = BA;  // columns [0, wi) from BA, [wi, wi+wj) from BB (contiguous only if wi == bw)
+                        for (int round = 0; round < nu2 - 1; ++round) {
+                            for (int slot = w; slot < nu2 / 2; slot += nw) {
+                                int x, y;
+                                rr_pair(nu2, round, slot, x, y);
+                                if (y >= nu) continue;
+                                T *cx = x < wi ? UB + (size_t) x * a : BB + (size_t) (x - wi) * a;
+                                T *cy = y < wi ? UB + (size_t) y * a : BB + (size_t) (y - wi) * a;
+                                if (jacobi_rotate(cx, cy, a, lane, tol) && lane == 0) s_rot = 1;
+                            }
+                            __syncthreads();
+                        }
+                    } else if (have_j) {
+                        // cross pairs only: round t pairs column i of BA with column (i + t) mod bw of BB
+                        for (int t = 0; t < bw; ++t) {
+                            for (int i = w; i < wi; i += nw) {
+                                const int j = (i + t) % bw;
+                                if (j >= wj) continue;
+                                if (jacobi_rotate(BA + (size_t) i * a, BB + (size_t) j * a, a, lane, tol) && lane == 0)
+                                    s_rot = 1;
+                            }
+                            __syncthreads();
+                        }
                     }
+                    // write the blocks back
+                    for (int idx = tid; idx < a * wi; idx += nthr) M[(size_t) ci0 * ldm + idx] = BA[idx];
+                    for (int idx = tid; idx < a * wj; idx += nthr) M[(size_t) cj0 * ldm + idx] = BB[idx];
+                    __syncthreads();
                 }
             }
-            __syncthreads();
+            converged = (s_rot == 0);
         }
-        converged = (s_rot == 0);
     }
     if (p.info && tid == 0) {
         if (!converged) atomicOr(p.info, 1);
         atomicOr(p.info, sweeps_used << 8);  // diagnostics: number of Jacobi sweeps in bits 8..15
     }
+    __syncthreads();
 
     // singular values = column norms
     for (int c = w; c < b; c += nw) {

@@ -7,6 +7,7 @@
 #pragma once
 #include "common.cuh"
 #include "kernels_blas.cuh"
+#include "kernels_qr.cuh"
 
 namespace hcb {
 
@@ -24,6 +25,11 @@ struct RecompProb {
     int *rk_new;       // scratch: rank chosen by the truncation rule
     int *info;
     int m, n, r, p, q, a, b, transposed, max_rank, active;
+    // blocked-QR scratch (per side: 0 = U stack, 1 = V stack)
+    T *VC[2];   // clean reflector panels (same shape / ld as UW, VW)
+    T *TB[2];   // T blocks: NBQ*NBQ elements per block, block b at TB + b*NBQ*NBQ
+    T *WB[2];   // NBQ x (r or rank) GEMM temporaries (ld NBQ), two per side: W at WB, W2 at WB + NBQ*wcols
+    int wcols;  // columns each W temporary can hold
 };
 
 template<typename T>
@@ -34,6 +40,8 @@ struct SetupArgs {
     // per-tile scratch (element offsets inside one tile's slab) and slab stride
     T *ws;
     size_t slab, o_w1, o_w2, o_uw, o_vw, o_tauu, o_tauv, o_m, o_j, o_us, o_vs, o_sig, o_vn;
+    size_t o_vcu, o_vcv, o_tbu, o_tbv, o_wbu, o_wbv;  // blocked-QR scratch
+    int wcols;
     int kA_b, kB_b, kC_b, r_b;  // rank bounds the scratch was sized for
     int *rk_new;                // n_tiles ints
     int *info;                  // n_tiles ints (may be null)
@@ -155,6 +163,10 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
                 rc.CU = CU; rc.CV = CV; rc.VN = slab + s.o_vn; rc.rank_ptr = C.d_rank; rc.rk_new = s.rk_new + t;
                 rc.info = s.info ? s.info + t : nullptr;
                 rc.m = m; rc.n = n; rc.r = r; rc.p = p; rc.q = q; rc.max_rank = C.max_rank; rc.active = 1;
+                rc.VC[0] = slab + s.o_vcu; rc.VC[1] = slab + s.o_vcv;
+                rc.TB[0] = slab + s.o_tbu; rc.TB[1] = slab + s.o_tbv;
+                rc.WB[0] = slab + s.o_wbu; rc.WB[1] = slab + s.o_wbv;
+                rc.wcols = s.wcols;
                 rc.transposed = p < q;
                 rc.a = rc.transposed ? q : p;
                 rc.b = rc.transposed ? p : q;
@@ -183,6 +195,82 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
     s.rf[2 * t + 0] = r0; s.rf[2 * t + 1] = r1;
     s.svd[t] = sv;
     s.rc[t] = rc;
+}
+
+// Descriptors of the blocked QR of both stacks, for every NBQ-column block at once.  One thread per (block, panel);
+// arrays are indexed [blk * npan + pan], pan = 2*tile + side.
+template<typename T>
+struct QrBlockArrays {
+    QrProb<T> *qr;
+    LarftProb<T> *lf;
+    GemmProb<T> *gw, *gw2, *gup;
+    int nblk, npan;
+};
+
+template<typename T>
+__global__ void k_setup_qr_blocks(const RecompProb<T> *__restrict__ rcs, QrBlockArrays<T> o) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= o.nblk * o.npan) return;
+    const int blk = idx / o.npan, pan = idx % o.npan, side = pan & 1;
+    const RecompProb<T> rc = rcs[pan >> 1];
+    QrProb<T> q{nullptr, nullptr, 0, 0, 1};
+    LarftProb<T> lf{nullptr, nullptr, nullptr, nullptr, 1, 1, 0, 0};
+    GemmProb<T> gz = mk_gemm<T>(nullptr, 1, 0, nullptr, 1, 0, nullptr, 1, 0, 0, 0, T(0), T(0)), gw = gz, gw2 = gz, gup = gz;
+    if (rc.active) {
+        const int m = side ? rc.n : rc.m, r = rc.r, kmax = m < r ? m : r, j0 = blk * NBQ;
+        if (j0 < kmax) {
+            const int jb = (kmax - j0) < NBQ ? (kmax - j0) : NBQ;
+            T *A = side ? rc.VW : rc.UW;
+            T *tau = side ? rc.tauV : rc.tauU;
+            T *blkA = A + (size_t) j0 + (size_t) j0 * m;
+            T *Vc = rc.VC[side] + (size_t) j0 + (size_t) j0 * m;
+            T *Tm = rc.TB[side] + (size_t) blk * NBQ * NBQ;
+            T *W = rc.WB[side], *W2 = W + (size_t) NBQ * rc.wcols;
+            q = QrProb<T>{blkA, tau + j0, m - j0, jb, m};
+            lf = LarftProb<T>{blkA, tau + j0, Vc, Tm, m, m, m - j0, jb};
+            const int nt = r - (j0 + jb);  // trailing columns
+            if (nt > 0) {
+                T *A2 = A + (size_t) j0 + (size_t) (j0 + jb) * m;
+                gw = mk_gemm<T>(Vc, m, 1, A2, m, 0, W, NBQ, jb, nt, m - j0, T(1), T(0));       // W  = Vc^T A2
+                gw2 = mk_gemm<T>(Tm, NBQ, 1, W, NBQ, 0, W2, NBQ, jb, nt, jb, T(1), T(0));       // W2 = T^T W
+                gup = mk_gemm<T>(Vc, m, 0, W2, NBQ, 0, A2, m, m - j0, nt, jb, T(-1), T(1));     // A2 -= Vc W2
+            }
+        }
+    }
+    o.qr[idx] = q; o.lf[idx] = lf; o.gw[idx] = gw; o.gw2[idx] = gw2; o.gup[idx] = gup;
+}
+
+// Descriptors of the blocked rebuild C := Q [X;0] (C = CU for side 0, VN for side 1), blocks applied last-to-first:
+// W = Vc_b^T C[j0:,:] ; W2 = T_b W ; C[j0:,:] -= Vc_b W2.  The column count is the rank chosen on the device.
+template<typename T>
+struct ApplyBlockArrays {
+    GemmProb<T> *gw, *gw2, *gup;
+    int nblk, npan;
+};
+
+template<typename T>
+__global__ void k_setup_apply_blocks(const RecompProb<T> *__restrict__ rcs, ApplyBlockArrays<T> o) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= o.nblk * o.npan) return;
+    const int blk = idx / o.npan, pan = idx % o.npan, side = pan & 1;
+    const RecompProb<T> rc = rcs[pan >> 1];
+    GemmProb<T> gz = mk_gemm<T>(nullptr, 1, 0, nullptr, 1, 0, nullptr, 1, 0, 0, 0, T(0), T(0)), gw = gz, gw2 = gz, gup = gz;
+    if (rc.active) {
+        const int m = side ? rc.n : rc.m, r = rc.r, kmax = m < r ? m : r, j0 = blk * NBQ;
+        int rk = *rc.rk_new;
+        if (rk > rc.wcols) rk = 0;  // cannot happen (wcols >= max_rank bound); guard against scratch overrun
+        if (j0 < kmax && rk > 0) {
+            const int jb = (kmax - j0) < NBQ ? (kmax - j0) : NBQ;
+            T *Cm = (side ? rc.VN : rc.CU) + j0;
+            T *Vc = rc.VC[side] + (size_t) j0 + (size_t) j0 * m;
+            T *Tm = rc.TB[side] + (size_t) blk * NBQ * NBQ;
+            T *W = rc.WB[side], *W2 = W + (size_t) NBQ * rc.wcols;
+            gw = mk_gemm<T>(Vc, m, 1, Cm, m, 0, W, NBQ, jb, rk, m - j0, T(1), T(0));
+            gw2 = mk_gemm<T>(Tm, NBQ, 0, W, NBQ, 0, W2, NBQ, jb, rk, jb, T(1), T(0));
+            gup = mk_gemm<T>(Vc, m, 0, W2, NBQ, 0, Cm, m, m - j0, rk, jb, T(-1), T(1));
+        }
+    }
+    o.gw[idx] = gw; o.gw2[idx] = gw2; o.gup[idx] = gup;
 }
 
 // core = RU * RV^T with RU = triu(UW[:p, :r]), RV = triu(VW[:q, :r]) (Compressed.cpp:363-370, 442-461), written as
