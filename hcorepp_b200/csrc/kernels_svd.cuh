@@ -23,8 +23,12 @@ __device__ __forceinline__ void rr_pair(int nb2, int round, int slot, int &x, in
 }
 
 // One Jacobi rotation of the column pair (mx, my) of length a, done by one warp. Returns true if it rotated.
+//  * de Rijk ordering: the column that ends up with the larger norm is stored in mx (the lower index), so the
+//    columns sort themselves by decreasing norm while they converge -- far fewer sweeps on graded spectra;
+//  * noise2 = (eps * largest column norm)^2: a column at or below rounding level is left alone (its singular value is
+//    zero to working precision; chasing its direction would only keep the sweep count up).
 template<typename T>
-__device__ __forceinline__ bool jacobi_rotate(T *__restrict__ mx, T *__restrict__ my, int a, int lane, T tol) {
+__device__ __forceinline__ bool jacobi_rotate(T *__restrict__ mx, T *__restrict__ my, int a, int lane, T tol, T noise2) {
     T alpha = T(0), beta = T(0), gamma = T(0);
     for (int i = lane; i < a; i += 32) {
         const T u = mx[i], v = my[i];
@@ -35,16 +39,35 @@ __device__ __forceinline__ bool jacobi_rotate(T *__restrict__ mx, T *__restrict_
     alpha = warp_sum(alpha);
     beta = warp_sum(beta);
     gamma = warp_sum(gamma);
+    const bool swap = beta > alpha;
     const T lim = tol * t_sqrt(alpha) * t_sqrt(beta);
-    if (!(t_abs(gamma) > lim) || gamma == T(0)) return false;
+    const bool rotate = (t_abs(gamma) > lim) && gamma != T(0) && (alpha > noise2) && (beta > noise2);
+    if (!rotate) {
+        if (swap && (beta > noise2)) {  // keep the ordering moving even when the pair is already orthogonal
+            for (int i = lane; i < a; i += 32) {
+                const T u = mx[i], v = my[i];
+                mx[i] = v;
+                my[i] = u;
+            }
+        }
+        return false;
+    }
     const T zeta = (beta - alpha) / (T(2) * gamma);
     const T t = (zeta >= T(0) ? T(1) : T(-1)) / (t_abs(zeta) + t_sqrt(fma(zeta, zeta, T(1))));
     const T c = T(1) / t_sqrt(fma(t, t, T(1)));
     const T s = c * t;
-    for (int i = lane; i < a; i += 32) {
-        const T u = mx[i], v = my[i];
-        mx[i] = fma(-s, v, c * u);
-        my[i] = fma(s, u, c * v);
+    if (!swap) {
+        for (int i = lane; i < a; i += 32) {
+            const T u = mx[i], v = my[i];
+            mx[i] = fma(-s, v, c * u);
+            my[i] = fma(s, u, c * v);
+        }
+    } else {
+        for (int i = lane; i < a; i += 32) {
+            const T u = mx[i], v = my[i];
+            mx[i] = fma(s, u, c * v);
+            my[i] = fma(-s, v, c * u);
+        }
     }
     return true;
 }
@@ -90,6 +113,28 @@ __global__ void __launch_bounds__(1024) k_jacobi_svd(const SvdProb<T> *__restric
     __syncthreads();
 
     const T tol = Eps<T>::v() * t_sqrt((T) a);
+    // noise floor from the largest column norm of the input
+    __shared__ T s_noise2;
+    {
+        T mx2 = T(0);
+        for (int c = w; c < b; c += nw) {
+            const T *mc = M + (size_t) c * ldm;
+            T ss = T(0);
+            for (int i = lane; i < a; i += 32) ss = fma(mc[i], mc[i], ss);
+            ss = warp_sum(ss);
+            mx2 = ss > mx2 ? ss : mx2;
+        }
+        __shared__ T s_red[32];
+        if (lane == 0) s_red[w] = mx2;
+        __syncthreads();
+        if (tid == 0) {
+            T m2 = T(0);
+            for (int i = 0; i < nw; ++i) m2 = s_red[i] > m2 ? s_red[i] : m2;
+            s_noise2 = m2 * Eps<T>::v() * Eps<T>::v();
+        }
+        __syncthreads();
+    }
+    const T noise2 = s_noise2;
     bool converged = (b < 2);
     int sweeps_used = 0;
     if (fits || bw == 0) {
@@ -105,7 +150,7 @@ __global__ void __launch_bounds__(1024) k_jacobi_svd(const SvdProb<T> *__restric
                     int x, y;
                     rr_pair(nb2, round, slot, x, y);
                     if (y >= b) continue;  // dummy player (odd b)
-                    if (jacobi_rotate(M + (size_t) x * ldm, M + (size_t) y * ldm, a, lane, tol) && lane == 0) s_rot = 1;
+                    if (jacobi_rotate(M + (size_t) x * ldm, M + (size_t) y * ldm, a, lane, tol, noise2) && lane == 0) s_rot = 1;
                 }
                 __syncthreads();
             }
@@ -145,7 +190,7 @@ __global__ void __launch_bounds__(1024) k_jacobi_svd(const SvdProb<T> *__restric
                                 if (y >= nu) continue;
                                 T *cx = x < wi ? UB + (size_t) x * a : BB + (size_t) (x - wi) * a;
                                 T *cy = y < wi ? UB + (size_t) y * a : BB + (size_t) (y - wi) * a;
-                                if (jacobi_rotate(cx, cy, a, lane, tol) && lane == 0) s_rot = 1;
+                                if (jacobi_rotate(cx, cy, a, lane, tol, noise2) && lane == 0) s_rot = 1;
                             }
                             __syncthreads();
                         }
@@ -155,7 +200,7 @@ __global__ void __launch_bounds__(1024) k_jacobi_svd(const SvdProb<T> *__restric
                             for (int i = w; i < wi; i += nw) {
                                 const int j = (i + t) % bw;
                                 if (j >= wj) continue;
-                                if (jacobi_rotate(BA + (size_t) i * a, BB + (size_t) j * a, a, lane, tol) && lane == 0)
+                                if (jacobi_rotate(BA + (size_t) i * a, BB + (size_t) j * a, a, lane, tol, noise2) && lane == 0)
                                     s_rot = 1;
                             }
                             __syncthreads();

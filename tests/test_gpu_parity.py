@@ -198,14 +198,16 @@ def test_svd_vs_lapack(ctx, dt, shape):
     assert np.max(np.abs(S - s_ref)) <= 4 * max(m, n) * eps * s_ref[0]        # absolute agreement with gesdd
     assert relerr((U * S) @ VT, A) < 200 * eps                                # reconstructs A
     big = S > 1e3 * eps * S[0]
-    assert np.max(np.abs(U[:, big].T @ U[:, big] - np.eye(big.sum()))) < 1e3 * eps
-    # The right factor is recovered as V = A^T U / sigma (what the recompression consumes is V*sigma, accurate to
-    # eps*sigma_0 absolutely): row i of VT is orthonormal to ~ eps * sigma_0 / sigma_i, so weigh the check by sigma.
-    W = (S[big, None] * VT[big]) / S[0]
-    G = W @ W.T - np.diag((S[big] / S[0]) ** 2)
-    assert np.max(np.abs(G)) < 1e3 * eps
+    # The Jacobi factor (left vectors of the taller of A / A^T) is orthonormal to rounding; the other factor is
+    # recovered as X = A^T U / sigma (what the recompression consumes is X*sigma, accurate to eps*sigma_0
+    # absolutely), so its vector i is orthonormal to ~ eps*sigma_0/sigma_i: weigh that check by sigma.
+    direct, derived = (U[:, big], VT[big].T) if m >= n else (VT[big].T, U[:, big])
+    assert np.max(np.abs(direct.T @ direct - np.eye(big.sum()))) < 1e3 * eps
+    W = derived * (S[big] / S[0])[None, :]
+    assert np.max(np.abs(W.T @ W - np.diag((S[big] / S[0]) ** 2))) < 1e3 * eps
     lead = S > 1e-3 * S[0]
-    assert np.max(np.abs(VT[lead] @ VT[lead].T - np.eye(lead.sum()))) < 1e6 * eps
+    dl = VT[lead].T if m >= n else U[:, lead]
+    assert np.max(np.abs(dl.T @ dl - np.eye(lead.sum()))) < 1e6 * eps
 
 
 # ------------------------------------------------------------------------------------------------ tile level
