@@ -305,6 +305,7 @@ def main():
             "baseline_config": "BASELINE.json configs[2]" if (T, nb, world) == (16, 1024, 1) else "custom",
             "l2": "inputs larger than L2 (A+B live factors %.0f MB per GPU, C scratch re-written every k)" % (
                 2 * T * T * 2 * nb * krank * 8 / 1e6)},
+        "library": _capi.lib.hcb_version().decode(),
         "gpu_launches": launches, "jacobi_or_bound_flags": bad, "jacobi_sweeps_last_step_max": sweeps,
         "c_rank_bound": args.kc_bound,
     }

@@ -781,7 +781,9 @@ using namespace hcb;
 extern "C" {
 
 const char *hcb_last_error(void) { return g_last_error.c_str(); }
-const char *hcb_version(void) { return "hcore_b200 0.1 (sm_100a; batched TLR GEMM + recompression; no CPU fallback)"; }
+const char *hcb_version(void) {
+    return "hcore_b200 0.1 (sm_100a; batched TLR GEMM + recompression; no CPU fallback; built " __DATE__ " " __TIME__ ")";
+}
 uint64_t hcb_launch_count(void) { return g_launches.load(); }
 void hcb_launch_count_reset(void) { g_launches.store(0); }
 

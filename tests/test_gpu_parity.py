@@ -470,3 +470,15 @@ def test_full_size_tile_properties(hc, ctx):
     U2, V2 = Ct.factors()
     assert (torch.linalg.norm(U2 @ V2 - before) / torch.linalg.norm(before)).item() <= 10 * acc
     assert abs(Ct.GetTileRank() - ranks[-1]) <= 1
+
+
+def test_cpp_host_layer_replays_reference_tests():
+    """include/hcorepp_b200/hcorepp.hpp (the C++ mirror of the reference API) over the C ABI: the reference's own
+    operator/API known answers (tests/cpp/test_api.cpp), built by __graft_entry__.build() with plain g++."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "test_api")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/test_api not built (run __graft_entry__.build())")
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "0 failure(s)" in r.stdout
