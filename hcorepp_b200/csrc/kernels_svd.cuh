@@ -50,6 +50,9 @@ __device__ __forceinline__ bool jacobi_rotate(T *__restrict__ mx, T *__restrict_
                 mx[i] = v;
                 my[i] = u;
             }
+            // a swap moves vectors between round-robin positions, so some vector pairs may not have met in this
+            // sweep: it must count as activity, otherwise the "quiet sweep" convergence test could fire too early
+            return true;
         }
         return false;
     }
