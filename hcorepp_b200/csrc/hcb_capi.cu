@@ -396,7 +396,8 @@ static inline int bound_of(const hcb_tile &t) {
 template<typename T>
 struct Layout {
     size_t slab = 0, o_w1 = 0, o_w2 = 0, o_uw = 0, o_vw = 0, o_tauu = 0, o_tauv = 0, o_m = 0, o_j = 0, o_us = 0,
-           o_vs = 0, o_sig = 0, o_vn = 0, o_vcu = 0, o_vcv = 0, o_tbu = 0, o_tbv = 0, o_wbu = 0, o_wbv = 0;
+           o_vs = 0, o_sig = 0, o_vn = 0, o_vcu = 0, o_vcv = 0, o_tbu = 0, o_tbv = 0, o_wbu = 0, o_wbv = 0, o_mt = 0,
+           o_taum = 0, o_lb = 0, o_vcm = 0, o_tbm = 0, o_wbm = 0;
     int r_b = 0, pq_b = 0, wcols = 0, nblk = 0;
 };
 
@@ -442,6 +443,13 @@ Layout<T> make_layout(const BatchShape &s) {
         L.o_tbv = take((size_t) NBQ * NBQ * L.nblk);
         L.o_wbu = take((size_t) 2 * NBQ * L.wcols);
         L.o_wbv = take((size_t) 2 * NBQ * L.wcols);
+        // LQ preconditioning of the core
+        L.o_mt = take(sq);
+        L.o_taum = take(L.pq_b);
+        L.o_lb = take(sq);
+        L.o_vcm = take(sq);
+        L.o_tbm = take((size_t) NBQ * NBQ * L.nblk);
+        L.o_wbm = take((size_t) 2 * NBQ * L.wcols);
     }
     L.slab = off;
     return L;
@@ -452,6 +460,7 @@ struct DescArrays {  // device arrays living at the front of the scratch arena
     size_t bytes = 0;
     size_t o_g1, o_g2, o_g3, o_gv, o_cp, o_qr, o_rf, o_svd, o_rc, o_rk, o_tiles;
     size_t o_bqr = 0, o_blf = 0, o_bgw = 0, o_bgw2 = 0, o_bgup = 0, o_agw = 0, o_agw2 = 0, o_agup = 0;
+    size_t o_pds = 0, o_pdc = 0, o_qrc = 0;
     explicit DescArrays(int n, int nblk = 0) {
         size_t off = 0;
         auto take = [&](size_t b) { size_t o = off; off += align_up(b, 256); return o; };
@@ -466,6 +475,9 @@ struct DescArrays {  // device arrays living at the front of the scratch arena
         o_rc = take(sizeof(RecompProb<T>) * n);
         o_rk = take(sizeof(int) * n);
         o_tiles = take(sizeof(hcb_tile) * 3 * n);
+        o_pds = take(sizeof(PanelDesc<T>) * 2 * n);
+        o_pdc = take(sizeof(PanelDesc<T>) * n);
+        o_qrc = take(sizeof(QrProb<T>) * n);
         if (nblk > 0) {
             const size_t nb = (size_t) nblk * 2 * n;
             o_bqr = take(sizeof(QrProb<T>) * nb);
@@ -551,6 +563,10 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     sa.o_sig = L.o_sig; sa.o_vn = L.o_vn;
     sa.o_vcu = L.o_vcu; sa.o_vcv = L.o_vcv; sa.o_tbu = L.o_tbu; sa.o_tbv = L.o_tbv; sa.o_wbu = L.o_wbu; sa.o_wbv = L.o_wbv;
     sa.wcols = L.wcols;
+    sa.o_mt = L.o_mt; sa.o_taum = L.o_taum; sa.o_lb = L.o_lb; sa.o_vcm = L.o_vcm; sa.o_tbm = L.o_tbm; sa.o_wbm = L.o_wbm;
+    sa.pd_stack = reinterpret_cast<PanelDesc<T> *>(base + D.o_pds);
+    sa.pd_core = reinterpret_cast<PanelDesc<T> *>(base + D.o_pdc);
+    sa.qr_core = reinterpret_cast<QrProb<T> *>(base + D.o_qrc);
     sa.kA_b = s.kA; sa.kB_b = s.kB; sa.kC_b = s.kC; sa.r_b = L.r_b;
     sa.rk_new = reinterpret_cast<int *>(base + D.o_rk);
     sa.info = d_info;
@@ -604,37 +620,47 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
         HCB_TRY(launch_copy<T>(ctx, sa.cp, 4 * n, std::max(s.m, s.n), std::max(L.r_b, 1)));
     }
     const int npan = 2 * n, nbt = L.nblk * npan;
-    if (!blocked) {
-        PhaseScope ph(ctx, 3);
-        HCB_TRY(launch_qr<T>(ctx, sa.qr, 2 * n));
-    } else {
-        // blocked Householder QR: per NBQ-column block -- panel factorisation, T_b + clean V_b, then the trailing
-        // update A2 -= V_b T_b^T (V_b^T A2) as three batched GEMMs
-        PhaseScope ph(ctx, 3);
-        QrBlockArrays<T> qa{reinterpret_cast<QrProb<T> *>(base + D.o_bqr), reinterpret_cast<LarftProb<T> *>(base + D.o_blf),
-                            reinterpret_cast<GemmProb<T> *>(base + D.o_bgw), reinterpret_cast<GemmProb<T> *>(base + D.o_bgw2),
-                            reinterpret_cast<GemmProb<T> *>(base + D.o_bgup), L.nblk, npan};
-        k_setup_qr_blocks<T><<<cdiv(nbt, 128), 128, 0, ctx->stream>>>(sa.rc, qa);
+    QrBlockArrays<T> qa{reinterpret_cast<QrProb<T> *>(base + D.o_bqr), reinterpret_cast<LarftProb<T> *>(base + D.o_blf),
+                        reinterpret_cast<GemmProb<T> *>(base + D.o_bgw), reinterpret_cast<GemmProb<T> *>(base + D.o_bgw2),
+                        reinterpret_cast<GemmProb<T> *>(base + D.o_bgup), L.nblk, npan};
+    // blocked Householder QR of `cnt` panels: per NBQ-column block -- panel factorisation, T_b + clean V_b, then the
+    // trailing update A2 -= V_b T_b^T (V_b^T A2) as three batched GEMMs
+    auto blocked_qr = [&](const PanelDesc<T> *pds, int cnt, int rows_bound, int cols_bound) -> int {
+        QrBlockArrays<T> q = qa;
+        q.npan = cnt;
+        const int nblk_here = cdiv(std::min(rows_bound, cols_bound), NBQ);
+        q.nblk = nblk_here;
+        k_setup_qr_blocks<T><<<cdiv(nblk_here * cnt, 128), 128, 0, ctx->stream>>>(pds, q);
         HCB_LAUNCH_CHECK("k_setup_qr_blocks");
-        const int mx = std::max(s.m, s.n);
-        for (int b = 0; b < L.nblk; ++b) {
-            const size_t o = (size_t) b * npan;
-            HCB_TRY(launch_qr<T>(ctx, qa.qr + o, npan));
-            k_larft_extract<T><<<npan, 256, 0, ctx->stream>>>(qa.lf + o);
+        for (int b = 0; b < nblk_here; ++b) {
+            const size_t o = (size_t) b * cnt;
+            HCB_TRY(launch_qr<T>(ctx, q.qr + o, cnt));
+            k_larft_extract<T><<<cnt, 256, 0, ctx->stream>>>(q.lf + o);
             HCB_LAUNCH_CHECK("k_larft_extract");
-            const int nt_b = L.r_b - (b + 1) * NBQ;
+            const int nt_b = cols_bound - (b + 1) * NBQ;
             if (nt_b > 0) {
-                HCB_TRY(launch_gemm<T>(ctx, qa.gw + o, npan, NBQ, nt_b));
-                HCB_TRY(launch_gemm<T>(ctx, qa.gw2 + o, npan, NBQ, nt_b));
-                HCB_TRY(launch_gemm<T>(ctx, qa.gup + o, npan, mx - b * NBQ, nt_b));
+                HCB_TRY(launch_gemm<T>(ctx, q.gw + o, cnt, NBQ, nt_b));
+                HCB_TRY(launch_gemm<T>(ctx, q.gw2 + o, cnt, NBQ, nt_b));
+                HCB_TRY(launch_gemm<T>(ctx, q.gup + o, cnt, rows_bound - b * NBQ, nt_b));
             }
         }
+        return HCB_OK;
+    };
+    {
+        PhaseScope ph(ctx, 3);
+        if (!blocked) HCB_TRY(launch_qr<T>(ctx, sa.qr, 2 * n));
+        else HCB_TRY(blocked_qr(sa.pd_stack, npan, std::max(s.m, s.n), L.r_b));
     }
     {
         PhaseScope ph(ctx, 4);
         dim3 grid(std::max(1, std::min(64, cdiv((long long) L.pq_b * L.pq_b, 256))), n);
         k_core_build<T><<<grid, 256, 0, ctx->stream>>>(sa.rc);
         HCB_LAUNCH_CHECK("k_core_build");
+        // LQ preconditioning: QR of the transposed core, L = R^T goes to the Jacobi kernel
+        if (!blocked) HCB_TRY(launch_qr<T>(ctx, sa.qr_core, n));
+        else HCB_TRY(blocked_qr(sa.pd_core, n, L.pq_b, L.pq_b));
+        k_extract_l<T><<<grid, 256, 0, ctx->stream>>>(sa.rc);
+        HCB_LAUNCH_CHECK("k_extract_l");
         HCB_TRY(launch_svd<T>(ctx, sa.svd, n, L.pq_b, L.pq_b));
         HCB_TRY(launch_gemm<T>(ctx, sa.gv, n, L.pq_b, L.pq_b));
         k_truncate<T><<<n, 256, 0, ctx->stream>>>(sa.rc, (T) prm->accuracy, prm->truncated_svd, (int) prm->fixed_rank);

@@ -23,11 +23,10 @@ __device__ __forceinline__ void rr_pair(int nb2, int round, int slot, int &x, in
 }
 
 // One Jacobi rotation of the column pair (mx, my) of length a, done by one warp. Returns true if it rotated.
-//  * de Rijk ordering: the column that ends up with the larger norm is stored in mx (the lower index), so the
-//    columns sort themselves by decreasing norm while they converge -- far fewer sweeps on graded spectra;
-//  * noise2 = (a * eps * largest column norm)^2: a column at or below rounding level is left alone (its singular value
-//    is zero to working precision; rounding in the rotations with big columns re-randomises its direction every sweep,
-//    so chasing it only keeps the sweep count up -- measured 28 sweeps vs. ~10 on the 357 x 357 recompression cores).
+// noise2 = (eps * largest column norm)^2: a column at rounding level is left alone (its singular value is zero to
+// working precision).  (de Rijk's norm-ordering swaps were tried and made the round-robin ordering converge SLOWER on
+// the recompression cores -- 29 vs 18 sweeps in the numpy emulation -- so they are not used; what halves the sweep
+// count is the LQ preconditioning done before this kernel, see k_extract_l.)
 template<typename T>
 __device__ __forceinline__ bool jacobi_rotate(T *__restrict__ mx, T *__restrict__ my, int a, int lane, T tol, T noise2) {
     T alpha = T(0), beta = T(0), gamma = T(0);
@@ -40,38 +39,16 @@ __device__ __forceinline__ bool jacobi_rotate(T *__restrict__ mx, T *__restrict_
     alpha = warp_sum(alpha);
     beta = warp_sum(beta);
     gamma = warp_sum(gamma);
-    const bool swap = beta > alpha;
     const T lim = tol * t_sqrt(alpha) * t_sqrt(beta);
-    const bool rotate = (t_abs(gamma) > lim) && gamma != T(0) && (alpha > noise2) && (beta > noise2);
-    if (!rotate) {
-        if (swap && (beta > noise2)) {  // keep the ordering moving even when the pair is already orthogonal
-            for (int i = lane; i < a; i += 32) {
-                const T u = mx[i], v = my[i];
-                mx[i] = v;
-                my[i] = u;
-            }
-            // a swap moves vectors between round-robin positions, so some vector pairs may not have met in this
-            // sweep: it must count as activity, otherwise the "quiet sweep" convergence test could fire too early
-            return true;
-        }
-        return false;
-    }
+    if (!(t_abs(gamma) > lim) || gamma == T(0) || !(alpha > noise2) || !(beta > noise2)) return false;
     const T zeta = (beta - alpha) / (T(2) * gamma);
     const T t = (zeta >= T(0) ? T(1) : T(-1)) / (t_abs(zeta) + t_sqrt(fma(zeta, zeta, T(1))));
     const T c = T(1) / t_sqrt(fma(t, t, T(1)));
     const T s = c * t;
-    if (!swap) {
-        for (int i = lane; i < a; i += 32) {
-            const T u = mx[i], v = my[i];
-            mx[i] = fma(-s, v, c * u);
-            my[i] = fma(s, u, c * v);
-        }
-    } else {
-        for (int i = lane; i < a; i += 32) {
-            const T u = mx[i], v = my[i];
-            mx[i] = fma(s, u, c * v);
-            my[i] = fma(-s, v, c * u);
-        }
+    for (int i = lane; i < a; i += 32) {
+        const T u = mx[i], v = my[i];
+        mx[i] = fma(-s, v, c * u);
+        my[i] = fma(s, u, c * v);
     }
     return true;
 }
@@ -116,8 +93,7 @@ __global__ void __launch_bounds__(1024) k_jacobi_svd(const SvdProb<T> *__restric
     for (int idx = tid; idx < a * b; idx += nthr) M[idx] = p.M[(size_t) (idx % a) + (size_t) (idx / a) * p.ldm];
     __syncthreads();
 
-    // convergence threshold on |cos(angle)|: LAPACK xGESVJ's default, CTOL * eps with CTOL = number of rows
-    const T tol = Eps<T>::v() * (T) a;
+    const T tol = Eps<T>::v() * t_sqrt((T) a);  // threshold on |cos(angle)| of a column pair
     // noise floor from the largest column norm of the input
     __shared__ T s_noise2;
     {
@@ -135,8 +111,7 @@ __global__ void __launch_bounds__(1024) k_jacobi_svd(const SvdProb<T> *__restric
         if (tid == 0) {
             T m2 = T(0);
             for (int i = 0; i < nw; ++i) m2 = s_red[i] > m2 ? s_red[i] : m2;
-            // columns below a * eps * (largest column norm) carry no information (absolute error of ANY SVD of M)
-            s_noise2 = m2 * (Eps<T>::v() * (T) a) * (Eps<T>::v() * (T) a);
+            s_noise2 = m2 * Eps<T>::v() * Eps<T>::v();
         }
         __syncthreads();
     }
