@@ -140,6 +140,13 @@ struct SvdProb {  // one-sided Jacobi on M (a x b, a >= b): M = Uout * diag(sigm
     int a, b, ldm, ldu, ldv;
 };
 
+template<typename T>
+struct LqProb {   // LQ preconditioning: L = R^T of the QR-factored transpose (see k_extract_l)
+    const T *MT;  // QR-factored M^T (b x a, ld b): R in the upper trapezoid
+    T *Lb;        // a x b (ld a) receives L = R^T
+    int a, b;
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------------------

@@ -154,6 +154,45 @@ int launch_svd(hcb_ctx *ctx, const SvdProb<T> *d_probs, int n_probs, int a_bound
     return HCB_OK;
 }
 
+// Blocked Householder QR of `cnt` panels described on the device (pds): per NBQ-column block -- panel factorisation,
+// T_b + clean V_b, then the trailing update A2 -= V_b T_b^T (V_b^T A2) as three batched GEMMs.
+template<typename T>
+size_t qr_block_desc_bytes(int cnt, int nblk) {
+    const size_t nb = (size_t) cnt * nblk;
+    return align_up(sizeof(QrProb<T>) * nb, 256) + align_up(sizeof(LarftProb<T>) * nb, 256) +
+           3 * align_up(sizeof(GemmProb<T>) * nb, 256);
+}
+
+template<typename T>
+int run_blocked_qr(hcb_ctx *ctx, const PanelDesc<T> *d_pds, int cnt, int rows_bound, int cols_bound, char *desc_store) {
+    const int nblk = cdiv(std::min(rows_bound, cols_bound), NBQ);
+    const size_t nb = (size_t) cnt * nblk;
+    QrBlockArrays<T> q;
+    char *p = desc_store;
+    q.qr = reinterpret_cast<QrProb<T> *>(p); p += align_up(sizeof(QrProb<T>) * nb, 256);
+    q.lf = reinterpret_cast<LarftProb<T> *>(p); p += align_up(sizeof(LarftProb<T>) * nb, 256);
+    q.gw = reinterpret_cast<GemmProb<T> *>(p); p += align_up(sizeof(GemmProb<T>) * nb, 256);
+    q.gw2 = reinterpret_cast<GemmProb<T> *>(p); p += align_up(sizeof(GemmProb<T>) * nb, 256);
+    q.gup = reinterpret_cast<GemmProb<T> *>(p);
+    q.nblk = nblk;
+    q.npan = cnt;
+    k_setup_qr_blocks<T><<<cdiv(nblk * cnt, 128), 128, 0, ctx->stream>>>(d_pds, q);
+    HCB_LAUNCH_CHECK("k_setup_qr_blocks");
+    for (int b = 0; b < nblk; ++b) {
+        const size_t o = (size_t) b * cnt;
+        HCB_TRY(launch_qr<T>(ctx, q.qr + o, cnt));
+        k_larft_extract<T><<<cnt, 256, 0, ctx->stream>>>(q.lf + o);
+        HCB_LAUNCH_CHECK("k_larft_extract");
+        const int nt_b = cols_bound - (b + 1) * NBQ;
+        if (nt_b > 0) {
+            HCB_TRY(launch_gemm<T>(ctx, q.gw + o, cnt, NBQ, nt_b));
+            HCB_TRY(launch_gemm<T>(ctx, q.gw2 + o, cnt, NBQ, nt_b));
+            HCB_TRY(launch_gemm<T>(ctx, q.gup + o, cnt, rows_bound - b * NBQ, nt_b));
+        }
+    }
+    return HCB_OK;
+}
+
 // single host-side problem -> device (through the pinned ring) -> batched kernel with a batch of one
 template<typename P>
 int upload_one(hcb_ctx *ctx, const P &prob, const P **d_out) {
@@ -161,6 +200,105 @@ int upload_one(hcb_ctx *ctx, const P &prob, const P **d_out) {
     HCB_TRY(ring_upload(ctx, &prob, sizeof(P), &d));
     *d_out = reinterpret_cast<const P *>(d);
     return HCB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Batched SVD pipeline shared by the compat SVD entry point and the compressing constructor:
+//   M = op(src) (a x b, a >= b)  ->  MT = M^T, QR(MT), L = R^T  ->  Jacobi on L (left vectors Us, sigma)
+//   ->  Vs = M^T Us  (= V diag(sigma)).
+// ---------------------------------------------------------------------------------------------------------------
+template<typename T>
+struct SvdJob {
+    const T *src;  // dense source
+    int ld_src;
+    int trans_src;  // 1: M = src^T
+    int a, b;
+    T *Us, *Vs, *sigma;  // outputs: Us a x b (ld a), Vs b x b (ld b), sigma b
+};
+
+template<typename T>
+struct SvdJobLayout {
+    size_t eM, eTau, eTB, eWB, slab;
+    int nblk;
+    SvdJobLayout(int a, int b) {
+        nblk = cdiv(b, NBQ);
+        eM = align_up((size_t) a * b, 32);
+        eTau = align_up((size_t) b, 32);
+        eTB = align_up((size_t) NBQ * NBQ * nblk, 32);
+        eWB = align_up((size_t) 2 * NBQ * a, 32);
+        slab = 5 * eM + eTau + eTB + eWB;  // M | MT | Lb | Jwork | VC | tau | TB | WB
+    }
+};
+
+template<typename P>
+int stage_array(hcb_ctx *ctx, const std::vector<P> &host, P *d_dst) {
+    void *st = nullptr;
+    HCB_TRY(ring_upload(ctx, host.data(), sizeof(P) * host.size(), &st));
+    HCB_CUDA(cudaMemcpyAsync(d_dst, st, sizeof(P) * host.size(), cudaMemcpyDeviceToDevice, ctx->stream));
+    return HCB_OK;
+}
+
+// scratch: `ws` holds cnt slabs of SvdJobLayout(a_bound, b_bound).slab elements; desc: device bytes for descriptors
+template<typename T>
+size_t svd_jobs_desc_bytes(int cnt, int a_bound, int b_bound) {
+    const SvdJobLayout<T> L(a_bound, b_bound);
+    return 2 * align_up(sizeof(CopyProb<T>) * cnt, 256) + align_up(sizeof(PanelDesc<T>) * cnt, 256) +
+           align_up(sizeof(QrProb<T>) * cnt, 256) + align_up(sizeof(LqProb<T>) * cnt, 256) +
+           align_up(sizeof(SvdProb<T>) * cnt, 256) + align_up(sizeof(GemmProb<T>) * cnt, 256) +
+           qr_block_desc_bytes<T>(cnt, L.nblk) + 256;
+}
+
+template<typename T>
+int run_svd_jobs(hcb_ctx *ctx, const std::vector<SvdJob<T>> &jobs, int a_bound, int b_bound, T *ws, char *desc) {
+    const int cnt = (int) jobs.size();
+    if (cnt == 0) return HCB_OK;
+    const SvdJobLayout<T> L(a_bound, b_bound);
+    std::vector<CopyProb<T>> c1(cnt), c2(cnt);
+    std::vector<PanelDesc<T>> pd(cnt);
+    std::vector<QrProb<T>> qp(cnt);
+    std::vector<LqProb<T>> lq(cnt);
+    std::vector<SvdProb<T>> sv(cnt);
+    std::vector<GemmProb<T>> gv(cnt);
+    for (int t = 0; t < cnt; ++t) {
+        const SvdJob<T> &j = jobs[t];
+        T *M = ws + (size_t) t * L.slab, *MT = M + L.eM, *Lb = MT + L.eM, *Jw = Lb + L.eM, *VC = Jw + L.eM, *tau = VC + L.eM,
+          *TB = tau + L.eTau, *WB = TB + L.eTB;
+        c1[t] = CopyProb<T>{j.src, M, j.a, j.b, j.ld_src, j.a, j.trans_src, T(1)};           // M  = op(src)   (a x b)
+        c2[t] = CopyProb<T>{j.src, MT, j.b, j.a, j.ld_src, j.b, j.trans_src ? 0 : 1, T(1)};  // MT = op(src)^T (b x a)
+        pd[t] = PanelDesc<T>{MT, tau, VC, TB, WB, j.b, j.a, a_bound, 1};
+        qp[t] = QrProb<T>{MT, tau, j.b, j.a, j.b};
+        lq[t] = LqProb<T>{MT, Lb, j.a, j.b};
+        sv[t] = SvdProb<T>{Lb, Jw, j.Us, j.Vs, j.sigma, nullptr, j.a, j.b, j.a, j.a, j.b};
+        gv[t] = GemmProb<T>{M, j.Us, j.Vs, j.b, j.b, j.a, j.a, j.a, j.b, 1, 0, T(1), T(0)};  // Vs = M^T Us = V diag(sigma)
+    }
+    char *p = desc;
+    auto carve = [&](size_t bytes) { char *q = p; p += align_up(bytes, 256); return q; };
+    auto *d_c1 = reinterpret_cast<CopyProb<T> *>(carve(sizeof(CopyProb<T>) * cnt));
+    auto *d_c2 = reinterpret_cast<CopyProb<T> *>(carve(sizeof(CopyProb<T>) * cnt));
+    auto *d_pd = reinterpret_cast<PanelDesc<T> *>(carve(sizeof(PanelDesc<T>) * cnt));
+    auto *d_qp = reinterpret_cast<QrProb<T> *>(carve(sizeof(QrProb<T>) * cnt));
+    auto *d_lq = reinterpret_cast<LqProb<T> *>(carve(sizeof(LqProb<T>) * cnt));
+    auto *d_sv = reinterpret_cast<SvdProb<T> *>(carve(sizeof(SvdProb<T>) * cnt));
+    auto *d_gv = reinterpret_cast<GemmProb<T> *>(carve(sizeof(GemmProb<T>) * cnt));
+    char *d_blocks = p;
+    HCB_TRY(stage_array(ctx, c1, d_c1));
+    HCB_TRY(stage_array(ctx, c2, d_c2));
+    HCB_TRY(stage_array(ctx, pd, d_pd));
+    HCB_TRY(stage_array(ctx, qp, d_qp));
+    HCB_TRY(stage_array(ctx, lq, d_lq));
+    HCB_TRY(stage_array(ctx, sv, d_sv));
+    HCB_TRY(stage_array(ctx, gv, d_gv));
+    HCB_TRY(launch_copy<T>(ctx, d_c1, cnt, a_bound, b_bound));
+    HCB_TRY(launch_copy<T>(ctx, d_c2, cnt, b_bound, a_bound));
+    if (b_bound > 2 * NBQ) HCB_TRY(run_blocked_qr<T>(ctx, d_pd, cnt, b_bound, a_bound, d_blocks));
+    else HCB_TRY(launch_qr<T>(ctx, d_qp, cnt));
+    {
+        dim3 grid(std::max(1, std::min(64, cdiv((long long) a_bound * b_bound, 256))), cnt);
+        k_extract_l<T><<<grid, 256, 0, ctx->stream>>>(d_lq);
+        HCB_LAUNCH_CHECK("k_extract_l");
+    }
+    HCB_TRY(launch_svd<T>(ctx, d_sv, cnt, a_bound, b_bound));
+    return launch_gemm<T>(ctx, d_gv, cnt, b_bound, b_bound);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -328,21 +466,17 @@ int t_svd(hcb_ctx *ctx, int64_t m, int64_t n, T *A, int64_t lda, T *S, T *U, int
     if (m <= 0 || n <= 0) return HCB_OK;
     const int a = (int) std::max(m, n), b = (int) std::min(m, n);
     const bool transposed = m < n;
-    // scratch: M (a*b) | Mwork (a*b) | Us (a*b) | Vs (b*b)
-    const size_t eM = (size_t) a * b, eJ = (size_t) b * b;
-    HCB_TRY(ensure_ws(ctx, (3 * eM + eJ) * sizeof(T) + 1024));
-    T *M = reinterpret_cast<T *>(ctx->ws), *Mw = M + eM, *Us = Mw + eM, *Vs = Us + eM;
-    HCB_TRY(t_copy<T>(ctx, A, (int) lda, M, a, a, b, transposed ? 1 : 0, T(1)));
-    SvdProb<T> sp{M, Mw, Us, Vs, S, nullptr, a, b, a, a, b};
-    const SvdProb<T> *d;
-    HCB_TRY(upload_one(ctx, sp, &d));
-    HCB_TRY(launch_svd<T>(ctx, d, 1, a, b));
-    // Vs = M^T Us = V diag(S); normalise its columns to get V
-    GemmProb<T> g{M, Us, Vs, b, b, a, a, a, b, 1, 0, T(1), T(0)};
-    const GemmProb<T> *dg;
-    HCB_TRY(upload_one(ctx, g, &dg));
-    HCB_TRY(launch_gemm<T>(ctx, dg, 1, b, b));
-    {
+    const SvdJobLayout<T> L(a, b);
+    const size_t eOut = align_up((size_t) a * b, 32) + align_up((size_t) b * b, 32);
+    const size_t desc = svd_jobs_desc_bytes<T>(1, a, b);
+    HCB_TRY(ensure_ws(ctx, desc + (L.slab + eOut) * sizeof(T) + 1024));
+    char *base = reinterpret_cast<char *>(ctx->ws);
+    T *ws = reinterpret_cast<T *>(base + align_up(desc, 256));
+    T *Us = ws + L.slab, *Vs = Us + align_up((size_t) a * b, 32);
+    std::vector<SvdJob<T>> jobs(1);
+    jobs[0] = SvdJob<T>{A, (int) lda, transposed ? 1 : 0, a, b, Us, Vs, S};
+    HCB_TRY(run_svd_jobs<T>(ctx, jobs, a, b, ws, base));
+    {   // Vs = V diag(S): normalise its columns to get V
         dim3 block(32, 8), grid(cdiv(b, 32), cdiv(b, 8));
         k_unscale_cols<T><<<grid, block, 0, ctx->stream>>>(Vs, b, b, b, S);
         HCB_LAUNCH_CHECK("k_unscale_cols");
@@ -460,7 +594,7 @@ struct DescArrays {  // device arrays living at the front of the scratch arena
     size_t bytes = 0;
     size_t o_g1, o_g2, o_g3, o_gv, o_cp, o_qr, o_rf, o_svd, o_rc, o_rk, o_tiles;
     size_t o_bqr = 0, o_blf = 0, o_bgw = 0, o_bgw2 = 0, o_bgup = 0, o_agw = 0, o_agw2 = 0, o_agup = 0;
-    size_t o_pds = 0, o_pdc = 0, o_qrc = 0;
+    size_t o_pds = 0, o_pdc = 0, o_qrc = 0, o_lq = 0;
     explicit DescArrays(int n, int nblk = 0) {
         size_t off = 0;
         auto take = [&](size_t b) { size_t o = off; off += align_up(b, 256); return o; };
@@ -478,13 +612,10 @@ struct DescArrays {  // device arrays living at the front of the scratch arena
         o_pds = take(sizeof(PanelDesc<T>) * 2 * n);
         o_pdc = take(sizeof(PanelDesc<T>) * n);
         o_qrc = take(sizeof(QrProb<T>) * n);
+        o_lq = take(sizeof(LqProb<T>) * n);
         if (nblk > 0) {
             const size_t nb = (size_t) nblk * 2 * n;
-            o_bqr = take(sizeof(QrProb<T>) * nb);
-            o_blf = take(sizeof(LarftProb<T>) * nb);
-            o_bgw = take(sizeof(GemmProb<T>) * nb);
-            o_bgw2 = take(sizeof(GemmProb<T>) * nb);
-            o_bgup = take(sizeof(GemmProb<T>) * nb);
+            o_bqr = take(qr_block_desc_bytes<T>(2 * n, nblk));
             o_agw = take(sizeof(GemmProb<T>) * nb);
             o_agw2 = take(sizeof(GemmProb<T>) * nb);
             o_agup = take(sizeof(GemmProb<T>) * nb);
@@ -567,6 +698,7 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     sa.pd_stack = reinterpret_cast<PanelDesc<T> *>(base + D.o_pds);
     sa.pd_core = reinterpret_cast<PanelDesc<T> *>(base + D.o_pdc);
     sa.qr_core = reinterpret_cast<QrProb<T> *>(base + D.o_qrc);
+    sa.lq = reinterpret_cast<LqProb<T> *>(base + D.o_lq);
     sa.kA_b = s.kA; sa.kB_b = s.kB; sa.kC_b = s.kC; sa.r_b = L.r_b;
     sa.rk_new = reinterpret_cast<int *>(base + D.o_rk);
     sa.info = d_info;
@@ -620,36 +752,11 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
         HCB_TRY(launch_copy<T>(ctx, sa.cp, 4 * n, std::max(s.m, s.n), std::max(L.r_b, 1)));
     }
     const int npan = 2 * n, nbt = L.nblk * npan;
-    QrBlockArrays<T> qa{reinterpret_cast<QrProb<T> *>(base + D.o_bqr), reinterpret_cast<LarftProb<T> *>(base + D.o_blf),
-                        reinterpret_cast<GemmProb<T> *>(base + D.o_bgw), reinterpret_cast<GemmProb<T> *>(base + D.o_bgw2),
-                        reinterpret_cast<GemmProb<T> *>(base + D.o_bgup), L.nblk, npan};
-    // blocked Householder QR of `cnt` panels: per NBQ-column block -- panel factorisation, T_b + clean V_b, then the
-    // trailing update A2 -= V_b T_b^T (V_b^T A2) as three batched GEMMs
-    auto blocked_qr = [&](const PanelDesc<T> *pds, int cnt, int rows_bound, int cols_bound) -> int {
-        QrBlockArrays<T> q = qa;
-        q.npan = cnt;
-        const int nblk_here = cdiv(std::min(rows_bound, cols_bound), NBQ);
-        q.nblk = nblk_here;
-        k_setup_qr_blocks<T><<<cdiv(nblk_here * cnt, 128), 128, 0, ctx->stream>>>(pds, q);
-        HCB_LAUNCH_CHECK("k_setup_qr_blocks");
-        for (int b = 0; b < nblk_here; ++b) {
-            const size_t o = (size_t) b * cnt;
-            HCB_TRY(launch_qr<T>(ctx, q.qr + o, cnt));
-            k_larft_extract<T><<<cnt, 256, 0, ctx->stream>>>(q.lf + o);
-            HCB_LAUNCH_CHECK("k_larft_extract");
-            const int nt_b = cols_bound - (b + 1) * NBQ;
-            if (nt_b > 0) {
-                HCB_TRY(launch_gemm<T>(ctx, q.gw + o, cnt, NBQ, nt_b));
-                HCB_TRY(launch_gemm<T>(ctx, q.gw2 + o, cnt, NBQ, nt_b));
-                HCB_TRY(launch_gemm<T>(ctx, q.gup + o, cnt, rows_bound - b * NBQ, nt_b));
-            }
-        }
-        return HCB_OK;
-    };
+    char *blk_store = base + D.o_bqr;
     {
         PhaseScope ph(ctx, 3);
         if (!blocked) HCB_TRY(launch_qr<T>(ctx, sa.qr, 2 * n));
-        else HCB_TRY(blocked_qr(sa.pd_stack, npan, std::max(s.m, s.n), L.r_b));
+        else HCB_TRY(run_blocked_qr<T>(ctx, sa.pd_stack, npan, std::max(s.m, s.n), L.r_b, blk_store));
     }
     {
         PhaseScope ph(ctx, 4);
@@ -658,8 +765,8 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
         HCB_LAUNCH_CHECK("k_core_build");
         // LQ preconditioning: QR of the transposed core, L = R^T goes to the Jacobi kernel
         if (!blocked) HCB_TRY(launch_qr<T>(ctx, sa.qr_core, n));
-        else HCB_TRY(blocked_qr(sa.pd_core, n, L.pq_b, L.pq_b));
-        k_extract_l<T><<<grid, 256, 0, ctx->stream>>>(sa.rc);
+        else HCB_TRY(run_blocked_qr<T>(ctx, sa.pd_core, n, L.pq_b, L.pq_b, blk_store));
+        k_extract_l<T><<<grid, 256, 0, ctx->stream>>>(sa.lq);
         HCB_LAUNCH_CHECK("k_extract_l");
         HCB_TRY(launch_svd<T>(ctx, sa.svd, n, L.pq_b, L.pq_b));
         HCB_TRY(launch_gemm<T>(ctx, sa.gv, n, L.pq_b, L.pq_b));
@@ -733,50 +840,32 @@ int t_compress_batched(hcb_ctx *ctx, int64_t n64, const T *const *dense, int64_t
         n = std::max(n, out[t].n);
     }
     const int a = std::max(m, n), b = std::min(m, n);
-    const size_t eM = align_up((size_t) a * b, 32), eJ = align_up((size_t) b * b, 32), eS = align_up((size_t) b, 32);
-    const size_t slab = 3 * eM + eJ + eS;
+    const SvdJobLayout<T> L(a, b);
+    const size_t eUs = align_up((size_t) a * b, 32), eVs = align_up((size_t) b * b, 32), eS = align_up((size_t) b, 32);
+    const size_t slab = L.slab + eUs + eVs + eS;
     // chunk the batch so that the scratch stays below ~8 GiB
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n64, (int64_t) (((size_t) 8 << 30) / (slab * sizeof(T)))));
     for (int64_t c0 = 0; c0 < n64; c0 += chunk) {
         const int cnt = (int) std::min<int64_t>(chunk, n64 - c0);
-        const size_t desc = align_up(sizeof(CopyProb<T>) * cnt, 256) + align_up(sizeof(SvdProb<T>) * cnt, 256) +
-                            align_up(sizeof(CompressProb<T>) * cnt, 256) + align_up(sizeof(GemmProb<T>) * cnt, 256);
-        HCB_TRY(ensure_ws(ctx, desc + slab * sizeof(T) * cnt + 256));
+        const size_t desc = svd_jobs_desc_bytes<T>(cnt, a, b) + align_up(sizeof(CompressProb<T>) * cnt, 256);
+        HCB_TRY(ensure_ws(ctx, desc + slab * sizeof(T) * cnt + 512));
         char *base = reinterpret_cast<char *>(ctx->ws);
-        CopyProb<T> *d_cp = reinterpret_cast<CopyProb<T> *>(base);
-        SvdProb<T> *d_sv = reinterpret_cast<SvdProb<T> *>(base + align_up(sizeof(CopyProb<T>) * cnt, 256));
-        CompressProb<T> *d_fp = reinterpret_cast<CompressProb<T> *>(reinterpret_cast<char *>(d_sv) +
-                                                                    align_up(sizeof(SvdProb<T>) * cnt, 256));
-        GemmProb<T> *d_gv = reinterpret_cast<GemmProb<T> *>(reinterpret_cast<char *>(d_fp) +
-                                                            align_up(sizeof(CompressProb<T>) * cnt, 256));
+        CompressProb<T> *d_fp = reinterpret_cast<CompressProb<T> *>(base + svd_jobs_desc_bytes<T>(cnt, a, b));
         T *ws = reinterpret_cast<T *>(base + align_up(desc, 256));
-        std::vector<GemmProb<T>> gv(cnt);
-        std::vector<CopyProb<T>> cp(cnt);
-        std::vector<SvdProb<T>> sv(cnt);
+        T *outs = ws + (size_t) cnt * L.slab;
+        std::vector<SvdJob<T>> jobs(cnt);
         std::vector<CompressProb<T>> fp(cnt);
         for (int t = 0; t < cnt; ++t) {
             const hcb_tile &o = out[c0 + t];
             const int tm = o.m, tn = o.n, ta = std::max(tm, tn), tb = std::min(tm, tn);
             const bool tr = tm < tn;
-            T *M = ws + (size_t) t * slab, *Mw = M + eM, *Us = Mw + eM, *Vs = Us + eM, *sg = Vs + eJ;
-            cp[t] = CopyProb<T>{dense[c0 + t], M, ta, tb, (int) ld, ta, tr ? 1 : 0, T(1)};
-            sv[t] = SvdProb<T>{M, Mw, Us, Vs, sg, nullptr, ta, tb, ta, ta, tb};
-            gv[t] = GemmProb<T>{M, Us, Vs, tb, tb, ta, ta, ta, tb, 1, 0, T(1), T(0)};  // Vs = M^T Us = V diag(sigma)
+            T *Us = outs + (size_t) t * (eUs + eVs + eS), *Vs = Us + eUs, *sg = Vs + eVs;
+            jobs[t] = SvdJob<T>{dense[c0 + t], (int) ld, tr ? 1 : 0, ta, tb, Us, Vs, sg};
             T *U = reinterpret_cast<T *>(o.d_data), *V = U + (size_t) tm * o.max_rank;
             fp[t] = CompressProb<T>{Us, Vs, sg, U, V, o.d_rank, nullptr, tm, tn, tb, ta, tr ? 1 : 0, o.max_rank};
         }
-        void *st = nullptr;
-        HCB_TRY(ring_upload(ctx, cp.data(), sizeof(CopyProb<T>) * cnt, &st));
-        HCB_CUDA(cudaMemcpyAsync(d_cp, st, sizeof(CopyProb<T>) * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
-        HCB_TRY(ring_upload(ctx, sv.data(), sizeof(SvdProb<T>) * cnt, &st));
-        HCB_CUDA(cudaMemcpyAsync(d_sv, st, sizeof(SvdProb<T>) * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
-        HCB_TRY(ring_upload(ctx, fp.data(), sizeof(CompressProb<T>) * cnt, &st));
-        HCB_CUDA(cudaMemcpyAsync(d_fp, st, sizeof(CompressProb<T>) * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
-        HCB_TRY(ring_upload(ctx, gv.data(), sizeof(GemmProb<T>) * cnt, &st));
-        HCB_CUDA(cudaMemcpyAsync(d_gv, st, sizeof(GemmProb<T>) * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
-        HCB_TRY(launch_copy<T>(ctx, d_cp, cnt, a, b));
-        HCB_TRY(launch_svd<T>(ctx, d_sv, cnt, a, b));
-        HCB_TRY(launch_gemm<T>(ctx, d_gv, cnt, b, b));
+        HCB_TRY(stage_array(ctx, fp, d_fp));
+        HCB_TRY(run_svd_jobs<T>(ctx, jobs, a, b, ws, base));
         k_compress_finalize<T><<<cnt, 256, 0, ctx->stream>>>(d_fp, (T) prm->accuracy, prm->truncated_svd,
                                                               (int) prm->fixed_rank);
         HCB_LAUNCH_CHECK("k_compress_finalize");

@@ -23,8 +23,9 @@ __device__ __forceinline__ void rr_pair(int nb2, int round, int slot, int &x, in
 }
 
 // One Jacobi rotation of the column pair (mx, my) of length a, done by one warp. Returns true if it rotated.
-// noise2 = (eps * largest column norm)^2: a column at rounding level is left alone (its singular value is zero to
-// working precision).  (de Rijk's norm-ordering swaps were tried and made the round-robin ordering converge SLOWER on
+// noise2: columns whose squared norm is <= noise2 are left alone (currently 0: only exactly-zero columns -- a larger
+// floor leaves the vectors of negligible singular values non-orthogonal, which the compat SVD entry point must not do).
+// (de Rijk's norm-ordering swaps were tried and made the round-robin ordering converge SLOWER on
 // the recompression cores -- 29 vs 18 sweeps in the numpy emulation -- so they are not used; what halves the sweep
 // count is the LQ preconditioning done before this kernel, see k_extract_l.)
 template<typename T>
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(1024) k_jacobi_svd(const SvdProb<T> *__restric
         if (tid == 0) {
             T m2 = T(0);
             for (int i = 0; i < nw; ++i) m2 = s_red[i] > m2 ? s_red[i] : m2;
-            s_noise2 = m2 * Eps<T>::v() * Eps<T>::v();
+            s_noise2 = T(0) * m2;  // only exactly-zero columns are skipped: every other column is orthogonalised
         }
         __syncthreads();
     }

@@ -58,6 +58,7 @@ struct SetupArgs {
     PanelDesc<T> *pd_stack;  // 2 per tile (U stack, V stack)
     PanelDesc<T> *pd_core;   // 1 per tile (transposed core)
     QrProb<T> *qr_core;      // 1 per tile: unblocked QR of the transposed core (small-rank path)
+    LqProb<T> *lq;           // 1 per tile
     int kA_b, kB_b, kC_b, r_b;  // rank bounds the scratch was sized for
     int *rk_new;                // n_tiles ints
     int *info;                  // n_tiles ints (may be null)
@@ -109,6 +110,7 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
     PanelDesc<T> pdu, pdv, pdm;
     memset(&pdu, 0, sizeof(pdu)); memset(&pdv, 0, sizeof(pdv)); memset(&pdm, 0, sizeof(pdm));
     QrProb<T> qm{nullptr, nullptr, 0, 0, 1};
+    LqProb<T> lq{nullptr, nullptr, 0, 0};
     int bad = 0;
     if ((ac && (ka > s.kA_b || ka < 0)) || (bc && (kb > s.kB_b || kb < 0)) || (cc && (kc > s.kC_b || kc < 0))) bad = 1;
 
@@ -196,6 +198,7 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
                 pdv = PanelDesc<T>{VW, rc.tauV, rc.VC[1], rc.TB[1], rc.WB[1], n, r, s.wcols, 1};
                 pdm = PanelDesc<T>{rc.MT, rc.tauM, slab + s.o_vcm, slab + s.o_tbm, slab + s.o_wbm, rc.b, rc.a, s.wcols, 1};
                 qm = QrProb<T>{rc.MT, rc.tauM, rc.b, rc.a, rc.b};
+                lq = LqProb<T>{rc.MT, rc.Lb, rc.a, rc.b};
                 gv = mk_gemm<T>(rc.M, rc.a, 1, rc.Us, rc.a, 0, rc.Vs, rc.b, rc.b, rc.b, rc.a, one, zero);
                 // rebuild (Compressed.cpp:551-560, 611-628): CU = Q_U [Unew;0], VN = Q_V [Vfac;0], rank read on device
                 r0 = ReflProb<T>{UW, rc.tauU, CU, m, p, m, m, 0, m, 0, 0, rc.rk_new};
@@ -212,6 +215,7 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
         rc.active = 0;
         pdu.active = pdv.active = pdm.active = 0;
         qm.m = qm.n = 0;
+        lq.a = lq.b = 0;
         if (s.info) s.info[t] = 4;  // rank exceeded the bound the scratch was sized for: tile left untouched
     } else if (s.info) {
         s.info[t] = 0;
@@ -225,6 +229,7 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
     s.pd_stack[2 * t + 0] = pdu; s.pd_stack[2 * t + 1] = pdv;
     s.pd_core[t] = pdm;
     s.qr_core[t] = qm;
+    s.lq[t] = lq;
 }
 
 // Descriptors of the blocked QR of both stacks, for every NBQ-column block at once.  One thread per (block, panel);
@@ -326,12 +331,12 @@ __global__ void __launch_bounds__(256) k_core_build(const RecompProb<T> *__restr
 
 // LQ preconditioning (Drmac-Veselic style, without pivoting): M^T = Q R  =>  M = L Q^T with L = R^T (a x b, lower
 // trapezoidal).  L has the same singular values and LEFT singular vectors as M, and one-sided Jacobi on a triangular
-// factor needs about half the sweeps (numpy emulation on recompression cores: 20 -> 11 at r = 126).
-// grid = (chunks, n_tiles)
+// factor needs far fewer sweeps (numpy emulation: 20 -> 11 on a 126 x 126 recompression core, 42 -> 11 on a 200 x 200
+// matrix with singular values spread over 14 decades).
+// grid = (chunks, n_problems)
 template<typename T>
-__global__ void __launch_bounds__(256) k_extract_l(const RecompProb<T> *__restrict__ probs) {
-    const RecompProb<T> p = probs[blockIdx.y];
-    if (!p.active) return;
+__global__ void __launch_bounds__(256) k_extract_l(const LqProb<T> *__restrict__ probs) {
+    const LqProb<T> p = probs[blockIdx.y];
     const int total = p.a * p.b;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int i = idx % p.a, j = idx / p.a;  // L(i, j) = R(j, i) for j <= i
