@@ -1,7 +1,7 @@
 """ctypes binding of libhcore_b200.so (include/hcore_b200.h).
 
 The CUDA library is the product: if it is missing this module raises at import time -- there is no Python, NumPy or
-CPU fallback behind it (and nothing here ever imports oracle/).
+CPU fallback behind it (and nothing here ever imports the test-only checker package).
 """
 from __future__ import annotations
 

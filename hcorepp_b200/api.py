@@ -10,7 +10,7 @@ Same names, argument meaning and error behaviour as the reference (file:line rel
   tile_matrix_multiplication   examples/matrix_multiplication/omp_main.cpp:70-154
 
 PyTorch is used for device memory and streams only (plumbing); all arithmetic happens in libhcore_b200.so.
-Nothing here imports oracle/ and there is no CPU path: every call ends in a CUDA kernel or raises.
+Nothing here imports the test-only checker package and there is no CPU path: every call ends in a CUDA kernel or raises.
 """
 from __future__ import annotations
 
