@@ -324,15 +324,17 @@ def main():
             fc, fr = flops_ccc(nb, ka, kb, kc_all, rk_all)
             b_qr = 8 * (2 * 2 * nb * r)                 # read both stacks + write both reflector panels, per tile-GEMM
             b_recomp = 8 * (2 * nb * (3 * r + rk_all) + 6 * r * r)
-            dom = max(("panel_qr", "core_svd", "apply_q", "contraction", "stack"), key=lambda n: phases[n]["ms_per_step"])
-            alg = {"panel_qr": b_qr.sum(), "core_svd": (8 * 6 * r * r).sum(), "apply_q": (8 * (2 * nb * r + 2 * nb * rk_all)).sum(),
+            dom = max(("panel_qr", "jacobi_svd", "core_lq", "apply_q", "contraction", "stack"), key=lambda n: phases[n]["ms_per_step"])
+            alg = {"panel_qr": b_qr.sum(), "jacobi_svd": (8 * 3 * r * r).sum(), "core_lq": (8 * 4 * r * r).sum(),
+                   "apply_q": (8 * (2 * nb * r + 2 * nb * rk_all)).sum(),
                    "contraction": (8 * (2 * nb * (ka + kb) + nb * r)).sum(), "stack": (8 * 2 * 2 * nb * r).sum()}[dom]
             t_dom = phases[dom]["ms_per_step"] * 1e-3
             ach = alg / t_dom / 1e9
             result["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                                   "traffic": None, "peak_source": src,
                                   "launch_ms": phases[dom]["ms_per_step"] / max(phases[dom]["launches_per_step"], 1)}
-            t_rec = sum(phases[n]["ms_per_step"] for n in ("stack", "panel_qr", "core_svd", "apply_q", "finalize")) * 1e-3
+            t_rec = sum(phases[n]["ms_per_step"] for n in ("stack", "panel_qr", "core_lq", "jacobi_svd", "vsigma_truncate",
+                                                           "apply_q", "finalize")) * 1e-3
             t_con = phases["contraction"]["ms_per_step"] * 1e-3
             result["effective"] = {
                 "dense_equivalent_gflops": 2.0 * (T * nb) ** 3 / (ms_per_step * 1e-3) / 1e9,

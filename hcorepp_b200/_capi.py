@@ -57,7 +57,7 @@ lib.hcb_ctx_phase_timing.argtypes = [vp, C.c_int]
 lib.hcb_ctx_phase_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
 lib.hcb_phase_name.argtypes = [C.c_int]
 lib.hcb_phase_name.restype = C.c_char_p
-N_PHASES = 7
+N_PHASES = 9
 lib.hcb_last_error.restype = C.c_char_p
 lib.hcb_version.restype = C.c_char_p
 lib.hcb_launch_count.restype = C.c_uint64

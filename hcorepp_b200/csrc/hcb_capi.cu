@@ -3,6 +3,7 @@
 // CPU arithmetic path and no fallback -- without a CUDA device every compute entry point returns HCB_ENODEVICE.
 #include "common.cuh"
 #include "kernels_blas.cuh"
+#include "kernels_dmma.cuh"
 #include "kernels_qr.cuh"
 #include "kernels_svd.cuh"
 #include "kernels_tlr.cuh"
@@ -93,14 +94,33 @@ int launch_gemm(hcb_ctx *ctx, const GemmProb<T> *d_probs, int n_probs, int m_bou
         if (m_bound <= 32 && n_bound <= 32) {
             dim3 grid(1, cnt);
             k_gemm_batched<T, 32, 32, 16><<<grid, 256, 0, ctx->stream>>>(d_probs + off);
-        } else if (m_bound <= 32) {
-            dim3 grid(std::max(1, cdiv(n_bound, 64)), cnt);
-            k_gemm_batched<T, 32, 64, 16><<<grid, 256, 0, ctx->stream>>>(d_probs + off);
-        } else {
-            dim3 grid(std::max(1, cdiv(m_bound, 64) * cdiv(n_bound, 64)), cnt);
-            k_gemm_batched<T, 64, 64, 16><<<grid, 256, 0, ctx->stream>>>(d_probs + off);
+            HCB_LAUNCH_CHECK("k_gemm_batched");
+            continue;
         }
-        HCB_LAUNCH_CHECK("k_gemm_batched");
+        if constexpr (std::is_same<T, double>::value) {
+            // FP64: tensor pipe (DMMA). Tile shape follows the skinny dimension.
+            if (m_bound <= 32) {
+                dim3 grid(std::max(1, cdiv(n_bound, 128)), cnt);
+                k_gemm_dmma<1, 4><<<grid, 128, 0, ctx->stream>>>(d_probs + off);
+            } else if (n_bound <= 32) {
+                dim3 grid(std::max(1, cdiv(m_bound, 128)), cnt);
+                k_gemm_dmma<4, 1><<<grid, 128, 0, ctx->stream>>>(d_probs + off);
+            } else {
+                dim3 grid(std::max(1, cdiv(m_bound, 64) * cdiv(n_bound, 64)), cnt);
+                k_gemm_dmma<2, 2><<<grid, 128, 0, ctx->stream>>>(d_probs + off);
+            }
+            HCB_LAUNCH_CHECK("k_gemm_dmma");
+        } else {
+            // FP32: FFMA (TF32 tensor MMA would cost ~1e-3 relative error, incompatible with accuracy <= 1e-4)
+            if (m_bound <= 32) {
+                dim3 grid(std::max(1, cdiv(n_bound, 64)), cnt);
+                k_gemm_batched<T, 32, 64, 16><<<grid, 256, 0, ctx->stream>>>(d_probs + off);
+            } else {
+                dim3 grid(std::max(1, cdiv(m_bound, 64) * cdiv(n_bound, 64)), cnt);
+                k_gemm_batched<T, 64, 64, 16><<<grid, 256, 0, ctx->stream>>>(d_probs + off);
+            }
+            HCB_LAUNCH_CHECK("k_gemm_batched");
+        }
     }
     return HCB_OK;
 }
@@ -768,7 +788,13 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
         else HCB_TRY(run_blocked_qr<T>(ctx, sa.pd_core, n, L.pq_b, L.pq_b, blk_store));
         k_extract_l<T><<<grid, 256, 0, ctx->stream>>>(sa.lq);
         HCB_LAUNCH_CHECK("k_extract_l");
+    }
+    {
+        PhaseScope ph(ctx, 7);
         HCB_TRY(launch_svd<T>(ctx, sa.svd, n, L.pq_b, L.pq_b));
+    }
+    {
+        PhaseScope ph(ctx, 8);
         HCB_TRY(launch_gemm<T>(ctx, sa.gv, n, L.pq_b, L.pq_b));
         k_truncate<T><<<n, 256, 0, ctx->stream>>>(sa.rc, (T) prm->accuracy, prm->truncated_svd, (int) prm->fixed_rank);
         HCB_LAUNCH_CHECK("k_truncate");
@@ -962,7 +988,8 @@ int hcb_ctx_phase_times(hcb_ctx *c, double *ms, uint64_t *launches) {
     return HCB_OK;
 }
 const char *hcb_phase_name(int phase) {
-    static const char *names[HCB_N_PHASES] = {"setup", "contraction", "stack", "panel_qr", "core_svd", "apply_q", "finalize"};
+    static const char *names[HCB_N_PHASES] = {"setup", "contraction", "stack", "panel_qr", "core_lq", "apply_q",
+                                              "finalize", "jacobi_svd", "vsigma_truncate"};
     return (phase >= 0 && phase < HCB_N_PHASES) ? names[phase] : "?";
 }
 

@@ -55,9 +55,10 @@ int hcb_memcpy(hcb_ctx *ctx, void *dst, const void *src, size_t bytes, int kind)
 int hcb_memset(hcb_ctx *ctx, void *d_dst, int value, size_t bytes);  /* memory::Memset */
 /* Per-phase device timing of the fused batched path, measured with CUDA events recorded on the context's stream
  * (the stream the kernels are launched on). Phases: 0 setup, 1 contraction GEMMs, 2 stack assembly, 3 panel QR,
- * 4 core build + Jacobi SVD + truncation, 5 apply-Q rebuild, 6 finalize.  hcb_ctx_phase_times synchronises, adds the
- * elapsed milliseconds / launch counts since the last call into ms[7] / launches[7] and clears the records. */
-#define HCB_N_PHASES 7
+ * 4 core build + LQ preconditioning, 5 apply-Q rebuild, 6 finalize, 7 Jacobi SVD, 8 V*Sigma GEMM + truncation.
+ * hcb_ctx_phase_times synchronises, adds the elapsed milliseconds / launch counts since the last call into
+ * ms[HCB_N_PHASES] / launches[HCB_N_PHASES] and clears the records. */
+#define HCB_N_PHASES 9
 int hcb_ctx_phase_timing(hcb_ctx *ctx, int enable);
 int hcb_ctx_phase_times(hcb_ctx *ctx, double *ms, uint64_t *launches);
 const char *hcb_phase_name(int phase);
