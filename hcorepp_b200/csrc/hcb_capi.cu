@@ -160,16 +160,22 @@ int launch_refl(hcb_ctx *ctx, const ReflProb<T> *d_probs, int n_probs, int nvec_
 template<typename T>
 int launch_svd(hcb_ctx *ctx, const SvdProb<T> *d_probs, int n_probs, int a_bound, int b_bound) {
     if (n_probs <= 0) return HCB_OK;
-    // shared memory: enough for the whole bound-sized problem, capped at the opt-in limit; the kernel decides per
-    // problem (from its true a, b) whether it fits, and otherwise rotates a global copy with only sigma in smem.
-    size_t want = ((size_t) a_bound * b_bound + (size_t) b_bound) * sizeof(T);
+    // shared memory: enough for the whole bound-sized problem (zero-padded column pitch of 64 rows), capped at the
+    // opt-in limit; the kernel decides per problem (from its true a, b) which regime applies.
+    const size_t pitch = (size_t) cdiv(a_bound, 64) * 64;
+    size_t want = (pitch * b_bound + (size_t) b_bound) * sizeof(T);
     const size_t cap = ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0;
     if (want > cap) want = cap / 16 * 16;
     if ((size_t) std::max(b_bound, 1) * sizeof(T) > want) return fail(HCB_EUNSUPPORTED, "svd: problem too large");
     want = align_up(want, 16);
-    HCB_CUDA(cudaFuncSetAttribute(k_jacobi_svd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) want));
-    const int threads = b_bound >= 96 ? 1024 : (b_bound >= 32 ? 512 : 256);  // one warp per column pair
-    k_jacobi_svd<T><<<n_probs, threads, want, ctx->stream>>>(d_probs, (int) (want / sizeof(T)), 40);
+    if (a_bound <= 128) {  // one warp per column pair, 64 registers per thread
+        HCB_CUDA(cudaFuncSetAttribute(k_jacobi_svd<T, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) want));
+        const int threads = b_bound >= 48 ? 1024 : (b_bound >= 24 ? 512 : 256);
+        k_jacobi_svd<T, 1024><<<n_probs, threads, want, ctx->stream>>>(d_probs, (int) (want / sizeof(T)), 40);
+    } else {               // 128 registers per thread: both columns of a pair stay in registers up to 512 rows
+        HCB_CUDA(cudaFuncSetAttribute(k_jacobi_svd<T, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) want));
+        k_jacobi_svd<T, 512><<<n_probs, 512, want, ctx->stream>>>(d_probs, (int) (want / sizeof(T)), 40);
+    }
     HCB_LAUNCH_CHECK("k_jacobi_svd");
     return HCB_OK;
 }

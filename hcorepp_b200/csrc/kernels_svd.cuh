@@ -54,73 +54,96 @@ __device__ __forceinline__ bool jacobi_rotate(T *__restrict__ mx, T *__restrict_
     return true;
 }
 
-// One CTA per problem. M (a x b, a >= b) = Uout diag(sigma) V^T; only the LEFT factor is produced here:
-// the rotations are not accumulated.  The caller gets the scaled right factor V diag(sigma) = M^T Uout with one
-// batched GEMM afterwards (exactly the quantity the recompression needs, Compressed.cpp:598-622), which halves the
-// Jacobi work and its shared-memory footprint.  p.M is left untouched.
+// Register-resident variant of the rotation for columns stored with a zero-padded pitch of 64*NI rows (16-byte
+// aligned): lane l owns rows {64 i + 2 l, 64 i + 2 l + 1}, i < NI.  Both columns are read ONCE with 128-bit shared
+// loads, kept in registers across the reductions, rotated and written back with 128-bit stores -- the ncu profile of
+// the loop-based version showed the FP64 pipe only 34 % busy with 63 % of the issued instructions being LDS/STS/loop
+// overhead (profiles/r01_jacobi_full_summary.txt); this form issues ~7 FP64 instructions per 2 memory instructions.
+template<typename T> struct alignas(2 * sizeof(T)) Vec2 { T x, y; };
+
+template<typename T, int NI>
+__device__ __forceinline__ bool jacobi_rotate_reg(T *__restrict__ mx, T *__restrict__ my, int lane, T tol) {
+    Vec2<T> u[NI], v[NI];
+    T alpha = T(0), beta = T(0), gamma = T(0);
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        u[i] = *reinterpret_cast<const Vec2<T> *>(mx + 64 * i + 2 * lane);
+        v[i] = *reinterpret_cast<const Vec2<T> *>(my + 64 * i + 2 * lane);
+        alpha = fma(u[i].x, u[i].x, alpha); alpha = fma(u[i].y, u[i].y, alpha);
+        beta = fma(v[i].x, v[i].x, beta);   beta = fma(v[i].y, v[i].y, beta);
+        gamma = fma(u[i].x, v[i].x, gamma); gamma = fma(u[i].y, v[i].y, gamma);
+    }
+    alpha = warp_sum(alpha);
+    beta = warp_sum(beta);
+    gamma = warp_sum(gamma);
+    // |gamma| > tol * sqrt(alpha * beta)  <=>  gamma^2 > tol^2 * alpha * beta   (no square roots on the hot path)
+    if (!(gamma * gamma > tol * tol * alpha * beta) || gamma == T(0)) return false;
+    const T zeta = (beta - alpha) / (T(2) * gamma);
+    const T t = (zeta >= T(0) ? T(1) : T(-1)) / (t_abs(zeta) + t_sqrt(fma(zeta, zeta, T(1))));
+    const T c = T(1) / t_sqrt(fma(t, t, T(1)));
+    const T s = c * t;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        Vec2<T> nu, nv;
+        nu.x = fma(-s, v[i].x, c * u[i].x); nu.y = fma(-s, v[i].y, c * u[i].y);
+        nv.x = fma(s, u[i].x, c * v[i].x);  nv.y = fma(s, u[i].y, c * v[i].y);
+        *reinterpret_cast<Vec2<T> *>(mx + 64 * i + 2 * lane) = nu;
+        *reinterpret_cast<Vec2<T> *>(my + 64 * i + 2 * lane) = nv;
+    }
+    return true;
+}
+
+// The sweeps.  NI > 0: shared-memory columns have pitch 64*NI (zero padded), rotations are register resident.
+// NI == 0: generic form, pitch = a, loop-based rotations (any size; also the global-memory fallback).
+//
+// M (a x b, a >= b) = Uout diag(sigma) V^T; only the LEFT factor is produced here: the rotations are not accumulated.
+// The caller gets the scaled right factor V diag(sigma) = M^T Uout with one batched GEMM afterwards (exactly the
+// quantity the recompression needs, Compressed.cpp:598-622), which halves the Jacobi work and its shared-memory
+// footprint.  p.M is left untouched.
 //
 // Three regimes, chosen per problem from its true size (dynamic shared memory = smem_elems elements of T):
-//   (A) a*b + b fits            : the whole matrix lives in shared memory, plain cyclic (round-robin) one-sided Jacobi;
+//   (A) pitch*b + b fits        : the whole matrix lives in shared memory, cyclic (round-robin) one-sided Jacobi;
 //   (B) two column blocks fit   : BLOCK one-sided Jacobi -- the rotated copy of M lives in global memory (p.J, L2
 //                                 resident), pairs of w-column blocks are staged in shared memory, all w*w cross pairs
 //                                 (and, once per sweep, the pairs inside each block) are rotated there, blocks go back;
 //   (C) otherwise               : rotations directly on the global copy (slow, correctness-only fallback).
-template<typename T>
-__global__ void __launch_bounds__(1024) k_jacobi_svd(const SvdProb<T> *__restrict__ probs, int smem_elems,
-                                                     int max_sweeps) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sm = reinterpret_cast<T *>(smem_raw);
+template<typename T, int NI>
+__device__ void jacobi_sweeps(T *sm, const SvdProb<T> &p, int smem_elems, int max_sweeps) {
     __shared__ int s_rot;
-    const SvdProb<T> p = probs[blockIdx.x];
     const int a = p.a, b = p.b;
-    if (a <= 0 || b <= 0) return;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
-    const bool fits = (size_t) a * b + (size_t) b <= (size_t) smem_elems;
+    const int P = NI > 0 ? 64 * NI : a;  // shared-memory column pitch
+    const bool fits = (size_t) P * b + (size_t) b <= (size_t) smem_elems;
     int bw = 0;  // block width of regime (B)
     if (!fits) {
         bw = 32;
-        while (bw >= 2 && (size_t) 2 * a * bw + (size_t) b > (size_t) smem_elems) bw >>= 1;
+        while (bw >= 2 && (size_t) 2 * P * bw + (size_t) b > (size_t) smem_elems) bw >>= 1;
         if (bw < 2) bw = 0;
     }
-    T *M, *sig;
-    const int ldm = a;
-    if (fits) {
-        M = sm;
-        sig = sm + (size_t) a * b;
+    const bool in_smem = fits, blocked = !fits && bw > 0;
+    T *M = in_smem ? sm : p.J;              // the rotated copy
+    const int ldm = in_smem ? P : a;
+    T *sig = in_smem ? sm + (size_t) P * b : (blocked ? sm + (size_t) 2 * P * bw : sm);
+    if (in_smem) {
+        for (int idx = tid; idx < P * b; idx += nthr) {
+            const int i = idx % P, c = idx / P;
+            M[idx] = i < a ? p.M[(size_t) i + (size_t) c * p.ldm] : T(0);
+        }
     } else {
-        M = p.J;
-        sig = sm + (size_t) 2 * a * bw;
+        for (int idx = tid; idx < a * b; idx += nthr) M[idx] = p.M[(size_t) (idx % a) + (size_t) (idx / a) * p.ldm];
     }
-    for (int idx = tid; idx < a * b; idx += nthr) M[idx] = p.M[(size_t) (idx % a) + (size_t) (idx / a) * p.ldm];
     __syncthreads();
 
     const T tol = Eps<T>::v() * t_sqrt((T) a);  // threshold on |cos(angle)| of a column pair
-    // noise floor from the largest column norm of the input
-    __shared__ T s_noise2;
-    {
-        T mx2 = T(0);
-        for (int c = w; c < b; c += nw) {
-            const T *mc = M + (size_t) c * ldm;
-            T ss = T(0);
-            for (int i = lane; i < a; i += 32) ss = fma(mc[i], mc[i], ss);
-            ss = warp_sum(ss);
-            mx2 = ss > mx2 ? ss : mx2;
-        }
-        __shared__ T s_red[32];
-        if (lane == 0) s_red[w] = mx2;
-        __syncthreads();
-        if (tid == 0) {
-            T m2 = T(0);
-            for (int i = 0; i < nw; ++i) m2 = s_red[i] > m2 ? s_red[i] : m2;
-            s_noise2 = T(0) * m2;  // only exactly-zero columns are skipped: every other column is orthogonalised
-        }
-        __syncthreads();
-    }
-    const T noise2 = s_noise2;
+    auto rotate = [&](T *cx, T *cy) -> bool {
+        if constexpr (NI > 0) return jacobi_rotate_reg<T, NI>(cx, cy, lane, tol);
+        else return jacobi_rotate<T>(cx, cy, a, lane, tol, T(0));
+    };
     bool converged = (b < 2);
     int sweeps_used = 0;
-    if (fits || bw == 0) {
-        // ---- regimes (A) and (C): cyclic one-sided Jacobi over all column pairs, one warp per pair
+    if (!blocked) {
+        // ---- regimes (A) and (C): cyclic one-sided Jacobi over all column pairs, one warp per pair.
+        // (C) with NI > 0 cannot use the padded register form on the unpadded global copy -> generic rotation.
         const int nb2 = (b + 1) & ~1;
         for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
             ++sweeps_used;
@@ -132,7 +155,9 @@ __global__ void __launch_bounds__(1024) k_jacobi_svd(const SvdProb<T> *__restric
                     int x, y;
                     rr_pair(nb2, round, slot, x, y);
                     if (y >= b) continue;  // dummy player (odd b)
-                    if (jacobi_rotate(M + (size_t) x * ldm, M + (size_t) y * ldm, a, lane, tol, noise2) && lane == 0) s_rot = 1;
+                    T *cx = M + (size_t) x * ldm, *cy = M + (size_t) y * ldm;
+                    const bool r = in_smem ? rotate(cx, cy) : jacobi_rotate<T>(cx, cy, a, lane, tol, T(0));
+                    if (r && lane == 0) s_rot = 1;
                 }
                 __syncthreads();
             }
@@ -140,7 +165,7 @@ __global__ void __launch_bounds__(1024) k_jacobi_svd(const SvdProb<T> *__restric
         }
     } else {
         // ---- regime (B): block one-sided Jacobi
-        T *BA = sm, *BB = sm + (size_t) a * bw;
+        T *BA = sm, *BB = sm + (size_t) P * bw;
         const int nblk = (b + bw - 1) / bw, nblk2 = (nblk + 1) & ~1;
         for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
             ++sweeps_used;
@@ -156,23 +181,28 @@ __global__ void __launch_bounds__(1024) k_jacobi_svd(const SvdProb<T> *__restric
                     const bool have_j = bj < nblk;
                     const int ci0 = bi * bw, cj0 = bj * bw;
                     const int wi = min(bw, b - ci0), wj = have_j ? min(bw, b - cj0) : 0;
-                    // stage the two column blocks
-                    for (int idx = tid; idx < a * wi; idx += nthr) BA[idx] = M[(size_t) ci0 * ldm + idx];
-                    for (int idx = tid; idx < a * wj; idx += nthr) BB[idx] = M[(size_t) cj0 * ldm + idx];
+                    // stage the two column blocks (zero padded to the pitch)
+                    for (int idx = tid; idx < P * wi; idx += nthr) {
+                        const int i = idx % P, c = idx / P;
+                        BA[idx] = i < a ? M[(size_t) (ci0 + c) * a + i] : T(0);
+                    }
+                    for (int idx = tid; idx < P * wj; idx += nthr) {
+                        const int i = idx % P, c = idx / P;
+                        BB[idx] = i < a ? M[(size_t) (cj0 + c) * a + i] : T(0);
+                    }
                     __syncthreads();
                     if (bround == 0) {
                         // once per sweep every block meets exactly one partner in round 0: rotate ALL pairs of the
-                        // union (inside-block pairs included); BA and BB are contiguous, so the union is one array
+                        // union (inside-block pairs included)
                         const int nu = wi + wj, nu2 = (nu + 1) & ~1;
-                        T *UB = BA;  // columns [0, wi) from BA, [wi, wi+wj) from BB (contiguous only if wi == bw)
                         for (int round = 0; round < nu2 - 1; ++round) {
                             for (int slot = w; slot < nu2 / 2; slot += nw) {
                                 int x, y;
                                 rr_pair(nu2, round, slot, x, y);
                                 if (y >= nu) continue;
-                                T *cx = x < wi ? UB + (size_t) x * a : BB + (size_t) (x - wi) * a;
-                                T *cy = y < wi ? UB + (size_t) y * a : BB + (size_t) (y - wi) * a;
-                                if (jacobi_rotate(cx, cy, a, lane, tol, noise2) && lane == 0) s_rot = 1;
+                                T *cx = x < wi ? BA + (size_t) x * P : BB + (size_t) (x - wi) * P;
+                                T *cy = y < wi ? BA + (size_t) y * P : BB + (size_t) (y - wi) * P;
+                                if (rotate(cx, cy) && lane == 0) s_rot = 1;
                             }
                             __syncthreads();
                         }
@@ -182,15 +212,20 @@ __global__ void __launch_bounds__(1024) k_jacobi_svd(const SvdProb<T> *__restric
                             for (int i = w; i < wi; i += nw) {
                                 const int j = (i + t) % bw;
                                 if (j >= wj) continue;
-                                if (jacobi_rotate(BA + (size_t) i * a, BB + (size_t) j * a, a, lane, tol, noise2) && lane == 0)
-                                    s_rot = 1;
+                                if (rotate(BA + (size_t) i * P, BB + (size_t) j * P) && lane == 0) s_rot = 1;
                             }
                             __syncthreads();
                         }
                     }
                     // write the blocks back
-                    for (int idx = tid; idx < a * wi; idx += nthr) M[(size_t) ci0 * ldm + idx] = BA[idx];
-                    for (int idx = tid; idx < a * wj; idx += nthr) M[(size_t) cj0 * ldm + idx] = BB[idx];
+                    for (int idx = tid; idx < P * wi; idx += nthr) {
+                        const int i = idx % P, c = idx / P;
+                        if (i < a) M[(size_t) (ci0 + c) * a + i] = BA[idx];
+                    }
+                    for (int idx = tid; idx < P * wj; idx += nthr) {
+                        const int i = idx % P, c = idx / P;
+                        if (i < a) M[(size_t) (cj0 + c) * a + i] = BB[idx];
+                    }
                     __syncthreads();
                 }
             }
@@ -225,6 +260,37 @@ __global__ void __launch_bounds__(1024) k_jacobi_svd(const SvdProb<T> *__restric
         const T *mc = M + (size_t) c * ldm;
         T *uo = p.Uout + (size_t) pos * p.ldu;
         for (int i = lane; i < a; i += 32) uo[i] = (sc > T(0)) ? mc[i] / sc : T(0);
+    }
+}
+
+// One CTA per problem.  THREADS = 1024 (64 registers/thread: register-resident rotations up to 128 rows) or 512
+// (128 registers/thread: up to 512 rows); taller problems use the generic loop-based rotations.
+template<typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_jacobi_svd(const SvdProb<T> *__restrict__ probs, int smem_elems,
+                                                        int max_sweeps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    const SvdProb<T> p = probs[blockIdx.x];
+    if (p.a <= 0 || p.b <= 0) return;
+    const int ni = (p.a + 63) / 64;
+    if constexpr (THREADS == 1024) {
+        switch (ni) {
+            case 1: jacobi_sweeps<T, 1>(sm, p, smem_elems, max_sweeps); break;
+            case 2: jacobi_sweeps<T, 2>(sm, p, smem_elems, max_sweeps); break;
+            default: jacobi_sweeps<T, 0>(sm, p, smem_elems, max_sweeps); break;
+        }
+    } else {
+        switch (ni) {
+            case 1: jacobi_sweeps<T, 1>(sm, p, smem_elems, max_sweeps); break;
+            case 2: jacobi_sweeps<T, 2>(sm, p, smem_elems, max_sweeps); break;
+            case 3: jacobi_sweeps<T, 3>(sm, p, smem_elems, max_sweeps); break;
+            case 4: jacobi_sweeps<T, 4>(sm, p, smem_elems, max_sweeps); break;
+            case 5: jacobi_sweeps<T, 5>(sm, p, smem_elems, max_sweeps); break;
+            case 6: jacobi_sweeps<T, 6>(sm, p, smem_elems, max_sweeps); break;
+            case 7: jacobi_sweeps<T, 7>(sm, p, smem_elems, max_sweeps); break;
+            case 8: jacobi_sweeps<T, 8>(sm, p, smem_elems, max_sweeps); break;
+            default: jacobi_sweeps<T, 0>(sm, p, smem_elems, max_sweeps); break;
+        }
     }
 }
 
