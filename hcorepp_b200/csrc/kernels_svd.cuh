@@ -61,27 +61,37 @@ __device__ __forceinline__ bool jacobi_rotate(T *__restrict__ mx, T *__restrict_
 // overhead (profiles/r01_jacobi_full_summary.txt); this form issues ~7 FP64 instructions per 2 memory instructions.
 template<typename T> struct alignas(2 * sizeof(T)) Vec2 { T x, y; };
 
+template<typename T> __device__ __forceinline__ T t_rsqrt(T x);
+template<> __device__ __forceinline__ double t_rsqrt(double x) { return rsqrt(x); }
+template<> __device__ __forceinline__ float t_rsqrt(float x) { return rsqrtf(x); }
+
+// nx2 / ny2: CACHED squared column norms (shared memory), so that only the inner product gamma has to be formed
+// (LAPACK xGESVJ does the same): alpha' = alpha - t*gamma, beta' = beta + t*gamma, recomputed from the registers when
+// the update cancels badly.  The rotation scalars use one reciprocal square root each instead of divisions and square
+// roots:  t = 2*gamma / (d + sign(d)*sqrt(d^2 + 4*gamma^2)),  d = beta - alpha;  c = rsqrt(1 + t^2);  s = c*t.
 template<typename T, int NI>
-__device__ __forceinline__ bool jacobi_rotate_reg(T *__restrict__ mx, T *__restrict__ my, int lane, T tol) {
+__device__ __forceinline__ bool jacobi_rotate_reg(T *__restrict__ mx, T *__restrict__ my, T *nx2, T *ny2, int lane, T tol2) {
     Vec2<T> u[NI], v[NI];
-    T alpha = T(0), beta = T(0), gamma = T(0);
+    T gamma = T(0);
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
         u[i] = *reinterpret_cast<const Vec2<T> *>(mx + 64 * i + 2 * lane);
         v[i] = *reinterpret_cast<const Vec2<T> *>(my + 64 * i + 2 * lane);
-        alpha = fma(u[i].x, u[i].x, alpha); alpha = fma(u[i].y, u[i].y, alpha);
-        beta = fma(v[i].x, v[i].x, beta);   beta = fma(v[i].y, v[i].y, beta);
-        gamma = fma(u[i].x, v[i].x, gamma); gamma = fma(u[i].y, v[i].y, gamma);
+        gamma = fma(u[i].x, v[i].x, gamma);
+        gamma = fma(u[i].y, v[i].y, gamma);
     }
-    alpha = warp_sum(alpha);
-    beta = warp_sum(beta);
+    const T alpha = *nx2, beta = *ny2;
     gamma = warp_sum(gamma);
-    // |gamma| > tol * sqrt(alpha * beta)  <=>  gamma^2 > tol^2 * alpha * beta   (no square roots on the hot path)
-    if (!(gamma * gamma > tol * tol * alpha * beta) || gamma == T(0)) return false;
-    const T zeta = (beta - alpha) / (T(2) * gamma);
-    const T t = (zeta >= T(0) ? T(1) : T(-1)) / (t_abs(zeta) + t_sqrt(fma(zeta, zeta, T(1))));
-    const T c = T(1) / t_sqrt(fma(t, t, T(1)));
+    // |gamma| > tol * sqrt(alpha * beta)  <=>  gamma^2 > tol^2 * alpha * beta
+    if (!(gamma * gamma > tol2 * alpha * beta)) return false;
+    const T d = beta - alpha, g2 = gamma + gamma;
+    const T h = fma(d, d, g2 * g2);          // > 0 because gamma != 0 here
+    const T den = t_abs(d) + h * t_rsqrt(h);  // |d| + sqrt(d^2 + 4 gamma^2) > 0
+    const T rd = t_rsqrt(den);
+    const T t = (d >= T(0) ? g2 : -g2) * (rd * rd);
+    const T c = t_rsqrt(fma(t, t, T(1)));
     const T s = c * t;
+    T na = T(0), nb = T(0);
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
         Vec2<T> nu, nv;
@@ -89,7 +99,21 @@ __device__ __forceinline__ bool jacobi_rotate_reg(T *__restrict__ mx, T *__restr
         nv.x = fma(s, u[i].x, c * v[i].x);  nv.y = fma(s, u[i].y, c * v[i].y);
         *reinterpret_cast<Vec2<T> *>(mx + 64 * i + 2 * lane) = nu;
         *reinterpret_cast<Vec2<T> *>(my + 64 * i + 2 * lane) = nv;
+        u[i] = nu;
+        v[i] = nv;
     }
+    const T tg = t * gamma;
+    T a2 = alpha - tg, b2 = beta + tg;
+    if (a2 < T(0.01) * alpha || b2 < T(0.01) * beta) {  // cancellation: recompute both norms from the registers
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            na = fma(u[i].x, u[i].x, na); na = fma(u[i].y, u[i].y, na);
+            nb = fma(v[i].x, v[i].x, nb); nb = fma(v[i].y, v[i].y, nb);
+        }
+        a2 = warp_sum(na);
+        b2 = warp_sum(nb);
+    }
+    if (lane == 0) { *nx2 = a2; *ny2 = b2; }
     return true;
 }
 
@@ -113,17 +137,20 @@ __device__ void jacobi_sweeps(T *sm, const SvdProb<T> &p, int smem_elems, int ma
     const int a = p.a, b = p.b;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
     const int P = NI > 0 ? 64 * NI : a;  // shared-memory column pitch
-    const bool fits = (size_t) P * b + (size_t) b <= (size_t) smem_elems;
+    // shared-memory budget: columns + sigma (b) + cached squared norms (register form only: b, or 2*bw when blocked)
+    const size_t nrm_a = NI > 0 ? (size_t) b : 0;
+    const bool fits = (size_t) P * b + (size_t) b + nrm_a <= (size_t) smem_elems;
     int bw = 0;  // block width of regime (B)
     if (!fits) {
         bw = 32;
-        while (bw >= 2 && (size_t) 2 * P * bw + (size_t) b > (size_t) smem_elems) bw >>= 1;
+        while (bw >= 2 && (size_t) 2 * P * bw + (size_t) b + (NI > 0 ? (size_t) 2 * bw : 0) > (size_t) smem_elems) bw >>= 1;
         if (bw < 2) bw = 0;
     }
     const bool in_smem = fits, blocked = !fits && bw > 0;
     T *M = in_smem ? sm : p.J;              // the rotated copy
     const int ldm = in_smem ? P : a;
     T *sig = in_smem ? sm + (size_t) P * b : (blocked ? sm + (size_t) 2 * P * bw : sm);
+    T *nrm = sig + b;  // cached squared norms (NI > 0 only): b entries in regime A, 2*bw in regime B
     if (in_smem) {
         for (int idx = tid; idx < P * b; idx += nthr) {
             const int i = idx % P, c = idx / P;
@@ -135,9 +162,20 @@ __device__ void jacobi_sweeps(T *sm, const SvdProb<T> &p, int smem_elems, int ma
     __syncthreads();
 
     const T tol = Eps<T>::v() * t_sqrt((T) a);  // threshold on |cos(angle)| of a column pair
-    auto rotate = [&](T *cx, T *cy) -> bool {
-        if constexpr (NI > 0) return jacobi_rotate_reg<T, NI>(cx, cy, lane, tol);
+    const T tol2 = tol * tol;
+    auto rotate = [&](T *cx, T *cy, T *nx, T *ny) -> bool {
+        if constexpr (NI > 0) return jacobi_rotate_reg<T, NI>(cx, cy, nx, ny, lane, tol2);
         else return jacobi_rotate<T>(cx, cy, a, lane, tol, T(0));
+    };
+    // squared norms of `cnt` staged columns (pitch P) into out[]
+    auto norms_of = [&](const T *cols, int cnt, T *out) {
+        for (int c = w; c < cnt; c += nw) {
+            const T *mc = cols + (size_t) c * P;
+            T ss = T(0);
+            for (int i = lane; i < P; i += 32) ss = fma(mc[i], mc[i], ss);
+            ss = warp_sum(ss);
+            if (lane == 0) out[c] = ss;
+        }
     };
     bool converged = (b < 2);
     int sweeps_used = 0;
@@ -149,6 +187,7 @@ __device__ void jacobi_sweeps(T *sm, const SvdProb<T> &p, int smem_elems, int ma
             ++sweeps_used;
             __syncthreads();
             if (tid == 0) s_rot = 0;
+            if (NI > 0 && in_smem) norms_of(M, b, nrm);  // refresh the cached norms once per sweep
             __syncthreads();
             for (int round = 0; round < nb2 - 1; ++round) {
                 for (int slot = w; slot < nb2 / 2; slot += nw) {
@@ -156,7 +195,7 @@ __device__ void jacobi_sweeps(T *sm, const SvdProb<T> &p, int smem_elems, int ma
                     rr_pair(nb2, round, slot, x, y);
                     if (y >= b) continue;  // dummy player (odd b)
                     T *cx = M + (size_t) x * ldm, *cy = M + (size_t) y * ldm;
-                    const bool r = in_smem ? rotate(cx, cy) : jacobi_rotate<T>(cx, cy, a, lane, tol, T(0));
+                    const bool r = in_smem ? rotate(cx, cy, nrm + x, nrm + y) : jacobi_rotate<T>(cx, cy, a, lane, tol, T(0));
                     if (r && lane == 0) s_rot = 1;
                 }
                 __syncthreads();
@@ -164,70 +203,68 @@ __device__ void jacobi_sweeps(T *sm, const SvdProb<T> &p, int smem_elems, int ma
             converged = (s_rot == 0);
         }
     } else {
-        // ---- regime (B): block one-sided Jacobi
+        // ---- regime (B): block one-sided Jacobi, row-cyclic over column blocks: block I stays in shared memory while
+        // every later block J streams through (stage J, rotate the bw x bw cross pairs, write J back).
         T *BA = sm, *BB = sm + (size_t) P * bw;
-        const int nblk = (b + bw - 1) / bw, nblk2 = (nblk + 1) & ~1;
+        const int nblk = (b + bw - 1) / bw;
+        auto stage = [&](T *dst, int c0, int wc) {
+            for (int idx = tid; idx < P * wc; idx += nthr) {
+                const int i = idx % P, c = idx / P;
+                dst[idx] = i < a ? M[(size_t) (c0 + c) * a + i] : T(0);
+            }
+        };
+        auto unstage = [&](const T *src, int c0, int wc) {
+            for (int idx = tid; idx < P * wc; idx += nthr) {
+                const int i = idx % P, c = idx / P;
+                if (i < a) M[(size_t) (c0 + c) * a + i] = src[idx];
+            }
+        };
         for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
             ++sweeps_used;
             __syncthreads();
             if (tid == 0) s_rot = 0;
             __syncthreads();
-            for (int bround = 0; bround < (nblk2 > 1 ? nblk2 - 1 : 1); ++bround) {
-                for (int bslot = 0; bslot < nblk2 / 2; ++bslot) {
-                    int bi, bj;
-                    if (nblk2 > 1) rr_pair(nblk2, bround, bslot, bi, bj);
-                    else { bi = 0; bj = 1; }
-                    if (bi >= nblk) continue;
-                    const bool have_j = bj < nblk;
-                    const int ci0 = bi * bw, cj0 = bj * bw;
-                    const int wi = min(bw, b - ci0), wj = have_j ? min(bw, b - cj0) : 0;
-                    // stage the two column blocks (zero padded to the pitch)
-                    for (int idx = tid; idx < P * wi; idx += nthr) {
-                        const int i = idx % P, c = idx / P;
-                        BA[idx] = i < a ? M[(size_t) (ci0 + c) * a + i] : T(0);
-                    }
-                    for (int idx = tid; idx < P * wj; idx += nthr) {
-                        const int i = idx % P, c = idx / P;
-                        BB[idx] = i < a ? M[(size_t) (cj0 + c) * a + i] : T(0);
-                    }
+            for (int bi = 0; bi < nblk; ++bi) {
+                const int ci0 = bi * bw, wi = min(bw, b - ci0);
+                stage(BA, ci0, wi);
+                __syncthreads();
+                if (NI > 0) {
+                    norms_of(BA, wi, nrm);
                     __syncthreads();
-                    if (bround == 0) {
-                        // once per sweep every block meets exactly one partner in round 0: rotate ALL pairs of the
-                        // union (inside-block pairs included)
-                        const int nu = wi + wj, nu2 = (nu + 1) & ~1;
-                        for (int round = 0; round < nu2 - 1; ++round) {
-                            for (int slot = w; slot < nu2 / 2; slot += nw) {
-                                int x, y;
-                                rr_pair(nu2, round, slot, x, y);
-                                if (y >= nu) continue;
-                                T *cx = x < wi ? BA + (size_t) x * P : BB + (size_t) (x - wi) * P;
-                                T *cy = y < wi ? BA + (size_t) y * P : BB + (size_t) (y - wi) * P;
-                                if (rotate(cx, cy) && lane == 0) s_rot = 1;
-                            }
-                            __syncthreads();
-                        }
-                    } else if (have_j) {
-                        // cross pairs only: round t pairs column i of BA with column (i + t) mod bw of BB
-                        for (int t = 0; t < bw; ++t) {
-                            for (int i = w; i < wi; i += nw) {
-                                const int j = (i + t) % bw;
-                                if (j >= wj) continue;
-                                if (rotate(BA + (size_t) i * P, BB + (size_t) j * P) && lane == 0) s_rot = 1;
-                            }
-                            __syncthreads();
-                        }
-                    }
-                    // write the blocks back
-                    for (int idx = tid; idx < P * wi; idx += nthr) {
-                        const int i = idx % P, c = idx / P;
-                        if (i < a) M[(size_t) (ci0 + c) * a + i] = BA[idx];
-                    }
-                    for (int idx = tid; idx < P * wj; idx += nthr) {
-                        const int i = idx % P, c = idx / P;
-                        if (i < a) M[(size_t) (cj0 + c) * a + i] = BB[idx];
+                }
+                // pairs inside block I (round-robin over its wi columns)
+                const int nu2 = (wi + 1) & ~1;
+                for (int round = 0; round < nu2 - 1; ++round) {
+                    for (int slot = w; slot < nu2 / 2; slot += nw) {
+                        int x, y;
+                        rr_pair(nu2, round, slot, x, y);
+                        if (y >= wi) continue;
+                        if (rotate(BA + (size_t) x * P, BA + (size_t) y * P, nrm + x, nrm + y) && lane == 0) s_rot = 1;
                     }
                     __syncthreads();
                 }
+                for (int bj = bi + 1; bj < nblk; ++bj) {
+                    const int cj0 = bj * bw, wj = min(bw, b - cj0);
+                    stage(BB, cj0, wj);
+                    __syncthreads();
+                    if (NI > 0) {
+                        norms_of(BB, wj, nrm + bw);
+                        __syncthreads();
+                    }
+                    // cross pairs: round t pairs column i of BA with column (i + t) mod bw of BB
+                    for (int t = 0; t < bw; ++t) {
+                        for (int i = w; i < wi; i += nw) {
+                            const int j = (i + t) % bw;
+                            if (j >= wj) continue;
+                            if (rotate(BA + (size_t) i * P, BB + (size_t) j * P, nrm + i, nrm + bw + j) && lane == 0) s_rot = 1;
+                        }
+                        __syncthreads();
+                    }
+                    unstage(BB, cj0, wj);
+                    __syncthreads();
+                }
+                unstage(BA, ci0, wi);
+                __syncthreads();
             }
             converged = (s_rot == 0);
         }
