@@ -557,7 +557,7 @@ template<typename T>
 struct Layout {
     size_t slab = 0, o_w1 = 0, o_w2 = 0, o_uw = 0, o_vw = 0, o_tauu = 0, o_tauv = 0, o_m = 0, o_j = 0, o_us = 0,
            o_vs = 0, o_sig = 0, o_vn = 0, o_vcu = 0, o_vcv = 0, o_tbu = 0, o_tbv = 0, o_wbu = 0, o_wbv = 0, o_mt = 0,
-           o_taum = 0, o_lb = 0, o_vcm = 0, o_tbm = 0, o_wbm = 0;
+           o_taum = 0, o_lb = 0, o_vcm = 0, o_tbm = 0, o_wbm = 0, o_pj = 0, o_pos = 0;
     int r_b = 0, pq_b = 0, wcols = 0, nblk = 0;
 };
 
@@ -568,7 +568,7 @@ Layout<T> make_layout(const BatchShape &s) {
     auto take = [&](size_t elems) { size_t o = off; off += align_up(std::max<size_t>(elems, 1), 32); return o; };
     size_t w1 = 0, w2 = 0;
     switch (s.mix) {
-        case CCC: w1 = (size_t) s.kA * s.kB; break;
+        case CCC: w1 = (size_t) s.kA * s.kB; w2 = (size_t) s.kA * s.kB; break;
         case CCD: w1 = (size_t) s.kA * s.kB; w2 = (size_t) s.kA * s.n; break;
         case CDD: w1 = (size_t) s.kA * s.n; break;
         case DCD: w1 = (size_t) s.m * s.kB; break;
@@ -610,6 +610,8 @@ Layout<T> make_layout(const BatchShape &s) {
         L.o_vcm = take(sq);
         L.o_tbm = take((size_t) NBQ * NBQ * L.nblk);
         L.o_wbm = take((size_t) 2 * NBQ * L.wcols);
+        L.o_pj = take((size_t) s.kA * s.kA);
+        L.o_pos = take((size_t) L.r_b);  // r_b ints in T-sized slots
     }
     L.slab = off;
     return L;
@@ -620,7 +622,7 @@ struct DescArrays {  // device arrays living at the front of the scratch arena
     size_t bytes = 0;
     size_t o_g1, o_g2, o_g3, o_gv, o_cp, o_qr, o_rf, o_svd, o_rc, o_rk, o_tiles;
     size_t o_bqr = 0, o_blf = 0, o_bgw = 0, o_bgw2 = 0, o_bgup = 0, o_agw = 0, o_agw2 = 0, o_agup = 0;
-    size_t o_pds = 0, o_pdc = 0, o_qrc = 0, o_lq = 0;
+    size_t o_pds = 0, o_pdc = 0, o_qrc = 0, o_lq = 0, o_pc = 0;
     explicit DescArrays(int n, int nblk = 0) {
         size_t off = 0;
         auto take = [&](size_t b) { size_t o = off; off += align_up(b, 256); return o; };
@@ -639,6 +641,7 @@ struct DescArrays {  // device arrays living at the front of the scratch arena
         o_pdc = take(sizeof(PanelDesc<T>) * n);
         o_qrc = take(sizeof(QrProb<T>) * n);
         o_lq = take(sizeof(LqProb<T>) * n);
+        o_pc = take(sizeof(PrecondProb<T>) * n);
         if (nblk > 0) {
             const size_t nb = (size_t) nblk * 2 * n;
             o_bqr = take(qr_block_desc_bytes<T>(2 * n, nblk));
@@ -725,6 +728,9 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     sa.pd_core = reinterpret_cast<PanelDesc<T> *>(base + D.o_pdc);
     sa.qr_core = reinterpret_cast<QrProb<T> *>(base + D.o_qrc);
     sa.lq = reinterpret_cast<LqProb<T> *>(base + D.o_lq);
+    sa.pc = reinterpret_cast<PrecondProb<T> *>(base + D.o_pc);
+    sa.o_pj = L.o_pj; sa.o_pos = L.o_pos;
+    sa.use_lq = 0;  // sorted + preconditioned stacks: Jacobi converges in ~6 sweeps on the core itself
     sa.kA_b = s.kA; sa.kB_b = s.kB; sa.kC_b = s.kC; sa.r_b = L.r_b;
     sa.rk_new = reinterpret_cast<int *>(base + D.o_rk);
     sa.info = d_info;
@@ -759,9 +765,20 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     {
         PhaseScope ph(ctx, 1);
         HCB_TRY(launch_gemm<T>(ctx, sa.g1, n, g1m, g1n));
+        if (s.mix == CCC) {
+            // orthogonalise the product term's right factor (small Jacobi in shared memory, one CTA per tile)
+            size_t want = ((size_t) s.kA * s.kB + (size_t) s.kA * s.kA + (size_t) s.kB) * sizeof(T);
+            const size_t cap = ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0;
+            if (want > cap) want = 0;  // does not fit: the kernel writes J = I
+            want = align_up(want, 16);
+            HCB_CUDA(cudaFuncSetAttribute(k_precond_product<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(want, 16)));
+            k_precond_product<T><<<n, 256, want, ctx->stream>>>(sa.pc, (int) (want / sizeof(T)));
+            HCB_LAUNCH_CHECK("k_precond_product");
+        }
         if (s.mix == CCC || s.mix == CCD || s.mix == CDD || s.mix == DCD || s.mix == DDC)
             HCB_TRY(launch_gemm<T>(ctx, sa.g2, n, g2m, g2n));
         if (s.mix == CCD) HCB_TRY(launch_gemm<T>(ctx, sa.g3, n, s.m, s.n));
+        if (s.mix == CCC) HCB_TRY(launch_gemm<T>(ctx, sa.g3, n, s.m, s.kA));
     }
 
     if (s.mix == DDC) {
@@ -776,6 +793,13 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     {
         PhaseScope ph(ctx, 2);
         HCB_TRY(launch_copy<T>(ctx, sa.cp, 4 * n, std::max(s.m, s.n), std::max(L.r_b, 1)));
+        // sort the stack columns by decreasing V-stack norm (same permutation on both stacks)
+        const size_t want = align_up((size_t) std::max(L.r_b, 1) * sizeof(T), 16);
+        k_stack_order<T><<<n, 256, want, ctx->stream>>>(sa.rc, (int) (want / sizeof(T)));
+        HCB_LAUNCH_CHECK("k_stack_order");
+        dim3 grid(std::max(1, std::min(L.r_b, 64)), 2 * n);
+        k_permute_stacks<T><<<grid, 256, 0, ctx->stream>>>(sa.rc);
+        HCB_LAUNCH_CHECK("k_permute_stacks");
     }
     const int npan = 2 * n, nbt = L.nblk * npan;
     char *blk_store = base + D.o_bqr;
@@ -789,11 +813,13 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
         dim3 grid(std::max(1, std::min(64, cdiv((long long) L.pq_b * L.pq_b, 256))), n);
         k_core_build<T><<<grid, 256, 0, ctx->stream>>>(sa.rc);
         HCB_LAUNCH_CHECK("k_core_build");
-        // LQ preconditioning: QR of the transposed core, L = R^T goes to the Jacobi kernel
-        if (!blocked) HCB_TRY(launch_qr<T>(ctx, sa.qr_core, n));
-        else HCB_TRY(run_blocked_qr<T>(ctx, sa.pd_core, n, L.pq_b, L.pq_b, blk_store));
-        k_extract_l<T><<<grid, 256, 0, ctx->stream>>>(sa.lq);
-        HCB_LAUNCH_CHECK("k_extract_l");
+        if (sa.use_lq) {
+            // LQ preconditioning: QR of the transposed core, L = R^T goes to the Jacobi kernel
+            if (!blocked) HCB_TRY(launch_qr<T>(ctx, sa.qr_core, n));
+            else HCB_TRY(run_blocked_qr<T>(ctx, sa.pd_core, n, L.pq_b, L.pq_b, blk_store));
+            k_extract_l<T><<<grid, 256, 0, ctx->stream>>>(sa.lq);
+            HCB_LAUNCH_CHECK("k_extract_l");
+        }
     }
     {
         PhaseScope ph(ctx, 7);

@@ -32,6 +32,23 @@ struct RecompProb {
     int wcols;  // columns each W temporary can hold
     // LQ preconditioning of the core before the Jacobi sweeps: MT = M^T (b x a, ld b) is QR-factored, L = R^T
     T *MT, *tauM, *Lb;  // Lb: a x b (ld a) lower-trapezoidal factor handed to the Jacobi kernel
+    // column ordering of the stacks: they are assembled unsorted in SU0 / SV0 (the VC buffers, free until the QR) and
+    // gathered into UW / VW sorted by decreasing V-stack column norm; pos[c] = destination column of stack column c
+    T *SU0, *SV0;
+    int *pos;
+};
+
+// Preconditioning of the product term (CCC): an orthogonal J (ka x ka) that makes the rows of J^T (T1 * BR) mutually
+// orthogonal.  U_AB' = AL * J and V_AB' = J^T * T2 give the SAME product AL * T2, but the V stack then has orthogonal
+// columns inside each of its two parts, and -- with the columns sorted by norm -- the core K = RU * RV^T needs ~6
+// Jacobi sweeps instead of ~20 (11 with LQ preconditioning); numpy emulation of the exact kernel logic, r = 126..204.
+template<typename T>
+struct PrecondProb {
+    const T *T1;   // ka x kb (ld ka)
+    const T *BR;   // right factor of op(B): kb x n as (ptr, ld, trans)
+    T *J;          // ka x ka (ld ka)
+    T *T1J;        // kb x ka (ld kb) = T1^T * J
+    int ka, kb, n, ldbr, tbr, active;
 };
 
 // One panel to be QR-factored by the blocked machinery (a stack panel of the recompression, or the transposed core).
@@ -55,8 +72,11 @@ struct SetupArgs {
     size_t o_vcu, o_vcv, o_tbu, o_tbv, o_wbu, o_wbv;  // blocked-QR scratch
     size_t o_mt, o_taum, o_lb, o_vcm, o_tbm, o_wbm;     // core LQ preconditioning scratch
     int wcols;
+    int use_lq;              // 1: LQ-precondition the core before the Jacobi sweeps
     PanelDesc<T> *pd_stack;  // 2 per tile (U stack, V stack)
     PanelDesc<T> *pd_core;   // 1 per tile (transposed core)
+    PrecondProb<T> *pc;      // 1 per tile (CCC only)
+    size_t o_pj, o_pos;      // J (kA_b^2 elements) and pos (r_b ints, stored in T-sized slots)
     QrProb<T> *qr_core;      // 1 per tile: unblocked QR of the transposed core (small-rank path)
     LqProb<T> *lq;           // 1 per tile
     int kA_b, kB_b, kC_b, r_b;  // rank bounds the scratch was sized for
@@ -126,6 +146,10 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
     const T *BRp = s.opB ? BU : BV; const int BRld = s.opB ? B.m : kb, BRt = s.opB;
     T *CU = Cd, *CV = Cd + (size_t) C.m * C.max_rank;
     T *W1 = slab + s.o_w1, *W2 = slab + s.o_w2, *UW = slab + s.o_uw, *VW = slab + s.o_vw;
+    T *SU0 = slab + s.o_vcu, *SV0 = slab + s.o_vcv;  // unsorted stacks live in the (still unused) VC buffers
+    T *PJ = slab + s.o_pj;
+    PrecondProb<T> pc;
+    memset(&pc, 0, sizeof(pc));
     const T one = T(1), zero = T(0);
     int kp = 0;  // rank of the product term entering the recompression
 
@@ -153,19 +177,21 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
                 break;
             case CDC:  // U_AB = AL (m x ka) ; V_AB^T = op(B)^T * AR^T (n x ka)
                 kp = ka;
-                c1 = mk_copy<T>(ALp, ALld, UW + (size_t) m * kc, m, m, ka, ALt, s.alpha);
-                g1 = mk_gemm<T>(Bd, B.ld, !s.opB, ARp, ARld, !ARt, VW + (size_t) n * kc, n, n, ka, kdim, one, zero);
+                c1 = mk_copy<T>(ALp, ALld, SU0 + (size_t) m * kc, m, m, ka, ALt, s.alpha);
+                g1 = mk_gemm<T>(Bd, B.ld, !s.opB, ARp, ARld, !ARt, SV0 + (size_t) n * kc, n, n, ka, kdim, one, zero);
                 break;
             case DCC:  // U_AB = alpha*op(A)*BL (m x kb) ; V_AB^T = BR^T (n x kb)
                 kp = kb;
-                g1 = mk_gemm<T>(Ad, A.ld, s.opA, BLp, BLld, BLt, UW + (size_t) m * kc, m, m, kb, kdim, s.alpha, zero);
-                c1 = mk_copy<T>(BRp, BRld, VW + (size_t) n * kc, n, n, kb, !BRt, one);
+                g1 = mk_gemm<T>(Ad, A.ld, s.opA, BLp, BLld, BLt, SU0 + (size_t) m * kc, m, m, kb, kdim, s.alpha, zero);
+                c1 = mk_copy<T>(BRp, BRld, SV0 + (size_t) n * kc, n, n, kb, !BRt, one);
                 break;
             case CCC:  // T1 = AR*BL (ka x kb) ; V_AB^T = BR^T * T1^T (n x ka) ; U_AB = AL  (HCore.cpp:221-232,300-313)
                 kp = ka;
                 g1 = mk_gemm<T>(ARp, ARld, ARt, BLp, BLld, BLt, W1, ka, ka, kb, kdim, one, zero);
-                g2 = mk_gemm<T>(BRp, BRld, !BRt, W1, ka, 1, VW + (size_t) n * kc, n, n, ka, kb, one, zero);
-                c1 = mk_copy<T>(ALp, ALld, UW + (size_t) m * kc, m, m, ka, ALt, s.alpha);
+                // k_precond_product: J, T1J = T1^T J (W2).  V_AB'^T = BR^T * T1J, U_AB' = alpha * AL * J
+                pc = PrecondProb<T>{W1, BRp, PJ, W2, ka, kb, n, BRld, BRt, 1};
+                g2 = mk_gemm<T>(BRp, BRld, !BRt, W2, kb, 0, SV0 + (size_t) n * kc, n, n, ka, kb, one, zero);
+                g3 = mk_gemm<T>(ALp, ALld, ALt, PJ, ka, 0, SU0 + (size_t) m * kc, m, m, ka, ka, s.alpha, zero);
                 break;
         }
         if (cc && s.mix != DDC) {
@@ -174,8 +200,10 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
             if (r > s.r_b) {
                 bad = 1;
             } else {
-                c0 = mk_copy<T>(CU, m, UW, m, m, kc, 0, one);
-                c2 = mk_copy<T>(CV, kc, VW, n, n, kc, 1, s.beta);
+                c0 = mk_copy<T>(CU, m, SU0, m, m, kc, 0, one);
+                c2 = mk_copy<T>(CV, kc, SV0, n, n, kc, 1, s.beta);
+                rc.SU0 = SU0; rc.SV0 = SV0;
+                rc.pos = reinterpret_cast<int *>(slab + s.o_pos);
                 const int p = m < r ? m : r, q = n < r ? n : r;
                 q0 = QrProb<T>{UW, slab + s.o_tauu, m, r, m};
                 q1 = QrProb<T>{VW, slab + s.o_tauv, n, r, n};
@@ -192,8 +220,8 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
                 rc.transposed = p < q;
                 rc.a = rc.transposed ? q : p;
                 rc.b = rc.transposed ? p : q;
-                // Jacobi runs on the LQ factor L of M (same left vectors and singular values, about half the sweeps)
-                sv = SvdProb<T>{rc.Lb, slab + s.o_j, rc.Us, rc.Vs, rc.sigma, rc.info, rc.a, rc.b, rc.a, rc.a, rc.b};
+                // Jacobi runs on M itself when the stacks are sorted (use_lq == 0), else on its LQ factor L
+                sv = SvdProb<T>{s.use_lq ? rc.Lb : rc.M, slab + s.o_j, rc.Us, rc.Vs, rc.sigma, rc.info, rc.a, rc.b, rc.a, rc.a, rc.b};
                 pdu = PanelDesc<T>{UW, rc.tauU, rc.VC[0], rc.TB[0], rc.WB[0], m, r, s.wcols, 1};
                 pdv = PanelDesc<T>{VW, rc.tauV, rc.VC[1], rc.TB[1], rc.WB[1], n, r, s.wcols, 1};
                 pdm = PanelDesc<T>{rc.MT, rc.tauM, slab + s.o_vcm, slab + s.o_tbm, slab + s.o_wbm, rc.b, rc.a, s.wcols, 1};
@@ -214,6 +242,7 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
         sv.a = sv.b = 0;
         rc.active = 0;
         pdu.active = pdv.active = pdm.active = 0;
+        pc.active = 0;
         qm.m = qm.n = 0;
         lq.a = lq.b = 0;
         if (s.info) s.info[t] = 4;  // rank exceeded the bound the scratch was sized for: tile left untouched
@@ -229,7 +258,147 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
     s.pd_stack[2 * t + 0] = pdu; s.pd_stack[2 * t + 1] = pdv;
     s.pd_core[t] = pdm;
     s.qr_core[t] = qm;
+    s.pc[t] = pc;
     s.lq[t] = lq;
+}
+
+// One CTA (256 threads) per tile.  N = (T1 * D)^T with D = row norms of BR (kb x ka, columns = rows of T1*D) is
+// orthogonalised by one-sided Jacobi while the rotations are accumulated in J (orthogonal to rounding by
+// construction); then T1J = T1^T * J.  Everything lives in shared memory; if it does not fit, J = I (no
+// preconditioning, same product).
+template<typename T>
+__global__ void __launch_bounds__(256) k_precond_product(const PrecondProb<T> *__restrict__ probs, int smem_elems) {
+    extern __shared__ __align__(16) unsigned char smem_raw_pc[];
+    T *sm = reinterpret_cast<T *>(smem_raw_pc);
+    const PrecondProb<T> p = probs[blockIdx.x];
+    if (!p.active) return;
+    const int ka = p.ka, kb = p.kb;
+    if (ka <= 0 || kb <= 0) return;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
+    __shared__ int s_rot;
+    const bool fits = (size_t) ka * kb + (size_t) ka * ka + (size_t) kb <= (size_t) smem_elems;
+    if (!fits) {
+        for (int idx = tid; idx < ka * ka; idx += nthr) p.J[idx] = (idx % ka == idx / ka) ? T(1) : T(0);
+        for (int idx = tid; idx < kb * ka; idx += nthr) p.T1J[idx] = p.T1[(size_t) (idx / kb) + (size_t) (idx % kb) * ka];
+        return;
+    }
+    T *N = sm, *J = sm + (size_t) ka * kb, *d = J + (size_t) ka * ka;
+    for (int j = w; j < kb; j += nw) {  // row norms of BR
+        T ss = T(0);
+        for (int c = lane; c < p.n; c += 32) {
+            const T x = p.tbr ? p.BR[(size_t) c + (size_t) j * p.ldbr] : p.BR[(size_t) j + (size_t) c * p.ldbr];
+            ss = fma(x, x, ss);
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) d[j] = t_sqrt(ss);
+    }
+    for (int idx = tid; idx < ka * ka; idx += nthr) J[idx] = (idx % ka == idx / ka) ? T(1) : T(0);
+    __syncthreads();
+    for (int idx = tid; idx < ka * kb; idx += nthr) {
+        const int j = idx % kb, i = idx / kb;  // N(j, i) = T1(i, j) * d(j)
+        N[idx] = p.T1[(size_t) i + (size_t) j * ka] * d[j];
+    }
+    __syncthreads();
+    const T tol = Eps<T>::v() * t_sqrt((T) kb);
+    const int nb2 = (ka + 1) & ~1;
+    bool converged = ka < 2;
+    for (int sweep = 0; sweep < 30 && !converged; ++sweep) {
+        __syncthreads();
+        if (tid == 0) s_rot = 0;
+        __syncthreads();
+        for (int round = 0; round < nb2 - 1; ++round) {
+            for (int slot = w; slot < nb2 / 2; slot += nw) {
+                int x, y;
+                const int mod = nb2 - 1;
+                if (slot == 0) { x = mod; y = round % mod; } else { x = (round + slot) % mod; y = (round - slot + mod) % mod; }
+                if (x > y) { const int tt = x; x = y; y = tt; }
+                if (y >= ka) continue;
+                T *nx = N + (size_t) x * kb, *ny = N + (size_t) y * kb;
+                T alpha = T(0), beta = T(0), gamma = T(0);
+                for (int i = lane; i < kb; i += 32) {
+                    const T u = nx[i], v = ny[i];
+                    alpha = fma(u, u, alpha); beta = fma(v, v, beta); gamma = fma(u, v, gamma);
+                }
+                alpha = warp_sum(alpha); beta = warp_sum(beta); gamma = warp_sum(gamma);
+                if (!(t_abs(gamma) > tol * t_sqrt(alpha) * t_sqrt(beta)) || gamma == T(0)) continue;
+                if (lane == 0) s_rot = 1;
+                const T zeta = (beta - alpha) / (T(2) * gamma);
+                const T t = (zeta >= T(0) ? T(1) : T(-1)) / (t_abs(zeta) + t_sqrt(fma(zeta, zeta, T(1))));
+                const T c = T(1) / t_sqrt(fma(t, t, T(1))), sn = c * t;
+                for (int i = lane; i < kb; i += 32) {
+                    const T u = nx[i], v = ny[i];
+                    nx[i] = fma(-sn, v, c * u);
+                    ny[i] = fma(sn, u, c * v);
+                }
+                T *jx = J + (size_t) x * ka, *jy = J + (size_t) y * ka;
+                for (int i = lane; i < ka; i += 32) {
+                    const T u = jx[i], v = jy[i];
+                    jx[i] = fma(-sn, v, c * u);
+                    jy[i] = fma(sn, u, c * v);
+                }
+            }
+            __syncthreads();
+        }
+        converged = (s_rot == 0);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < ka * ka; idx += nthr) p.J[idx] = J[idx];
+    for (int idx = tid; idx < kb * ka; idx += nthr) {  // T1J(j, i') = sum_i T1(i, j) * J(i, i')
+        const int j = idx % kb, ip = idx / kb;
+        T acc = T(0);
+        for (int i = 0; i < ka; ++i) acc = fma(p.T1[(size_t) i + (size_t) j * ka], J[(size_t) i + (size_t) ip * ka], acc);
+        p.T1J[idx] = acc;
+    }
+}
+
+// Column order of the stacks: pos[c] = rank of V-stack column c by decreasing norm (stable).  One CTA per tile.
+template<typename T>
+__global__ void __launch_bounds__(256) k_stack_order(const RecompProb<T> *__restrict__ probs, int smem_elems) {
+    extern __shared__ __align__(16) unsigned char smem_raw_so[];
+    T *nrm = reinterpret_cast<T *>(smem_raw_so);
+    const RecompProb<T> p = probs[blockIdx.x];
+    if (!p.active) return;
+    const int r = p.r, n = p.n;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (r > smem_elems) {  // cannot rank in shared memory: keep the natural order
+        for (int c = threadIdx.x; c < r; c += blockDim.x) p.pos[c] = c;
+        return;
+    }
+    for (int c = w; c < r; c += nw) {
+        const T *col = p.SV0 + (size_t) c * n;
+        T ss = T(0);
+        for (int i = lane; i < n; i += 32) ss = fma(col[i], col[i], ss);
+        ss = warp_sum(ss);
+        if (lane == 0) nrm[c] = ss;
+    }
+    __syncthreads();
+    for (int c = w; c < r; c += nw) {
+        const T sc = nrm[c];
+        int pos = 0;
+        for (int o = lane; o < r; o += 32) {
+            const T so = nrm[o];
+            pos += (so > sc || (so == sc && o < c)) ? 1 : 0;
+        }
+        pos = warp_sum(pos);
+        if (lane == 0) p.pos[c] = pos;
+    }
+}
+
+// UW[:, pos[c]] = SU0[:, c], VW[:, pos[c]] = SV0[:, c]  -- the same permutation on both stacks leaves SU * SV^T
+// unchanged.  grid = (column chunks, 2 * n_tiles)
+template<typename T>
+__global__ void __launch_bounds__(256) k_permute_stacks(const RecompProb<T> *__restrict__ probs) {
+    const RecompProb<T> p = probs[blockIdx.y >> 1];
+    if (!p.active) return;
+    const int side = blockIdx.y & 1;
+    const int rows = side ? p.n : p.m;
+    const T *src = side ? p.SV0 : p.SU0;
+    T *dst = side ? p.VW : p.UW;
+    for (int c = blockIdx.x; c < p.r; c += gridDim.x) {
+        const T *s = src + (size_t) c * rows;
+        T *d = dst + (size_t) p.pos[c] * rows;
+        for (int i = threadIdx.x; i < rows; i += blockDim.x) d[i] = s[i];
+    }
 }
 
 // Descriptors of the blocked QR of both stacks, for every NBQ-column block at once.  One thread per (block, panel);
