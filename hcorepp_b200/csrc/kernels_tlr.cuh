@@ -283,15 +283,35 @@ __global__ void __launch_bounds__(256) k_precond_product(const PrecondProb<T> *_
         return;
     }
     T *N = sm, *J = sm + (size_t) ka * kb, *d = J + (size_t) ka * ka;
-    for (int j = w; j < kb; j += nw) {  // row norms of BR
-        T ss = T(0);
-        for (int c = lane; c < p.n; c += 32) {
-            const T x = p.tbr ? p.BR[(size_t) c + (size_t) j * p.ldbr] : p.BR[(size_t) j + (size_t) c * p.ldbr];
-            ss = fma(x, x, ss);
+    // row norms of BR (kb x n).  Stored N (ld = kb): consecutive threads walk down a column (rows j contiguous), a
+    // group of kbp threads per column, nthr / kbp columns in flight; stored T: lanes run along the row.
+    for (int j = tid; j < kb; j += nthr) d[j] = T(0);
+    __syncthreads();
+    if (!p.tbr) {
+        int kbp = 32;
+        while (kbp < kb && kbp < nthr) kbp <<= 1;      // threads per column (power of two >= min(kb, nthr))
+        const int groups = nthr / kbp, gidx = tid / kbp, jl = tid % kbp;
+        for (int j = jl; j < kb; j += kbp) {
+            T ss = T(0);
+            for (int c = gidx; c < p.n; c += groups) {
+                const T x = p.BR[(size_t) j + (size_t) c * p.ldbr];
+                ss = fma(x, x, ss);
+            }
+            atomicAdd(&d[j], ss);
         }
-        ss = warp_sum(ss);
-        if (lane == 0) d[j] = t_sqrt(ss);
+    } else {
+        for (int j = w; j < kb; j += nw) {
+            T ss = T(0);
+            for (int c = lane; c < p.n; c += 32) {
+                const T x = p.BR[(size_t) c + (size_t) j * p.ldbr];
+                ss = fma(x, x, ss);
+            }
+            ss = warp_sum(ss);
+            if (lane == 0) d[j] = ss;
+        }
     }
+    __syncthreads();
+    for (int j = tid; j < kb; j += nthr) d[j] = t_sqrt(d[j]);
     for (int idx = tid; idx < ka * ka; idx += nthr) J[idx] = (idx % ka == idx / ka) ? T(1) : T(0);
     __syncthreads();
     for (int idx = tid; idx < ka * kb; idx += nthr) {
