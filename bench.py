@@ -242,6 +242,13 @@ def main():
     else:
         one_pass, Cm, info, n_local_gemms, A, B = setup_distributed(args, hc, ctx, dist, torch, synth, krank, cap_in, P, Q,
                                                                     pr, pc, prm)
+        if args.kc_bound == 0:  # untimed calibration pass, bound agreed across ranks
+            one_pass()
+            ctx.Sync()
+            mx = Cm.ranks.max().to(torch.int64)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            args.kc_bound = int(min(Cm.max_rank, (int(mx.item()) + 8 + 7) // 8 * 8))
+            Cm.set_rank_bound(args.kc_bound)
     total_gemms = n_local_gemms * world
 
     # ---- warm-up (also grows the scratch arena once), then the timed region
