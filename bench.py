@@ -242,6 +242,7 @@ def main():
     else:
         one_pass, Cm, info, n_local_gemms, A, B = setup_distributed(args, hc, ctx, dist, torch, synth, krank, cap_in, P, Q,
                                                                     pr, pc, prm)
+        verify = lambda: verify_distributed(args, torch, hc, synth, Cm, krank, P, Q, pr, pc)
         if args.kc_bound == 0:  # untimed calibration pass, bound agreed across ranks
             one_pass()
             ctx.Sync()
@@ -316,6 +317,8 @@ def main():
         "gpu_launches": launches, "jacobi_or_bound_flags": bad, "jacobi_sweeps_last_step_max": sweeps,
         "c_rank_bound": args.kc_bound,
     }
+    if world > 1 and rank_env == 0:
+        result["parity"] = verify()
     if rank_env == 0:
         result["clocks"] = clocks
         phases = {}
@@ -549,6 +552,37 @@ def setup_distributed(args, hc, ctx, dist, torch, synth, krank, cap_in, P, Q, pr
             check(fn(ctx.h, n, da, 0, db, 0, Cm.descs, C.c_double(1.0), C.c_double(1.0), C.byref(cprm), info.data_ptr()))
             done[b].record(main)
     return one_pass, Cm, info, mt_l * nt_l * kt, A_loc, B_loc
+
+
+def verify_distributed(args, torch, hc, synth, Cm, krank, P, Q, pr, pc):
+    """Rank-local plumbing check for N > 1: this rank's C(0,0) tile against the dense sum over k of A(j,k) B(k,i), with
+    the A / B tiles REGENERATED here from their owners' deterministic generator streams (so a panel that was broadcast
+    from the wrong owner, or landed in the wrong slot, shows up as an O(1) error).  The TLR arithmetic itself is
+    checked against the reference in the single-GPU run."""
+    from hcorepp_b200 import partition as part
+    T, nb = args.tiles, args.nb
+    kt = T
+    dense = torch.zeros(nb, nb, dtype=torch.float64, device=Cm.buf.device)
+    cache = {}
+
+    def owner_tiles(kind, owner):
+        if (kind, owner) not in cache:
+            opr, opc = part.grid_pos(owner, P, Q)
+            cnt = len(part.owned_indices(kt, Q, opc)) if kind == "A" else len(part.owned_indices(kt, P, opr))
+            cache[(kind, owner)] = synth(T * max(cnt, 1), (1000 if kind == "A" else 2000) + owner)
+        return cache[(kind, owner)]
+    for k in range(kt):
+        oa, ob = part.owner_of_a(pr, k, P, Q), part.owner_of_b(k, pc, P, Q)
+        Ua, Va = owner_tiles("A", oa)
+        Ub, Vb = owner_tiles("B", ob)
+        la, lb = 0 + (k // Q) * T, 0 + (k // P) * T      # local linear index of A(jl=0, kl) / B(il=0, kl) at the owner
+        Am = Ua[la].t() @ Va[la].t()                      # (nb x k)(k x nb)
+        Bm = Ub[lb].t() @ Vb[lb].t()
+        dense += Am @ Bm
+    U, V = Cm.GetTile(0, 0).factors()
+    err = (torch.linalg.norm(U @ V - dense) / torch.linalg.norm(dense)).item()
+    return {"rel_fro_err_tile00_vs_dense": err, "tolerance": 1e-5, "pass": bool(err <= 1e-5),
+            "note": "distributed plumbing check; TLR-vs-reference parity is the N=1 block"}
 
 
 def _lib():
