@@ -12,6 +12,36 @@ namespace hcb {
 // One CTA per panel. Per column j: (1) CTA-wide norm of A[j+1:, j]; (2) thread 0 forms beta/tau; (3) v scaled in
 // place; (4) every warp owns a set of trailing columns and applies H_j = I - tau v v^T to each of them with one
 // fused pass (dot product, warp-shuffle reduction, rank-1 update); column reads are fully coalesced.
+// 4-way unrolled strided dot product / axpy over rows [i0, m): independent accumulators keep 8 loads in flight per
+// lane (the straight loop serialised on L2 latency: 1.06 ms per 512-panel launch, ncu launch list r01).
+template<typename T>
+__device__ __forceinline__ T lane_dot(const T *__restrict__ x, const T *__restrict__ y, int i0, int m, int lane) {
+    T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);
+    int i = i0 + lane;
+    for (; i + 96 < m; i += 128) {
+        d0 = fma(x[i], y[i], d0);
+        d1 = fma(x[i + 32], y[i + 32], d1);
+        d2 = fma(x[i + 64], y[i + 64], d2);
+        d3 = fma(x[i + 96], y[i + 96], d3);
+    }
+    for (; i < m; i += 32) d0 = fma(x[i], y[i], d0);
+    return (d0 + d1) + (d2 + d3);
+}
+
+template<typename T>
+__device__ __forceinline__ void lane_axpy(T t, const T *__restrict__ x, T *__restrict__ y, int i0, int m, int lane) {
+    int i = i0 + lane;
+    for (; i + 96 < m; i += 128) {
+        const T a0 = x[i], a1 = x[i + 32], a2 = x[i + 64], a3 = x[i + 96];
+        const T b0 = y[i], b1 = y[i + 32], b2 = y[i + 64], b3 = y[i + 96];
+        y[i] = fma(-t, a0, b0);
+        y[i + 32] = fma(-t, a1, b1);
+        y[i + 64] = fma(-t, a2, b2);
+        y[i + 96] = fma(-t, a3, b3);
+    }
+    for (; i < m; i += 32) y[i] = fma(-t, x[i], y[i]);
+}
+
 template<typename T>
 __global__ void __launch_bounds__(512) k_geqrf_batched(const QrProb<T> *__restrict__ probs) {
     const QrProb<T> p = probs[blockIdx.x];
@@ -26,9 +56,17 @@ __global__ void __launch_bounds__(512) k_geqrf_batched(const QrProb<T> *__restri
     for (int j = 0; j < kmax; ++j) {
         T *col = A + (size_t) j * lda;
         // (1) ||A[j+1:m, j]||^2
-        T ss = T(0);
-        for (int i = j + 1 + tid; i < m; i += nthr) { const T x = col[i]; ss = fma(x, x, ss); }
-        ss = block_sum(ss, red);
+        T s0 = T(0), s1 = T(0);
+        {
+            int i = j + 1 + tid;
+            for (; i + nthr < m; i += 2 * nthr) {
+                const T x = col[i], y = col[i + nthr];
+                s0 = fma(x, x, s0);
+                s1 = fma(y, y, s1);
+            }
+            for (; i < m; i += nthr) { const T x = col[i]; s0 = fma(x, x, s0); }
+        }
+        const T ss = block_sum(s0 + s1, red);
         // (2) Householder scalars
         if (tid == 0) {
             const T alpha = col[j];
@@ -53,14 +91,13 @@ __global__ void __launch_bounds__(512) k_geqrf_batched(const QrProb<T> *__restri
             // (4) trailing update, one warp per column
             for (int c = j + 1 + w; c < n; c += nw) {
                 T *cc = A + (size_t) c * lda;
-                T dot = T(0);
-                for (int i = j + 1 + lane; i < m; i += 32) dot = fma(col[i], cc[i], dot);
+                T dot = lane_dot<T>(col, cc, j + 1, m, lane);
                 dot = warp_sum(dot);
                 dot += cc[j];  // v(0) = 1
                 const T t = tau * dot;
                 __syncwarp();  // every lane has read cc[j] before lane 0 overwrites it
                 if (lane == 0) cc[j] -= t;
-                for (int i = j + 1 + lane; i < m; i += 32) cc[i] = fma(-t, col[i], cc[i]);
+                lane_axpy<T>(t, col, cc, j + 1, m, lane);
             }
         }
         __syncthreads();
@@ -91,13 +128,15 @@ __global__ void __launch_bounds__(256) k_apply_reflectors(const ReflProb<T> *__r
             if (tau == T(0)) continue;
             const T *v = p.V + (size_t) j * p.ldv;
             T dot = T(0);
-            for (int i = j + 1 + lane; i < len; i += 32) dot = fma(v[i], x[(size_t) i * estride], dot);
+            if (estride == 1) dot = lane_dot<T>(v, x, j + 1, len, lane);
+            else for (int i = j + 1 + lane; i < len; i += 32) dot = fma(v[i], x[(size_t) i * estride], dot);
             dot = warp_sum(dot);
             dot += x[(size_t) j * estride];
             const T t = tau * dot;
             __syncwarp();
             if (lane == 0) x[(size_t) j * estride] -= t;
-            for (int i = j + 1 + lane; i < len; i += 32) x[(size_t) i * estride] = fma(-t, v[i], x[(size_t) i * estride]);
+            if (estride == 1) lane_axpy<T>(t, v, x, j + 1, len, lane);
+            else for (int i = j + 1 + lane; i < len; i += 32) x[(size_t) i * estride] = fma(-t, v[i], x[(size_t) i * estride]);
             __syncwarp();
         }
     }
@@ -142,8 +181,7 @@ __global__ void __launch_bounds__(256) k_larft_extract(const LarftProb<T> *__res
         const int i = pr / jb, j = pr % jb;
         if (i >= j) continue;
         const T *vi = p.Vc + (size_t) i * p.ldvc, *vj = p.Vc + (size_t) j * p.ldvc;
-        T d = T(0);
-        for (int r = j + lane; r < rows; r += 32) d = fma(vi[r], vj[r], d);  // vj is zero above row j
+        T d = lane_dot<T>(vi, vj, j, rows, lane);  // vj is zero above row j
         d = warp_sum(d);
         if (lane == 0) G[i][j] = d;
     }

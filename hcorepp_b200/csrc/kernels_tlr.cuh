@@ -504,9 +504,17 @@ __global__ void __launch_bounds__(256) k_core_build(const RecompProb<T> *__restr
     const int total = p.p * p.q;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int i = idx % p.p, j = idx / p.p;
-        T acc = T(0);
-        for (int l = (i > j ? i : j); l < p.r; ++l)
-            acc = fma(p.UW[(size_t) i + (size_t) l * p.m], p.VW[(size_t) j + (size_t) l * p.n], acc);
+        T acc0 = T(0), acc1 = T(0), acc2 = T(0), acc3 = T(0);
+        int l = (i > j ? i : j);
+        const T *pu = p.UW + (size_t) i, *pv = p.VW + (size_t) j;
+        for (; l + 3 < p.r; l += 4) {  // independent accumulators: 8 loads in flight
+            acc0 = fma(pu[(size_t) l * p.m], pv[(size_t) l * p.n], acc0);
+            acc1 = fma(pu[(size_t) (l + 1) * p.m], pv[(size_t) (l + 1) * p.n], acc1);
+            acc2 = fma(pu[(size_t) (l + 2) * p.m], pv[(size_t) (l + 2) * p.n], acc2);
+            acc3 = fma(pu[(size_t) (l + 3) * p.m], pv[(size_t) (l + 3) * p.n], acc3);
+        }
+        for (; l < p.r; ++l) acc0 = fma(pu[(size_t) l * p.m], pv[(size_t) l * p.n], acc0);
+        const T acc = (acc0 + acc1) + (acc2 + acc3);
         // M (a x b, ld a) and its transpose MT (b x a, ld b), which is the one that gets QR-factored
         if (p.transposed) {
             p.M[(size_t) j + (size_t) i * p.a] = acc;
