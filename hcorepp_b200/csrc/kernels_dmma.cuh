@@ -37,22 +37,11 @@ __global__ void __launch_bounds__(128, 3) k_gemm_dmma(const GemmProb<double> *__
 
     for (int tile = blockIdx.x; tile < tiles_m * tiles_n; tile += gridDim.x) {
         const int row0 = (tile % tiles_m) * BM, col0 = (tile / tiles_m) * BN;
-        // accumulators start as beta*C: the C tile is requested up front, together with the first operand stage, so
-        // its DRAM latency overlaps the staging instead of being exposed after the last DMMA (rank-32 updates spend
-        // most of their time on the C read-modify-write).  alpha is folded into the staged A operand.
         double acc[4][4][2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int gc = col0 + wn * 32 + j * 8 + 2 * c + h;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int gr = row0 + wm * 32 + i * 8 + g;
-                    acc[i][j][h] = (p.beta != 0.0 && gr < p.m && gc < p.n)
-                                       ? p.beta * p.C[(size_t) gr + (size_t) gc * p.ldc] : 0.0;
-                }
-            }
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
         double ra[A_PER_THR], rb[B_PER_THR];
 
         auto fetch = [&](int k0) {
@@ -63,7 +52,7 @@ __global__ void __launch_bounds__(128, 3) k_gemm_dmma(const GemmProb<double> *__
                 if (p.ta == 0) { r = idx % BM; kk = idx / BM; } else { kk = idx % BK; r = idx / BK; }
                 const int gr = row0 + r, gk = k0 + kk;
                 ra[q] = (gr < p.m && gk < p.k)
-                            ? p.alpha * (p.ta == 0 ? p.A[(size_t) gr + (size_t) gk * p.lda] : p.A[(size_t) gk + (size_t) gr * p.lda])
+                            ? (p.ta == 0 ? p.A[(size_t) gr + (size_t) gk * p.lda] : p.A[(size_t) gk + (size_t) gr * p.lda])
                             : 0.0;
             }
 #pragma unroll
@@ -131,7 +120,10 @@ __global__ void __launch_bounds__(128, 3) k_gemm_dmma(const GemmProb<double> *__
                 for (int i = 0; i < 4; ++i) {
                     const int gr = row0 + wm * 32 + i * 8 + g;
                     if (gr >= p.m) continue;
-                    p.C[(size_t) gr + (size_t) gc * p.ldc] = acc[i][j][h];
+                    double *cp = p.C + (size_t) gr + (size_t) gc * p.ldc;
+                    double v = p.alpha * acc[i][j][h];
+                    if (p.beta != 0.0) v = fma(p.beta, *cp, v);
+                    *cp = v;
                 }
             }
         }

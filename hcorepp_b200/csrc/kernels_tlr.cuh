@@ -319,10 +319,17 @@ __global__ void __launch_bounds__(256) k_precond_product(const PrecondProb<T> *_
         N[idx] = p.T1[(size_t) i + (size_t) j * ka] * d[j];
     }
     __syncthreads();
-    const T tol = Eps<T>::v() * t_sqrt((T) kb);
+    // J only has to be a good preconditioner (ANY orthogonal J gives the same product), so the sweeps stop at a loose
+    // relative orthogonality of sqrt(eps), ignore columns at rounding level, and are capped at 8.
+    const T tol = t_sqrt(Eps<T>::v());
+    T t1max = T(0);
+    for (int idx = lane; idx < ka * kb; idx += 32) t1max = t_abs(N[idx]) > t1max ? t_abs(N[idx]) : t1max;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const T other = __shfl_xor_sync(0xffffffffu, t1max, o); t1max = other > t1max ? other : t1max; }
+    const T noise2 = (Eps<T>::v() * t1max) * (Eps<T>::v() * t1max) * (T) kb;
     const int nb2 = (ka + 1) & ~1;
     bool converged = ka < 2;
-    for (int sweep = 0; sweep < 30 && !converged; ++sweep) {
+    for (int sweep = 0; sweep < 8 && !converged; ++sweep) {
         __syncthreads();
         if (tid == 0) s_rot = 0;
         __syncthreads();
@@ -341,6 +348,7 @@ __global__ void __launch_bounds__(256) k_precond_product(const PrecondProb<T> *_
                 }
                 alpha = warp_sum(alpha); beta = warp_sum(beta); gamma = warp_sum(gamma);
                 if (!(t_abs(gamma) > tol * t_sqrt(alpha) * t_sqrt(beta)) || gamma == T(0)) continue;
+                if (!(alpha > noise2) || !(beta > noise2)) continue;
                 if (lane == 0) s_rot = 1;
                 const T zeta = (beta - alpha) / (T(2) * gamma);
                 const T t = (zeta >= T(0) ? T(1) : T(-1)) / (t_abs(zeta) + t_sqrt(fma(zeta, zeta, T(1))));
@@ -365,9 +373,17 @@ __global__ void __launch_bounds__(256) k_precond_product(const PrecondProb<T> *_
     for (int idx = tid; idx < ka * ka; idx += nthr) p.J[idx] = J[idx];
     for (int idx = tid; idx < kb * ka; idx += nthr) {  // T1J(j, i') = sum_i T1(i, j) * J(i, i')
         const int j = idx % kb, ip = idx / kb;
-        T acc = T(0);
-        for (int i = 0; i < ka; ++i) acc = fma(p.T1[(size_t) i + (size_t) j * ka], J[(size_t) i + (size_t) ip * ka], acc);
-        p.T1J[idx] = acc;
+        const T *t1 = p.T1 + (size_t) j * ka, *jc = J + (size_t) ip * ka;
+        T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+        int i = 0;
+        for (; i + 3 < ka; i += 4) {
+            a0 = fma(t1[i], jc[i], a0);
+            a1 = fma(t1[i + 1], jc[i + 1], a1);
+            a2 = fma(t1[i + 2], jc[i + 2], a2);
+            a3 = fma(t1[i + 3], jc[i + 3], a3);
+        }
+        for (; i < ka; ++i) a0 = fma(t1[i], jc[i], a0);
+        p.T1J[idx] = (a0 + a1) + (a2 + a3);
     }
 }
 
