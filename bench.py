@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--kc-bound", type=int, default=0,
                     help="rank bound used to size scratch for C tiles (0: calibrate with one untimed pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     return ap.parse_args()
 
@@ -355,7 +356,7 @@ def main():
                 "c_rank_final_mean": float(rk_all[-1].mean()), "c_rank_max": float(rk_all.max()),
             }
         # ---- end-to-end: same pass through the public API with HOST buffers (pinned), H2D + D2H inside the timing
-        if world == 1:
+        if world == 1 and not args.no_e2e:
             result["e2e"] = run_e2e(args, torch, hc, ctx, A, B, Cm, Ua, Va, Ub, Vb, krank, prm, info, total_gemms)
             if not args.no_cpu_baseline:
                 try:

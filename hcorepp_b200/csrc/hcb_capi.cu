@@ -183,23 +183,52 @@ int launch_svd(hcb_ctx *ctx, const SvdProb<T> *d_probs, int n_probs, int a_bound
 // Blocked Householder QR of `cnt` panels described on the device (pds): per NBQ-column block -- panel factorisation,
 // T_b + clean V_b, then the trailing update A2 -= V_b T_b^T (V_b^T A2) as three batched GEMMs.
 template<typename T>
-size_t qr_block_desc_bytes(int cnt, int nblk) {
-    const size_t nb = (size_t) cnt * nblk;
+size_t qr_block_desc_bytes(int cnt, int cols_bound) {  // one descriptor set per (column block, panel)
+    const size_t nb = (size_t) cnt * cdiv(cols_bound, NBQ);
     return align_up(sizeof(QrProb<T>) * nb, 256) + align_up(sizeof(LarftProb<T>) * nb, 256) +
-           3 * align_up(sizeof(GemmProb<T>) * nb, 256);
+           3 * align_up(sizeof(GemmProb<T>) * nb, 256) + align_up(sizeof(StripJob) * nb, 256);
+}
+
+// cluster launch of the strip-resident block-reflector kernel: `cnt` jobs, rows_bound rows
+inline bool strip_path_ok(const hcb_ctx *ctx, int rows_bound) {
+    return rows_bound <= 8 * SK_ROWS && SK_SMEM_BYTES <= ctx->smem_optin;
+}
+inline int launch_strips(hcb_ctx *ctx, const StripJob *jobs, int cnt, int rows_bound) {
+    if (cnt <= 0) return HCB_OK;
+    HCB_CUDA(cudaFuncSetAttribute(k_strip_reflect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SK_SMEM_BYTES));
+    int cs = 1;
+    while (cs * SK_ROWS < rows_bound) cs <<= 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned) (cs * cnt));
+    cfg.blockDim = dim3(SK_THREADS);
+    cfg.dynamicSmemBytes = SK_SMEM_BYTES;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned) cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    HCB_CUDA(cudaLaunchKernelEx(&cfg, k_strip_reflect, jobs));
+    HCB_LAUNCH_CHECK("k_strip_reflect");
+    return HCB_OK;
 }
 
 template<typename T>
 int run_blocked_qr(hcb_ctx *ctx, const PanelDesc<T> *d_pds, int cnt, int rows_bound, int cols_bound, char *desc_store) {
-    const int nblk = cdiv(std::min(rows_bound, cols_bound), NBQ);
+    const int nfac = cdiv(std::min(rows_bound, cols_bound), NBQ);  // blocks that hold reflectors
+    const int nblk = cdiv(cols_bound, NBQ);                         // column blocks (>= nfac for a wide panel)
     const size_t nb = (size_t) cnt * nblk;
+    const bool strips = std::is_same<T, double>::value && strip_path_ok(ctx, rows_bound);
     QrBlockArrays<T> q;
     char *p = desc_store;
     q.qr = reinterpret_cast<QrProb<T> *>(p); p += align_up(sizeof(QrProb<T>) * nb, 256);
     q.lf = reinterpret_cast<LarftProb<T> *>(p); p += align_up(sizeof(LarftProb<T>) * nb, 256);
     q.gw = reinterpret_cast<GemmProb<T> *>(p); p += align_up(sizeof(GemmProb<T>) * nb, 256);
     q.gw2 = reinterpret_cast<GemmProb<T> *>(p); p += align_up(sizeof(GemmProb<T>) * nb, 256);
-    q.gup = reinterpret_cast<GemmProb<T> *>(p);
+    q.gup = reinterpret_cast<GemmProb<T> *>(p); p += align_up(sizeof(GemmProb<T>) * nb, 256);
+    q.sj = strips ? reinterpret_cast<StripJob *>(p) : nullptr;
     q.nblk = nblk;
     q.npan = cnt;
     k_setup_qr_blocks<T><<<cdiv(nblk * cnt, 128), 128, 0, ctx->stream>>>(d_pds, q);
@@ -209,6 +238,9 @@ int run_blocked_qr(hcb_ctx *ctx, const PanelDesc<T> *d_pds, int cnt, int rows_bo
     if (on_chip) HCB_CUDA(cudaFuncSetAttribute(k_panel_qr_cluster<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pq_smem));
     for (int b = 0; b < nblk; ++b) {
         const size_t o = (size_t) b * cnt;
+        // left-looking: bring column block b up to date with blocks 0..b-1 while it sits in cluster shared memory
+        if (strips && b > 0) HCB_TRY(launch_strips(ctx, q.sj + o, cnt, rows_bound));
+        if (b >= nfac) continue;
         if (on_chip) {
             // cluster of 1/2/4/8 CTAs per panel block, 512 rows each, block resident in (distributed) shared memory
             const int rows_b = std::max(1, rows_bound - b * NBQ);
@@ -236,7 +268,7 @@ int run_blocked_qr(hcb_ctx *ctx, const PanelDesc<T> *d_pds, int cnt, int rows_bo
             HCB_LAUNCH_CHECK("k_larft_extract");
         }
         const int nt_b = cols_bound - (b + 1) * NBQ;
-        if (nt_b > 0) {
+        if (!strips && nt_b > 0) {
             HCB_TRY(launch_gemm<T>(ctx, q.gw + o, cnt, NBQ, nt_b));
             HCB_TRY(launch_gemm<T>(ctx, q.gw2 + o, cnt, NBQ, nt_b));
             HCB_TRY(launch_gemm<T>(ctx, q.gup + o, cnt, rows_bound - b * NBQ, nt_b));
@@ -297,7 +329,7 @@ size_t svd_jobs_desc_bytes(int cnt, int a_bound, int b_bound) {
     return 2 * align_up(sizeof(CopyProb<T>) * cnt, 256) + align_up(sizeof(PanelDesc<T>) * cnt, 256) +
            align_up(sizeof(QrProb<T>) * cnt, 256) + align_up(sizeof(LqProb<T>) * cnt, 256) +
            align_up(sizeof(SvdProb<T>) * cnt, 256) + align_up(sizeof(GemmProb<T>) * cnt, 256) +
-           qr_block_desc_bytes<T>(cnt, L.nblk) + 256;
+           qr_block_desc_bytes<T>(cnt, a_bound) + 256;
 }
 
 template<typename T>
@@ -648,8 +680,8 @@ struct DescArrays {  // device arrays living at the front of the scratch arena
     size_t bytes = 0;
     size_t o_g1, o_g2, o_g3, o_gv, o_cp, o_qr, o_rf, o_svd, o_rc, o_rk, o_tiles;
     size_t o_bqr = 0, o_blf = 0, o_bgw = 0, o_bgw2 = 0, o_bgup = 0, o_agw = 0, o_agw2 = 0, o_agup = 0;
-    size_t o_pds = 0, o_pdc = 0, o_qrc = 0, o_lq = 0, o_pc = 0;
-    explicit DescArrays(int n, int nblk = 0) {
+    size_t o_pds = 0, o_pdc = 0, o_qrc = 0, o_lq = 0, o_pc = 0, o_asj = 0;
+    explicit DescArrays(int n, int nblk = 0, int qr_cols = 0, int rk_bound = 0) {
         size_t off = 0;
         auto take = [&](size_t b) { size_t o = off; off += align_up(b, 256); return o; };
         o_g1 = take(sizeof(GemmProb<T>) * n);
@@ -670,7 +702,8 @@ struct DescArrays {  // device arrays living at the front of the scratch arena
         o_pc = take(sizeof(PrecondProb<T>) * n);
         if (nblk > 0) {
             const size_t nb = (size_t) nblk * 2 * n;
-            o_bqr = take(qr_block_desc_bytes<T>(2 * n, nblk));
+            o_bqr = take(qr_block_desc_bytes<T>(2 * n, qr_cols));
+            o_asj = take(sizeof(StripJob) * (size_t) cdiv(std::max(rk_bound, 1), NBQ) * 2 * n);
             o_agw = take(sizeof(GemmProb<T>) * nb);
             o_agw2 = take(sizeof(GemmProb<T>) * nb);
             o_agup = take(sizeof(GemmProb<T>) * nb);
@@ -722,7 +755,8 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     HCB_TRY(classify(A, B, C, n, opA, opB, s));
     const Layout<T> L = make_layout<T>(s);
     const bool blocked = L.r_b > 2 * NBQ;  // compact-WY path once the stacked rank spans more than two blocks
-    const DescArrays<T> D(n, blocked ? L.nblk : 0);
+    const int rk_bound = std::max(1, std::min(L.pq_b, s.maxrankC));
+    const DescArrays<T> D(n, blocked ? L.nblk : 0, std::max(L.r_b, L.pq_b), rk_bound);
     const size_t total = D.bytes + L.slab * sizeof(T) * (size_t) n + 256;
     HCB_TRY(ensure_ws(ctx, total));
     char *base = reinterpret_cast<char *>(ctx->ws);
@@ -857,10 +891,17 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
         k_truncate<T><<<n, 256, 0, ctx->stream>>>(sa.rc, (T) prm->accuracy, prm->truncated_svd, (int) prm->fixed_rank);
         HCB_LAUNCH_CHECK("k_truncate");
     }
-    const int rk_bound = std::max(1, std::min(L.pq_b, s.maxrankC));
     if (!blocked) {
         PhaseScope ph(ctx, 5);
         HCB_TRY(launch_refl<T>(ctx, sa.rf, 2 * n, rk_bound));
+    } else if (std::is_same<T, double>::value && strip_path_ok(ctx, std::max(s.m, s.n))) {
+        // rebuild C := Q [X;0], strip-resident: every 32-column strip of C takes all reflector blocks in one kernel
+        PhaseScope ph(ctx, 5);
+        StripJob *sj = reinterpret_cast<StripJob *>(base + D.o_asj);
+        const int nstrips = cdiv(rk_bound, NBQ);
+        k_setup_apply_strips<T><<<cdiv(nstrips * npan, 128), 128, 0, ctx->stream>>>(sa.rc, sj, nstrips, npan);
+        HCB_LAUNCH_CHECK("k_setup_apply_strips");
+        HCB_TRY(launch_strips(ctx, sj, nstrips * npan, std::max(s.m, s.n)));
     } else {
         // blocked rebuild C := Q [X;0]: blocks last-to-first, three batched GEMMs per block, rank read on the device
         PhaseScope ph(ctx, 5);
@@ -966,7 +1007,7 @@ size_t t_workspace(int64_t n_tiles, int64_t m, int64_t n, int64_t k, int64_t r_b
     s.kC = (int) (r_bound - s.kA);
     s.maxrankC = (int) std::max<int64_t>(1, std::min(m, n) / 3);
     const Layout<T> L = make_layout<T>(s);
-    const DescArrays<T> D((int) n_tiles, L.nblk);
+    const DescArrays<T> D((int) n_tiles, L.nblk, std::max(L.r_b, L.pq_b), std::max(1, std::min(L.pq_b, s.maxrankC)));
     return D.bytes + L.slab * sizeof(T) * (size_t) n_tiles + 512;
 }
 

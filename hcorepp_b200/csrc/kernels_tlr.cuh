@@ -6,6 +6,8 @@
 // The reference runs ~20 launches + 5 cuSOLVER calls + 1 host sync PER TILE; here one launch per phase covers the batch.
 #pragma once
 #include "common.cuh"
+#include "kernels_strip.cuh"
+#include <type_traits>
 #include "kernels_blas.cuh"
 #include "kernels_qr.cuh"
 
@@ -445,6 +447,7 @@ struct QrBlockArrays {
     LarftProb<T> *lf;
     GemmProb<T> *gw, *gw2, *gup;
     int nblk, npan;
+    StripJob *sj;  // fp64 strip-resident path (left-looking updates): one job per (block, panel); nullptr otherwise
 };
 
 template<typename T>
@@ -476,6 +479,20 @@ __global__ void k_setup_qr_blocks(const PanelDesc<T> *__restrict__ pds, QrBlockA
         }
     }
     o.qr[idx] = q; o.lf[idx] = lf; o.gw[idx] = gw; o.gw2[idx] = gw2; o.gup[idx] = gup;
+    if constexpr (std::is_same<T, double>::value) {
+        if (o.sj) {  // block `blk` of the panel, brought up to date with reflector blocks 0..blk-1 (Q^T)
+            StripJob j{nullptr, nullptr, nullptr, 1, 1, 0, 0, 0, 0, 0, 1, 1};
+            if (pd.active) {
+                const int m = pd.m, r = pd.n, kmax = m < r ? m : r, j0 = blk * NBQ;
+                if (j0 < r && blk > 0) {
+                    const int nc = (r - j0) < NBQ ? (r - j0) : NBQ;
+                    const int np = blk < (kmax + NBQ - 1) / NBQ ? blk : (kmax + NBQ - 1) / NBQ;
+                    j = StripJob{pd.A + (size_t) j0 * m, pd.VC, pd.TB, m, m, m, nc, kmax, 0, np, 1, 1};
+                }
+            }
+            o.sj[idx] = j;
+        }
+    }
 }
 
 // Descriptors of the blocked rebuild C := Q [X;0] (C = CU for side 0, VN for side 1), blocks applied last-to-first:
@@ -485,6 +502,30 @@ struct ApplyBlockArrays {
     GemmProb<T> *gw, *gw2, *gup;
     int nblk, npan;
 };
+
+// Strip jobs of the rebuild: strip s (32 columns) of CU / VN, all reflector blocks last-to-first (Q).
+template<typename T>
+__global__ void k_setup_apply_strips(const RecompProb<T> *__restrict__ rcs, StripJob *__restrict__ out, int nstrips, int npan) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nstrips * npan) return;
+    const int st = idx / npan, pan = idx % npan, side = pan & 1;
+    const RecompProb<T> rc = rcs[pan >> 1];
+    StripJob j{nullptr, nullptr, nullptr, 1, 1, 0, 0, 0, 0, 0, -1, 0};
+    if constexpr (std::is_same<T, double>::value) {
+        if (rc.active) {
+            const int m = side ? rc.n : rc.m, r = rc.r, kmax = m < r ? m : r;
+            int rk = *rc.rk_new;
+            if (rk > rc.wcols) rk = 0;
+            const int c0 = st * NBQ;
+            if (c0 < rk && kmax > 0) {
+                const int nb = (kmax + NBQ - 1) / NBQ;
+                j = StripJob{(side ? rc.VN : rc.CU) + (size_t) c0 * m, rc.VC[side], rc.TB[side], m, m, m,
+                             (rk - c0) < NBQ ? (rk - c0) : NBQ, kmax, nb - 1, nb, -1, 0};
+            }
+        }
+    }
+    out[idx] = j;
+}
 
 template<typename T>
 __global__ void k_setup_apply_blocks(const RecompProb<T> *__restrict__ rcs, ApplyBlockArrays<T> o) {

@@ -1,4 +1,5 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: time share per kernel name."""
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: time share per kernel name.
+usage: summarize_launches.py launches.csv [last_n]"""
 import csv
 import re
 import sys
@@ -13,6 +14,8 @@ for r in csv.DictReader(lines):
         unit = r.get("Metric Unit", "ns")
         scale = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "nsecond": 1e-3, "ms": 1e3, "msecond": 1e3}.get(unit, 1e-3)
         rows.append((r["Kernel Name"], v * scale))
+if len(sys.argv) > 2:  # keep only the last N launches (e.g. the last k step of the timed pass)
+    rows = rows[-int(sys.argv[2]):]
 tot = sum(v for _, v in rows)
 agg = defaultdict(lambda: [0, 0.0])
 for k, v in rows:
