@@ -233,22 +233,22 @@ int run_blocked_qr(hcb_ctx *ctx, const PanelDesc<T> *d_pds, int cnt, int rows_bo
     q.npan = cnt;
     k_setup_qr_blocks<T><<<cdiv(nblk * cnt, 128), 128, 0, ctx->stream>>>(d_pds, q);
     HCB_LAUNCH_CHECK("k_setup_qr_blocks");
-    const size_t pq_smem = (size_t) NBQ * PQ_ROWS * sizeof(T);
-    const bool on_chip = rows_bound <= 8 * PQ_ROWS && pq_smem + 8192 <= ctx->smem_optin;
-    if (on_chip) HCB_CUDA(cudaFuncSetAttribute(k_panel_qr_cluster<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pq_smem));
+    const size_t pq_smem = pr_smem_bytes<T>();
+    const bool on_chip = rows_bound <= PR_MAXCS * PR_ROWS && pq_smem + 1024 <= ctx->smem_optin;
+    if (on_chip) HCB_CUDA(cudaFuncSetAttribute(k_panel_qr_regs<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pq_smem));
     for (int b = 0; b < nblk; ++b) {
         const size_t o = (size_t) b * cnt;
         // left-looking: bring column block b up to date with blocks 0..b-1 while it sits in cluster shared memory
         if (strips && b > 0) HCB_TRY(launch_strips(ctx, q.sj + o, cnt, rows_bound));
         if (b >= nfac) continue;
         if (on_chip) {
-            // cluster of 1/2/4/8 CTAs per panel block, 512 rows each, block resident in (distributed) shared memory
+            // cluster of 1/2/4/8 CTAs per panel block, 512 rows each, block resident in registers
             const int rows_b = std::max(1, rows_bound - b * NBQ);
             int cs = 1;
-            while (cs * PQ_ROWS < rows_b) cs <<= 1;
+            while (cs * PR_ROWS < rows_b) cs <<= 1;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned) (cs * cnt));
-            cfg.blockDim = dim3(PQ_ROWS);
+            cfg.blockDim = dim3(PR_THREADS);
             cfg.dynamicSmemBytes = pq_smem;
             cfg.stream = ctx->stream;
             cudaLaunchAttribute at[1];
@@ -260,8 +260,8 @@ int run_blocked_qr(hcb_ctx *ctx, const PanelDesc<T> *d_pds, int cnt, int rows_bo
             cfg.numAttrs = 1;
             const QrProb<T> *qarg = q.qr + o;
             const LarftProb<T> *larg = q.lf + o;
-            HCB_CUDA(cudaLaunchKernelEx(&cfg, k_panel_qr_cluster<T>, qarg, larg));
-            HCB_LAUNCH_CHECK("k_panel_qr_cluster");
+            HCB_CUDA(cudaLaunchKernelEx(&cfg, k_panel_qr_regs<T>, qarg, larg));
+            HCB_LAUNCH_CHECK("k_panel_qr_regs");
         } else {
             HCB_TRY(launch_qr<T>(ctx, q.qr + o, cnt));
             k_larft_extract<T><<<cnt, 256, 0, ctx->stream>>>(q.lf + o);

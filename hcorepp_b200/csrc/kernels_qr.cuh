@@ -7,6 +7,7 @@
 #pragma once
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include <type_traits>
 
 namespace hcb {
 
@@ -369,6 +370,253 @@ __global__ void __launch_bounds__(PQ_ROWS) k_panel_qr_cluster(const QrProb<T> *_
         if (t < jb) q.tau[t] = s_tau[t];
         for (int idx = t; idx < NBQ * NBQ; idx += PQ_ROWS) lp.Tm[idx] = Ts[idx % NBQ][idx / NBQ];
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_panel_qr_regs: same job as k_panel_qr_cluster with the block in REGISTERS.  256 threads per CTA, two rows per
+// thread (local rows t and t + 256), 64 doubles of row data per thread.  The pivot column is always register slot 0:
+// the trailing update writes column c into slot c-1, so the loop over the 32 columns stays a rolled loop with
+// compile-time register indices.  Per step: 64 FMAs form the thread's products, two 16-value transposed butterflies
+// reduce them over the warp, each warp stores its totals straight into every CTA of the cluster (DSMEM stores),
+// ONE cluster barrier, 32 threads sum the 8*CS warp partials, ONE block barrier, update.  Finished reflector columns
+// go to shared memory; V^T V for the dlarft recurrence is one DMMA pass over them at the end.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PR_THREADS = 256, PR_ROWS = 512, PR_MAXCS = 8;
+
+template<typename T>
+__device__ __forceinline__ T warp_reduce_16(T (&pr)[16], int lane) {  // lane l returns the total of index (l >> 1) & 15
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const bool up = lane & 16;
+        const T send = up ? pr[k] : pr[k + 8];
+        const T keep = up ? pr[k + 8] : pr[k];
+        pr[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const bool up = lane & 8;
+        const T send = up ? pr[k] : pr[k + 4];
+        const T keep = up ? pr[k + 4] : pr[k];
+        pr[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const bool up = lane & 4;
+        const T send = up ? pr[k] : pr[k + 2];
+        const T keep = up ? pr[k + 2] : pr[k];
+        pr[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        const bool up = lane & 2;
+        const T send = up ? pr[0] : pr[1];
+        const T keep = up ? pr[1] : pr[0];
+        pr[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    pr[0] += __shfl_xor_sync(0xffffffffu, pr[0], 1);
+    return pr[0];
+}
+
+template<typename T>
+constexpr size_t pr_smem_bytes() {
+    return sizeof(T) * ((size_t) NBQ * PR_ROWS + 2 * PR_MAXCS * (PR_THREADS / 32) * NBQ + 2 * NBQ + 2 * NBQ +
+                        3 * NBQ * (NBQ + 1) + NBQ * NBQ + 2 * NBQ);
+}
+
+__device__ __forceinline__ int pr_addr(int row, int col) { return col * PR_ROWS + ((row + 4 * col) & (PR_ROWS - 1)); }
+
+template<typename T>
+__global__ void __launch_bounds__(PR_THREADS, 1) k_panel_qr_regs(const QrProb<T> *__restrict__ qps,
+                                                                 const LarftProb<T> *__restrict__ lps) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int) cluster.num_blocks(), crank = (int) cluster.block_rank();
+    const int panel = blockIdx.x / CS;
+    const QrProb<T> q = qps[panel];
+    const LarftProb<T> lp = lps[panel];
+    const int m = q.m, jb = q.n < m ? q.n : m, lda = q.lda;
+    if (m <= 0 || jb <= 0) return;  // uniform over the cluster
+    constexpr int NW = PR_THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw_pr[];
+    T *P = reinterpret_cast<T *>(smem_raw_pr);            // finished reflector columns, pr_addr layout
+    T *zpart = P + NBQ * PR_ROWS;                         // [2][PR_MAXCS][NW][NBQ] warp partials from every CTA
+    T *zrow = zpart + 2 * PR_MAXCS * NW * NBQ;            // [2][NBQ] pivot row (slot 0 = alpha)
+    T *zsum = zrow + 2 * NBQ;                             // [NBQ] (+ NBQ spare)
+    T *Ts = zsum + 2 * NBQ;                               // [NBQ][NBQ+1]
+    T *Rs = Ts + NBQ * (NBQ + 1);                         // [NBQ][NBQ+1] R entries of the block (CTA 0)
+    T *G = Rs + NBQ * (NBQ + 1);                          // [NBQ][NBQ+1] V^T V
+    T *Gp = G + NBQ * (NBQ + 1);                          // [NBQ][NBQ] per-CTA partial of V^T V
+    T *s_tau = Gp + NBQ * NBQ;                            // [NBQ]
+    T *tcol = s_tau + NBQ;                                // [NBQ]
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int gr0 = crank * PR_ROWS + t, gr1 = gr0 + PR_THREADS;
+    const bool have0 = gr0 < m, have1 = gr1 < m;
+    T r0v[NBQ], r1v[NBQ];
+#pragma unroll
+    for (int c = 0; c < NBQ; ++c) {
+        r0v[c] = (have0 && c < jb) ? q.A[(size_t) gr0 + (size_t) c * lda] : T(0);
+        r1v[c] = (have1 && c < jb) ? q.A[(size_t) gr1 + (size_t) c * lda] : T(0);
+    }
+    for (int idx = t; idx < 3 * NBQ * (NBQ + 1); idx += PR_THREADS) Ts[idx] = T(0);  // Ts, Rs, G
+    cluster.sync();
+
+    for (int j = 0; j < jb; ++j) {
+        const int par = j & 1;
+        const T x0 = (have0 && gr0 > j) ? r0v[0] : T(0);
+        const T x1 = (have1 && gr1 > j) ? r1v[0] : T(0);
+        T tot;
+        {
+            T pr[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) pr[c] = fma(x0, r0v[c], x1 * r1v[c]);
+            const T lo = warp_reduce_16<T>(pr, lane);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) pr[c] = fma(x0, r0v[c + 16], x1 * r1v[c + 16]);
+            const T hi = warp_reduce_16<T>(pr, lane);
+            tot = (lane & 1) ? hi : lo;  // even lanes: slot lane/2, odd lanes: slot 16 + lane/2
+        }
+        const int slot = (lane >> 1) + 16 * (lane & 1);
+        T *zdst = zpart + ((par * PR_MAXCS + crank) * NW + w) * NBQ + slot;
+        for (int rk = 0; rk < CS; ++rk) *cluster.map_shared_rank(zdst, rk) = tot;
+        if (gr0 == j) {  // pivot row: slot 0 = alpha, slots 1.. = A[j][j+1..]
+            for (int rk = 0; rk < CS; ++rk) {
+                T *zr = cluster.map_shared_rank(zrow + par * NBQ, rk);
+#pragma unroll
+                for (int c = 0; c < NBQ; ++c) zr[c] = r0v[c];
+            }
+        }
+        cluster.sync();
+        if (t < NBQ) {
+            T sacc = T(0);
+            for (int src = 0; src < CS; ++src)
+#pragma unroll
+                for (int ww = 0; ww < NW; ++ww) sacc += zpart[((par * PR_MAXCS + src) * NW + ww) * NBQ + t];
+            zsum[t] = sacc;
+        }
+        __syncthreads();
+        const T ss = zsum[0], alpha = zrow[par * NBQ];
+        T tau = T(0), scale = T(0), beta = alpha;
+        if (ss != T(0)) {
+            const T nrm = t_sqrt(fma(alpha, alpha, ss));
+            beta = alpha >= T(0) ? -nrm : nrm;
+            tau = (beta - alpha) / beta;
+            scale = T(1) / (alpha - beta);
+        }
+        // reflector entries of my rows (unit diagonal, zeros above) -> shared memory; trailing update + slot shift
+        const T v0 = (gr0 > j) ? x0 * scale : (gr0 == j ? T(1) : T(0));
+        const T v1 = x1 * scale;
+        P[pr_addr(t, j)] = v0;
+        P[pr_addr(t + PR_THREADS, j)] = v1;
+        const T tv0 = (have0 && gr0 >= j) ? tau * v0 : T(0), tv1 = tau * v1;
+        if (gr0 == j) {  // my row becomes row j of R
+            Rs[j * (NBQ + 1) + j] = beta;
+#pragma unroll
+            for (int c = 1; c < NBQ; ++c) {
+                const T wc = fma(scale, zsum[c], zrow[par * NBQ + c]);
+                if (j + c < jb) Rs[j * (NBQ + 1) + j + c] = fma(-tau, wc, r0v[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 1; c < NBQ; ++c) {
+            const T wc = fma(scale, zsum[c], zrow[par * NBQ + c]);  // v^T A[:, j + c]
+            r0v[c - 1] = fma(-tv0, wc, r0v[c]);
+            r1v[c - 1] = fma(-tv1, wc, r1v[c]);
+        }
+        r0v[NBQ - 1] = T(0);
+        r1v[NBQ - 1] = T(0);
+        if (t == 0) s_tau[j] = tau;
+        // zsum is rewritten only after the next cluster barrier; zrow / zpart are double buffered
+    }
+    for (int j = jb; j < NBQ; ++j) {  // unused reflector columns are zero
+        P[pr_addr(t, j)] = T(0);
+        P[pr_addr(t + PR_THREADS, j)] = T(0);
+    }
+    __syncthreads();
+    // ---- G = V^T V: per-CTA partial over the local rows, cluster sum in CTA 0
+    if constexpr (std::is_same<T, double>::value) {
+        // DMMA: warp w owns the 8x8 tiles (ti, tj0) and (ti, tj0 + 1), K = 512 local rows
+        const int g = lane >> 2, tq = lane & 3, ti = w >> 1, tj0 = 2 * (w & 1);
+        double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+        const int colA = 8 * ti + g, colB0 = 8 * tj0 + g, colB1 = colB0 + 8;
+        const double *pa = P + colA * PR_ROWS, *pb0 = P + colB0 * PR_ROWS, *pb1 = P + colB1 * PR_ROWS;
+        const int ra = 4 * colA + tq, rb0 = 4 * colB0 + tq, rb1 = 4 * colB1 + tq;
+#pragma unroll 4
+        for (int ks = 0; ks < PR_ROWS / 4; ks += 2) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int rr = 4 * (ks + h);
+                const double a = pa[(rr + ra) & (PR_ROWS - 1)];
+                const double b0 = pb0[(rr + rb0) & (PR_ROWS - 1)];
+                const double b1 = pb1[(rr + rb1) & (PR_ROWS - 1)];
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(acc[0][h][0]), "+d"(acc[0][h][1]) : "d"(a), "d"(b0));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(acc[1][h][0]), "+d"(acc[1][h][1]) : "d"(a), "d"(b1));
+            }
+        }
+#pragma unroll
+        for (int jx = 0; jx < 2; ++jx)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                Gp[(8 * ti + g) * NBQ + 8 * (tj0 + jx) + 2 * tq + h] = acc[jx][0][h] + acc[jx][1][h];
+    } else {
+        for (int qd = 0; qd < 4; ++qd) {
+            const int idx = t + qd * PR_THREADS, i = idx / NBQ, jj = idx % NBQ;
+            T acc = T(0);
+            if (i < jj && jj < jb) {
+                const T *pi = P + i * PR_ROWS, *pj = P + jj * PR_ROWS;
+                const int ri = 4 * i, rj = 4 * jj;
+                for (int r = 0; r < PR_ROWS; ++r) acc = fma(pi[(r + ri) & (PR_ROWS - 1)], pj[(r + rj) & (PR_ROWS - 1)], acc);
+            }
+            Gp[idx] = acc;
+        }
+    }
+    cluster.sync();
+    if (crank == 0) {
+        for (int qd = 0; qd < 4; ++qd) {
+            const int idx = t + qd * PR_THREADS, i = idx / NBQ, jj = idx % NBQ;
+            T sacc = T(0);
+            for (int rk = 0; rk < CS; ++rk) sacc += cluster.map_shared_rank(Gp, rk)[idx];
+            G[i * (NBQ + 1) + jj] = sacc;
+        }
+    }
+    cluster.sync();  // remote reads of Gp are done; nobody exits early
+    // ---- write back the reflectors (A below the diagonal + clean copy)
+#pragma unroll 1
+    for (int c = 0; c < jb; ++c) {
+        const T a0 = P[pr_addr(t, c)], a1 = P[pr_addr(t + PR_THREADS, c)];
+        if (have0) {
+            lp.Vc[(size_t) gr0 + (size_t) c * lp.ldvc] = a0;
+            if (gr0 > c) q.A[(size_t) gr0 + (size_t) c * lda] = a0;
+        }
+        if (have1) {
+            lp.Vc[(size_t) gr1 + (size_t) c * lp.ldvc] = a1;
+            q.A[(size_t) gr1 + (size_t) c * lda] = a1;
+        }
+    }
+    if (crank != 0) return;
+    __syncthreads();
+    // R entries (rows 0..jb-1, columns >= row) and tau
+    for (int idx = t; idx < NBQ * NBQ; idx += PR_THREADS) {
+        const int i = idx % NBQ, c = idx / NBQ;
+        if (i <= c && c < jb && i < m) q.A[(size_t) i + (size_t) c * lda] = Rs[i * (NBQ + 1) + c];
+    }
+    if (t < jb) q.tau[t] = s_tau[t];
+    if (w == 0) {
+        for (int i = 0; i < jb; ++i) {
+            const T ti = s_tau[i];
+            if (lane < i) tcol[lane] = -ti * G[lane * (NBQ + 1) + i];
+            __syncwarp();
+            T acc = T(0);
+            if (lane < i)
+                for (int c = lane; c < i; ++c) acc = fma(Ts[lane * (NBQ + 1) + c], tcol[c], acc);
+            __syncwarp();
+            if (lane < i) Ts[lane * (NBQ + 1) + i] = acc;
+            if (lane == i) Ts[i * (NBQ + 1) + i] = ti;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int idx = t; idx < NBQ * NBQ; idx += PR_THREADS) lp.Tm[idx] = Ts[(idx % NBQ) * (NBQ + 1) + idx / NBQ];
 }
 
 }  // namespace hcb
