@@ -179,4 +179,16 @@ namespace hcb {
 // Copies `bytes` of host descriptors to the device through the pinned ring; returns the device address.
 int ring_upload(hcb_ctx *ctx, const void *host, size_t bytes, void **d_out);
 int ensure_ws(hcb_ctx *ctx, size_t bytes);
+// Ampere-style asynchronous global -> shared copies (LDGSTS): 16-byte (L2 only) and 8-byte variants
+__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
+    const unsigned s = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_8(void *smem, const void *gmem) {
+    const unsigned s = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 }  // namespace hcb

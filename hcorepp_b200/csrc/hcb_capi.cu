@@ -6,6 +6,7 @@
 #include "kernels_dmma.cuh"
 #include "kernels_qr.cuh"
 #include "kernels_svd.cuh"
+#include "kernels_svd_rx.cuh"
 #include "kernels_tlr.cuh"
 
 #include <algorithm>
@@ -165,6 +166,16 @@ int launch_svd(hcb_ctx *ctx, const SvdProb<T> *d_probs, int n_probs, int a_bound
     const size_t pitch = (size_t) cdiv(a_bound, 64) * 64;
     size_t want = (pitch * b_bound + (size_t) b_bound) * sizeof(T);
     const size_t cap = ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0;
+    if (a_bound > 128 && a_bound <= 64 * RX_MAX_NI && want + (size_t) b_bound * sizeof(T) > cap) {
+        // does not fit shared memory as a whole: block Jacobi with the pivot block in registers
+        const size_t rx = align_up(rx_smem_bytes<T>(cdiv(a_bound, 64), b_bound), 16);
+        if (rx <= cap) {
+            HCB_CUDA(cudaFuncSetAttribute(k_jacobi_svd_rx<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) rx));
+            k_jacobi_svd_rx<T><<<n_probs, RX_THREADS, rx, ctx->stream>>>(d_probs, 40);
+            HCB_LAUNCH_CHECK("k_jacobi_svd_rx");
+            return HCB_OK;
+        }
+    }
     if (want > cap) want = cap / 16 * 16;
     if ((size_t) std::max(b_bound, 1) * sizeof(T) > want) return fail(HCB_EUNSUPPORTED, "svd: problem too large");
     want = align_up(want, 16);

@@ -39,17 +39,6 @@ struct StripJob {
 // pairs per half-warp without padding (3 x 64 KB blocks + the small matrices must fit 227 KB).
 __device__ __forceinline__ int sk_addr(int row, int col) { return col * SK_ROWS + ((row + 4 * col) & (SK_ROWS - 1)); }
 
-__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
-    const unsigned s = (unsigned) __cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_8(void *smem, const void *gmem) {
-    const unsigned s = (unsigned) __cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-
 constexpr size_t SK_SMEM_BYTES =
     sizeof(double) * (3 * (size_t) NBQ * SK_ROWS + 2 * NBQ * NBQ + NBQ * SK_WP + NBQ * NBQ);
 
@@ -68,23 +57,34 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_strip_reflect(const StripJob 
     double *Ts = Wf + NBQ * SK_WP;               // op(T_p), stored so that lane i reads op(T)[i][k] at Ts[k*32+i]
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
-    const int m = jb_.m, ncols = jb_.ncols, r0 = crank * SK_ROWS;
+    const int m = jb_.m, ncols = jb_.ncols;
+    // rows are dealt to the CTAs of the cluster in groups of 32 (group gg -> CTA gg % CS): the reflector blocks are zero
+    // above their diagonal, so a contiguous split would leave the first CTAs idle for the later blocks
+    auto grow = [&](int lr) { return 32 * ((lr >> 5) * CS + crank) + (lr & 31); };
 
-    // ---- strip -> shared memory (zero padded)
-    for (int idx = tid; idx < NBQ * SK_ROWS; idx += SK_THREADS) {
-        const int col = idx / SK_ROWS, row = idx % SK_ROWS, gr = r0 + row;
-        Sb[sk_addr(row, col)] = (gr < m && col < ncols) ? jb_.S[(size_t) gr + (size_t) col * jb_.lds] : 0.0;
+    // ---- strip -> shared memory (zero padded), asynchronously: all 64 KB in flight at once (the scalar
+    // load/store loop was 30 % of the kernel's stall samples, profiles/r01_strip_reflect_ncu.txt)
+    for (int q = tid; q < NBQ * SK_ROWS / 2; q += SK_THREADS) {
+        const int col = q / (SK_ROWS / 2), row = 2 * (q % (SK_ROWS / 2)), gr = grow(row);
+        const double *src = jb_.S + (size_t) col * jb_.lds + gr;
+        double *dst = Sb + sk_addr(row, col);
+        const bool v0 = col < ncols && gr < m, v1 = col < ncols && gr + 1 < m;
+        if (v0 && v1 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) cp_async_16(dst, src);
+        else {
+            if (v0) cp_async_8(dst, src); else dst[0] = 0.0;
+            if (v1) cp_async_8(dst + 1, src + 1); else dst[1] = 0.0;
+        }
     }
 
     auto block_cols = [&](int p) { const int left = jb_.kmax - p * NBQ; return left < NBQ ? left : NBQ; };
-    auto cta_active = [&](int p) { return r0 + SK_ROWS > p * NBQ && r0 < m; };
+    auto cta_active = [&](int p) { return grow(SK_ROWS - 1) >= p * NBQ && 32 * crank < m; };
     // cp.async prefetch of V_p rows [r0, r0+256) into buffer `buf` (rows above the block, beyond m and columns >= jb are 0)
     auto prefetch_v = [&](int p, int buf) {
         if (!cta_active(p)) return;
         double *Vb = Vb0 + buf * NBQ * SK_ROWS;
         const int j0 = p * NBQ, jb = block_cols(p);
         for (int q = tid; q < NBQ * SK_ROWS / 2; q += SK_THREADS) {
-            const int col = q / (SK_ROWS / 2), row = 2 * (q % (SK_ROWS / 2)), gr = r0 + row;
+            const int col = q / (SK_ROWS / 2), row = 2 * (q % (SK_ROWS / 2)), gr = grow(row);
             const double *src = jb_.Vc + (size_t) (j0 + col) * jb_.ldv + gr;
             double *dst = Vb + sk_addr(row, col);
             const bool v0 = col < jb && gr >= j0 && gr < m, v1 = col < jb && gr + 1 >= j0 && gr + 1 < m;
@@ -136,8 +136,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_strip_reflect(const StripJob 
                 const int colA = 8 * ti + g, colB0 = 8 * tj0 + g, colB1 = colB0 + 8;
                 const double *pa = Vb + colA * SK_ROWS, *pb0 = Sb + colB0 * SK_ROWS, *pb1 = Sb + colB1 * SK_ROWS;
                 const int ra = 4 * colA + t, rb0 = 4 * colB0 + t, rb1 = 4 * colB1 + t;
-                int ks0 = j0 > r0 ? (j0 - r0) / 4 : 0;  // V is zero above row j0
-                ks0 &= ~1;
+                // V is zero above row j0: skip the local 32-row groups that lie entirely above it
+                const int gfirst = j0 / 32 - crank;
+                const int ks0 = gfirst > 0 ? 8 * ((gfirst + CS - 1) / CS) : 0;
 #pragma unroll 4
                 for (int ks = ks0; ks < SK_ROWS / 4; ks += 2) {
 #pragma unroll
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_strip_reflect(const StripJob 
         }
         __syncthreads();
         // ---- phase 3: S_loc += V_loc (-W2); warp w owns rows 32w..32w+31
-        if (active && r0 + 32 * w + 32 > j0 && r0 + 32 * w < m) {
+        if (active && grow(32 * w) + 32 > j0 && grow(32 * w) < m) {
             double acc[4][4][2];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_strip_reflect(const StripJob 
     cp_async_wait_all();
     // ---- strip back to global memory
     for (int idx = tid; idx < NBQ * SK_ROWS; idx += SK_THREADS) {
-        const int col = idx / SK_ROWS, row = idx % SK_ROWS, gr = r0 + row;
+        const int col = idx / SK_ROWS, row = idx % SK_ROWS, gr = grow(row);
         if (gr < m && col < ncols) jb_.S[(size_t) gr + (size_t) col * jb_.lds] = Sb[sk_addr(row, col)];
     }
     cluster.sync();  // nobody leaves while a neighbour may still read its partial sums

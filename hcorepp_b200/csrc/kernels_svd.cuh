@@ -117,6 +117,38 @@ __device__ __forceinline__ bool jacobi_rotate_reg(T *__restrict__ mx, T *__restr
     return true;
 }
 
+// Epilogue shared by the Jacobi kernels: singular values = column norms of the rotated copy M (ld ldm), rank-sort
+// (descending, stable) and scatter of the normalised left factor.  sig: b elements of shared memory.
+template<typename T>
+__device__ void jacobi_finish(const T *M, int ldm, T *sig, const SvdProb<T> &p) {
+    const int a = p.a, b = p.b;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
+    (void) tid;
+    // singular values = column norms
+    for (int c = w; c < b; c += nw) {
+        const T *mc = M + (size_t) c * ldm;
+        T ss = T(0);
+        for (int i = lane; i < a; i += 32) ss = fma(mc[i], mc[i], ss);
+        ss = warp_sum(ss);
+        if (lane == 0) sig[c] = t_sqrt(ss);
+    }
+    __syncthreads();
+    // rank-sort (descending, stable) and scatter the normalised / permuted left factor
+    for (int c = w; c < b; c += nw) {
+        const T sc = sig[c];
+        int pos = 0;
+        for (int o = lane; o < b; o += 32) {
+            const T so = sig[o];
+            pos += (so > sc || (so == sc && o < c)) ? 1 : 0;
+        }
+        pos = warp_sum(pos);
+        if (lane == 0) p.sigma[pos] = sc;
+        const T *mc = M + (size_t) c * ldm;
+        T *uo = p.Uout + (size_t) pos * p.ldu;
+        for (int i = lane; i < a; i += 32) uo[i] = (sc > T(0)) ? mc[i] / sc : T(0);
+    }
+}
+
 // The sweeps.  NI > 0: shared-memory columns have pitch 64*NI (zero padded), rotations are register resident.
 // NI == 0: generic form, pitch = a, loop-based rotations (any size; also the global-memory fallback).
 //
@@ -275,29 +307,7 @@ __device__ void jacobi_sweeps(T *sm, const SvdProb<T> &p, int smem_elems, int ma
     }
     __syncthreads();
 
-    // singular values = column norms
-    for (int c = w; c < b; c += nw) {
-        const T *mc = M + (size_t) c * ldm;
-        T ss = T(0);
-        for (int i = lane; i < a; i += 32) ss = fma(mc[i], mc[i], ss);
-        ss = warp_sum(ss);
-        if (lane == 0) sig[c] = t_sqrt(ss);
-    }
-    __syncthreads();
-    // rank-sort (descending, stable) and scatter the normalised / permuted left factor
-    for (int c = w; c < b; c += nw) {
-        const T sc = sig[c];
-        int pos = 0;
-        for (int o = lane; o < b; o += 32) {
-            const T so = sig[o];
-            pos += (so > sc || (so == sc && o < c)) ? 1 : 0;
-        }
-        pos = warp_sum(pos);
-        if (lane == 0) p.sigma[pos] = sc;
-        const T *mc = M + (size_t) c * ldm;
-        T *uo = p.Uout + (size_t) pos * p.ldu;
-        for (int i = lane; i < a; i += 32) uo[i] = (sc > T(0)) ? mc[i] / sc : T(0);
-    }
+    jacobi_finish<T>(M, ldm, sig, p);
 }
 
 // One CTA per problem.  THREADS = 1024 (64 registers/thread: register-resident rotations up to 128 rows) or 512

@@ -1,0 +1,322 @@
+// kernels_svd_rx.cuh -- block one-sided Jacobi with the pivot block in REGISTERS (a <= 384 rows, any b).
+//
+// The shared-memory block Jacobi of kernels_svd.cuh reads and writes both columns of every pair from shared memory:
+// 4 * 8 * a bytes per rotation, i.e. ~96 cycles of the SM's 128 B/clk shared-memory port per rotation at a = 357 --
+// that, not the FP64 pipe (~50 cycles), is what its ~110 cycles per rotation were made of (ncu r01_jacobi_full).
+// Here the 32 columns of the pivot block I live in the registers of the 8 warps (4 columns each) for the whole pass
+// over the later blocks J; a warp loads TWO columns of J, rotates them against its four x columns (8 rotations, as four
+// steps of two independent pairs, so two dependency chains are in flight per warp) and stores them back:
+// 2 * 8 * a bytes of shared-memory traffic per 4 rotations.  The rotations are "fast" (scaled) rotations,
+//     x' = x - (t dy/dx) y,   y' = y + (t dx/dy) x,   dx' = c dx,  dy' = c dy,
+// two FMAs per element instead of four; the per-column scales are folded back when a block leaves shared memory /
+// registers.  Block J+1 is prefetched with cp.async into the other shared-memory region while block J is rotated.
+// The pairs INSIDE a block are done once per sweep in shared memory with jacobi_rotate_reg (kernels_svd.cuh).
+#pragma once
+#include "common.cuh"
+#include "kernels_svd.cuh"
+
+namespace hcb {
+
+constexpr int RX_THREADS = 256;
+constexpr int RX_BW = 32;  // block width (columns): 8 warps x 4 register-resident columns
+constexpr int RX_MAX_NI = 6;
+
+// per-column metadata in shared memory: squared norm (true), scale d, 1/d
+template<typename T>
+struct RxMeta {
+    T *n2, *d, *id;
+};
+
+// scalar part of one fast rotation; g = inner product of the STORED columns.  All lanes compute the same values;
+// lane 0 writes the metadata.  Returns the rotation factors (fx, fy) and whether the pair was rotated; `redo`
+// is set when the norm update cancelled and the norms have to be recomputed from the rotated columns.
+template<typename T>
+__device__ __forceinline__ bool rx_scalars(T g, int ix, int iy, const RxMeta<T> &mt, int lane, T tol2, T &fx, T &fy,
+                                           bool &redo) {
+    const T alpha = mt.n2[ix], beta = mt.n2[iy];
+    const T dx = mt.d[ix], dy = mt.d[iy], idx = mt.id[ix], idy = mt.id[iy];
+    const T gam = g * dx * dy;
+    redo = false;
+    if (!(gam * gam > tol2 * alpha * beta)) return false;
+    const T d = beta - alpha, g2 = gam + gam;
+    const T h = fma(d, d, g2 * g2);
+    const T den = t_abs(d) + h * t_rsqrt(h);
+    const T rd = t_rsqrt(den);
+    const T t = (d >= T(0) ? g2 : -g2) * (rd * rd);
+    const T q = fma(t, t, T(1));
+    const T c = t_rsqrt(q);
+    fx = t * dy * idx;
+    fy = t * dx * idy;
+    const T tg = t * gam, a2 = alpha - tg, b2 = beta + tg, rc = q * c;  // rc = 1 / c
+    redo = (a2 < T(0.01) * alpha) || (b2 < T(0.01) * beta);
+    __syncwarp();
+    if (lane == 0) {
+        mt.n2[ix] = a2; mt.n2[iy] = b2;
+        mt.d[ix] = c * dx; mt.d[iy] = c * dy;
+        mt.id[ix] = rc * idx; mt.id[iy] = rc * idy;
+    }
+    __syncwarp();
+    return true;
+}
+
+template<typename T, int NI>
+__device__ __forceinline__ T rx_sumsq(const Vec2<T> (&x)[NI]) {
+    T s = T(0);
+#pragma unroll
+    for (int i = 0; i < NI; ++i) { s = fma(x[i].x, x[i].x, s); s = fma(x[i].y, x[i].y, s); }
+    return warp_sum(s);
+}
+
+// two independent pairs (xa, ya) and (xb, yb) at once; ix*/iy* index the metadata arrays
+template<typename T, int NI>
+__device__ __forceinline__ bool rx_duo(Vec2<T> (&xa)[NI], int ixa, Vec2<T> (&ya)[NI], int iya, Vec2<T> (&xb)[NI], int ixb,
+                                       Vec2<T> (&yb)[NI], int iyb, const RxMeta<T> &mt, int lane, T tol2) {
+    T ga = T(0), gb = T(0);
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        ga = fma(xa[i].x, ya[i].x, ga); ga = fma(xa[i].y, ya[i].y, ga);
+        gb = fma(xb[i].x, yb[i].x, gb); gb = fma(xb[i].y, yb[i].y, gb);
+    }
+    {   // both warp sums with 6 shuffles: the halves of the warp reduce one value each, then swap
+        const bool hi = lane & 16;
+        T v = (hi ? gb : ga) + __shfl_xor_sync(0xffffffffu, hi ? ga : gb, 16);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        const T o = __shfl_xor_sync(0xffffffffu, v, 16);
+        ga = hi ? o : v;
+        gb = hi ? v : o;
+    }
+    T fxa = T(0), fya = T(0), fxb = T(0), fyb = T(0);
+    bool redo_a, redo_b;
+    const bool ra = rx_scalars<T>(ga, ixa, iya, mt, lane, tol2, fxa, fya, redo_a);
+    const bool rb = rx_scalars<T>(gb, ixb, iyb, mt, lane, tol2, fxb, fyb, redo_b);
+    if (ra) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const T ux = xa[i].x, uy = xa[i].y;
+            xa[i].x = fma(-fxa, ya[i].x, ux); xa[i].y = fma(-fxa, ya[i].y, uy);
+            ya[i].x = fma(fya, ux, ya[i].x);  ya[i].y = fma(fya, uy, ya[i].y);
+        }
+    }
+    if (rb) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const T ux = xb[i].x, uy = xb[i].y;
+            xb[i].x = fma(-fxb, yb[i].x, ux); xb[i].y = fma(-fxb, yb[i].y, uy);
+            yb[i].x = fma(fyb, ux, yb[i].x);  yb[i].y = fma(fyb, uy, yb[i].y);
+        }
+    }
+    if (redo_a) {  // rare: recompute the true squared norms d^2 * |stored|^2
+        const T sx = rx_sumsq<T, NI>(xa), sy = rx_sumsq<T, NI>(ya);
+        if (lane == 0) { mt.n2[ixa] = mt.d[ixa] * mt.d[ixa] * sx; mt.n2[iya] = mt.d[iya] * mt.d[iya] * sy; }
+        __syncwarp();
+    }
+    if (redo_b) {
+        const T sx = rx_sumsq<T, NI>(xb), sy = rx_sumsq<T, NI>(yb);
+        if (lane == 0) { mt.n2[ixb] = mt.d[ixb] * mt.d[ixb] * sx; mt.n2[iyb] = mt.d[iyb] * mt.d[iyb] * sy; }
+        __syncwarp();
+    }
+    return ra || rb;
+}
+
+template<typename T, int NI>
+__device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
+    constexpr int P = 64 * NI, BW = RX_BW;
+    __shared__ int s_rot;
+    const int a = p.a, b = p.b;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    constexpr int NW = RX_THREADS / 32;
+    T *R0 = sm, *R1 = sm + (size_t) P * BW;      // two column-block regions
+    T *sig = R1 + (size_t) P * BW;               // b singular values
+    T *meta = sig + b;                           // 3 x 64 metadata: x columns [0,32), y columns [32,64)
+    RxMeta<T> mt{meta, meta + 2 * BW, meta + 4 * BW};
+    T *M = p.J;  // rotated copy (global / L2), ld a
+    for (int idx = tid; idx < a * b; idx += RX_THREADS) M[idx] = p.M[(size_t) (idx % a) + (size_t) (idx / a) * p.ldm];
+    __syncthreads();
+    const T tol = Eps<T>::v() * t_sqrt((T) a);
+    const T tol2 = tol * tol;
+    const int nblk = (b + BW - 1) / BW;
+
+    // asynchronous staging of columns [c0, c0 + wc) into dst (pitch P, zero padded rows and columns)
+    auto stage_async = [&](T *dst, int c0, int wc) {
+        for (int q = tid; q < BW * P / 2; q += RX_THREADS) {
+            const int c = q / (P / 2), row = 2 * (q % (P / 2));
+            T *d = dst + (size_t) c * P + row;
+            const T *src = M + (size_t) (c0 + c) * a + row;
+            const bool v0 = c < wc && row < a, v1 = c < wc && row + 1 < a;
+            if (sizeof(T) == 8) {
+                if (v0 && v1 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) cp_async_16(d, src);
+                else {
+                    if (v0) cp_async_8(d, src); else d[0] = T(0);
+                    if (v1) cp_async_8(d + 1, src + 1); else d[1] = T(0);
+                }
+            } else {
+                d[0] = v0 ? src[0] : T(0);
+                d[1] = v1 ? src[1] : T(0);
+            }
+        }
+        cp_async_commit();
+    };
+    // squared norms of the 32 staged columns -> metadata slots [m0, m0 + 32), scales reset to 1
+    auto init_meta = [&](const T *cols, int m0) {
+        for (int c = w; c < BW; c += NW) {
+            const T *mc = cols + (size_t) c * P;
+            T ss = T(0);
+            for (int i = lane; i < P; i += 32) ss = fma(mc[i], mc[i], ss);
+            ss = warp_sum(ss);
+            if (lane == 0) { mt.n2[m0 + c] = ss; mt.d[m0 + c] = T(1); mt.id[m0 + c] = T(1); }
+        }
+    };
+    // columns [c0, c0 + wc) of a staged block back to the global copy, scales folded in
+    auto unstage = [&](const T *src, int c0, int wc, int m0) {
+        for (int idx = tid; idx < P * wc; idx += RX_THREADS) {
+            const int i = idx % P, c = idx / P;
+            if (i < a) M[(size_t) (c0 + c) * a + i] = src[idx] * mt.d[m0 + c];
+        }
+    };
+
+    bool converged = (b < 2);
+    int sweeps_used = 0;
+    for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
+        ++sweeps_used;
+        __syncthreads();
+        if (tid == 0) s_rot = 0;
+        __syncthreads();
+        for (int bi = 0; bi < nblk; ++bi) {
+            const int ci0 = bi * BW, wi = min(BW, b - ci0);
+            // block I -> R0 (and block I+1 -> R1 right behind it)
+            stage_async(R0, ci0, wi);
+            if (bi + 1 < nblk) stage_async(R1, ci0 + BW, min(BW, b - ci0 - BW));
+            cp_async_wait_all();
+            __syncthreads();
+            init_meta(R0, 0);
+            __syncthreads();
+            // ---- pairs inside block I: round-robin in shared memory (plain rotations on the cached norms)
+            {
+                const int nu2 = (wi + 1) & ~1;
+                for (int round = 0; round < nu2 - 1; ++round) {
+                    for (int slot = w; slot < nu2 / 2; slot += NW) {
+                        int x, y;
+                        rr_pair(nu2, round, slot, x, y);
+                        if (y >= wi) continue;
+                        if (jacobi_rotate_reg<T, NI>(R0 + (size_t) x * P, R0 + (size_t) y * P, mt.n2 + x, mt.n2 + y, lane, tol2) &&
+                            lane == 0)
+                            s_rot = 1;
+                    }
+                    __syncthreads();
+                }
+            }
+            if (bi + 1 == nblk) {  // last block: nothing to pair it with
+                unstage(R0, ci0, wi, 0);
+                __syncthreads();
+                continue;
+            }
+            // ---- block I -> registers: warp w owns columns 4w .. 4w+3
+            Vec2<T> x0[NI], x1[NI], x2[NI], x3[NI];
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                x0[i] = *reinterpret_cast<const Vec2<T> *>(R0 + (size_t) (4 * w + 0) * P + 64 * i + 2 * lane);
+                x1[i] = *reinterpret_cast<const Vec2<T> *>(R0 + (size_t) (4 * w + 1) * P + 64 * i + 2 * lane);
+                x2[i] = *reinterpret_cast<const Vec2<T> *>(R0 + (size_t) (4 * w + 2) * P + 64 * i + 2 * lane);
+                x3[i] = *reinterpret_cast<const Vec2<T> *>(R0 + (size_t) (4 * w + 3) * P + 64 * i + 2 * lane);
+            }
+            __syncthreads();  // R0 is free from here on
+            bool any = false;
+            for (int bj = bi + 1; bj < nblk; ++bj) {
+                const int k = bj - bi - 1;             // pass number: block J sits in R1 for even k, R0 for odd k
+                T *BB = (k & 1) ? R0 : R1, *other = (k & 1) ? R1 : R0;
+                const int cj0 = bj * BW, wj = min(BW, b - cj0);
+                if (k > 0) {  // (pass 0's block was staged together with block I)
+                    cp_async_wait_all();
+                    __syncthreads();
+                }
+                if (bj + 1 < nblk) stage_async(other, cj0 + BW, min(BW, b - cj0 - BW));  // flies during this pass
+                init_meta(BB, BW);
+                __syncthreads();
+                for (int s = 0; s < BW / 2; ++s) {
+                    const int q = (w + s) & (BW / 2 - 1), ja = 2 * q, jb = 2 * q + 1;
+                    Vec2<T> ya[NI], yb[NI];
+                    T *pa = BB + (size_t) ja * P + 2 * lane, *pb = BB + (size_t) jb * P + 2 * lane;
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) {
+                        ya[i] = *reinterpret_cast<const Vec2<T> *>(pa + 64 * i);
+                        yb[i] = *reinterpret_cast<const Vec2<T> *>(pb + 64 * i);
+                    }
+                    const int ix = 4 * w, iya = BW + ja, iyb = BW + jb;
+                    any |= rx_duo<T, NI>(x0, ix + 0, ya, iya, x1, ix + 1, yb, iyb, mt, lane, tol2);
+                    any |= rx_duo<T, NI>(x1, ix + 1, ya, iya, x0, ix + 0, yb, iyb, mt, lane, tol2);
+                    any |= rx_duo<T, NI>(x2, ix + 2, ya, iya, x3, ix + 3, yb, iyb, mt, lane, tol2);
+                    any |= rx_duo<T, NI>(x3, ix + 3, ya, iya, x2, ix + 2, yb, iyb, mt, lane, tol2);
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) {
+                        *reinterpret_cast<Vec2<T> *>(pa + 64 * i) = ya[i];
+                        *reinterpret_cast<Vec2<T> *>(pb + 64 * i) = yb[i];
+                    }
+                    __syncthreads();
+                }
+                unstage(BB, cj0, wj, BW);
+                // fold the x scales so that they cannot drift far from 1
+                {
+                    const T d0 = mt.d[4 * w], d1 = mt.d[4 * w + 1], d2 = mt.d[4 * w + 2], d3 = mt.d[4 * w + 3];
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) {
+                        x0[i].x *= d0; x0[i].y *= d0; x1[i].x *= d1; x1[i].y *= d1;
+                        x2[i].x *= d2; x2[i].y *= d2; x3[i].x *= d3; x3[i].y *= d3;
+                    }
+                    __syncwarp();
+                    if (lane < 4) { mt.d[4 * w + lane] = T(1); mt.id[4 * w + lane] = T(1); }
+                }
+                __syncthreads();
+            }
+            if (any && lane == 0) s_rot = 1;
+            // ---- block I: registers -> global copy (scales are 1 after the last fold)
+            {
+                auto put = [&](const Vec2<T> (&x)[NI], int c) {
+                    if (c >= wi) return;
+                    T *dst = M + (size_t) (ci0 + c) * a;
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) {
+                        const int r = 64 * i + 2 * lane;
+                        if (r < a) dst[r] = x[i].x;
+                        if (r + 1 < a) dst[r + 1] = x[i].y;
+                    }
+                };
+                put(x0, 4 * w); put(x1, 4 * w + 1); put(x2, 4 * w + 2); put(x3, 4 * w + 3);
+            }
+            __syncthreads();
+        }
+        converged = (s_rot == 0);
+    }
+    if (p.info && tid == 0) {
+        if (!converged) atomicOr(p.info, 1);
+        atomicOr(p.info, sweeps_used << 8);
+    }
+    __syncthreads();
+    jacobi_finish<T>(M, a, sig, p);
+}
+
+template<typename T>
+constexpr size_t rx_smem_bytes(int ni, int b_bound) {
+    return sizeof(T) * ((size_t) 2 * 64 * ni * RX_BW + (size_t) b_bound + 6 * RX_BW);
+}
+
+// One CTA of 256 threads per problem; a <= 384.  Dynamic shared memory: rx_smem_bytes(ceil(a_bound / 64), b_bound).
+template<typename T>
+__global__ void __launch_bounds__(RX_THREADS, 1) k_jacobi_svd_rx(const SvdProb<T> *__restrict__ probs, int max_sweeps) {
+    extern __shared__ __align__(16) unsigned char smem_raw_rx[];
+    T *sm = reinterpret_cast<T *>(smem_raw_rx);
+    const SvdProb<T> p = probs[blockIdx.x];
+    if (p.a <= 0 || p.b <= 0) return;
+    switch ((p.a + 63) / 64) {
+        case 1: jacobi_sweeps_rx<T, 1>(sm, p, max_sweeps); break;
+        case 2: jacobi_sweeps_rx<T, 2>(sm, p, max_sweeps); break;
+        case 3: jacobi_sweeps_rx<T, 3>(sm, p, max_sweeps); break;
+        case 4: jacobi_sweeps_rx<T, 4>(sm, p, max_sweeps); break;
+        case 5: jacobi_sweeps_rx<T, 5>(sm, p, max_sweeps); break;
+        default: jacobi_sweeps_rx<T, 6>(sm, p, max_sweeps); break;
+    }
+}
+
+}  // namespace hcb
