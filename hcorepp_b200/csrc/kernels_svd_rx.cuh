@@ -3,10 +3,10 @@
 // The shared-memory block Jacobi of kernels_svd.cuh reads and writes both columns of every pair from shared memory:
 // 4 * 8 * a bytes per rotation, i.e. ~96 cycles of the SM's 128 B/clk shared-memory port per rotation at a = 357 --
 // that, not the FP64 pipe (~50 cycles), is what its ~110 cycles per rotation were made of (ncu r01_jacobi_full).
-// Here the 32 columns of the pivot block I live in the registers of the 8 warps (4 columns each) for the whole pass
-// over the later blocks J; a warp loads TWO columns of J, rotates them against its four x columns (8 rotations, as four
+// Here the 32 columns of the pivot block I live in the registers of the 16 warps (2 columns each) for the whole pass
+// over the later blocks J; a warp loads TWO columns of J, rotates them against its two x columns (4 rotations, as two
 // steps of two independent pairs, so two dependency chains are in flight per warp) and stores them back:
-// 2 * 8 * a bytes of shared-memory traffic per 4 rotations.  The rotations are "fast" (scaled) rotations,
+// 4 * 8 * a bytes of shared-memory traffic per 4 rotations.  The rotations are "fast" (scaled) rotations,
 //     x' = x - (t dy/dx) y,   y' = y + (t dx/dy) x,   dx' = c dx,  dy' = c dy,
 // two FMAs per element instead of four; the per-column scales are folded back when a block leaves shared memory /
 // registers.  Block J+1 is prefetched with cp.async into the other shared-memory region while block J is rotated.
@@ -17,11 +17,32 @@
 
 namespace hcb {
 
-constexpr int RX_THREADS = 256;
-constexpr int RX_BW = 32;  // block width (columns): 8 warps x 4 register-resident columns
+constexpr int RX_THREADS = 512;
+constexpr int RX_BW = 32;  // block width (columns): 16 warps x 2 register-resident columns
 constexpr int RX_MAX_NI = 6;
 
 // per-column metadata in shared memory: squared norm (true), scale d, 1/d
+// t = 2 gamma / (d + sign(d) sqrt(d^2 + 4 gamma^2)) needs sqrt and a reciprocal; both from the MUFU approximations
+// plus ONE Newton step (~1e-12 relative): an inexact angle only leaves a residual cosine of that size for the next
+// sweep, orthogonality depends on c = rsqrt(1 + t^2) alone, which stays at full precision (and off the critical path:
+// the column updates need only t).
+__device__ __forceinline__ double rx_tangent(double d, double g2) {
+    const double h = fma(d, d, g2 * g2);
+    double rs, r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rs) : "d"(h));
+    double sh = h * rs;
+    sh = fma(0.5 * rs, fma(-sh, sh, h), sh);
+    const double den = fabs(d) + sh;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    r = fma(r, fma(-den, r, 1.0), r);
+    return (d >= 0.0 ? g2 : -g2) * r;
+}
+__device__ __forceinline__ float rx_tangent(float d, float g2) {
+    const float h = fmaf(d, d, g2 * g2);
+    const float den = fabsf(d) + h * rsqrtf(h);
+    return (d >= 0.0f ? g2 : -g2) / den;
+}
+
 template<typename T>
 struct RxMeta {
     T *n2, *d, *id;
@@ -39,10 +60,7 @@ __device__ __forceinline__ bool rx_scalars(T g, int ix, int iy, const RxMeta<T> 
     redo = false;
     if (!(gam * gam > tol2 * alpha * beta)) return false;
     const T d = beta - alpha, g2 = gam + gam;
-    const T h = fma(d, d, g2 * g2);
-    const T den = t_abs(d) + h * t_rsqrt(h);
-    const T rd = t_rsqrt(den);
-    const T t = (d >= T(0) ? g2 : -g2) * (rd * rd);
+    const T t = rx_tangent(d, g2);
     const T q = fma(t, t, T(1));
     const T c = t_rsqrt(q);
     fx = t * dy * idx;
@@ -71,12 +89,14 @@ __device__ __forceinline__ T rx_sumsq(const Vec2<T> (&x)[NI]) {
 template<typename T, int NI>
 __device__ __forceinline__ bool rx_duo(Vec2<T> (&xa)[NI], int ixa, Vec2<T> (&ya)[NI], int iya, Vec2<T> (&xb)[NI], int ixb,
                                        Vec2<T> (&yb)[NI], int iyb, const RxMeta<T> &mt, int lane, T tol2) {
-    T ga = T(0), gb = T(0);
+    T ga = T(0), gb = T(0), ga2 = T(0), gb2 = T(0);
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
-        ga = fma(xa[i].x, ya[i].x, ga); ga = fma(xa[i].y, ya[i].y, ga);
-        gb = fma(xb[i].x, yb[i].x, gb); gb = fma(xb[i].y, yb[i].y, gb);
+        ga = fma(xa[i].x, ya[i].x, ga); ga2 = fma(xa[i].y, ya[i].y, ga2);
+        gb = fma(xb[i].x, yb[i].x, gb); gb2 = fma(xb[i].y, yb[i].y, gb2);
     }
+    ga += ga2;
+    gb += gb2;
     {   // both warp sums with 6 shuffles: the halves of the warp reduce one value each, then swap
         const bool hi = lane & 16;
         T v = (hi ? gb : ga) + __shfl_xor_sync(0xffffffffu, hi ? ga : gb, 16);
@@ -213,14 +233,12 @@ __device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
                 __syncthreads();
                 continue;
             }
-            // ---- block I -> registers: warp w owns columns 4w .. 4w+3
-            Vec2<T> x0[NI], x1[NI], x2[NI], x3[NI];
+            // ---- block I -> registers: warp w owns columns 2w, 2w+1
+            Vec2<T> x0[NI], x1[NI];
 #pragma unroll
             for (int i = 0; i < NI; ++i) {
-                x0[i] = *reinterpret_cast<const Vec2<T> *>(R0 + (size_t) (4 * w + 0) * P + 64 * i + 2 * lane);
-                x1[i] = *reinterpret_cast<const Vec2<T> *>(R0 + (size_t) (4 * w + 1) * P + 64 * i + 2 * lane);
-                x2[i] = *reinterpret_cast<const Vec2<T> *>(R0 + (size_t) (4 * w + 2) * P + 64 * i + 2 * lane);
-                x3[i] = *reinterpret_cast<const Vec2<T> *>(R0 + (size_t) (4 * w + 3) * P + 64 * i + 2 * lane);
+                x0[i] = *reinterpret_cast<const Vec2<T> *>(R0 + (size_t) (2 * w + 0) * P + 64 * i + 2 * lane);
+                x1[i] = *reinterpret_cast<const Vec2<T> *>(R0 + (size_t) (2 * w + 1) * P + 64 * i + 2 * lane);
             }
             __syncthreads();  // R0 is free from here on
             bool any = false;
@@ -244,11 +262,9 @@ __device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
                         ya[i] = *reinterpret_cast<const Vec2<T> *>(pa + 64 * i);
                         yb[i] = *reinterpret_cast<const Vec2<T> *>(pb + 64 * i);
                     }
-                    const int ix = 4 * w, iya = BW + ja, iyb = BW + jb;
+                    const int ix = 2 * w, iya = BW + ja, iyb = BW + jb;
                     any |= rx_duo<T, NI>(x0, ix + 0, ya, iya, x1, ix + 1, yb, iyb, mt, lane, tol2);
                     any |= rx_duo<T, NI>(x1, ix + 1, ya, iya, x0, ix + 0, yb, iyb, mt, lane, tol2);
-                    any |= rx_duo<T, NI>(x2, ix + 2, ya, iya, x3, ix + 3, yb, iyb, mt, lane, tol2);
-                    any |= rx_duo<T, NI>(x3, ix + 3, ya, iya, x2, ix + 2, yb, iyb, mt, lane, tol2);
 #pragma unroll
                     for (int i = 0; i < NI; ++i) {
                         *reinterpret_cast<Vec2<T> *>(pa + 64 * i) = ya[i];
@@ -259,14 +275,13 @@ __device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
                 unstage(BB, cj0, wj, BW);
                 // fold the x scales so that they cannot drift far from 1
                 {
-                    const T d0 = mt.d[4 * w], d1 = mt.d[4 * w + 1], d2 = mt.d[4 * w + 2], d3 = mt.d[4 * w + 3];
+                    const T d0 = mt.d[2 * w], d1 = mt.d[2 * w + 1];
 #pragma unroll
                     for (int i = 0; i < NI; ++i) {
                         x0[i].x *= d0; x0[i].y *= d0; x1[i].x *= d1; x1[i].y *= d1;
-                        x2[i].x *= d2; x2[i].y *= d2; x3[i].x *= d3; x3[i].y *= d3;
                     }
                     __syncwarp();
-                    if (lane < 4) { mt.d[4 * w + lane] = T(1); mt.id[4 * w + lane] = T(1); }
+                    if (lane < 2) { mt.d[2 * w + lane] = T(1); mt.id[2 * w + lane] = T(1); }
                 }
                 __syncthreads();
             }
@@ -283,7 +298,7 @@ __device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
                         if (r + 1 < a) dst[r + 1] = x[i].y;
                     }
                 };
-                put(x0, 4 * w); put(x1, 4 * w + 1); put(x2, 4 * w + 2); put(x3, 4 * w + 3);
+                put(x0, 2 * w); put(x1, 2 * w + 1);
             }
             __syncthreads();
         }
@@ -302,7 +317,7 @@ constexpr size_t rx_smem_bytes(int ni, int b_bound) {
     return sizeof(T) * ((size_t) 2 * 64 * ni * RX_BW + (size_t) b_bound + 6 * RX_BW);
 }
 
-// One CTA of 256 threads per problem; a <= 384.  Dynamic shared memory: rx_smem_bytes(ceil(a_bound / 64), b_bound).
+// One CTA of 512 threads per problem; a <= 384.  Dynamic shared memory: rx_smem_bytes(ceil(a_bound / 64), b_bound).
 template<typename T>
 __global__ void __launch_bounds__(RX_THREADS, 1) k_jacobi_svd_rx(const SvdProb<T> *__restrict__ probs, int max_sweeps) {
     extern __shared__ __align__(16) unsigned char smem_raw_rx[];
