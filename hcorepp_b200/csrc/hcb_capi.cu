@@ -673,9 +673,9 @@ Layout<T> make_layout(const BatchShape &s) {
         L.o_wbu = take((size_t) 2 * NBQ * L.wcols);
         L.o_wbv = take((size_t) 2 * NBQ * L.wcols);
         // LQ preconditioning of the core
-        L.o_mt = take(sq);
+        L.o_mt = take((size_t) L.pq_b * L.r_b);  // M^T for the LQ path, or RU (p x r) for the GEMM core
         L.o_taum = take(L.pq_b);
-        L.o_lb = take(sq);
+        L.o_lb = take((size_t) L.pq_b * L.r_b);  // L for the LQ path, or RV (q x r)
         L.o_vcm = take(sq);
         L.o_tbm = take((size_t) NBQ * NBQ * L.nblk);
         L.o_wbm = take((size_t) 2 * NBQ * L.wcols);
@@ -689,7 +689,7 @@ Layout<T> make_layout(const BatchShape &s) {
 template<typename T>
 struct DescArrays {  // device arrays living at the front of the scratch arena
     size_t bytes = 0;
-    size_t o_g1, o_g2, o_g3, o_gv, o_cp, o_qr, o_rf, o_svd, o_rc, o_rk, o_tiles;
+    size_t o_g1, o_g2, o_g3, o_gv, o_gc, o_cp, o_qr, o_rf, o_svd, o_rc, o_rk, o_tiles;
     size_t o_bqr = 0, o_blf = 0, o_bgw = 0, o_bgw2 = 0, o_bgup = 0, o_agw = 0, o_agw2 = 0, o_agup = 0;
     size_t o_pds = 0, o_pdc = 0, o_qrc = 0, o_lq = 0, o_pc = 0, o_asj = 0;
     explicit DescArrays(int n, int nblk = 0, int qr_cols = 0, int rk_bound = 0) {
@@ -699,6 +699,7 @@ struct DescArrays {  // device arrays living at the front of the scratch arena
         o_g2 = take(sizeof(GemmProb<T>) * n);
         o_g3 = take(sizeof(GemmProb<T>) * n);
         o_gv = take(sizeof(GemmProb<T>) * n);
+        o_gc = take(sizeof(GemmProb<T>) * n);
         o_cp = take(sizeof(CopyProb<T>) * 4 * n);
         o_qr = take(sizeof(QrProb<T>) * 2 * n);
         o_rf = take(sizeof(ReflProb<T>) * 2 * n);
@@ -809,6 +810,7 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     sa.g2 = reinterpret_cast<GemmProb<T> *>(base + D.o_g2);
     sa.g3 = reinterpret_cast<GemmProb<T> *>(base + D.o_g3);
     sa.gv = reinterpret_cast<GemmProb<T> *>(base + D.o_gv);
+    sa.gc = reinterpret_cast<GemmProb<T> *>(base + D.o_gc);
     sa.cp = reinterpret_cast<CopyProb<T> *>(base + D.o_cp);
     sa.qr = reinterpret_cast<QrProb<T> *>(base + D.o_qr);
     sa.rf = reinterpret_cast<ReflProb<T> *>(base + D.o_rf);
@@ -843,7 +845,9 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
             if (want > cap) want = 0;  // does not fit: the kernel writes J = I
             want = align_up(want, 16);
             HCB_CUDA(cudaFuncSetAttribute(k_precond_product<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(want, 16)));
-            k_precond_product<T><<<n, 256, want, ctx->stream>>>(sa.pc, (int) (want / sizeof(T)));
+            // one warp per column pair of the round-robin (ka / 2 pairs per round)
+            const int pc_threads = std::min(1024, std::max(256, 32 * ((s.kA + 1) / 2)));
+            k_precond_product<T><<<n, pc_threads, want, ctx->stream>>>(sa.pc, (int) (want / sizeof(T)));
             HCB_LAUNCH_CHECK("k_precond_product");
         }
         if (s.mix == CCC || s.mix == CCD || s.mix == CDD || s.mix == DCD || s.mix == DDC)
@@ -882,8 +886,16 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     {
         PhaseScope ph(ctx, 4);
         dim3 grid(std::max(1, std::min(64, cdiv((long long) L.pq_b * L.pq_b, 256))), n);
-        k_core_build<T><<<grid, 256, 0, ctx->stream>>>(sa.rc);
-        HCB_LAUNCH_CHECK("k_core_build");
+        if (!sa.use_lq) {
+            // triangles out of the QR'd stacks, then core = RU RV^T as one batched (DMMA) GEMM
+            dim3 gx(std::max(1, std::min(128, cdiv((long long) 2 * L.pq_b * L.r_b, 256))), n);
+            k_extract_r<T><<<gx, 256, 0, ctx->stream>>>(sa.rc);
+            HCB_LAUNCH_CHECK("k_extract_r");
+            HCB_TRY(launch_gemm<T>(ctx, sa.gc, n, L.pq_b, L.pq_b));
+        } else {
+            k_core_build<T><<<grid, 256, 0, ctx->stream>>>(sa.rc);
+            HCB_LAUNCH_CHECK("k_core_build");
+        }
         if (sa.use_lq) {
             // LQ preconditioning: QR of the transposed core, L = R^T goes to the Jacobi kernel
             if (!blocked) HCB_TRY(launch_qr<T>(ctx, sa.qr_core, n));

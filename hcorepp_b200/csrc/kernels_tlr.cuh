@@ -10,6 +10,7 @@
 #include <type_traits>
 #include "kernels_blas.cuh"
 #include "kernels_qr.cuh"
+#include "kernels_svd_rx.cuh"
 
 namespace hcb {
 
@@ -85,6 +86,7 @@ struct SetupArgs {
     int *rk_new;                // n_tiles ints
     int *info;                  // n_tiles ints (may be null)
     GemmProb<T> *g1, *g2, *g3, *gv;  // gv: V diag(sigma) = M^T Us after the Jacobi kernel
+    GemmProb<T> *gc;                 // core = RU RV^T (or its transpose) from the extracted triangles, see k_extract_r
     CopyProb<T> *cp;            // 4 per tile
     QrProb<T> *qr;              // 2 per tile
     ReflProb<T> *rf;            // 2 per tile
@@ -122,7 +124,7 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
     const bool ac = A.type == HCB_TILE_COMPRESSED, bc = B.type == HCB_TILE_COMPRESSED, cc = C.type == HCB_TILE_COMPRESSED;
     const int ka = ac ? *A.d_rank : 0, kb = bc ? *B.d_rank : 0, kc = cc ? *C.d_rank : 0;
     T *slab = s.ws + (size_t) t * s.slab;
-    GemmProb<T> g1 = mk_gemm<T>(nullptr, 1, 0, nullptr, 1, 0, nullptr, 1, 0, 0, 0, T(0), T(0)), g2 = g1, g3 = g1, gv = g1;
+    GemmProb<T> g1 = mk_gemm<T>(nullptr, 1, 0, nullptr, 1, 0, nullptr, 1, 0, 0, 0, T(0), T(0)), g2 = g1, g3 = g1, gv = g1, gc = g1;
     CopyProb<T> c0 = mk_copy<T>(nullptr, 1, nullptr, 1, 0, 0, 0, T(0)), c1 = c0, c2 = c0, c3 = c0;
     QrProb<T> q0{nullptr, nullptr, 0, 0, 1}, q1 = q0;
     ReflProb<T> r0{nullptr, nullptr, nullptr, 0, 0, 1, 0, 0, 1, 0, 0, nullptr}, r1 = r0;
@@ -230,6 +232,9 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
                 qm = QrProb<T>{rc.MT, rc.tauM, rc.b, rc.a, rc.b};
                 lq = LqProb<T>{rc.MT, rc.Lb, rc.a, rc.b};
                 gv = mk_gemm<T>(rc.M, rc.a, 1, rc.Us, rc.a, 0, rc.Vs, rc.b, rc.b, rc.b, rc.a, one, zero);
+                // core from the extracted triangles RU (p x r, ld p, in MT) and RV (q x r, ld q, in Lb)
+                if (rc.transposed) gc = mk_gemm<T>(rc.Lb, q, 0, rc.MT, p, 1, rc.M, rc.a, q, p, r, one, zero);
+                else gc = mk_gemm<T>(rc.MT, p, 0, rc.Lb, q, 1, rc.M, rc.a, p, q, r, one, zero);
                 // rebuild (Compressed.cpp:551-560, 611-628): CU = Q_U [Unew;0], VN = Q_V [Vfac;0], rank read on device
                 r0 = ReflProb<T>{UW, rc.tauU, CU, m, p, m, m, 0, m, 0, 0, rc.rk_new};
                 r1 = ReflProb<T>{VW, rc.tauV, rc.VN, n, q, n, n, 0, n, 0, 0, rc.rk_new};
@@ -237,7 +242,7 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
         }
     }
     if (bad) {
-        g1.m = g2.m = g3.m = gv.m = 0;
+        g1.m = g2.m = g3.m = gv.m = gc.m = 0;
         c0.rows = c1.rows = c2.rows = c3.rows = 0;
         q0.m = q1.m = 0;
         r0.k = r1.k = 0; r0.nc = r1.nc = 0; r0.nc_dev = r1.nc_dev = nullptr;
@@ -251,7 +256,7 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
     } else if (s.info) {
         s.info[t] = 0;
     }
-    s.g1[t] = g1; s.g2[t] = g2; s.g3[t] = g3; s.gv[t] = gv;
+    s.g1[t] = g1; s.g2[t] = g2; s.g3[t] = g3; s.gv[t] = gv; s.gc[t] = gc;
     s.cp[4 * t + 0] = c0; s.cp[4 * t + 1] = c1; s.cp[4 * t + 2] = c2; s.cp[4 * t + 3] = c3;
     s.qr[2 * t + 0] = q0; s.qr[2 * t + 1] = q1;
     s.rf[2 * t + 0] = r0; s.rf[2 * t + 1] = r1;
@@ -269,7 +274,7 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
 // construction); then T1J = T1^T * J.  Everything lives in shared memory; if it does not fit, J = I (no
 // preconditioning, same product).
 template<typename T>
-__global__ void __launch_bounds__(256) k_precond_product(const PrecondProb<T> *__restrict__ probs, int smem_elems) {
+__global__ void __launch_bounds__(1024) k_precond_product(const PrecondProb<T> *__restrict__ probs, int smem_elems) {
     extern __shared__ __align__(16) unsigned char smem_raw_pc[];
     T *sm = reinterpret_cast<T *>(smem_raw_pc);
     const PrecondProb<T> p = probs[blockIdx.x];
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(256) k_precond_product(const PrecondProb<T> *_
         int kbp = 32;
         while (kbp < kb && kbp < nthr) kbp <<= 1;      // threads per column (power of two >= min(kb, nthr))
         const int groups = nthr / kbp, gidx = tid / kbp, jl = tid % kbp;
-        for (int j = jl; j < kb; j += kbp) {
+        for (int j = jl; j < kb && gidx < groups; j += kbp) {  // (a partial last group sits out)
             T ss = T(0);
             for (int c = gidx; c < p.n; c += groups) {
                 const T x = p.BR[(size_t) j + (size_t) c * p.ldbr];
@@ -352,9 +357,8 @@ __global__ void __launch_bounds__(256) k_precond_product(const PrecondProb<T> *_
                 if (!(t_abs(gamma) > tol * t_sqrt(alpha) * t_sqrt(beta)) || gamma == T(0)) continue;
                 if (!(alpha > noise2) || !(beta > noise2)) continue;
                 if (lane == 0) s_rot = 1;
-                const T zeta = (beta - alpha) / (T(2) * gamma);
-                const T t = (zeta >= T(0) ? T(1) : T(-1)) / (t_abs(zeta) + t_sqrt(fma(zeta, zeta, T(1))));
-                const T c = T(1) / t_sqrt(fma(t, t, T(1))), sn = c * t;
+                const T t = rx_tangent(beta - alpha, gamma + gamma);
+                const T c = t_rsqrt(fma(t, t, T(1))), sn = c * t;
                 for (int i = lane; i < kb; i += 32) {
                     const T u = nx[i], v = ny[i];
                     nx[i] = fma(-sn, v, c * u);
@@ -579,6 +583,25 @@ __global__ void __launch_bounds__(256) k_core_build(const RecompProb<T> *__restr
         } else {
             p.M[(size_t) i + (size_t) j * p.a] = acc;
             p.MT[(size_t) j + (size_t) i * p.b] = acc;
+        }
+    }
+}
+
+// RU = triu(UW[:p, :r]) -> MT (p x r, ld p), RV = triu(VW[:q, :r]) -> Lb (q x r, ld q): the triangles of the two QR'd
+// stacks with the reflectors below the diagonal masked out, so that the core is ONE batched DMMA GEMM (k_core_build's
+// strided dot products ran at 7.5 ms per 256 tiles at r = 357, ncu launch list r01).  grid = (chunks, n_tiles)
+template<typename T>
+__global__ void __launch_bounds__(256) k_extract_r(const RecompProb<T> *__restrict__ probs) {
+    const RecompProb<T> p = probs[blockIdx.y];
+    if (!p.active) return;
+    const int nu = p.p * p.r, total = nu + p.q * p.r;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        if (idx < nu) {
+            const int i = idx % p.p, l = idx / p.p;
+            p.MT[idx] = i <= l ? p.UW[(size_t) i + (size_t) l * p.m] : T(0);
+        } else {
+            const int e = idx - nu, j = e % p.q, l = e / p.q;
+            p.Lb[e] = j <= l ? p.VW[(size_t) j + (size_t) l * p.n] : T(0);
         }
     }
 }
