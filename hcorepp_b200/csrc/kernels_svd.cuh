@@ -70,7 +70,8 @@ template<> __device__ __forceinline__ float t_rsqrt(float x) { return rsqrtf(x);
 // the update cancels badly.  The rotation scalars use one reciprocal square root each instead of divisions and square
 // roots:  t = 2*gamma / (d + sign(d)*sqrt(d^2 + 4*gamma^2)),  d = beta - alpha;  c = rsqrt(1 + t^2);  s = c*t.
 template<typename T, int NI>
-__device__ __forceinline__ bool jacobi_rotate_reg(T *__restrict__ mx, T *__restrict__ my, T *nx2, T *ny2, int lane, T tol2) {
+__device__ __forceinline__ int jacobi_rotate_reg(T *__restrict__ mx, T *__restrict__ my, T *nx2, T *ny2, int lane, T tol2,
+                                                 T big2 = T(3.0e38)) {  // returns 1 if rotated, | 2 if cos^2 > big2
     Vec2<T> u[NI], v[NI];
     T gamma = T(0);
 #pragma unroll
@@ -83,7 +84,8 @@ __device__ __forceinline__ bool jacobi_rotate_reg(T *__restrict__ mx, T *__restr
     const T alpha = *nx2, beta = *ny2;
     gamma = warp_sum(gamma);
     // |gamma| > tol * sqrt(alpha * beta)  <=>  gamma^2 > tol^2 * alpha * beta
-    if (!(gamma * gamma > tol2 * alpha * beta)) return false;
+    if (!(gamma * gamma > tol2 * alpha * beta)) return 0;
+    const int ret = (gamma * gamma > big2 * alpha * beta) ? 3 : 1;
     const T d = beta - alpha, g2 = gamma + gamma;
     const T h = fma(d, d, g2 * g2);          // > 0 because gamma != 0 here
     const T den = t_abs(d) + h * t_rsqrt(h);  // |d| + sqrt(d^2 + 4 gamma^2) > 0
@@ -114,7 +116,7 @@ __device__ __forceinline__ bool jacobi_rotate_reg(T *__restrict__ mx, T *__restr
         b2 = warp_sum(nb);
     }
     if (lane == 0) { *nx2 = a2; *ny2 = b2; }
-    return true;
+    return ret;
 }
 
 // Epilogue shared by the Jacobi kernels: singular values = column norms of the rotated copy M (ld ldm), rank-sort

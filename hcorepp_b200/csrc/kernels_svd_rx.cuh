@@ -48,34 +48,15 @@ struct RxMeta {
     T *n2, *d, *id;
 };
 
-// scalar part of one fast rotation; g = inner product of the STORED columns.  All lanes compute the same values;
-// lane 0 writes the metadata.  Returns the rotation factors (fx, fy) and whether the pair was rotated; `redo`
-// is set when the norm update cancelled and the norms have to be recomputed from the rotated columns.
-template<typename T>
-__device__ __forceinline__ bool rx_scalars(T g, int ix, int iy, const RxMeta<T> &mt, int lane, T tol2, T &fx, T &fy,
-                                           bool &redo) {
-    const T alpha = mt.n2[ix], beta = mt.n2[iy];
-    const T dx = mt.d[ix], dy = mt.d[iy], idx = mt.id[ix], idy = mt.id[iy];
-    const T gam = g * dx * dy;
-    redo = false;
-    if (!(gam * gam > tol2 * alpha * beta)) return false;
-    const T d = beta - alpha, g2 = gam + gam;
-    const T t = rx_tangent(d, g2);
-    const T q = fma(t, t, T(1));
-    const T c = t_rsqrt(q);
-    fx = t * dy * idx;
-    fy = t * dx * idy;
-    const T tg = t * gam, a2 = alpha - tg, b2 = beta + tg, rc = q * c;  // rc = 1 / c
-    redo = (a2 < T(0.01) * alpha) || (b2 < T(0.01) * beta);
-    __syncwarp();
-    if (lane == 0) {
-        mt.n2[ix] = a2; mt.n2[iy] = b2;
-        mt.d[ix] = c * dx; mt.d[iy] = c * dy;
-        mt.id[ix] = rc * idx; mt.id[iy] = rc * idy;
-    }
-    __syncwarp();
-    return true;
+// full-precision reciprocal square root without the library's special-case path (argument is 1 + t^2 >= 1)
+__device__ __forceinline__ double rx_rsqrt(double q) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q));
+    y = fma(0.5 * y, fma(-q * y, y, 1.0), y);
+    y = fma(0.5 * y, fma(-q * y, y, 1.0), y);
+    return y;
 }
+__device__ __forceinline__ float rx_rsqrt(float q) { return rsqrtf(q); }
 
 template<typename T, int NI>
 __device__ __forceinline__ T rx_sumsq(const Vec2<T> (&x)[NI]) {
@@ -85,10 +66,13 @@ __device__ __forceinline__ T rx_sumsq(const Vec2<T> (&x)[NI]) {
     return warp_sum(s);
 }
 
-// two independent pairs (xa, ya) and (xb, yb) at once; ix*/iy* index the metadata arrays
+// Two independent pairs (xa, ya) and (xb, yb) at once; ix*/iy* index the metadata arrays.  The scalar part of the two
+// rotations is PACKED: lanes 0-15 carry pair a, lanes 16-31 pair b through one branch-free instruction stream (the
+// scalars were half of the instructions of a rotation when every lane computed both), then the four factors are
+// broadcast.  Returns bit 0: something rotated; bit 1: some pair was still above big2 (see the sweep loop).
 template<typename T, int NI>
-__device__ __forceinline__ bool rx_duo(Vec2<T> (&xa)[NI], int ixa, Vec2<T> (&ya)[NI], int iya, Vec2<T> (&xb)[NI], int ixb,
-                                       Vec2<T> (&yb)[NI], int iyb, const RxMeta<T> &mt, int lane, T tol2) {
+__device__ __forceinline__ int rx_duo(Vec2<T> (&xa)[NI], int ixa, Vec2<T> (&ya)[NI], int iya, Vec2<T> (&xb)[NI], int ixb,
+                                      Vec2<T> (&yb)[NI], int iyb, const RxMeta<T> &mt, int lane, T tol2, T big2) {
     T ga = T(0), gb = T(0), ga2 = T(0), gb2 = T(0);
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
@@ -97,22 +81,37 @@ __device__ __forceinline__ bool rx_duo(Vec2<T> (&xa)[NI], int ixa, Vec2<T> (&ya)
     }
     ga += ga2;
     gb += gb2;
-    {   // both warp sums with 6 shuffles: the halves of the warp reduce one value each, then swap
-        const bool hi = lane & 16;
-        T v = (hi ? gb : ga) + __shfl_xor_sync(0xffffffffu, hi ? ga : gb, 16);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        const T o = __shfl_xor_sync(0xffffffffu, v, 16);
-        ga = hi ? o : v;
-        gb = hi ? v : o;
+    const bool hi = lane & 16;
+    // both warp sums with 5 shuffles: each half of the warp ends up with the total of ITS pair
+    T g = (hi ? gb : ga) + __shfl_xor_sync(0xffffffffu, hi ? ga : gb, 16);
+    g += __shfl_xor_sync(0xffffffffu, g, 8);
+    g += __shfl_xor_sync(0xffffffffu, g, 4);
+    g += __shfl_xor_sync(0xffffffffu, g, 2);
+    g += __shfl_xor_sync(0xffffffffu, g, 1);
+    const int ix = hi ? ixb : ixa, iy = hi ? iyb : iya;
+    const T alpha = mt.n2[ix], beta = mt.n2[iy];
+    const T dx = mt.d[ix], dy = mt.d[iy], idx = mt.id[ix], idy = mt.id[iy];
+    const T gam = g * dx * dy, gg = gam * gam, ab = alpha * beta;
+    const bool rot = gg > tol2 * ab;
+    const bool big = gg > big2 * ab;
+    const T d = rot ? beta - alpha : T(1), g2 = rot ? gam + gam : T(0);  // benign inputs where nothing rotates
+    const T t = rx_tangent(d, g2);
+    const T q = fma(t, t, T(1));
+    const T c = rx_rsqrt(q);
+    const T fx = t * dy * idx, fy = t * dx * idy;  // zero when !rot (t == 0)
+    const T tg = t * gam, a2 = alpha - tg, b2 = beta + tg, rc = q * c;  // rc = 1 / c
+    const bool redo = rot && ((a2 < T(0.01) * alpha) || (b2 < T(0.01) * beta));
+    __syncwarp();
+    if (rot && (lane & 15) == 0) {
+        mt.n2[ix] = a2; mt.n2[iy] = b2;
+        mt.d[ix] = c * dx; mt.d[iy] = c * dy;
+        mt.id[ix] = rc * idx; mt.id[iy] = rc * idy;
     }
-    T fxa = T(0), fya = T(0), fxb = T(0), fyb = T(0);
-    bool redo_a, redo_b;
-    const bool ra = rx_scalars<T>(ga, ixa, iya, mt, lane, tol2, fxa, fya, redo_a);
-    const bool rb = rx_scalars<T>(gb, ixb, iyb, mt, lane, tol2, fxb, fyb, redo_b);
-    if (ra) {
+    const unsigned brot = __ballot_sync(0xffffffffu, rot), bredo = __ballot_sync(0xffffffffu, redo);
+    const unsigned bbig = __ballot_sync(0xffffffffu, big);
+    const T fxa = __shfl_sync(0xffffffffu, fx, 0), fya = __shfl_sync(0xffffffffu, fy, 0);
+    const T fxb = __shfl_sync(0xffffffffu, fx, 16), fyb = __shfl_sync(0xffffffffu, fy, 16);
+    if (brot & 1u) {
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
             const T ux = xa[i].x, uy = xa[i].y;
@@ -120,7 +119,7 @@ __device__ __forceinline__ bool rx_duo(Vec2<T> (&xa)[NI], int ixa, Vec2<T> (&ya)
             ya[i].x = fma(fya, ux, ya[i].x);  ya[i].y = fma(fya, uy, ya[i].y);
         }
     }
-    if (rb) {
+    if (brot & 0x10000u) {
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
             const T ux = xb[i].x, uy = xb[i].y;
@@ -128,23 +127,22 @@ __device__ __forceinline__ bool rx_duo(Vec2<T> (&xa)[NI], int ixa, Vec2<T> (&ya)
             yb[i].x = fma(fyb, ux, yb[i].x);  yb[i].y = fma(fyb, uy, yb[i].y);
         }
     }
-    if (redo_a) {  // rare: recompute the true squared norms d^2 * |stored|^2
+    if (bredo & 1u) {  // rare: the norm update cancelled -- recompute the true squared norms d^2 * |stored|^2
         const T sx = rx_sumsq<T, NI>(xa), sy = rx_sumsq<T, NI>(ya);
         if (lane == 0) { mt.n2[ixa] = mt.d[ixa] * mt.d[ixa] * sx; mt.n2[iya] = mt.d[iya] * mt.d[iya] * sy; }
-        __syncwarp();
     }
-    if (redo_b) {
+    if (bredo & 0x10000u) {
         const T sx = rx_sumsq<T, NI>(xb), sy = rx_sumsq<T, NI>(yb);
         if (lane == 0) { mt.n2[ixb] = mt.d[ixb] * mt.d[ixb] * sx; mt.n2[iyb] = mt.d[iyb] * mt.d[iyb] * sy; }
-        __syncwarp();
     }
-    return ra || rb;
+    __syncwarp();
+    return (brot ? 1 : 0) | (bbig ? 2 : 0);
 }
 
 template<typename T, int NI>
 __device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
     constexpr int P = 64 * NI, BW = RX_BW;
-    __shared__ int s_rot;
+    __shared__ int s_rot, s_big;
     const int a = p.a, b = p.b;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     constexpr int NW = RX_THREADS / 32;
@@ -157,6 +155,9 @@ __device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
     __syncthreads();
     const T tol = Eps<T>::v() * t_sqrt((T) a);
     const T tol2 = tol * tol;
+    // Predictive stop: the sweep after one in which every pair was already below cos = sqrt(tol) would only verify
+    // (quadratic convergence leaves residual cosines ~ tol), so it is skipped.
+    const T big2 = tol;
     const int nblk = (b + BW - 1) / BW;
 
     // asynchronous staging of columns [c0, c0 + wc) into dst (pitch P, zero padded rows and columns)
@@ -202,7 +203,7 @@ __device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
     for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
         ++sweeps_used;
         __syncthreads();
-        if (tid == 0) s_rot = 0;
+        if (tid == 0) { s_rot = 0; s_big = 0; }
         __syncthreads();
         for (int bi = 0; bi < nblk; ++bi) {
             const int ci0 = bi * BW, wi = min(BW, b - ci0);
@@ -221,9 +222,10 @@ __device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
                         int x, y;
                         rr_pair(nu2, round, slot, x, y);
                         if (y >= wi) continue;
-                        if (jacobi_rotate_reg<T, NI>(R0 + (size_t) x * P, R0 + (size_t) y * P, mt.n2 + x, mt.n2 + y, lane, tol2) &&
-                            lane == 0)
-                            s_rot = 1;
+                        const int rr = jacobi_rotate_reg<T, NI>(R0 + (size_t) x * P, R0 + (size_t) y * P, mt.n2 + x, mt.n2 + y,
+                                                                lane, tol2, big2);
+                        if ((rr & 1) && lane == 0) s_rot = 1;
+                        if ((rr & 2) && lane == 0) s_big = 1;
                     }
                     __syncthreads();
                 }
@@ -241,7 +243,7 @@ __device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
                 x1[i] = *reinterpret_cast<const Vec2<T> *>(R0 + (size_t) (2 * w + 1) * P + 64 * i + 2 * lane);
             }
             __syncthreads();  // R0 is free from here on
-            bool any = false;
+            int any = 0;
             for (int bj = bi + 1; bj < nblk; ++bj) {
                 const int k = bj - bi - 1;             // pass number: block J sits in R1 for even k, R0 for odd k
                 T *BB = (k & 1) ? R0 : R1, *other = (k & 1) ? R1 : R0;
@@ -263,8 +265,8 @@ __device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
                         yb[i] = *reinterpret_cast<const Vec2<T> *>(pb + 64 * i);
                     }
                     const int ix = 2 * w, iya = BW + ja, iyb = BW + jb;
-                    any |= rx_duo<T, NI>(x0, ix + 0, ya, iya, x1, ix + 1, yb, iyb, mt, lane, tol2);
-                    any |= rx_duo<T, NI>(x1, ix + 1, ya, iya, x0, ix + 0, yb, iyb, mt, lane, tol2);
+                    any |= rx_duo<T, NI>(x0, ix + 0, ya, iya, x1, ix + 1, yb, iyb, mt, lane, tol2, big2);
+                    any |= rx_duo<T, NI>(x1, ix + 1, ya, iya, x0, ix + 0, yb, iyb, mt, lane, tol2, big2);
 #pragma unroll
                     for (int i = 0; i < NI; ++i) {
                         *reinterpret_cast<Vec2<T> *>(pa + 64 * i) = ya[i];
@@ -285,7 +287,8 @@ __device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
                 }
                 __syncthreads();
             }
-            if (any && lane == 0) s_rot = 1;
+            if ((any & 1) && lane == 0) s_rot = 1;
+            if ((any & 2) && lane == 0) s_big = 1;
             // ---- block I: registers -> global copy (scales are 1 after the last fold)
             {
                 auto put = [&](const Vec2<T> (&x)[NI], int c) {
@@ -302,7 +305,7 @@ __device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
             }
             __syncthreads();
         }
-        converged = (s_rot == 0);
+        converged = (s_rot == 0) || (s_big == 0);
     }
     if (p.info && tid == 0) {
         if (!converged) atomicOr(p.info, 1);
