@@ -137,6 +137,25 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def fp64_peak():
+    """The path computes in f64: no tcgen05 kind exists for it, the tensor instruction is DMMA.  MEASURED_PEAKS.json
+    only holds bf16, so the yardstick is cuBLAS DGEMM measured on this pool's B200 by scripts/fp64_peak.py."""
+    try:
+        p = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_yardstick.json")))
+        return float(p["dgemm_tflops"]), "measured cuBLAS DGEMM 8192^3 f64 (profiles/r01_fp64_yardstick.json; MEASURED_PEAKS.json has no f64 entry)"
+    except Exception:
+        return 35.5, "fallback: cuBLAS DGEMM measured in round 1 (35.5 TFLOP/s)"
+
+
+def ncu_traffic(kernel):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (or None)."""
+    try:
+        p = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        return p.get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # reference CPU arm / baseline (oracle/_ref = the reference's own sources compiled unmodified)
 # --------------------------------------------------------------------------------------------------------------------
@@ -290,19 +309,21 @@ def main():
     ms_per_step = ms / args.steps
     value = total_gemms / (ms_per_step * 1e-3)
 
-    # ---- rank trace (untimed): kc before / rk after every k-step, for the flop and byte accounting
+    # ---- rank trace (untimed): kc before / rk after / Jacobi sweeps of every k-step, for the flop and byte accounting
     if world == 1:
         Cm.reset_to_zero()
-        kc_hist, rk_hist = [], []
+        kc_hist, rk_hist, sw_hist = [], [], []
         for k in range(T):
             kc_hist.append(Cm.ranks.clone())
-            hc.tile_matrix_multiplication(A, B, Cm, 1.0, 1.0, ctx, prm, k_range=(k, k + 1))
+            hc.tile_matrix_multiplication(A, B, Cm, 1.0, 1.0, ctx, prm, k_range=(k, k + 1), info=info)
             rk_hist.append(Cm.ranks.clone())
+            sw_hist.append(((info >> 8) & 0xff).clone())
         ctx.Sync()
         kc_all = torch.stack(kc_hist).cpu().numpy().astype(np.float64)
         rk_all = torch.stack(rk_hist).cpu().numpy().astype(np.float64)
+        sw_all = torch.stack(sw_hist).cpu().numpy().astype(np.float64)
     else:
-        kc_all = rk_all = None
+        kc_all = rk_all = sw_all = None
 
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -336,14 +357,27 @@ def main():
             b_qr = 8 * (2 * 2 * nb * r)                 # read both stacks + write both reflector panels, per tile-GEMM
             b_recomp = 8 * (2 * nb * (3 * r + rk_all) + 6 * r * r)
             dom = max(("panel_qr", "jacobi_svd", "core_lq", "apply_q", "contraction", "stack"), key=lambda n: phases[n]["ms_per_step"])
-            alg = {"panel_qr": b_qr.sum(), "jacobi_svd": (8 * 3 * r * r).sum(), "core_lq": (8 * 4 * r * r).sum(),
-                   "apply_q": (8 * (2 * nb * r + 2 * nb * rk_all)).sum(),
-                   "contraction": (8 * (2 * nb * (ka + kb) + nb * r)).sum(), "stack": (8 * 2 * 2 * nb * r).sum()}[dom]
             t_dom = phases[dom]["ms_per_step"] * 1e-3
-            ach = alg / t_dom / 1e9
-            result["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                                  "traffic": None, "peak_source": src,
-                                  "launch_ms": phases[dom]["ms_per_step"] / max(phases[dom]["launches_per_step"], 1)}
+            launch_ms = phases[dom]["ms_per_step"] / max(phases[dom]["launches_per_step"], 1)
+            # algorithmic flops of the FP64-bound phases (DESIGN.md "rooflines"): Jacobi = sweeps * r(r-1)/2 rotations
+            # of 6r flops; QR = 2 stacks of 2 m r^2 - 2/3 r^3; rebuild = 2 sides of 4 m r rk - 2 r^2 rk
+            alg_flops = {"jacobi_svd": (sw_all * (r * (r - 1) / 2) * 6 * r).sum(),
+                         "panel_qr": (2 * (2 * nb * r * r - 2.0 / 3.0 * r ** 3)).sum(),
+                         "apply_q": (2 * (4 * nb * r * rk_all - 2 * r * r * rk_all)).sum()}
+            if dom in alg_flops:
+                pk, pk_src = fp64_peak()
+                ach = float(alg_flops[dom]) / t_dom / 1e12
+                tr = ncu_traffic(dom)
+                result["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk, "unit": "TFLOP/s",
+                                      "frac": ach / pk, "traffic": tr, "peak_source": pk_src, "launch_ms": launch_ms,
+                                      "note": "f64 path: flop-bound (C ranks grow to ~313, r = kc + 44); the FP64 pipe "
+                                              "/ DMMA rate is the ceiling, HBM traffic is <1% of peak"}
+            else:
+                alg = {"core_lq": (8 * 4 * r * r).sum(), "contraction": (8 * (2 * nb * (ka + kb) + nb * r)).sum(),
+                       "stack": (8 * 2 * 2 * nb * r).sum()}[dom]
+                ach = alg / t_dom / 1e9
+                result["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s",
+                                      "frac": ach / hbm, "traffic": ncu_traffic(dom), "peak_source": src, "launch_ms": launch_ms}
             t_rec = sum(phases[n]["ms_per_step"] for n in ("stack", "panel_qr", "core_lq", "jacobi_svd", "vsigma_truncate",
                                                            "apply_q", "finalize")) * 1e-3
             t_con = phases["contraction"]["ms_per_step"] * 1e-3
