@@ -166,6 +166,8 @@ struct hcb_ctx {
     bool own_stream = false;
     void *ws = nullptr;  // grow-only scratch arena
     size_t ws_bytes = 0;
+    int *svd_sched = nullptr;  // work counters of the persistent Jacobi kernel (2 + problems ints, grow-only)
+    size_t svd_sched_n = 0;
     hcb::ParamRing ring;
     // optional per-phase device timing of the fused path (CUDA events on this stream; see hcb_ctx_phase_timing)
     bool timing = false;

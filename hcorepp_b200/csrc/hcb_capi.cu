@@ -171,7 +171,17 @@ int launch_svd(hcb_ctx *ctx, const SvdProb<T> *d_probs, int n_probs, int a_bound
         const size_t rx = align_up(rx_smem_bytes<T>(cdiv(a_bound, 64), b_bound), 16);
         if (rx <= cap) {
             HCB_CUDA(cudaFuncSetAttribute(k_jacobi_svd_rx<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) rx));
-            k_jacobi_svd_rx<T><<<n_probs, RX_THREADS, rx, ctx->stream>>>(d_probs, 40);
+            const size_t need = (size_t) n_probs + 2;
+            if (need > ctx->svd_sched_n) {
+                if (ctx->svd_sched) { HCB_CUDA(cudaStreamSynchronize(ctx->stream)); HCB_CUDA(cudaFree(ctx->svd_sched)); }
+                ctx->svd_sched = nullptr; ctx->svd_sched_n = 0;
+                HCB_CUDA(cudaMalloc(&ctx->svd_sched, need * 2 * sizeof(int)));
+                ctx->svd_sched_n = need * 2;
+            }
+            HCB_CUDA(cudaMemsetAsync(ctx->svd_sched, 0, need * sizeof(int), ctx->stream));
+            // persistent: one CTA per SM (shared memory allows one), (sweep, problem) items from an atomic counter
+            const int grid = std::max(1, std::min(n_probs, ctx->sm_count));
+            k_jacobi_svd_rx<T><<<grid, RX_THREADS, rx, ctx->stream>>>(d_probs, n_probs, 40, ctx->svd_sched);
             HCB_LAUNCH_CHECK("k_jacobi_svd_rx");
             return HCB_OK;
         }
@@ -1083,6 +1093,7 @@ int hcb_ctx_destroy(hcb_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->ws) cudaFree(c->ws);
+    if (c->svd_sched) cudaFree(c->svd_sched);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->ring.h) cudaFreeHost(c->ring.h);
     if (c->ring.d) cudaFree(c->ring.d);

@@ -121,8 +121,9 @@ __device__ __forceinline__ int jacobi_rotate_reg(T *__restrict__ mx, T *__restri
 
 // Epilogue shared by the Jacobi kernels: singular values = column norms of the rotated copy M (ld ldm), rank-sort
 // (descending, stable) and scatter of the normalised left factor.  sig: b elements of shared memory.
-template<typename T>
+template<typename T, bool L2 = false>  // L2: read M with ld.global.cg (written by other SMs in earlier sweeps)
 __device__ void jacobi_finish(const T *M, int ldm, T *sig, const SvdProb<T> &p) {
+    auto ld = [](const T *q) { return L2 ? __ldcg(q) : *q; };
     const int a = p.a, b = p.b;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
     (void) tid;
@@ -130,7 +131,7 @@ __device__ void jacobi_finish(const T *M, int ldm, T *sig, const SvdProb<T> &p) 
     for (int c = w; c < b; c += nw) {
         const T *mc = M + (size_t) c * ldm;
         T ss = T(0);
-        for (int i = lane; i < a; i += 32) ss = fma(mc[i], mc[i], ss);
+        for (int i = lane; i < a; i += 32) { const T v = ld(mc + i); ss = fma(v, v, ss); }
         ss = warp_sum(ss);
         if (lane == 0) sig[c] = t_sqrt(ss);
     }
@@ -147,7 +148,7 @@ __device__ void jacobi_finish(const T *M, int ldm, T *sig, const SvdProb<T> &p) 
         if (lane == 0) p.sigma[pos] = sc;
         const T *mc = M + (size_t) c * ldm;
         T *uo = p.Uout + (size_t) pos * p.ldu;
-        for (int i = lane; i < a; i += 32) uo[i] = (sc > T(0)) ? mc[i] / sc : T(0);
+        for (int i = lane; i < a; i += 32) uo[i] = (sc > T(0)) ? ld(mc + i) / sc : T(0);
     }
 }
 

@@ -139,8 +139,11 @@ __device__ __forceinline__ int rx_duo(Vec2<T> (&xa)[NI], int ixa, Vec2<T> (&ya)[
     return (brot ? 1 : 0) | (bbig ? 2 : 0);
 }
 
+// ONE sweep over all column pairs of problem p (the rotated copy lives in p.J between sweeps; `first` makes it from
+// p.M).  Returns bit 0: something rotated, bit 1: some pair was above the predictive-stop level.  When `last_allowed`
+// or the sweep converged, the epilogue (sigma, sort, scatter of the left factor, info) runs too and bit 2 is set.
 template<typename T, int NI>
-__device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
+__device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sweeps) {
     constexpr int P = 64 * NI, BW = RX_BW;
     __shared__ int s_rot, s_big;
     const int a = p.a, b = p.b;
@@ -151,7 +154,9 @@ __device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
     T *meta = sig + b;                           // 3 x 64 metadata: x columns [0,32), y columns [32,64)
     RxMeta<T> mt{meta, meta + 2 * BW, meta + 4 * BW};
     T *M = p.J;  // rotated copy (global / L2), ld a
-    for (int idx = tid; idx < a * b; idx += RX_THREADS) M[idx] = p.M[(size_t) (idx % a) + (size_t) (idx / a) * p.ldm];
+    if (sweep == 0) {
+        for (int idx = tid; idx < a * b; idx += RX_THREADS) M[idx] = p.M[(size_t) (idx % a) + (size_t) (idx / a) * p.ldm];
+    }
     __syncthreads();
     const T tol = Eps<T>::v() * t_sqrt((T) a);
     const T tol2 = tol * tol;
@@ -170,12 +175,12 @@ __device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
             if (sizeof(T) == 8) {
                 if (v0 && v1 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) cp_async_16(d, src);
                 else {
-                    if (v0) cp_async_8(d, src); else d[0] = T(0);
-                    if (v1) cp_async_8(d + 1, src + 1); else d[1] = T(0);
+                    d[0] = v0 ? __ldcg(src) : T(0);  // (L2 loads: another SM may have run this problem's last sweep)
+                    d[1] = v1 ? __ldcg(src + 1) : T(0);
                 }
             } else {
-                d[0] = v0 ? src[0] : T(0);
-                d[1] = v1 ? src[1] : T(0);
+                d[0] = v0 ? __ldcg(src) : T(0);
+                d[1] = v1 ? __ldcg(src + 1) : T(0);
             }
         }
         cp_async_commit();
@@ -199,9 +204,7 @@ __device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
     };
 
     bool converged = (b < 2);
-    int sweeps_used = 0;
-    for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
-        ++sweeps_used;
+    if (!converged) {
         __syncthreads();
         if (tid == 0) { s_rot = 0; s_big = 0; }
         __syncthreads();
@@ -307,12 +310,15 @@ __device__ void jacobi_sweeps_rx(T *sm, const SvdProb<T> &p, int max_sweeps) {
         }
         converged = (s_rot == 0) || (s_big == 0);
     }
+    const int flags = converged ? 0 : 3;
+    if (!converged && sweep + 1 < max_sweeps) return flags;
     if (p.info && tid == 0) {
         if (!converged) atomicOr(p.info, 1);
-        atomicOr(p.info, sweeps_used << 8);
+        atomicOr(p.info, (b < 2 ? 0 : sweep + 1) << 8);
     }
     __syncthreads();
-    jacobi_finish<T>(M, a, sig, p);
+    jacobi_finish<T, true>(M, a, sig, p);
+    return flags | 4;
 }
 
 template<typename T>
@@ -320,20 +326,64 @@ constexpr size_t rx_smem_bytes(int ni, int b_bound) {
     return sizeof(T) * ((size_t) 2 * 64 * ni * RX_BW + (size_t) b_bound + 6 * RX_BW);
 }
 
-// One CTA of 512 threads per problem; a <= 384.  Dynamic shared memory: rx_smem_bytes(ceil(a_bound / 64), b_bound).
+// Persistent kernel: grid = min(n_probs, resident CTAs) CTAs of 512 threads; a <= 384.  Work items are (sweep, problem)
+// pairs handed out sweep-major through an atomic counter, so that the 256 problems of a batch do not run as 1.73
+// "waves" of whole problems on 148 SMs (the second one 73 % full): a CTA that finishes a sweep takes the next item,
+// whichever problem it belongs to.  sched[0] = next item, sched[1] = finished problems, sched[2 + t] = state of problem
+// t: number of completed sweeps, or -1 when finished.  Items are claimed in increasing order and all CTAs are
+// resident, so waiting for a problem's previous sweep (claimed earlier, hence running) cannot deadlock.
+// Dynamic shared memory: rx_smem_bytes(ceil(a_bound / 64), b_bound).  sched must be zeroed before the launch.
 template<typename T>
-__global__ void __launch_bounds__(RX_THREADS, 1) k_jacobi_svd_rx(const SvdProb<T> *__restrict__ probs, int max_sweeps) {
+__global__ void __launch_bounds__(RX_THREADS, 1) k_jacobi_svd_rx(const SvdProb<T> *__restrict__ probs, int n_probs,
+                                                                 int max_sweeps, int *__restrict__ sched) {
     extern __shared__ __align__(16) unsigned char smem_raw_rx[];
     T *sm = reinterpret_cast<T *>(smem_raw_rx);
-    const SvdProb<T> p = probs[blockIdx.x];
-    if (p.a <= 0 || p.b <= 0) return;
-    switch ((p.a + 63) / 64) {
-        case 1: jacobi_sweeps_rx<T, 1>(sm, p, max_sweeps); break;
-        case 2: jacobi_sweeps_rx<T, 2>(sm, p, max_sweeps); break;
-        case 3: jacobi_sweeps_rx<T, 3>(sm, p, max_sweeps); break;
-        case 4: jacobi_sweeps_rx<T, 4>(sm, p, max_sweeps); break;
-        case 5: jacobi_sweeps_rx<T, 5>(sm, p, max_sweeps); break;
-        default: jacobi_sweeps_rx<T, 6>(sm, p, max_sweeps); break;
+    __shared__ int s_item, s_state;
+    const int tid = threadIdx.x;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            int item = -1;
+            if (*reinterpret_cast<volatile int *>(sched + 1) < n_probs) item = atomicAdd(sched, 1);
+            int state = 0;
+            if (item >= 0 && item < n_probs * max_sweeps) {
+                const int pr = item % n_probs, sw = item / n_probs;
+                volatile int *st = reinterpret_cast<volatile int *>(sched + 2 + pr);
+                while ((state = *st) >= 0 && state < sw) __nanosleep(200);  // previous sweep still running elsewhere
+                __threadfence();
+            } else {
+                item = -1;
+            }
+            s_item = item;
+            s_state = state;
+        }
+        __syncthreads();
+        const int item = s_item;
+        if (item < 0) break;
+        if (s_state < 0) continue;  // problem already finished
+        const int pr = item % n_probs, sw = item / n_probs;
+        const SvdProb<T> p = probs[pr];
+        int flags = 4;
+        if (p.a > 0 && p.b > 0) {
+            switch ((p.a + 63) / 64) {
+                case 1: flags = jacobi_sweep_rx<T, 1>(sm, p, sw, max_sweeps); break;
+                case 2: flags = jacobi_sweep_rx<T, 2>(sm, p, sw, max_sweeps); break;
+                case 3: flags = jacobi_sweep_rx<T, 3>(sm, p, sw, max_sweeps); break;
+                case 4: flags = jacobi_sweep_rx<T, 4>(sm, p, sw, max_sweeps); break;
+                case 5: flags = jacobi_sweep_rx<T, 5>(sm, p, sw, max_sweeps); break;
+                default: flags = jacobi_sweep_rx<T, 6>(sm, p, sw, max_sweeps); break;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();  // the rotated copy / outputs are visible before the state moves on
+            if (flags & 4) {
+                *reinterpret_cast<volatile int *>(sched + 2 + pr) = -1;
+                atomicAdd(sched + 1, 1);
+            } else {
+                *reinterpret_cast<volatile int *>(sched + 2 + pr) = sw + 1;
+            }
+        }
     }
 }
 
