@@ -212,7 +212,7 @@ size_t qr_block_desc_bytes(int cnt, int cols_bound) {  // one descriptor set per
 
 // cluster launch of the strip-resident block-reflector kernel: `cnt` jobs, rows_bound rows
 inline bool strip_path_ok(const hcb_ctx *ctx, int rows_bound) {
-    return rows_bound <= 8 * SK_ROWS && SK_SMEM_BYTES <= ctx->smem_optin;
+    return rows_bound <= SK_MAXCS * SK_ROWS && SK_SMEM_BYTES <= ctx->smem_optin;
 }
 inline int launch_strips(hcb_ctx *ctx, const StripJob *jobs, int cnt, int rows_bound) {
     if (cnt <= 0) return HCB_OK;

@@ -20,9 +20,10 @@
 
 namespace hcb {
 
-constexpr int SK_ROWS = 256;     // rows per CTA
-constexpr int SK_THREADS = 256;  // 8 warps
+constexpr int SK_ROWS = 128;     // rows per CTA
+constexpr int SK_THREADS = 128;  // 4 warps; two CTAs (of different clusters) share an SM and fill each other's barrier gaps
 constexpr int SK_WP = 36;        // pitch of the W / W2 matrix (conflict-free DMMA B-fragment loads)
+constexpr int SK_MAXCS = 8;      // portable cluster size limit: up to 1024 rows per strip
 
 struct StripJob {
     double *S;         // strip: column 0, row 0 (ld lds); ncols <= NBQ columns, m rows
@@ -34,16 +35,16 @@ struct StripJob {
     int trans_t;                   // 1: Q^T (W2 = T^T W), 0: Q (W2 = T W)
 };
 
-// shared-memory position of element (row, col) of a 256 x 32 block: column-major with the rows of column c rotated by
+// shared-memory position of element (row, col) of a 128 x 32 block: column-major with the rows of column c rotated by
 // 4c, so that both DMMA fragment patterns (4 rows x 4..8 columns and 8 rows x 4 columns) touch 16 distinct 8-byte bank
-// pairs per half-warp without padding (3 x 64 KB blocks + the small matrices must fit 227 KB).
+// pairs per half-warp without padding.
 __device__ __forceinline__ int sk_addr(int row, int col) { return col * SK_ROWS + ((row + 4 * col) & (SK_ROWS - 1)); }
 
 constexpr size_t SK_SMEM_BYTES =
-    sizeof(double) * (3 * (size_t) NBQ * SK_ROWS + 2 * NBQ * NBQ + NBQ * SK_WP + NBQ * NBQ);
+    sizeof(double) * (2 * (size_t) NBQ * SK_ROWS + 2 * NBQ * NBQ + NBQ * SK_WP + NBQ * NBQ);  // 97 KB: two CTAs per SM
 
 // grid.x = cluster_size * n_jobs, cluster (cluster_size,1,1), block SK_THREADS, dynamic smem SK_SMEM_BYTES
-__global__ void __launch_bounds__(SK_THREADS, 1) k_strip_reflect(const StripJob *__restrict__ jobs) {
+__global__ void __launch_bounds__(SK_THREADS, 2) k_strip_reflect(const StripJob *__restrict__ jobs) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int CS = (int) cluster.num_blocks(), crank = (int) cluster.block_rank();
@@ -51,8 +52,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_strip_reflect(const StripJob 
     if (jb_.ncols <= 0 || jb_.p_count <= 0 || jb_.m <= 0) return;  // uniform over the cluster
     extern __shared__ __align__(16) unsigned char smem_raw_sk[];
     double *Sb = reinterpret_cast<double *>(smem_raw_sk);
-    double *Vb0 = Sb + NBQ * SK_ROWS;            // two reflector buffers
-    double *Wp = Vb0 + 2 * NBQ * SK_ROWS;        // two partial-W buffers (read by the other CTAs of the cluster)
+    double *Vb = Sb + NBQ * SK_ROWS;             // reflector block (single buffer: the co-resident CTA hides its load)
+    double *Wp = Vb + NBQ * SK_ROWS;             // two partial-W buffers (read by the other CTAs of the cluster)
     double *Wf = Wp + 2 * NBQ * NBQ;             // summed W, then -W2 (pitch SK_WP)
     double *Ts = Wf + NBQ * SK_WP;               // op(T_p), stored so that lane i reads op(T)[i][k] at Ts[k*32+i]
 
@@ -62,8 +63,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_strip_reflect(const StripJob 
     // above their diagonal, so a contiguous split would leave the first CTAs idle for the later blocks
     auto grow = [&](int lr) { return 32 * ((lr >> 5) * CS + crank) + (lr & 31); };
 
-    // ---- strip -> shared memory (zero padded), asynchronously: all 64 KB in flight at once (the scalar
-    // load/store loop was 30 % of the kernel's stall samples, profiles/r01_strip_reflect_ncu.txt)
+    // ---- strip -> shared memory (zero padded), asynchronously: everything in flight at once (a scalar
+    // load/store loop was 30 % of the first version's stall samples, profiles/r01_ncu_strip_reflect.txt)
     for (int q = tid; q < NBQ * SK_ROWS / 2; q += SK_THREADS) {
         const int col = q / (SK_ROWS / 2), row = 2 * (q % (SK_ROWS / 2)), gr = grow(row);
         const double *src = jb_.S + (size_t) col * jb_.lds + gr;
@@ -78,10 +79,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_strip_reflect(const StripJob 
 
     auto block_cols = [&](int p) { const int left = jb_.kmax - p * NBQ; return left < NBQ ? left : NBQ; };
     auto cta_active = [&](int p) { return grow(SK_ROWS - 1) >= p * NBQ && 32 * crank < m; };
-    // cp.async prefetch of V_p rows [r0, r0+256) into buffer `buf` (rows above the block, beyond m and columns >= jb are 0)
-    auto prefetch_v = [&](int p, int buf) {
+    // cp.async load of V_p, local rows, into Vb (rows above the block, beyond m and columns >= jb are 0)
+    auto load_v = [&](int p) {
         if (!cta_active(p)) return;
-        double *Vb = Vb0 + buf * NBQ * SK_ROWS;
         const int j0 = p * NBQ, jb = block_cols(p);
         for (int q = tid; q < NBQ * SK_ROWS / 2; q += SK_THREADS) {
             const int col = q / (SK_ROWS / 2), row = 2 * (q % (SK_ROWS / 2)), gr = grow(row);
@@ -95,93 +95,96 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_strip_reflect(const StripJob 
             }
         }
     };
-    double treg[4];
+    constexpr int TQ = NBQ * NBQ / SK_THREADS;  // T elements per thread
+    double treg[TQ];
     auto fetch_t = [&](int p) {
         const double *Tg = jb_.Tb + (size_t) p * NBQ * NBQ;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) treg[q] = Tg[tid + q * SK_THREADS];
+        for (int q = 0; q < TQ; ++q) treg[q] = Tg[tid + q * SK_THREADS];
     };
-
-    int p = jb_.p_first;
-    prefetch_v(p, 0);
-    cp_async_commit();
-    fetch_t(p);
-
-    for (int it = 0; it < jb_.p_count; ++it, p += jb_.p_step) {
-        const int buf = it & 1;
-        const double *Vb = Vb0 + buf * NBQ * SK_ROWS;
-        double *Wpb = Wp + buf * NBQ * NBQ;
-        const int j0 = p * NBQ;
-        const bool active = cta_active(p);
-        cp_async_wait_all();
-        // op(T_p) -> Ts
+    auto store_t = [&]() {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < TQ; ++q) {
             const int idx = tid + q * SK_THREADS, i = idx % NBQ, k = idx / NBQ;  // treg = T[i][k]
             if (jb_.trans_t) Ts[i * NBQ + k] = treg[q];  // op(T)[k][i] = T[i][k]
             else Ts[k * NBQ + i] = treg[q];
         }
-        __syncthreads();
-        if (it + 1 < jb_.p_count) {  // next block's reflectors fly in while this one is applied
-            prefetch_v(p + jb_.p_step, buf ^ 1);
-            fetch_t(p + jb_.p_step);
-        }
-        cp_async_commit();
+    };
 
-        // ---- phase 1: partial W = V_loc^T S_loc; warp w owns output tiles (ti, tj0) and (ti, tj0+1)
+    int p = jb_.p_first;
+    load_v(p);
+    cp_async_commit();
+    fetch_t(p);
+    store_t();
+
+    for (int it = 0; it < jb_.p_count; ++it, p += jb_.p_step) {
+        double *Wpb = Wp + (it & 1) * NBQ * NBQ;
+        const int j0 = p * NBQ;
+        const bool active = cta_active(p);
+        if (it + 1 < jb_.p_count) fetch_t(p + jb_.p_step);  // next T: in registers until this block's phase 2 is over
+        cp_async_wait_all();
+        __syncthreads();  // S, V_p and op(T_p) are in place (previous phase 3 finished)
+
+        // ---- phase 1: partial W = V_loc^T S_loc; warp w owns the output tiles (w, 0..3)
         {
-            const int ti = w >> 1, tj0 = 2 * (w & 1);
-            double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+            double acc[4][2][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][0][0] = acc[j][0][1] = acc[j][1][0] = acc[j][1][1] = 0.0;
             if (active) {
-                const int colA = 8 * ti + g, colB0 = 8 * tj0 + g, colB1 = colB0 + 8;
-                const double *pa = Vb + colA * SK_ROWS, *pb0 = Sb + colB0 * SK_ROWS, *pb1 = Sb + colB1 * SK_ROWS;
-                const int ra = 4 * colA + t, rb0 = 4 * colB0 + t, rb1 = 4 * colB1 + t;
+                const int colA = 8 * w + g;
+                const double *pa = Vb + colA * SK_ROWS;
+                const int ra = 4 * colA + t;
                 // V is zero above row j0: skip the local 32-row groups that lie entirely above it
                 const int gfirst = j0 / 32 - crank;
                 const int ks0 = gfirst > 0 ? 8 * ((gfirst + CS - 1) / CS) : 0;
-#pragma unroll 4
+#pragma unroll 2
                 for (int ks = ks0; ks < SK_ROWS / 4; ks += 2) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int rr = 4 * (ks + h);
                         const double a = pa[(rr + ra) & (SK_ROWS - 1)];
-                        const double b0 = pb0[(rr + rb0) & (SK_ROWS - 1)];
-                        const double b1 = pb1[(rr + rb1) & (SK_ROWS - 1)];
-                        dmma_m8n8k4(acc[0][h][0], acc[0][h][1], a, b0);
-                        dmma_m8n8k4(acc[1][h][0], acc[1][h][1], a, b1);
+                        double b[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) b[j] = Sb[(8 * j + g) * SK_ROWS + ((rr + 4 * (8 * j + g) + t) & (SK_ROWS - 1))];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[j][h][0], acc[j][h][1], a, b[j]);
                     }
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    Wpb[(8 * ti + g) * NBQ + 8 * (tj0 + j) + 2 * t + h] = acc[j][0][h] + acc[j][1][h];
+                for (int h = 0; h < 2; ++h) Wpb[(8 * w + g) * NBQ + 8 * j + 2 * t + h] = acc[j][0][h] + acc[j][1][h];
         }
         cluster.sync();
-        // ---- cluster sum of the partials
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int idx = tid + q * SK_THREADS, i = idx / NBQ, j = idx % NBQ;
-            double s = 0.0;
-            for (int rk = 0; rk < CS; ++rk) s += cluster.map_shared_rank(Wpb, rk)[idx];
-            Wf[i * SK_WP + j] = s;
-        }
-        __syncthreads();
-        // ---- phase 2: W2 = op(T) W, stored negated in place; warp w owns columns 4w..4w+3, lane = row
+        // ---- cluster sum + phase 2 without a block barrier in between: warp w sums and transforms ITS 8 columns
         {
-            double o[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 8
+            double wsum[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) wsum[c] = 0.0;
+            for (int rk = 0; rk < CS; ++rk) {
+                const double *rp = cluster.map_shared_rank(Wpb, rk) + lane * NBQ + 8 * w;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) wsum[c] += rp[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) Wf[lane * SK_WP + 8 * w + c] = wsum[c];
+            __syncwarp();
+            double o[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o[c] = 0.0;
+#pragma unroll 4
             for (int k = 0; k < NBQ; ++k) {
                 const double tv = Ts[k * NBQ + lane];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) o[c] = fma(tv, Wf[k * SK_WP + 4 * w + c], o[c]);
+                for (int c = 0; c < 8; ++c) o[c] = fma(tv, Wf[k * SK_WP + 8 * w + c], o[c]);
             }
             __syncwarp();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) Wf[lane * SK_WP + 4 * w + c] = -o[c];
+            for (int c = 0; c < 8; ++c) Wf[lane * SK_WP + 8 * w + c] = -o[c];
         }
         __syncthreads();
+        if (it + 1 < jb_.p_count) store_t();  // op(T) of the next block (Ts is not read in phase 3)
         // ---- phase 3: S_loc += V_loc (-W2); warp w owns rows 32w..32w+31
         if (active && grow(32 * w) + 32 > j0 && grow(32 * w) < m) {
             double acc[4][4][2];
@@ -211,9 +214,13 @@ __global__ void __launch_bounds__(SK_THREADS, 1) k_strip_reflect(const StripJob 
 #pragma unroll
                     for (int h = 0; h < 2; ++h) Sb[sk_addr(32 * w + 8 * i + g, 8 * j + 2 * t + h)] = acc[i][j][h];
         }
-        __syncthreads();
+        if (it + 1 < jb_.p_count) {
+            __syncthreads();  // everybody is done with V_p
+            load_v(p + jb_.p_step);
+            cp_async_commit();
+        }
     }
-    cp_async_wait_all();
+    __syncthreads();
     // ---- strip back to global memory
     for (int idx = tid; idx < NBQ * SK_ROWS; idx += SK_THREADS) {
         const int col = idx / SK_ROWS, row = idx % SK_ROWS, gr = grow(row);
