@@ -20,10 +20,8 @@
 
 namespace hcb {
 
-constexpr int SK_ROWS = 128;     // rows per CTA
-constexpr int SK_THREADS = 128;  // 4 warps; two CTAs (of different clusters) share an SM and fill each other's barrier gaps
-constexpr int SK_WP = 36;        // pitch of the W / W2 matrix (conflict-free DMMA B-fragment loads)
-constexpr int SK_MAXCS = 8;      // portable cluster size limit: up to 1024 rows per strip
+constexpr int SK_WP = 36;    // pitch of the W2 matrix (conflict-free DMMA B-fragment loads)
+constexpr int SK_MAXCS = 8;  // portable cluster size limit
 
 struct StripJob {
     double *S;         // strip: column 0, row 0 (ld lds); ncols <= NBQ columns, m rows
@@ -35,40 +33,60 @@ struct StripJob {
     int trans_t;                   // 1: Q^T (W2 = T^T W), 0: Q (W2 = T W)
 };
 
-// shared-memory position of element (row, col) of a 128 x 32 block: column-major with the rows of column c rotated by
-// 4c, so that both DMMA fragment patterns (4 rows x 4..8 columns and 8 rows x 4 columns) touch 16 distinct 8-byte bank
-// pairs per half-warp without padding.
-__device__ __forceinline__ int sk_addr(int row, int col) { return col * SK_ROWS + ((row + 4 * col) & (SK_ROWS - 1)); }
+// distributed shared memory through explicit shared::cluster addresses (a generic pointer from map_shared_rank makes
+// the compiler emit LD.E through the global load path: lg_throttle was the top stall of such a version)
+__device__ __forceinline__ unsigned dsmem_addr(const void *smem_ptr, unsigned rank) {
+    const unsigned a = (unsigned) __cvta_generic_to_shared(smem_ptr);
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ double ld_dsmem(unsigned addr) {
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
 
-constexpr size_t SK_SMEM_BYTES =
-    sizeof(double) * (2 * (size_t) NBQ * SK_ROWS + 2 * NBQ * NBQ + NBQ * SK_WP + NBQ * NBQ);  // 97 KB: two CTAs per SM
+// ROWS rows per CTA (ROWS / 32 warps), VBUFS reflector buffers.
+//   <256, 2>: one CTA per SM, next block prefetched while the current one is applied; 1024 rows = cluster of 4
+//   <128, 1>: two CTAs per SM; 1024 rows = cluster of 8 (4x the DSMEM traffic per block: measured slower)
+template<int ROWS, int VBUFS>
+struct StripCfg {
+    static constexpr int THREADS = ROWS;  // one warp per 32 rows
+    static constexpr size_t SMEM = sizeof(double) * ((1 + VBUFS) * (size_t) NBQ * ROWS + 2 * NBQ * NBQ + NBQ * SK_WP + NBQ * NBQ);
+};
 
-// grid.x = cluster_size * n_jobs, cluster (cluster_size,1,1), block SK_THREADS, dynamic smem SK_SMEM_BYTES
-__global__ void __launch_bounds__(SK_THREADS, 2) k_strip_reflect(const StripJob *__restrict__ jobs) {
+// grid.x = cluster_size * n_jobs, cluster (cluster_size,1,1), block ROWS threads, dynamic smem StripCfg::SMEM
+template<int ROWS, int VBUFS>
+__global__ void __launch_bounds__(ROWS, ROWS == 128 ? 2 : 1) k_strip_reflect(const StripJob *__restrict__ jobs) {
     namespace cg = cooperative_groups;
+    constexpr int THREADS = ROWS, NWARP = ROWS / 32, TPW = 16 / NWARP, CPW = NBQ / NWARP;
     cg::cluster_group cluster = cg::this_cluster();
     const int CS = (int) cluster.num_blocks(), crank = (int) cluster.block_rank();
     const StripJob jb_ = jobs[blockIdx.x / CS];
     if (jb_.ncols <= 0 || jb_.p_count <= 0 || jb_.m <= 0) return;  // uniform over the cluster
     extern __shared__ __align__(16) unsigned char smem_raw_sk[];
     double *Sb = reinterpret_cast<double *>(smem_raw_sk);
-    double *Vb = Sb + NBQ * SK_ROWS;             // reflector block (single buffer: the co-resident CTA hides its load)
-    double *Wp = Vb + NBQ * SK_ROWS;             // two partial-W buffers (read by the other CTAs of the cluster)
-    double *Wf = Wp + 2 * NBQ * NBQ;             // summed W, then -W2 (pitch SK_WP)
+    double *Vb0 = Sb + NBQ * ROWS;               // reflector buffer(s)
+    double *Wp = Vb0 + VBUFS * NBQ * ROWS;       // two partial-W buffers, TRANSPOSED ([S column][reflector]), read remotely
+    double *Wf = Wp + 2 * NBQ * NBQ;             // summed W, then -W2 ([reflector][S column], pitch SK_WP)
     double *Ts = Wf + NBQ * SK_WP;               // op(T_p), stored so that lane i reads op(T)[i][k] at Ts[k*32+i]
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
     const int m = jb_.m, ncols = jb_.ncols;
+    // shared-memory position of (row, col) of a ROWS x 32 block: column-major with the rows of column c rotated by 4c:
+    // both DMMA fragment patterns touch 16 distinct 8-byte bank pairs per half-warp without padding
+    auto sk = [](int row, int col) { return col * ROWS + ((row + 4 * col) & (ROWS - 1)); };
     // rows are dealt to the CTAs of the cluster in groups of 32 (group gg -> CTA gg % CS): the reflector blocks are zero
     // above their diagonal, so a contiguous split would leave the first CTAs idle for the later blocks
     auto grow = [&](int lr) { return 32 * ((lr >> 5) * CS + crank) + (lr & 31); };
 
     // ---- strip -> shared memory (zero padded), asynchronously: everything in flight at once (a scalar
     // load/store loop was 30 % of the first version's stall samples, profiles/r01_ncu_strip_reflect.txt)
-    for (int q = tid; q < NBQ * SK_ROWS / 2; q += SK_THREADS) {
-        const int col = q / (SK_ROWS / 2), row = 2 * (q % (SK_ROWS / 2)), gr = grow(row);
+    for (int q = tid; q < NBQ * ROWS / 2; q += THREADS) {
+        const int col = q / (ROWS / 2), row = 2 * (q % (ROWS / 2)), gr = grow(row);
         const double *src = jb_.S + (size_t) col * jb_.lds + gr;
-        double *dst = Sb + sk_addr(row, col);
+        double *dst = Sb + sk(row, col);
         const bool v0 = col < ncols && gr < m, v1 = col < ncols && gr + 1 < m;
         if (v0 && v1 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) cp_async_16(dst, src);
         else {
@@ -78,15 +96,15 @@ __global__ void __launch_bounds__(SK_THREADS, 2) k_strip_reflect(const StripJob 
     }
 
     auto block_cols = [&](int p) { const int left = jb_.kmax - p * NBQ; return left < NBQ ? left : NBQ; };
-    auto cta_active = [&](int p) { return grow(SK_ROWS - 1) >= p * NBQ && 32 * crank < m; };
-    // cp.async load of V_p, local rows, into Vb (rows above the block, beyond m and columns >= jb are 0)
-    auto load_v = [&](int p) {
+    auto cta_active = [&](int p) { return grow(ROWS - 1) >= p * NBQ && 32 * crank < m; };
+    // cp.async load of V_p, local rows (rows above the block, beyond m and columns >= jb are 0)
+    auto load_v = [&](int p, double *Vb) {
         if (!cta_active(p)) return;
         const int j0 = p * NBQ, jb = block_cols(p);
-        for (int q = tid; q < NBQ * SK_ROWS / 2; q += SK_THREADS) {
-            const int col = q / (SK_ROWS / 2), row = 2 * (q % (SK_ROWS / 2)), gr = grow(row);
+        for (int q = tid; q < NBQ * ROWS / 2; q += THREADS) {
+            const int col = q / (ROWS / 2), row = 2 * (q % (ROWS / 2)), gr = grow(row);
             const double *src = jb_.Vc + (size_t) (j0 + col) * jb_.ldv + gr;
-            double *dst = Vb + sk_addr(row, col);
+            double *dst = Vb + sk(row, col);
             const bool v0 = col < jb && gr >= j0 && gr < m, v1 = col < jb && gr + 1 >= j0 && gr + 1 < m;
             if (v0 && v1 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) cp_async_16(dst, src);
             else {
@@ -95,96 +113,107 @@ __global__ void __launch_bounds__(SK_THREADS, 2) k_strip_reflect(const StripJob 
             }
         }
     };
-    constexpr int TQ = NBQ * NBQ / SK_THREADS;  // T elements per thread
+    constexpr int TQ = NBQ * NBQ / THREADS;  // T elements per thread
     double treg[TQ];
     auto fetch_t = [&](int p) {
         const double *Tg = jb_.Tb + (size_t) p * NBQ * NBQ;
 #pragma unroll
-        for (int q = 0; q < TQ; ++q) treg[q] = Tg[tid + q * SK_THREADS];
+        for (int q = 0; q < TQ; ++q) treg[q] = Tg[tid + q * THREADS];
     };
     auto store_t = [&]() {
 #pragma unroll
         for (int q = 0; q < TQ; ++q) {
-            const int idx = tid + q * SK_THREADS, i = idx % NBQ, k = idx / NBQ;  // treg = T[i][k]
+            const int idx = tid + q * THREADS, i = idx % NBQ, k = idx / NBQ;  // treg = T[i][k]
             if (jb_.trans_t) Ts[i * NBQ + k] = treg[q];  // op(T)[k][i] = T[i][k]
             else Ts[k * NBQ + i] = treg[q];
         }
     };
 
     int p = jb_.p_first;
-    load_v(p);
+    load_v(p, Vb0);
     cp_async_commit();
     fetch_t(p);
     store_t();
 
     for (int it = 0; it < jb_.p_count; ++it, p += jb_.p_step) {
+        const double *Vb = Vb0 + (VBUFS == 2 ? (it & 1) : 0) * NBQ * ROWS;
         double *Wpb = Wp + (it & 1) * NBQ * NBQ;
         const int j0 = p * NBQ;
         const bool active = cta_active(p);
-        if (it + 1 < jb_.p_count) fetch_t(p + jb_.p_step);  // next T: in registers until this block's phase 2 is over
+        const bool more = it + 1 < jb_.p_count;
+        if (more) fetch_t(p + jb_.p_step);  // next T: in registers until this block's phase 2 is over
         cp_async_wait_all();
-        __syncthreads();  // S, V_p and op(T_p) are in place (previous phase 3 finished)
+        __syncthreads();  // S (previous phase 3), V_p and op(T_p) are in place
+        if (VBUFS == 2 && more) {  // next block's reflectors fly in while this one is applied
+            load_v(p + jb_.p_step, Vb0 + ((it + 1) & 1) * NBQ * ROWS);
+            cp_async_commit();
+        }
 
-        // ---- phase 1: partial W = V_loc^T S_loc; warp w owns the output tiles (w, 0..3)
+        // ---- phase 1: partial W = V_loc^T S_loc; warp w owns TPW of the 16 output tiles (same ti)
         {
-            double acc[4][2][2];
+            const int ti = (w * TPW) / 4, tj0 = (w * TPW) % 4;
+            double acc[TPW][2][2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j][0][0] = acc[j][0][1] = acc[j][1][0] = acc[j][1][1] = 0.0;
+            for (int j = 0; j < TPW; ++j) acc[j][0][0] = acc[j][0][1] = acc[j][1][0] = acc[j][1][1] = 0.0;
             if (active) {
-                const int colA = 8 * w + g;
-                const double *pa = Vb + colA * SK_ROWS;
+                const int colA = 8 * ti + g;
+                const double *pa = Vb + colA * ROWS;
                 const int ra = 4 * colA + t;
                 // V is zero above row j0: skip the local 32-row groups that lie entirely above it
                 const int gfirst = j0 / 32 - crank;
                 const int ks0 = gfirst > 0 ? 8 * ((gfirst + CS - 1) / CS) : 0;
 #pragma unroll 2
-                for (int ks = ks0; ks < SK_ROWS / 4; ks += 2) {
+                for (int ks = ks0; ks < ROWS / 4; ks += 2) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int rr = 4 * (ks + h);
-                        const double a = pa[(rr + ra) & (SK_ROWS - 1)];
-                        double b[4];
+                        const double a = pa[(rr + ra) & (ROWS - 1)];
+                        double b[TPW];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) b[j] = Sb[(8 * j + g) * SK_ROWS + ((rr + 4 * (8 * j + g) + t) & (SK_ROWS - 1))];
+                        for (int j = 0; j < TPW; ++j) {
+                            const int cb = 8 * (tj0 + j) + g;
+                            b[j] = Sb[cb * ROWS + ((rr + 4 * cb + t) & (ROWS - 1))];
+                        }
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[j][h][0], acc[j][h][1], a, b[j]);
+                        for (int j = 0; j < TPW; ++j) dmma_m8n8k4(acc[j][h][0], acc[j][h][1], a, b[j]);
                     }
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < TPW; ++j)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) Wpb[(8 * w + g) * NBQ + 8 * j + 2 * t + h] = acc[j][0][h] + acc[j][1][h];
+                for (int h = 0; h < 2; ++h)
+                    Wpb[(8 * (tj0 + j) + 2 * t + h) * NBQ + 8 * ti + g] = acc[j][0][h] + acc[j][1][h];
         }
         cluster.sync();
-        // ---- cluster sum + phase 2 without a block barrier in between: warp w sums and transforms ITS 8 columns
+        // ---- cluster sum + phase 2 without a block barrier in between: warp w sums and transforms ITS CPW columns
         {
-            double wsum[8];
+            double wsum[CPW];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) wsum[c] = 0.0;
+            for (int c = 0; c < CPW; ++c) wsum[c] = 0.0;
             for (int rk = 0; rk < CS; ++rk) {
-                const double *rp = cluster.map_shared_rank(Wpb, rk) + lane * NBQ + 8 * w;
+                const unsigned ra = dsmem_addr(Wpb + (CPW * w) * NBQ + lane, (unsigned) rk);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) wsum[c] += rp[c];
+                for (int c = 0; c < CPW; ++c) wsum[c] += ld_dsmem(ra + (unsigned) (c * NBQ * sizeof(double)));
             }
 #pragma unroll
-            for (int c = 0; c < 8; ++c) Wf[lane * SK_WP + 8 * w + c] = wsum[c];
+            for (int c = 0; c < CPW; ++c) Wf[lane * SK_WP + CPW * w + c] = wsum[c];
             __syncwarp();
-            double o[8];
+            double o[CPW];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) o[c] = 0.0;
+            for (int c = 0; c < CPW; ++c) o[c] = 0.0;
 #pragma unroll 4
             for (int k = 0; k < NBQ; ++k) {
                 const double tv = Ts[k * NBQ + lane];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) o[c] = fma(tv, Wf[k * SK_WP + 8 * w + c], o[c]);
+                for (int c = 0; c < CPW; ++c) o[c] = fma(tv, Wf[k * SK_WP + CPW * w + c], o[c]);
             }
             __syncwarp();
 #pragma unroll
-            for (int c = 0; c < 8; ++c) Wf[lane * SK_WP + 8 * w + c] = -o[c];
+            for (int c = 0; c < CPW; ++c) Wf[lane * SK_WP + CPW * w + c] = -o[c];
         }
         __syncthreads();
-        if (it + 1 < jb_.p_count) store_t();  // op(T) of the next block (Ts is not read in phase 3)
+        if (more) store_t();  // op(T) of the next block (Ts is not read in phase 3)
         // ---- phase 3: S_loc += V_loc (-W2); warp w owns rows 32w..32w+31
         if (active && grow(32 * w) + 32 > j0 && grow(32 * w) < m) {
             double acc[4][4][2];
@@ -193,13 +222,13 @@ __global__ void __launch_bounds__(SK_THREADS, 2) k_strip_reflect(const StripJob 
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) acc[i][j][h] = Sb[sk_addr(32 * w + 8 * i + g, 8 * j + 2 * t + h)];
+                    for (int h = 0; h < 2; ++h) acc[i][j][h] = Sb[sk(32 * w + 8 * i + g, 8 * j + 2 * t + h)];
 #pragma unroll
             for (int ks = 0; ks < NBQ / 4; ++ks) {
                 const int kc = 4 * ks + t;
                 double a[4], b[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = Vb[sk_addr(32 * w + 8 * i + g, kc)];
+                for (int i = 0; i < 4; ++i) a[i] = Vb[sk(32 * w + 8 * i + g, kc)];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) b[j] = Wf[kc * SK_WP + 8 * j + g];
 #pragma unroll
@@ -212,19 +241,19 @@ __global__ void __launch_bounds__(SK_THREADS, 2) k_strip_reflect(const StripJob 
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) Sb[sk_addr(32 * w + 8 * i + g, 8 * j + 2 * t + h)] = acc[i][j][h];
+                    for (int h = 0; h < 2; ++h) Sb[sk(32 * w + 8 * i + g, 8 * j + 2 * t + h)] = acc[i][j][h];
         }
-        if (it + 1 < jb_.p_count) {
+        if (VBUFS == 1 && more) {
             __syncthreads();  // everybody is done with V_p
-            load_v(p + jb_.p_step);
+            load_v(p + jb_.p_step, Vb0);
             cp_async_commit();
         }
     }
     __syncthreads();
     // ---- strip back to global memory
-    for (int idx = tid; idx < NBQ * SK_ROWS; idx += SK_THREADS) {
-        const int col = idx / SK_ROWS, row = idx % SK_ROWS, gr = grow(row);
-        if (gr < m && col < ncols) jb_.S[(size_t) gr + (size_t) col * jb_.lds] = Sb[sk_addr(row, col)];
+    for (int idx = tid; idx < NBQ * ROWS; idx += THREADS) {
+        const int col = idx / ROWS, row = idx % ROWS, gr = grow(row);
+        if (gr < m && col < ncols) jb_.S[(size_t) gr + (size_t) col * jb_.lds] = Sb[sk(row, col)];
     }
     cluster.sync();  // nobody leaves while a neighbour may still read its partial sums
 }
