@@ -60,7 +60,7 @@ struct StripCfg {
 template<int ROWS, int VBUFS>
 __global__ void __launch_bounds__(ROWS, ROWS == 128 ? 2 : 1) k_strip_reflect(const StripJob *__restrict__ jobs) {
     namespace cg = cooperative_groups;
-    constexpr int THREADS = ROWS, NWARP = ROWS / 32, TPW = 16 / NWARP, CPW = NBQ / NWARP;
+    constexpr int THREADS = ROWS, NWARP = ROWS / 32, CPW = NBQ / NWARP;
     cg::cluster_group cluster = cg::this_cluster();
     const int CS = (int) cluster.num_blocks(), crank = (int) cluster.block_rank();
     const StripJob jb_ = jobs[blockIdx.x / CS];
@@ -129,11 +129,22 @@ __global__ void __launch_bounds__(ROWS, ROWS == 128 ? 2 : 1) k_strip_reflect(con
         }
     };
 
+    cp_async_commit();
     int p = jb_.p_first;
     load_v(p, Vb0);
     cp_async_commit();
     fetch_t(p);
     store_t();
+    // the warp's 32 x 32 piece of the strip as DMMA accumulator fragments
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    __syncthreads();
+    double sacc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) sacc[i][j][h] = Sb[sk(32 * w + 8 * i + g, 8 * j + 2 * t + h)];
 
     for (int it = 0; it < jb_.p_count; ++it, p += jb_.p_step) {
         const double *Vb = Vb0 + (VBUFS == 2 ? (it & 1) : 0) * NBQ * ROWS;
@@ -149,41 +160,79 @@ __global__ void __launch_bounds__(ROWS, ROWS == 128 ? 2 : 1) k_strip_reflect(con
             cp_async_commit();
         }
 
-        // ---- phase 1: partial W = V_loc^T S_loc; warp w owns TPW of the 16 output tiles (same ti)
+        // ---- phase 1: partial W = V_loc^T S_loc.  Warp (kh, tg) = (w / TG, w % TG) accumulates a 2x2 block (or, with
+        // four warps, a 2x4 block) of the 16 output tiles over its share of the local rows: 2 A + 2 B fragment loads feed
+        // 4 DMMAs (one A + one B per tile would put more wavefronts on the shared-memory port than the DMMAs take).
         {
-            const int ti = (w * TPW) / 4, tj0 = (w * TPW) % 4;
-            double acc[TPW][2][2];
+            constexpr int KH = NWARP >= 8 ? NWARP / 4 : 1, TG = NWARP / KH;       // K splits, tile groups (4)
+            constexpr int NTJ = 16 / TG / 2;                                       // tile columns per group (2 or 4)
+            const int kh = w / TG, tg = w % TG;
+            const int ti0 = 2 * (tg / (4 / NTJ)), tj0 = NTJ * (tg % (4 / NTJ));
+            double acc[2][NTJ][2][2];
 #pragma unroll
-            for (int j = 0; j < TPW; ++j) acc[j][0][0] = acc[j][0][1] = acc[j][1][0] = acc[j][1][1] = 0.0;
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < NTJ; ++j) acc[i][j][0][0] = acc[i][j][0][1] = acc[i][j][1][0] = acc[i][j][1][1] = 0.0;
             if (active) {
-                const int colA = 8 * ti + g;
-                const double *pa = Vb + colA * ROWS;
-                const int ra = 4 * colA + t;
                 // V is zero above row j0: skip the local 32-row groups that lie entirely above it
                 const int gfirst = j0 / 32 - crank;
-                const int ks0 = gfirst > 0 ? 8 * ((gfirst + CS - 1) / CS) : 0;
+                const int ks_lo = gfirst > 0 ? 8 * ((gfirst + CS - 1) / CS) : 0;
+                constexpr int KSPAN = ROWS / 4 / KH;  // k-steps per K split
+                const int ks_beg = ks_lo > kh * KSPAN ? ks_lo : kh * KSPAN, ks_end = (kh + 1) * KSPAN;
 #pragma unroll 2
-                for (int ks = ks0; ks < ROWS / 4; ks += 2) {
+                for (int ks = ks_beg; ks < ks_end; ks += 2) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const int rr = 4 * (ks + h);
-                        const double a = pa[(rr + ra) & (ROWS - 1)];
-                        double b[TPW];
+                        const int rr = 4 * (ks + h) + t;
+                        double a[2], b[NTJ];
 #pragma unroll
-                        for (int j = 0; j < TPW; ++j) {
-                            const int cb = 8 * (tj0 + j) + g;
-                            b[j] = Sb[cb * ROWS + ((rr + 4 * cb + t) & (ROWS - 1))];
+                        for (int i = 0; i < 2; ++i) {
+                            const int ca = 8 * (ti0 + i) + g;
+                            a[i] = Vb[ca * ROWS + ((rr + 4 * ca) & (ROWS - 1))];
                         }
 #pragma unroll
-                        for (int j = 0; j < TPW; ++j) dmma_m8n8k4(acc[j][h][0], acc[j][h][1], a, b[j]);
+                        for (int j = 0; j < NTJ; ++j) {
+                            const int cb = 8 * (tj0 + j) + g;
+                            b[j] = Sb[cb * ROWS + ((rr + 4 * cb) & (ROWS - 1))];
+                        }
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                            for (int j = 0; j < NTJ; ++j) dmma_m8n8k4(acc[i][j][h][0], acc[i][j][h][1], a[i], b[j]);
                     }
                 }
             }
+            // K splits are added through a scratch area (aliases Wf, free until the cluster sum), pair-wise barriers
+            double *scr = Wf + tg * (2 * NTJ * 64);
+            for (int step = KH - 1; step >= 1; --step) {
+                if (kh == step) {
 #pragma unroll
-            for (int j = 0; j < TPW; ++j)
+                    for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    Wpb[(8 * (tj0 + j) + 2 * t + h) * NBQ + 8 * ti + g] = acc[j][0][h] + acc[j][1][h];
+                        for (int j = 0; j < NTJ; ++j)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) scr[((i * NTJ + j) * 2 + h) * 32 + lane] = acc[i][j][0][h] + acc[i][j][1][h];
+                }
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + tg), "r"(32 * KH) : "memory");
+                if (kh == step - 1) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < NTJ; ++j)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) acc[i][j][0][h] += scr[((i * NTJ + j) * 2 + h) * 32 + lane];
+                }
+                if (step > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + tg), "r"(32 * KH) : "memory");
+            }
+            if (kh == 0) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < NTJ; ++j)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            Wpb[(8 * (tj0 + j) + 2 * t + h) * NBQ + 8 * (ti0 + i) + g] = acc[i][j][0][h] + acc[i][j][1][h];
+            }
         }
         cluster.sync();
         // ---- cluster sum + phase 2 without a block barrier in between: warp w sums and transforms ITS CPW columns
@@ -214,15 +263,9 @@ __global__ void __launch_bounds__(ROWS, ROWS == 128 ? 2 : 1) k_strip_reflect(con
         }
         __syncthreads();
         if (more) store_t();  // op(T) of the next block (Ts is not read in phase 3)
-        // ---- phase 3: S_loc += V_loc (-W2); warp w owns rows 32w..32w+31
+        // ---- phase 3: S_loc += V_loc (-W2); warp w owns rows 32w..32w+31, whose fragments stay in registers (sacc) over
+        // all blocks: they are only STORED to the shared copy (the B operand of the next phase 1), never re-loaded
         if (active && grow(32 * w) + 32 > j0 && grow(32 * w) < m) {
-            double acc[4][4][2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) acc[i][j][h] = Sb[sk(32 * w + 8 * i + g, 8 * j + 2 * t + h)];
 #pragma unroll
             for (int ks = 0; ks < NBQ / 4; ++ks) {
                 const int kc = 4 * ks + t;
@@ -234,14 +277,14 @@ __global__ void __launch_bounds__(ROWS, ROWS == 128 ? 2 : 1) k_strip_reflect(con
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    for (int j = 0; j < 4; ++j) dmma_m8n8k4(sacc[i][j][0], sacc[i][j][1], a[i], b[j]);
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) Sb[sk(32 * w + 8 * i + g, 8 * j + 2 * t + h)] = acc[i][j][h];
+                    for (int h = 0; h < 2; ++h) Sb[sk(32 * w + 8 * i + g, 8 * j + 2 * t + h)] = sacc[i][j][h];
         }
         if (VBUFS == 1 && more) {
             __syncthreads();  // everybody is done with V_p
