@@ -81,37 +81,31 @@ __global__ void __launch_bounds__(ROWS, ROWS == 128 ? 2 : 1) k_strip_reflect(con
     // above their diagonal, so a contiguous split would leave the first CTAs idle for the later blocks
     auto grow = [&](int lr) { return 32 * ((lr >> 5) * CS + crank) + (lr & 31); };
 
-    // ---- strip -> shared memory (zero padded), asynchronously: everything in flight at once (a scalar
-    // load/store loop was 30 % of the first version's stall samples, profiles/r01_ncu_strip_reflect.txt)
-    for (int q = tid; q < NBQ * ROWS / 2; q += THREADS) {
-        const int col = q / (ROWS / 2), row = 2 * (q % (ROWS / 2)), gr = grow(row);
-        const double *src = jb_.S + (size_t) col * jb_.lds + gr;
-        double *dst = Sb + sk(row, col);
-        const bool v0 = col < ncols && gr < m, v1 = col < ncols && gr + 1 < m;
-        if (v0 && v1 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) cp_async_16(dst, src);
-        else {
-            if (v0) cp_async_8(dst, src); else dst[0] = 0.0;
-            if (v1) cp_async_8(dst + 1, src + 1); else dst[1] = 0.0;
-        }
-    }
-
-    auto block_cols = [&](int p) { const int left = jb_.kmax - p * NBQ; return left < NBQ ? left : NBQ; };
-    auto cta_active = [&](int p) { return grow(ROWS - 1) >= p * NBQ && 32 * crank < m; };
-    // cp.async load of V_p, local rows (rows above the block, beyond m and columns >= jb are 0)
-    auto load_v = [&](int p, double *Vb) {
-        if (!cta_active(p)) return;
-        const int j0 = p * NBQ, jb = block_cols(p);
-        for (int q = tid; q < NBQ * ROWS / 2; q += THREADS) {
-            const int col = q / (ROWS / 2), row = 2 * (q % (ROWS / 2)), gr = grow(row);
-            const double *src = jb_.Vc + (size_t) (j0 + col) * jb_.ldv + gr;
-            double *dst = Vb + sk(row, col);
-            const bool v0 = col < jb && gr >= j0 && gr < m, v1 = col < jb && gr + 1 >= j0 && gr + 1 < m;
+    // thread-invariant part of the block copies: thread handles the row pair (prow, prow + 1) of columns pc0, pc0 + 2, ..
+    const int prow = 2 * (tid % (ROWS / 2)), pc0 = tid / (ROWS / 2), pgr = grow(prow);
+    auto copy_cols = [&](double *dstb, const double *srcb, int ld, int ncol_valid, bool r0, bool r1) {
+        const double *src = srcb + (size_t) pc0 * ld + pgr;
+        for (int col = pc0; col < NBQ; col += THREADS / (ROWS / 2), src += (size_t) (THREADS / (ROWS / 2)) * ld) {
+            double *dst = dstb + col * ROWS + ((prow + 4 * col) & (ROWS - 1));
+            const bool v0 = r0 && col < ncol_valid, v1 = r1 && col < ncol_valid;
             if (v0 && v1 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) cp_async_16(dst, src);
             else {
                 if (v0) cp_async_8(dst, src); else dst[0] = 0.0;
                 if (v1) cp_async_8(dst + 1, src + 1); else dst[1] = 0.0;
             }
         }
+    };
+    // ---- strip -> shared memory (zero padded), asynchronously: everything in flight at once (a scalar
+    // load/store loop was 30 % of the first version's stall samples, profiles/r01_ncu_strip_reflect.txt)
+    copy_cols(Sb, jb_.S, jb_.lds, ncols, pgr < m, pgr + 1 < m);
+
+    auto block_cols = [&](int p) { const int left = jb_.kmax - p * NBQ; return left < NBQ ? left : NBQ; };
+    auto cta_active = [&](int p) { return grow(ROWS - 1) >= p * NBQ && 32 * crank < m; };
+    // cp.async load of V_p, local rows (rows above the block, beyond m and columns >= jb are 0)
+    auto load_v = [&](int p, double *Vb) {
+        if (!cta_active(p)) return;
+        const int j0 = p * NBQ;
+        copy_cols(Vb, jb_.Vc + (size_t) j0 * jb_.ldv, jb_.ldv, block_cols(p), pgr >= j0 && pgr < m, pgr + 1 >= j0 && pgr + 1 < m);
     };
     constexpr int TQ = NBQ * NBQ / THREADS;  // T elements per thread
     double treg[TQ];
@@ -240,10 +234,22 @@ __global__ void __launch_bounds__(ROWS, ROWS == 128 ? 2 : 1) k_strip_reflect(con
             double wsum[CPW];
 #pragma unroll
             for (int c = 0; c < CPW; ++c) wsum[c] = 0.0;
-            for (int rk = 0; rk < CS; ++rk) {
-                const unsigned ra = dsmem_addr(Wpb + (CPW * w) * NBQ + lane, (unsigned) rk);
+            if (CS == 4) {  // the common case (1024 rows): all 4 x CPW remote loads in flight before the first add
+                double v[4][CPW];
 #pragma unroll
-                for (int c = 0; c < CPW; ++c) wsum[c] += ld_dsmem(ra + (unsigned) (c * NBQ * sizeof(double)));
+                for (int rk = 0; rk < 4; ++rk) {
+                    const unsigned ra = dsmem_addr(Wpb + (CPW * w) * NBQ + lane, (unsigned) rk);
+#pragma unroll
+                    for (int c = 0; c < CPW; ++c) v[rk][c] = ld_dsmem(ra + (unsigned) (c * NBQ * sizeof(double)));
+                }
+#pragma unroll
+                for (int c = 0; c < CPW; ++c) wsum[c] = (v[0][c] + v[1][c]) + (v[2][c] + v[3][c]);
+            } else {
+                for (int rk = 0; rk < CS; ++rk) {
+                    const unsigned ra = dsmem_addr(Wpb + (CPW * w) * NBQ + lane, (unsigned) rk);
+#pragma unroll
+                    for (int c = 0; c < CPW; ++c) wsum[c] += ld_dsmem(ra + (unsigned) (c * NBQ * sizeof(double)));
+                }
             }
 #pragma unroll
             for (int c = 0; c < CPW; ++c) Wf[lane * SK_WP + CPW * w + c] = wsum[c];

@@ -512,7 +512,9 @@ template<typename T>
 __global__ void k_setup_apply_strips(const RecompProb<T> *__restrict__ rcs, StripJob *__restrict__ out, int nstrips, int npan) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nstrips * npan) return;
-    const int st = idx / npan, pan = idx % npan, side = pan & 1;
+    // the strips of one panel are neighbours in the grid: they run at the same time and share the panel's reflector
+    // blocks through L2 (strip-major order re-read them from HBM: 10 GB per launch in the ncu capture)
+    const int st = idx % nstrips, pan = idx / nstrips, side = pan & 1;
     const RecompProb<T> rc = rcs[pan >> 1];
     StripJob j{nullptr, nullptr, nullptr, 1, 1, 0, 0, 0, 0, 0, -1, 0};
     if constexpr (std::is_same<T, double>::value) {
