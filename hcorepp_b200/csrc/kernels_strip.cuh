@@ -244,6 +244,19 @@ __global__ void __launch_bounds__(ROWS, ROWS == 128 ? 2 : 1) k_strip_reflect(con
                 }
 #pragma unroll
                 for (int c = 0; c < CPW; ++c) wsum[c] = (v[0][c] + v[1][c]) + (v[2][c] + v[3][c]);
+            } else if (CS == 8) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    double v[4][CPW];
+#pragma unroll
+                    for (int rk = 0; rk < 4; ++rk) {
+                        const unsigned ra = dsmem_addr(Wpb + (CPW * w) * NBQ + lane, (unsigned) (4 * half + rk));
+#pragma unroll
+                        for (int c = 0; c < CPW; ++c) v[rk][c] = ld_dsmem(ra + (unsigned) (c * NBQ * sizeof(double)));
+                    }
+#pragma unroll
+                    for (int c = 0; c < CPW; ++c) wsum[c] += (v[0][c] + v[1][c]) + (v[2][c] + v[3][c]);
+                }
             } else {
                 for (int rk = 0; rk < CS; ++rk) {
                     const unsigned ra = dsmem_addr(Wpb + (CPW * w) * NBQ + lane, (unsigned) rk);
