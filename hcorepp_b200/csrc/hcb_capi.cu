@@ -211,20 +211,18 @@ size_t qr_block_desc_bytes(int cnt, int cols_bound) {  // one descriptor set per
 }
 
 // cluster launch of the strip-resident block-reflector kernel: `cnt` jobs, rows_bound rows
-constexpr int SKR = 256, SKV = 2;  // strip kernel geometry: rows per CTA, reflector buffers (see kernels_strip.cuh)
 inline bool strip_path_ok(const hcb_ctx *ctx, int rows_bound) {
-    return rows_bound <= SK_MAXCS * SKR && StripCfg<SKR, SKV>::SMEM <= ctx->smem_optin;
+    return rows_bound <= SK_MAXCS * SKR && SK_SMEM <= ctx->smem_optin;
 }
 inline int launch_strips(hcb_ctx *ctx, const StripJob *jobs, int cnt, int rows_bound) {
     if (cnt <= 0) return HCB_OK;
-    const size_t smem = StripCfg<SKR, SKV>::SMEM;
-    HCB_CUDA(cudaFuncSetAttribute(k_strip_reflect<SKR, SKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    HCB_CUDA(cudaFuncSetAttribute(k_strip_reflect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SK_SMEM));
     int cs = 1;
     while (cs * SKR < rows_bound) cs <<= 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned) (cs * cnt));
-    cfg.blockDim = dim3(StripCfg<SKR, SKV>::THREADS);
-    cfg.dynamicSmemBytes = smem;
+    cfg.blockDim = dim3(SKR);
+    cfg.dynamicSmemBytes = SK_SMEM;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -233,7 +231,7 @@ inline int launch_strips(hcb_ctx *ctx, const StripJob *jobs, int cnt, int rows_b
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    HCB_CUDA(cudaLaunchKernelEx(&cfg, k_strip_reflect<SKR, SKV>, jobs));
+    HCB_CUDA(cudaLaunchKernelEx(&cfg, k_strip_reflect, jobs));
     HCB_LAUNCH_CHECK("k_strip_reflect");
     return HCB_OK;
 }

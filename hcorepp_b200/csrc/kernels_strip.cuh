@@ -20,7 +20,6 @@
 
 namespace hcb {
 
-constexpr int SK_WP = 36;    // pitch of the W2 matrix (conflict-free DMMA B-fragment loads)
 constexpr int SK_MAXCS = 8;  // portable cluster size limit
 
 struct StripJob {
@@ -47,39 +46,48 @@ __device__ __forceinline__ double ld_dsmem(unsigned addr) {
     return v;
 }
 
-// ROWS rows per CTA (ROWS / 32 warps), VBUFS reflector buffers.
-//   <256, 2>: one CTA per SM, next block prefetched while the current one is applied; 1024 rows = cluster of 4
-//   <128, 1>: two CTAs per SM; 1024 rows = cluster of 8 (4x the DSMEM traffic per block: measured slower)
-template<int ROWS, int VBUFS>
-struct StripCfg {
-    static constexpr int THREADS = ROWS;  // one warp per 32 rows
-    static constexpr size_t SMEM = sizeof(double) * ((1 + VBUFS) * (size_t) NBQ * ROWS + 2 * NBQ * NBQ + NBQ * SK_WP + NBQ * NBQ);
-};
+// Geometry: 256 rows per CTA (cluster of 4 for 1024 rows, one CTA per SM), 8 warps in two groups of 4.
+//
+// The two groups work on the two 16-column HALVES of the strip, half a period apart.  Cluster barriers separate
+// "windows"; in every window one group runs phase 1 of a block (tensor pipe) while the other group runs the cluster sum
+// and the T product of the previous window's phase 1 (latency-bound: DSMEM loads, SIMT) followed by its phase 3 (tensor
+// pipe).  With all 8 warps in lock step the tensor pipe idled during sum / T product / barriers: 41 % active in the ncu
+// capture, 20 % of the samples in the sum + T product alone (profiles/r01_ncu_strip_reflect_v3.txt).
+//   window n, group A:  n even: phase 1 of block n/2        n odd : sum, T product, phase 3 of block (n-1)/2
+//             group B:  n odd : phase 1 of block (n-1)/2    n even: sum, T product, phase 3 of block (n-2)/2
+// V_b (buffer b & 1) is read in windows 2b .. 2b+2 and V_{b+2} is fetched during window 2b+3; op(T_b) is written by group A
+// at the start of window 2b+1 and read by group B in window 2b+2.
+constexpr int SKR = 256;                 // rows per CTA
+constexpr int SK_HP = 20;                // pitch of a group's W2 (16 columns; conflict-free DMMA B-fragment loads)
+constexpr size_t SK_SMEM = sizeof(double) * (3 * (size_t) NBQ * SKR + 2 * 16 * NBQ + 2 * NBQ * SK_HP + NBQ * NBQ);
 
-// grid.x = cluster_size * n_jobs, cluster (cluster_size,1,1), block ROWS threads, dynamic smem StripCfg::SMEM
-template<int ROWS, int VBUFS>
-__global__ void __launch_bounds__(ROWS, ROWS == 128 ? 2 : 1) k_strip_reflect(const StripJob *__restrict__ jobs) {
+// grid.x = cluster_size * n_jobs, cluster (cluster_size,1,1), block 256 threads, dynamic smem SK_SMEM
+__global__ void __launch_bounds__(SKR, 1) k_strip_reflect(const StripJob *__restrict__ jobs) {
     namespace cg = cooperative_groups;
-    constexpr int THREADS = ROWS, NWARP = ROWS / 32, CPW = NBQ / NWARP;
+    constexpr int ROWS = SKR, THREADS = SKR;
     cg::cluster_group cluster = cg::this_cluster();
     const int CS = (int) cluster.num_blocks(), crank = (int) cluster.block_rank();
     const StripJob jb_ = jobs[blockIdx.x / CS];
     if (jb_.ncols <= 0 || jb_.p_count <= 0 || jb_.m <= 0) return;  // uniform over the cluster
     extern __shared__ __align__(16) unsigned char smem_raw_sk[];
     double *Sb = reinterpret_cast<double *>(smem_raw_sk);
-    double *Vb0 = Sb + NBQ * ROWS;               // reflector buffer(s)
-    double *Wp = Vb0 + VBUFS * NBQ * ROWS;       // two partial-W buffers, TRANSPOSED ([S column][reflector]), read remotely
-    double *Wf = Wp + 2 * NBQ * NBQ;             // summed W, then -W2 ([reflector][S column], pitch SK_WP)
-    double *Ts = Wf + NBQ * SK_WP;               // op(T_p), stored so that lane i reads op(T)[i][k] at Ts[k*32+i]
+    double *Vb0 = Sb + NBQ * ROWS;               // two reflector buffers
+    double *Wp = Vb0 + 2 * NBQ * ROWS;           // per group: partial W, TRANSPOSED ([S column 16][reflector 32]), read remotely
+    double *Wf = Wp + 2 * 16 * NBQ;              // per group: summed W, then -W2 ([reflector][S column], pitch SK_HP)
+    double *Ts = Wf + 2 * NBQ * SK_HP;           // op(T_b), stored so that lane i reads op(T)[i][k] at Ts[k*32+i]
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
-    const int m = jb_.m, ncols = jb_.ncols;
+    const int grp = w >> 2, wg = w & 3;          // group (half strip) and warp inside the group
+    const int c0 = 16 * grp;                     // first strip column of this group's half
+    double *Wpg = Wp + grp * 16 * NBQ, *Wfg = Wf + grp * NBQ * SK_HP;
+    const int m = jb_.m, ncols = jb_.ncols, P = jb_.p_count;
     // shared-memory position of (row, col) of a ROWS x 32 block: column-major with the rows of column c rotated by 4c:
     // both DMMA fragment patterns touch 16 distinct 8-byte bank pairs per half-warp without padding
     auto sk = [](int row, int col) { return col * ROWS + ((row + 4 * col) & (ROWS - 1)); };
     // rows are dealt to the CTAs of the cluster in groups of 32 (group gg -> CTA gg % CS): the reflector blocks are zero
     // above their diagonal, so a contiguous split would leave the first CTAs idle for the later blocks
     auto grow = [&](int lr) { return 32 * ((lr >> 5) * CS + crank) + (lr & 31); };
+    auto group_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); };
 
     // thread-invariant part of the block copies: thread handles the row pair (prow, prow + 1) of columns pc0, pc0 + 2, ..
     const int prow = 2 * (tid % (ROWS / 2)), pc0 = tid / (ROWS / 2), pgr = grow(prow);
@@ -95,229 +103,196 @@ __global__ void __launch_bounds__(ROWS, ROWS == 128 ? 2 : 1) k_strip_reflect(con
             }
         }
     };
-    // ---- strip -> shared memory (zero padded), asynchronously: everything in flight at once (a scalar
-    // load/store loop was 30 % of the first version's stall samples, profiles/r01_ncu_strip_reflect.txt)
-    copy_cols(Sb, jb_.S, jb_.lds, ncols, pgr < m, pgr + 1 < m);
-
+    auto blk = [&](int b) { return jb_.p_first + b * jb_.p_step; };  // b-th block applied
     auto block_cols = [&](int p) { const int left = jb_.kmax - p * NBQ; return left < NBQ ? left : NBQ; };
     auto cta_active = [&](int p) { return grow(ROWS - 1) >= p * NBQ && 32 * crank < m; };
     // cp.async load of V_p, local rows (rows above the block, beyond m and columns >= jb are 0)
-    auto load_v = [&](int p, double *Vb) {
+    auto load_v = [&](int b) {
+        const int p = blk(b);
         if (!cta_active(p)) return;
         const int j0 = p * NBQ;
-        copy_cols(Vb, jb_.Vc + (size_t) j0 * jb_.ldv, jb_.ldv, block_cols(p), pgr >= j0 && pgr < m, pgr + 1 >= j0 && pgr + 1 < m);
+        copy_cols(Vb0 + (b & 1) * NBQ * ROWS, jb_.Vc + (size_t) j0 * jb_.ldv, jb_.ldv, block_cols(p), pgr >= j0 && pgr < m,
+                  pgr + 1 >= j0 && pgr + 1 < m);
     };
-    constexpr int TQ = NBQ * NBQ / THREADS;  // T elements per thread
-    double treg[TQ];
-    auto fetch_t = [&](int p) {
-        const double *Tg = jb_.Tb + (size_t) p * NBQ * NBQ;
+    // op(T) is handled by group A alone (128 threads, 8 elements each)
+    double treg[8];
+    auto fetch_t = [&](int b) {
+        const double *Tg = jb_.Tb + (size_t) blk(b) * NBQ * NBQ;
 #pragma unroll
-        for (int q = 0; q < TQ; ++q) treg[q] = Tg[tid + q * THREADS];
+        for (int q = 0; q < 8; ++q) treg[q] = Tg[(tid & 127) + q * 128];
     };
     auto store_t = [&]() {
 #pragma unroll
-        for (int q = 0; q < TQ; ++q) {
-            const int idx = tid + q * THREADS, i = idx % NBQ, k = idx / NBQ;  // treg = T[i][k]
+        for (int q = 0; q < 8; ++q) {
+            const int idx = (tid & 127) + q * 128, i = idx % NBQ, k = idx / NBQ;  // treg = T[i][k]
             if (jb_.trans_t) Ts[i * NBQ + k] = treg[q];  // op(T)[k][i] = T[i][k]
             else Ts[k * NBQ + i] = treg[q];
         }
     };
 
+    // ---- prologue: strip, V_0 (and V_1) in flight; T_0 in registers
+    copy_cols(Sb, jb_.S, jb_.lds, ncols, pgr < m, pgr + 1 < m);
+    load_v(0);
+    if (P > 1) load_v(1);
     cp_async_commit();
-    int p = jb_.p_first;
-    load_v(p, Vb0);
-    cp_async_commit();
-    fetch_t(p);
-    store_t();
-    // the warp's 32 x 32 piece of the strip as DMMA accumulator fragments
-    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    if (grp == 0) fetch_t(0);
+    cp_async_wait_all();
     __syncthreads();
-    double sacc[4][4][2];
+    // the warp's 64 x 16 piece of its half strip as DMMA accumulator fragments (rows 64 wg .. 64 wg + 63)
+    double sacc[8][2][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) sacc[i][j][h] = Sb[sk(32 * w + 8 * i + g, 8 * j + 2 * t + h)];
+            for (int h = 0; h < 2; ++h) sacc[i][j][h] = Sb[sk(64 * wg + 8 * i + g, c0 + 8 * j + 2 * t + h)];
 
-    for (int it = 0; it < jb_.p_count; ++it, p += jb_.p_step) {
-        const double *Vb = Vb0 + (VBUFS == 2 ? (it & 1) : 0) * NBQ * ROWS;
-        double *Wpb = Wp + (it & 1) * NBQ * NBQ;
-        const int j0 = p * NBQ;
-        const bool active = cta_active(p);
-        const bool more = it + 1 < jb_.p_count;
-        if (more) fetch_t(p + jb_.p_step);  // next T: in registers until this block's phase 2 is over
-        cp_async_wait_all();
-        __syncthreads();  // S (previous phase 3), V_p and op(T_p) are in place
-        if (VBUFS == 2 && more) {  // next block's reflectors fly in while this one is applied
-            load_v(p + jb_.p_step, Vb0 + ((it + 1) & 1) * NBQ * ROWS);
+    for (int n = 0; n <= 2 * P; ++n) {
+        // fetch V_{b+2} into the buffer that block b released after window 2b+2
+        if (n >= 3 && (n & 1) && (n + 1) / 2 < P) {
+            load_v((n + 1) / 2);
             cp_async_commit();
         }
-
-        // ---- phase 1: partial W = V_loc^T S_loc.  Warp (kh, tg) = (w / TG, w % TG) accumulates a 2x2 block (or, with
-        // four warps, a 2x4 block) of the 16 output tiles over its share of the local rows: 2 A + 2 B fragment loads feed
-        // 4 DMMAs (one A + one B per tile would put more wavefronts on the shared-memory port than the DMMAs take).
-        {
-            constexpr int KH = NWARP >= 8 ? NWARP / 4 : 1, TG = NWARP / KH;       // K splits, tile groups (4)
-            constexpr int NTJ = 16 / TG / 2;                                       // tile columns per group (2 or 4)
-            const int kh = w / TG, tg = w % TG;
-            const int ti0 = 2 * (tg / (4 / NTJ)), tj0 = NTJ * (tg % (4 / NTJ));
-            double acc[2][NTJ][2][2];
+        const int rel = n - grp;  // group-relative window: even -> phase 1 of block rel/2, odd -> finish block (rel-1)/2
+        if (rel >= 0 && !(rel & 1) && rel / 2 < P) {
+            // ================= phase 1 of block b: partial W = V_loc^T S_loc (32 x 16) =================
+            const int b = rel / 2, p = blk(b), j0 = p * NBQ;
+            const double *Vb = Vb0 + (b & 1) * NBQ * ROWS;
+            // warp (kh, tg): K half kh, tile rows 2 tg, 2 tg + 1, both tile columns of the half strip
+            const int kh = wg >> 1, tg = wg & 1, ti0 = 2 * tg;
+            double acc[2][2][2][2];
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < NTJ; ++j) acc[i][j][0][0] = acc[i][j][0][1] = acc[i][j][1][0] = acc[i][j][1][1] = 0.0;
-            if (active) {
+                for (int j = 0; j < 2; ++j) acc[i][j][0][0] = acc[i][j][0][1] = acc[i][j][1][0] = acc[i][j][1][1] = 0.0;
+            if (cta_active(p)) {
                 // V is zero above row j0: skip the local 32-row groups that lie entirely above it
                 const int gfirst = j0 / 32 - crank;
                 const int ks_lo = gfirst > 0 ? 8 * ((gfirst + CS - 1) / CS) : 0;
-                constexpr int KSPAN = ROWS / 4 / KH;  // k-steps per K split
+                constexpr int KSPAN = ROWS / 4 / 2;
                 const int ks_beg = ks_lo > kh * KSPAN ? ks_lo : kh * KSPAN, ks_end = (kh + 1) * KSPAN;
 #pragma unroll 2
                 for (int ks = ks_beg; ks < ks_end; ks += 2) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int rr = 4 * (ks + h) + t;
-                        double a[2], b[NTJ];
+                        double a[2], bb[2];
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
                             const int ca = 8 * (ti0 + i) + g;
                             a[i] = Vb[ca * ROWS + ((rr + 4 * ca) & (ROWS - 1))];
                         }
 #pragma unroll
-                        for (int j = 0; j < NTJ; ++j) {
-                            const int cb = 8 * (tj0 + j) + g;
-                            b[j] = Sb[cb * ROWS + ((rr + 4 * cb) & (ROWS - 1))];
+                        for (int j = 0; j < 2; ++j) {
+                            const int cb = c0 + 8 * j + g;
+                            bb[j] = Sb[cb * ROWS + ((rr + 4 * cb) & (ROWS - 1))];
                         }
 #pragma unroll
                         for (int i = 0; i < 2; ++i)
 #pragma unroll
-                            for (int j = 0; j < NTJ; ++j) dmma_m8n8k4(acc[i][j][h][0], acc[i][j][h][1], a[i], b[j]);
+                            for (int j = 0; j < 2; ++j) dmma_m8n8k4(acc[i][j][h][0], acc[i][j][h][1], a[i], bb[j]);
                     }
                 }
             }
-            // K splits are added through a scratch area (aliases Wf, free until the cluster sum), pair-wise barriers
-            double *scr = Wf + tg * (2 * NTJ * 64);
-            for (int step = KH - 1; step >= 1; --step) {
-                if (kh == step) {
+            // the two K halves are added through a scratch area (aliases this group's Wf, free in this window)
+            double *scr = Wfg + tg * 256;
+            if (kh == 1) {
 #pragma unroll
-                    for (int i = 0; i < 2; ++i)
+                for (int i = 0; i < 2; ++i)
 #pragma unroll
-                        for (int j = 0; j < NTJ; ++j)
+                    for (int j = 0; j < 2; ++j)
 #pragma unroll
-                            for (int h = 0; h < 2; ++h) scr[((i * NTJ + j) * 2 + h) * 32 + lane] = acc[i][j][0][h] + acc[i][j][1][h];
-                }
-                asm volatile("bar.sync %0, %1;" ::"r"(1 + tg), "r"(32 * KH) : "memory");
-                if (kh == step - 1) {
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-#pragma unroll
-                        for (int j = 0; j < NTJ; ++j)
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) acc[i][j][0][h] += scr[((i * NTJ + j) * 2 + h) * 32 + lane];
-                }
-                if (step > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + tg), "r"(32 * KH) : "memory");
+                        for (int h = 0; h < 2; ++h) scr[((i * 2 + j) * 2 + h) * 32 + lane] = acc[i][j][0][h] + acc[i][j][1][h];
             }
+            asm volatile("bar.sync %0, 64;" ::"r"(3 + 2 * grp + tg) : "memory");
             if (kh == 0) {
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
 #pragma unroll
-                    for (int j = 0; j < NTJ; ++j)
+                    for (int j = 0; j < 2; ++j)
 #pragma unroll
                         for (int h = 0; h < 2; ++h)
-                            Wpb[(8 * (tj0 + j) + 2 * t + h) * NBQ + 8 * (ti0 + i) + g] = acc[i][j][0][h] + acc[i][j][1][h];
+                            Wpg[(8 * j + 2 * t + h) * NBQ + 8 * (ti0 + i) + g] =
+                                acc[i][j][0][h] + acc[i][j][1][h] + scr[((i * 2 + j) * 2 + h) * 32 + lane];
             }
-        }
-        cluster.sync();
-        // ---- cluster sum + phase 2 without a block barrier in between: warp w sums and transforms ITS CPW columns
-        {
-            double wsum[CPW];
-#pragma unroll
-            for (int c = 0; c < CPW; ++c) wsum[c] = 0.0;
-            if (CS == 4) {  // the common case (1024 rows): all 4 x CPW remote loads in flight before the first add
-                double v[4][CPW];
+        } else if (rel >= 1 && (rel & 1) && (rel - 1) / 2 < P) {
+            // ================= cluster sum, T product, phase 3 of block b =================
+            const int b = (rel - 1) / 2, p = blk(b), j0 = p * NBQ;
+            const double *Vb = Vb0 + (b & 1) * NBQ * ROWS;
+            if (grp == 0) {
+                store_t();  // op(T_b); group B reads it one window later
+                if (b + 1 < P) fetch_t(b + 1);
+            }
+            // warp wg sums and transforms ITS 4 columns of the half strip: lane = reflector index
+            double wsum[4] = {0.0, 0.0, 0.0, 0.0};
+            if (CS == 4) {  // the common case (1024 rows): all 16 remote loads in flight before the first add
+                double v[4][4];
 #pragma unroll
                 for (int rk = 0; rk < 4; ++rk) {
-                    const unsigned ra = dsmem_addr(Wpb + (CPW * w) * NBQ + lane, (unsigned) rk);
+                    const unsigned ra = dsmem_addr(Wpg + (4 * wg) * NBQ + lane, (unsigned) rk);
 #pragma unroll
-                    for (int c = 0; c < CPW; ++c) v[rk][c] = ld_dsmem(ra + (unsigned) (c * NBQ * sizeof(double)));
+                    for (int c = 0; c < 4; ++c) v[rk][c] = ld_dsmem(ra + (unsigned) (c * NBQ * sizeof(double)));
                 }
 #pragma unroll
-                for (int c = 0; c < CPW; ++c) wsum[c] = (v[0][c] + v[1][c]) + (v[2][c] + v[3][c]);
-            } else if (CS == 8) {
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    double v[4][CPW];
-#pragma unroll
-                    for (int rk = 0; rk < 4; ++rk) {
-                        const unsigned ra = dsmem_addr(Wpb + (CPW * w) * NBQ + lane, (unsigned) (4 * half + rk));
-#pragma unroll
-                        for (int c = 0; c < CPW; ++c) v[rk][c] = ld_dsmem(ra + (unsigned) (c * NBQ * sizeof(double)));
-                    }
-#pragma unroll
-                    for (int c = 0; c < CPW; ++c) wsum[c] += (v[0][c] + v[1][c]) + (v[2][c] + v[3][c]);
-                }
+                for (int c = 0; c < 4; ++c) wsum[c] = (v[0][c] + v[1][c]) + (v[2][c] + v[3][c]);
             } else {
                 for (int rk = 0; rk < CS; ++rk) {
-                    const unsigned ra = dsmem_addr(Wpb + (CPW * w) * NBQ + lane, (unsigned) rk);
+                    const unsigned ra = dsmem_addr(Wpg + (4 * wg) * NBQ + lane, (unsigned) rk);
 #pragma unroll
-                    for (int c = 0; c < CPW; ++c) wsum[c] += ld_dsmem(ra + (unsigned) (c * NBQ * sizeof(double)));
+                    for (int c = 0; c < 4; ++c) wsum[c] += ld_dsmem(ra + (unsigned) (c * NBQ * sizeof(double)));
                 }
             }
 #pragma unroll
-            for (int c = 0; c < CPW; ++c) Wf[lane * SK_WP + CPW * w + c] = wsum[c];
-            __syncwarp();
-            double o[CPW];
-#pragma unroll
-            for (int c = 0; c < CPW; ++c) o[c] = 0.0;
+            for (int c = 0; c < 4; ++c) Wfg[lane * SK_HP + 4 * wg + c] = wsum[c];
+            group_bar();  // (group A: op(T_b) is complete; both: nobody still reads the K-split scratch)
+            double o[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 4
             for (int k = 0; k < NBQ; ++k) {
                 const double tv = Ts[k * NBQ + lane];
 #pragma unroll
-                for (int c = 0; c < CPW; ++c) o[c] = fma(tv, Wf[k * SK_WP + CPW * w + c], o[c]);
+                for (int c = 0; c < 4; ++c) o[c] = fma(tv, Wfg[k * SK_HP + 4 * wg + c], o[c]);
             }
             __syncwarp();
 #pragma unroll
-            for (int c = 0; c < CPW; ++c) Wf[lane * SK_WP + CPW * w + c] = -o[c];
-        }
-        __syncthreads();
-        if (more) store_t();  // op(T) of the next block (Ts is not read in phase 3)
-        // ---- phase 3: S_loc += V_loc (-W2); warp w owns rows 32w..32w+31, whose fragments stay in registers (sacc) over
-        // all blocks: they are only STORED to the shared copy (the B operand of the next phase 1), never re-loaded
-        if (active && grow(32 * w) + 32 > j0 && grow(32 * w) < m) {
+            for (int c = 0; c < 4; ++c) Wfg[lane * SK_HP + 4 * wg + c] = -o[c];
+            group_bar();
+            // phase 3: S_half += V_loc (-W2); warp wg owns rows 64 wg .. 64 wg + 63 (two 32-row groups)
+            if (cta_active(p)) {
 #pragma unroll
-            for (int ks = 0; ks < NBQ / 4; ++ks) {
-                const int kc = 4 * ks + t;
-                double a[4], b[4];
+                for (int half = 0; half < 2; ++half) {
+                    const int r0 = 64 * wg + 32 * half;
+                    if (!(grow(r0) + 32 > j0 && grow(r0) < m)) continue;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = Vb[sk(32 * w + 8 * i + g, kc)];
+                    for (int ks = 0; ks < NBQ / 4; ++ks) {
+                        const int kc = 4 * ks + t;
+                        double a[4], bb[2];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = Wf[kc * SK_WP + 8 * j + g];
+                        for (int i = 0; i < 4; ++i) a[i] = Vb[sk(r0 + 8 * i + g, kc)];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                        for (int j = 0; j < 2; ++j) bb[j] = Wfg[kc * SK_HP + 8 * j + g];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma_m8n8k4(sacc[i][j][0], sacc[i][j][1], a[i], b[j]);
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) dmma_m8n8k4(sacc[4 * half + i][j][0], sacc[4 * half + i][j][1], a[i], bb[j]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+                                Sb[sk(r0 + 8 * i + g, c0 + 8 * j + 2 * t + h)] = sacc[4 * half + i][j][h];
+                }
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) Sb[sk(32 * w + 8 * i + g, 8 * j + 2 * t + h)] = sacc[i][j][h];
         }
-        if (VBUFS == 1 && more) {
-            __syncthreads();  // everybody is done with V_p
-            load_v(p + jb_.p_step, Vb0);
-            cp_async_commit();
-        }
+        cp_async_wait_all();
+        cluster.sync();
     }
-    __syncthreads();
     // ---- strip back to global memory
     for (int idx = tid; idx < NBQ * ROWS; idx += THREADS) {
         const int col = idx / ROWS, row = idx % ROWS, gr = grow(row);
         if (gr < m && col < ncols) jb_.S[(size_t) gr + (size_t) col * jb_.lds] = Sb[sk(row, col)];
     }
-    cluster.sync();  // nobody leaves while a neighbour may still read its partial sums
 }
 
 }  // namespace hcb
