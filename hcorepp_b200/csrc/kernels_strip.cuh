@@ -40,6 +40,17 @@ __device__ __forceinline__ unsigned dsmem_addr(const void *smem_ptr, unsigned ra
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
     return r;
 }
+// Cluster barrier for the PULL pattern used here (a CTA writes its own shared memory, the others read it remotely after
+// the barrier).  cg::cluster_group::sync() compiles to MEMBAR.ALL.GPU + ERRBAR + arrive + wait: the GPU-scope fence
+// also waits for this thread's outstanding global traffic -- the cp.async prefetch of the next reflector block -- so
+// every barrier exposed the full L2 / HBM latency of that prefetch.  The data crossing the barrier is shared memory
+// written by the owning SM: a CTA-scope fence (the writes are performed in this SM's shared memory) + relaxed arrive
+// + acquiring wait is enough.
+__device__ __forceinline__ void cluster_sync_pull() {
+    asm volatile("fence.acq_rel.cta;\n" ::: "memory");
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
 __device__ __forceinline__ double ld_dsmem(unsigned addr) {
     double v;
     asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
@@ -286,7 +297,7 @@ __global__ void __launch_bounds__(SKR, 1) k_strip_reflect(const StripJob *__rest
             }
         }
         cp_async_wait_all();
-        cluster.sync();
+        cluster_sync_pull();
     }
     // ---- strip back to global memory
     for (int idx = tid; idx < NBQ * ROWS; idx += THREADS) {
