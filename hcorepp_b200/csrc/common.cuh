@@ -193,4 +193,19 @@ __device__ __forceinline__ void cp_async_8(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// CTA-scope mbarrier helpers (producer/consumer hand-off between warps without a block-wide barrier)
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;\n" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {  // release.cta
+    asm volatile("mbarrier.arrive.shared.b64 _, [%0];\n" ::"r"((unsigned) __cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {  // acquire.cta; phase k <-> parity k & 1
+    asm volatile(
+        "{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}\n" ::"r"(
+            (unsigned) __cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 }  // namespace hcb
