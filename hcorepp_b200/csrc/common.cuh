@@ -200,12 +200,18 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned coun
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {  // release.cta
     asm volatile("mbarrier.arrive.shared.b64 _, [%0];\n" ::"r"((unsigned) __cvta_generic_to_shared(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {  // acquire.cta; phase k <-> parity k & 1
-    asm volatile(
-        "{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}\n" ::"r"(
-            (unsigned) __cvta_generic_to_shared(bar)),
-        "r"(parity)
-        : "memory");
+__device__ __forceinline__ bool mbar_try(unsigned long long *bar, unsigned parity) {  // acquire.cta; phase k <-> parity k & 1
+    unsigned ok;
+    asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n"
+                 : "=r"(ok)
+                 : "r"((unsigned) __cvta_generic_to_shared(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    // watchdog: a protocol error must abort the kernel (sticky launch failure), never hang the GPU
+    for (unsigned spins = 0; !mbar_try(bar, parity); ++spins)
+        if (spins > (1u << 22)) __trap();
 }
 
 }  // namespace hcb

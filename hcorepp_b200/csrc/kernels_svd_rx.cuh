@@ -143,7 +143,7 @@ __device__ __forceinline__ int rx_duo(Vec2<T> (&xa)[NI], int ixa, Vec2<T> (&ya)[
 // p.M).  Returns bit 0: something rotated, bit 1: some pair was above the predictive-stop level.  When `last_allowed`
 // or the sweep converged, the epilogue (sigma, sort, scatter of the left factor, info) runs too and bit 2 is set.
 template<typename T, int NI>
-__device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sweeps, unsigned long long *ybar, unsigned &npass) {
+__device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sweeps) {
     constexpr int P = 64 * NI, BW = RX_BW;
     __shared__ int s_rot, s_big;
     const int a = p.a, b = p.b;
@@ -258,13 +258,8 @@ __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sw
                 if (bj + 1 < nblk) stage_async(other, cj0 + BW, min(BW, b - cj0 - BW));  // flies during this pass
                 init_meta(BB, BW);
                 __syncthreads();
-                // The y pair q = (w + s) & 15 passes from warp w+1 (round s-1) to warp w (round s): ONE mbarrier per pair
-                // instead of a block-wide barrier per round, so a warp only waits for its neighbour (the barrier stall was
-                // the third largest in the ncu capture: rotating and non-rotating pairs take different times).
-                // Phase index of barrier q: 15 per pass (rounds 0..14 produce, rounds 1..15 consume).
                 for (int s = 0; s < BW / 2; ++s) {
                     const int q = (w + s) & (BW / 2 - 1), ja = 2 * q, jb = 2 * q + 1;
-                    if (s > 0) mbar_wait(ybar + q, (npass * 15u + (unsigned) (s - 1)) & 1u);
                     Vec2<T> ya[NI], yb[NI];
                     T *pa = BB + (size_t) ja * P + 2 * lane, *pb = BB + (size_t) jb * P + 2 * lane;
 #pragma unroll
@@ -280,13 +275,11 @@ __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sw
                         *reinterpret_cast<Vec2<T> *>(pa + 64 * i) = ya[i];
                         *reinterpret_cast<Vec2<T> *>(pb + 64 * i) = yb[i];
                     }
-                    if (s + 1 < BW / 2) {
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(ybar + q);
-                    }
+                    // (a per-pair hand-off between neighbouring warps -- mbarriers, then ticket counters -- was tried in
+                    // place of this block barrier: correct with monotone tickets, but the polling warps cost more issue
+                    // slots than the barrier stalls they removed: 176 ms vs 162 ms per step)
+                    __syncthreads();
                 }
-                ++npass;
-                __syncthreads();
                 unstage(BB, cj0, wj, BW);
                 // fold the x scales so that they cannot drift far from 1
                 {
@@ -349,11 +342,7 @@ __global__ void __launch_bounds__(RX_THREADS, 1) k_jacobi_svd_rx(const SvdProb<T
     extern __shared__ __align__(16) unsigned char smem_raw_rx[];
     T *sm = reinterpret_cast<T *>(smem_raw_rx);
     __shared__ int s_item, s_state;
-    __shared__ unsigned long long ybar[RX_BW / 2];  // hand-off barriers of the y column pairs (one arrival: lane 0 of the producer)
     const int tid = threadIdx.x;
-    if (tid < RX_BW / 2) mbar_init(ybar + tid, 1);
-    unsigned npass = 0;  // completed passes over a J block (uniform over the CTA): 15 barrier phases each
-    __syncthreads();
     for (;;) {
         __syncthreads();
         if (tid == 0) {
@@ -363,7 +352,11 @@ __global__ void __launch_bounds__(RX_THREADS, 1) k_jacobi_svd_rx(const SvdProb<T
             if (item >= 0 && item < n_probs * max_sweeps) {
                 const int pr = item % n_probs, sw = item / n_probs;
                 volatile int *st = reinterpret_cast<volatile int *>(sched + 2 + pr);
-                while ((state = *st) >= 0 && state < sw) __nanosleep(200);  // previous sweep still running elsewhere
+                unsigned spins = 0;
+                while ((state = *st) >= 0 && state < sw) {  // previous sweep still running elsewhere
+                    __nanosleep(200);
+                    if (++spins > (1u << 26)) __trap();  // watchdog (> 10 s): abort instead of hanging the GPU
+                }
                 __threadfence();
             } else {
                 item = -1;
@@ -380,12 +373,12 @@ __global__ void __launch_bounds__(RX_THREADS, 1) k_jacobi_svd_rx(const SvdProb<T
         int flags = 4;
         if (p.a > 0 && p.b > 0) {
             switch ((p.a + 63) / 64) {
-                case 1: flags = jacobi_sweep_rx<T, 1>(sm, p, sw, max_sweeps, ybar, npass); break;
-                case 2: flags = jacobi_sweep_rx<T, 2>(sm, p, sw, max_sweeps, ybar, npass); break;
-                case 3: flags = jacobi_sweep_rx<T, 3>(sm, p, sw, max_sweeps, ybar, npass); break;
-                case 4: flags = jacobi_sweep_rx<T, 4>(sm, p, sw, max_sweeps, ybar, npass); break;
-                case 5: flags = jacobi_sweep_rx<T, 5>(sm, p, sw, max_sweeps, ybar, npass); break;
-                default: flags = jacobi_sweep_rx<T, 6>(sm, p, sw, max_sweeps, ybar, npass); break;
+                case 1: flags = jacobi_sweep_rx<T, 1>(sm, p, sw, max_sweeps); break;
+                case 2: flags = jacobi_sweep_rx<T, 2>(sm, p, sw, max_sweeps); break;
+                case 3: flags = jacobi_sweep_rx<T, 3>(sm, p, sw, max_sweeps); break;
+                case 4: flags = jacobi_sweep_rx<T, 4>(sm, p, sw, max_sweeps); break;
+                case 5: flags = jacobi_sweep_rx<T, 5>(sm, p, sw, max_sweeps); break;
+                default: flags = jacobi_sweep_rx<T, 6>(sm, p, sw, max_sweeps); break;
             }
         }
         __syncthreads();
