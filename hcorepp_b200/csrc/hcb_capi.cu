@@ -179,8 +179,11 @@ int launch_svd(hcb_ctx *ctx, const SvdProb<T> *d_probs, int n_probs, int a_bound
                 ctx->svd_sched_n = need * 2;
             }
             HCB_CUDA(cudaMemsetAsync(ctx->svd_sched, 0, need * sizeof(int), ctx->stream));
-            // persistent: one CTA per SM (shared memory allows one), (sweep, problem) items from an atomic counter
-            const int grid = std::max(1, std::min(n_probs, ctx->sm_count));
+            // persistent: as many CTAs as are resident at once (the item scheduler relies on it), (sweep, problem) items
+            // from an atomic counter
+            int per_sm = 1;
+            HCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jacobi_svd_rx<T>, RX_THREADS, rx));
+            const int grid = std::max(1, std::min(n_probs, ctx->sm_count * std::max(per_sm, 1)));
             k_jacobi_svd_rx<T><<<grid, RX_THREADS, rx, ctx->stream>>>(d_probs, n_probs, 40, ctx->svd_sched);
             HCB_LAUNCH_CHECK("k_jacobi_svd_rx");
             return HCB_OK;

@@ -17,8 +17,11 @@
 
 namespace hcb {
 
+// Geometry: RX_THREADS / 32 warps x 2 register-resident columns = RX_BW columns per block, one CTA per SM.
+// (256 threads / 16-column blocks with two CTAs per SM was measured: 190 ms vs 162 ms per step -- twice the block
+// staging per rotation outweighs the latency hiding.)
 constexpr int RX_THREADS = 512;
-constexpr int RX_BW = 32;  // block width (columns): 16 warps x 2 register-resident columns
+constexpr int RX_BW = RX_THREADS / 16;  // block width (columns)
 constexpr int RX_MAX_NI = 6;
 
 // per-column metadata in shared memory: squared norm (true), scale d, 1/d
