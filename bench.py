@@ -48,6 +48,8 @@ def parse():
                     help="rank bound used to size scratch for C tiles (0: calibrate with one untimed pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
+    ap.add_argument("--compress-tiles", type=int, default=8,
+                    help="initial-compression leg (SURVEY.md 8d: reported separately): dense tiles compressed (0: skip)")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     return ap.parse_args()
 
@@ -393,6 +395,11 @@ def main():
         # ---- end-to-end: same pass through the public API with HOST buffers (pinned), H2D + D2H inside the timing
         if world == 1 and not args.no_e2e:
             result["e2e"] = run_e2e(args, torch, hc, ctx, A, B, Cm, Ua, Va, Ub, Vb, krank, prm, info, total_gemms)
+            if args.compress_tiles > 0:
+                try:
+                    result["initial_compression"] = run_compression(args, torch, hc, ctx, prm, not args.no_cpu_baseline)
+                except Exception as e:  # a separate, reported-only leg
+                    result["initial_compression"] = {"error": repr(e)}
             if not args.no_cpu_baseline:
                 try:
                     result["cpu_baseline"], result["parity"] = run_cpu_baseline(args, torch, hc, ctx, A, B, Cm, Ua, Va, Ub, Vb,
@@ -467,6 +474,48 @@ def run_cpu_baseline(args, torch, hc, ctx, A, B, Cm, Ua, Va, Ub, Vb, krank, prm)
             "sample": "first %d of %d block-columns of C, all k (%d of %d tile-GEMMs), %.1f s" % (
                 cols, T, ref["tile_gemms"], T ** 3, ref["seconds"])}
     return base, parity
+
+
+def run_compression(args, torch, hc, ctx, prm, with_reference):
+    """Initial compression (the compressing constructor, Compressed.cpp:75-146; TileMatrix.cpp:150-171) of dense nb x nb
+    tiles that follow the reference generator's full spectrum law: ONE batched device call (LQ-preconditioned one-sided
+    Jacobi SVD + rank rule on the device).  Reported separately from the GEMM metric; the reference's own
+    constructor is timed on a 2-tile sample of the same tiles and its ranks / reconstruction compared."""
+    nb, n = args.nb, args.compress_tiles
+    dev = ctx.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(4242)
+    sig = torch.from_numpy(spectrum(nb)).to(dev)
+    qu, _ = torch.linalg.qr(torch.randn(n, nb, nb, generator=g, dtype=torch.float64, device=dev))
+    qv, _ = torch.linalg.qr(torch.randn(n, nb, nb, generator=g, dtype=torch.float64, device=dev))
+    tiles = (qu * sig[None, None, :]) @ qv.transpose(1, 2)            # (n, nb, nb)
+    raw = tiles.permute(1, 0, 2).reshape(nb, n * nb).contiguous()     # one block-row of n tiles
+    hc.TileMatrix.from_dense(raw, nb, nb, ctx, prm)                    # warm-up (scratch arena, module load)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    tm = hc.TileMatrix.from_dense(raw, nb, nb, ctx, prm)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    ranks = tm.rank_table().reshape(-1)
+    out = {"tiles": n, "nb": nb, "ms_total": ms, "tiles_per_s": n / (ms * 1e-3), "ranks": [int(r) for r in ranks],
+           "algorithmic_bytes_per_tile": int(8 * (nb * nb + 2 * nb * int(ranks.max())))}
+    if with_reference:
+        from oracle import ref as R
+        p = R.Params(args.acc)
+        t0 = time.time()
+        errs, rdiff, k = [], [], min(2, n)
+        for t in range(k):
+            a = np.asfortranarray(tiles[t].cpu().numpy())
+            rt = R.RefTile.compress(a, p)
+            d_ref = rt.to_dense()
+            d_gpu = tm.GetTile(0, t).to_dense()
+            errs.append(float(np.linalg.norm(d_gpu - d_ref) / np.linalg.norm(d_ref)))
+            rdiff.append(abs(int(rt.info()["rank"]) - int(ranks[t])))
+        out["reference_cpu"] = {"tiles": k, "s_per_tile": (time.time() - t0) / k, "cores": 1,
+                                "rel_fro_err_vs_reference": max(errs), "max_rank_diff": max(rdiff),
+                                "pass": bool(max(errs) <= 10 * args.acc and max(rdiff) <= 1)}
+    return out
 
 
 def run_reference_arm(args, krank):

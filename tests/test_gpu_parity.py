@@ -472,6 +472,56 @@ def test_full_size_tile_properties(hc, ctx):
     assert abs(Ct.GetTileRank() - ranks[-1]) <= 1
 
 
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", [(1000, 900, 500, 50, 50, 60), (257, 300, 128, 40, 40, 50), (999, 513, 256, 45, 45, 40),
+                                  (130, 700, 96, 30, 40, 45), (1024, 1024, 1024, 44, 44, 240)],
+                         ids=lambda d: "x".join(map(str, d)))
+def test_blocked_recompression_ragged_vs_oracle(hc, ctx, dims):
+    """Stacked rank > 64: the compact-WY path -- register panel QR clusters, strip-resident reflector clusters of 1 / 2 / 4
+    CTAs, odd row counts (8-byte cp.async path), wide V stacks, the register-block Jacobi -- against the oracle."""
+    m, n, k, ka, kb, kc = dims
+    dt, acc = np.float64, 1e-8
+    rng = np.random.default_rng(sum(dims))
+    AUV, BUV, CUV = lowrank(rng, m, k, ka, dt, 0.9), lowrank(rng, k, n, kb, dt, 0.9), lowrank(rng, m, n, kc, dt, 0.97)
+    cap = min(m, n)
+    a = mk_tile(hc, ctx, "C", None, *AUV, dt)
+    b = mk_tile(hc, ctx, "C", None, *BUV, dt)
+    c = mk_tile(hc, ctx, "C", None, *CUV, dt, max_rank=cap)
+    c.rank_bound = min(cap, kc + 2 * ka + 8)  # tight scratch bound (as the drivers set it): register-block Jacobi for r <= 384
+    oa, ob, oc = (oracle_tile("C", None, x, dt) for x in (AUV, BUV, CUV))
+    oc.max_rank = cap
+    for _ in range(2):  # second pass: C now carries the rank of the first result (orthonormal U, graded V)
+        hc.HCore.Gemm(1.0, a, False, b, False, 1.0, c, ctx, hc.CompressionParameters(acc))
+        O.hcore_gemm(dt(1.0), oa, False, ob, False, dt(1.0), oc, O.CompressionParameters(acc))
+        ref = oc.to_dense()
+        assert np.linalg.norm(c.to_dense() - ref) <= 10 * acc * max(np.linalg.norm(ref), 1.0)
+        assert abs(c.GetTileRank() - oc.rank) <= 1, (c.GetTileRank(), oc.rank)
+
+
+@pytest.mark.gpu
+def test_blocked_batch_of_different_shapes(hc, ctx):
+    """One batched call over tiles of different shapes and ranks (descriptors are per tile, grids from the bounds) must give
+    what the tiles give one by one."""
+    dt, acc = np.float64, 1e-8
+    shapes = [(1000, 900, 500, 50, 50, 60), (513, 257, 128, 40, 40, 50), (96, 80, 64, 10, 12, 9)]
+    rng = np.random.default_rng(7)
+    tiles, solo = [], []
+    for (m, n, k, ka, kb, kc) in shapes:
+        AUV, BUV, CUV = lowrank(rng, m, k, ka, dt, 0.9), lowrank(rng, k, n, kb, dt, 0.9), lowrank(rng, m, n, kc, dt, 0.97)
+        mk = lambda: (mk_tile(hc, ctx, "C", None, *AUV, dt), mk_tile(hc, ctx, "C", None, *BUV, dt),
+                      mk_tile(hc, ctx, "C", None, *CUV, dt, max_rank=min(m, n)))
+        tiles.append(mk())
+        solo.append(mk())
+    prm = hc.CompressionParameters(acc)
+    hc.gemm_batched(1.0, [t[0] for t in tiles], False, [t[1] for t in tiles], False, 1.0, [t[2] for t in tiles], ctx, prm)
+    for (a, b, c), (_, _, cb) in zip(solo, tiles):
+        hc.HCore.Gemm(1.0, a, False, b, False, 1.0, c, ctx, prm)
+        ref = c.to_dense()
+        assert np.linalg.norm(cb.to_dense() - ref) <= 1e-12 * max(np.linalg.norm(ref), 1.0)
+        assert cb.GetTileRank() == c.GetTileRank()
+
+
 def test_cpp_host_layer_replays_reference_tests():
     """include/hcorepp_b200/hcorepp.hpp (the C++ mirror of the reference API) over the C ABI: the reference's own
     operator/API known answers (tests/cpp/test_api.cpp), built by __graft_entry__.build() with plain g++."""
