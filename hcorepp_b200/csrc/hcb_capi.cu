@@ -987,11 +987,9 @@ int t_tlr_matmul(hcb_ctx *ctx, int64_t mt, int64_t nt, int64_t kt, const hcb_til
 }
 
 template<typename T>
-int t_compress_batched(hcb_ctx *ctx, int64_t n64, const T *const *dense, int64_t ld, const hcb_tile *out,
-                       const hcb_compress_params *prm, int32_t *d_info) {
-    HCB_TRY(check_ctx(ctx));
+int t_compress_full(hcb_ctx *ctx, int64_t n64, const T *const *dense, int64_t ld, const hcb_tile *out,
+                    const hcb_compress_params *prm, int32_t *d_info) {
     if (n64 <= 0) return HCB_OK;
-    if (!dense || !out || !prm) return fail(HCB_EINVAL, "compress_batched: null argument");
     (void) d_info;
     int m = 0, n = 0;
     for (int64_t t = 0; t < n64; ++t) {
@@ -1023,7 +1021,7 @@ int t_compress_batched(hcb_ctx *ctx, int64_t n64, const T *const *dense, int64_t
             T *Us = outs + (size_t) t * (eUs + eVs + eS), *Vs = Us + eUs, *sg = Vs + eVs;
             jobs[t] = SvdJob<T>{dense[c0 + t], (int) ld, tr ? 1 : 0, ta, tb, Us, Vs, sg};
             T *U = reinterpret_cast<T *>(o.d_data), *V = U + (size_t) tm * o.max_rank;
-            fp[t] = CompressProb<T>{Us, Vs, sg, U, V, o.d_rank, nullptr, tm, tn, tb, ta, tr ? 1 : 0, o.max_rank};
+            fp[t] = CompressProb<T>{Us, Vs, sg, U, V, o.d_rank, nullptr, tm, tn, tb, ta, tr ? 1 : 0, o.max_rank, ta, tb, 0};
         }
         HCB_TRY(stage_array(ctx, fp, d_fp));
         HCB_TRY(run_svd_jobs<T>(ctx, jobs, a, b, ws, base));
@@ -1031,6 +1029,138 @@ int t_compress_batched(hcb_ctx *ctx, int64_t n64, const T *const *dense, int64_t
                                                               (int) prm->fixed_rank);
         HCB_LAUNCH_CHECK("k_compress_finalize");
         if (c0 + chunk < n64) HCB_CUDA(cudaStreamSynchronize(ctx->stream));  // scratch is reused by the next chunk
+    }
+    return HCB_OK;
+}
+
+// Sketched compression (fp64, tiles up to 1024 rows): A ~ Q (Q^T A) with Q = orth(A Omega), k1 = 96 sketch columns;
+// the small factor B = Q^T A (k1 x n) goes through the batched SVD pipeline, U = Q U_B, V = Sigma W^T.  A tile whose
+// captured spectrum has not decayed two decades below the truncation threshold within k1 - 8 values is flagged on the
+// device and re-done with the full SVD.  ~0.5 GFLOP of GEMM-shaped work per 1024^2 tile instead of a 40 GFLOP Jacobi.
+constexpr int SKETCH_K = 96, SKETCH_TAIL = 8;
+
+template<typename T>
+int t_compress_sketched(hcb_ctx *ctx, int cnt, const T *const *dense, int64_t ld, const hcb_tile *out,
+                        const hcb_compress_params *prm, std::vector<int> &redo) {
+    const int k1 = SKETCH_K, nblk = cdiv(k1, NBQ);
+    int m = 0, n = 0;
+    for (int t = 0; t < cnt; ++t) { m = std::max(m, out[t].m); n = std::max(n, out[t].n); }
+    const SvdJobLayout<T> L(n, k1);
+    // per tile scratch (elements): Y | VC | Qx | Uq (m x k1 each) | B (k1 x n) | Us (n x k1) | Vs | tau | sigma | TB | WB
+    const size_t eMK = align_up((size_t) m * k1, 32), eKN = align_up((size_t) k1 * n, 32), eKK = align_up((size_t) k1 * k1, 32),
+                 eK = align_up((size_t) k1, 32), eTB = align_up((size_t) NBQ * NBQ * nblk, 32), eWB = align_up((size_t) 2 * NBQ * k1, 32);
+    const size_t slab = 4 * eMK + 2 * eKN + eKK + 2 * eK + eTB + eWB + L.slab;
+    const size_t nsj = (size_t) nblk * cnt;  // strip jobs of the explicit Q
+    const size_t desc = svd_jobs_desc_bytes<T>(cnt, n, k1) + align_up(sizeof(CompressProb<T>) * cnt, 256) +
+                        3 * align_up(sizeof(GemmProb<T>) * cnt, 256) + align_up(sizeof(PanelDesc<T>) * cnt, 256) +
+                        qr_block_desc_bytes<T>(cnt, k1) + align_up(sizeof(StripJob) * nsj, 256) +
+                        align_up(sizeof(T *) * cnt, 256) + 2 * align_up(sizeof(int) * cnt, 256) + 1024;
+    const size_t eOm = align_up((size_t) n * k1, 32);
+    HCB_TRY(ensure_ws(ctx, desc + (slab * cnt + eOm) * sizeof(T) + 512));
+    char *base = reinterpret_cast<char *>(ctx->ws);
+    char *pd = base + svd_jobs_desc_bytes<T>(cnt, n, k1);
+    auto carve = [&](size_t bytes) { char *q = pd; pd += align_up(bytes, 256); return q; };
+    auto *d_fp = reinterpret_cast<CompressProb<T> *>(carve(sizeof(CompressProb<T>) * cnt));
+    auto *d_gy = reinterpret_cast<GemmProb<T> *>(carve(sizeof(GemmProb<T>) * cnt));
+    auto *d_gb = reinterpret_cast<GemmProb<T> *>(carve(sizeof(GemmProb<T>) * cnt));
+    auto *d_gu = reinterpret_cast<GemmProb<T> *>(carve(sizeof(GemmProb<T>) * cnt));
+    auto *d_pan = reinterpret_cast<PanelDesc<T> *>(carve(sizeof(PanelDesc<T>) * cnt));
+    char *d_qrb = carve(qr_block_desc_bytes<T>(cnt, k1));
+    auto *d_sj = reinterpret_cast<StripJob *>(carve(sizeof(StripJob) * nsj));
+    auto *d_qx = reinterpret_cast<T **>(carve(sizeof(T *) * cnt));
+    auto *d_ms = reinterpret_cast<int *>(carve(sizeof(int) * cnt));
+    auto *d_flags = reinterpret_cast<int *>(carve(sizeof(int) * cnt));
+    T *ws = reinterpret_cast<T *>(base + align_up(desc, 256));
+    T *Om = ws + slab * cnt;
+    k_fill_uniform<T><<<148, 256, 0, ctx->stream>>>(Om, (size_t) n * k1, 0x5EEDull);
+    HCB_LAUNCH_CHECK("k_fill_uniform");
+
+    std::vector<CompressProb<T>> fp(cnt);
+    std::vector<GemmProb<T>> gy(cnt), gb(cnt), gu(cnt);
+    std::vector<PanelDesc<T>> pan(cnt);
+    std::vector<StripJob> sj(nsj);
+    std::vector<SvdJob<T>> jobs(cnt);
+    std::vector<T *> qx(cnt);
+    std::vector<int> ms(cnt);
+    T *svd_ws = ws;  // cnt * L.slab for the SVD pipeline, then the per-tile blocks
+    T *blk0 = ws + (size_t) cnt * L.slab;
+    const size_t per = slab - L.slab;
+    for (int t = 0; t < cnt; ++t) {
+        const hcb_tile &o = out[t];
+        const int tm = o.m, tn = o.n;
+        T *Y = blk0 + (size_t) t * per, *VC = Y + eMK, *Qx = VC + eMK, *Uq = Qx + eMK, *B = Uq + eMK, *Us = B + eKN,
+          *Vs = Us + eKN, *tau = Vs + eKK, *sg = tau + eK, *TB = sg + eK, *WB = TB + eTB;
+        gy[t] = GemmProb<T>{dense[t], Om, Y, tm, k1, tn, (int) ld, n, tm, 0, 0, T(1), T(0)};      // Y = A Omega
+        pan[t] = PanelDesc<T>{Y, tau, VC, TB, WB, tm, k1, k1, 1};
+        for (int st = 0; st < nblk; ++st)  // Qx = Q [I; 0]: every 32-column strip takes the blocks last to first
+            sj[(size_t) t * nblk + st] = StripJob{reinterpret_cast<double *>(Qx) + (size_t) st * NBQ * tm,
+                                                  reinterpret_cast<const double *>(VC), reinterpret_cast<const double *>(TB), tm, tm,
+                                                  tm, std::min(NBQ, k1 - st * NBQ), std::min(tm, k1), nblk - 1, nblk, -1, 0};
+        gb[t] = GemmProb<T>{Qx, dense[t], B, k1, tn, tm, tm, (int) ld, k1, 1, 0, T(1), T(0)};      // B = Qx^T A
+        jobs[t] = SvdJob<T>{B, k1, 1, tn, k1, Us, Vs, sg};                                       // M = B^T (n x k1)
+        gu[t] = GemmProb<T>{Qx, Vs, Uq, tm, k1, k1, tm, k1, tm, 0, 0, T(1), T(0)};                // Uq = Qx (U_B Sigma)
+        T *U = reinterpret_cast<T *>(o.d_data), *V = U + (size_t) tm * o.max_rank;
+        // A = (Qx U_B) Sigma W^T: the "transposed" branch of the finalize kernel with Vs := Uq (ld m), Us := W (ld n)
+        fp[t] = CompressProb<T>{Us, Uq, sg, U, V, o.d_rank, d_flags + t, tm, tn, k1, tn, 1, o.max_rank, tn, tm, SKETCH_TAIL};
+        qx[t] = Qx;
+        ms[t] = tm;
+    }
+    HCB_TRY(stage_array(ctx, fp, d_fp));
+    HCB_TRY(stage_array(ctx, gy, d_gy));
+    HCB_TRY(stage_array(ctx, gb, d_gb));
+    HCB_TRY(stage_array(ctx, gu, d_gu));
+    HCB_TRY(stage_array(ctx, pan, d_pan));
+    HCB_TRY(stage_array(ctx, sj, d_sj));
+    HCB_TRY(stage_array(ctx, qx, d_qx));
+    HCB_TRY(stage_array(ctx, ms, d_ms));
+    HCB_TRY(launch_gemm<T>(ctx, d_gy, cnt, m, k1));
+    HCB_TRY(run_blocked_qr<T>(ctx, d_pan, cnt, m, k1, d_qrb));
+    k_eye_batched<T><<<cnt, 256, 0, ctx->stream>>>(d_qx, d_ms, k1);
+    HCB_LAUNCH_CHECK("k_eye_batched");
+    HCB_TRY(launch_strips(ctx, d_sj, (int) nsj, m));
+    HCB_TRY(launch_gemm<T>(ctx, d_gb, cnt, k1, n));
+    HCB_TRY(run_svd_jobs<T>(ctx, jobs, n, k1, svd_ws, base));
+    HCB_TRY(launch_gemm<T>(ctx, d_gu, cnt, m, k1));
+    k_compress_finalize<T><<<cnt, 256, 0, ctx->stream>>>(d_fp, (T) prm->accuracy, prm->truncated_svd, 0);
+    HCB_LAUNCH_CHECK("k_compress_finalize");
+    std::vector<int> flags(cnt);
+    HCB_CUDA(cudaMemcpyAsync(flags.data(), d_flags, sizeof(int) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    HCB_CUDA(cudaStreamSynchronize(ctx->stream));  // (also: the scratch is reused by the fallback / next chunk)
+    for (int t = 0; t < cnt; ++t)
+        if (flags[t] != 0) redo.push_back(t);
+    return HCB_OK;
+}
+
+template<typename T>
+int t_compress_batched(hcb_ctx *ctx, int64_t n64, const T *const *dense, int64_t ld, const hcb_tile *out,
+                       const hcb_compress_params *prm, int32_t *d_info) {
+    HCB_TRY(check_ctx(ctx));
+    if (n64 <= 0) return HCB_OK;
+    if (!dense || !out || !prm) return fail(HCB_EINVAL, "compress_batched: null argument");
+    int m = 0, n = 0, mn_min = 1 << 30;
+    for (int64_t t = 0; t < n64; ++t) {
+        if (out[t].type != HCB_TILE_COMPRESSED || !out[t].d_rank || !out[t].d_data || !dense[t])
+            return fail(HCB_EINVAL, "compress_batched: bad output tile");
+        m = std::max(m, out[t].m);
+        n = std::max(n, out[t].n);
+        mn_min = std::min(mn_min, std::min(out[t].m, out[t].n));
+    }
+    // sketch when it pays (both dimensions well above the sketch width) and the strip kernels apply
+    const bool sketch = std::is_same<T, double>::value && prm->fixed_rank <= 0 && mn_min >= 3 * SKETCH_K &&
+                        strip_path_ok(ctx, m) && !getenv("HCB_COMPRESS_FULL_SVD");
+    if (!sketch) return t_compress_full<T>(ctx, n64, dense, ld, out, prm, d_info);
+    const int64_t chunk = 512;
+    for (int64_t c0 = 0; c0 < n64; c0 += chunk) {
+        const int cnt = (int) std::min<int64_t>(chunk, n64 - c0);
+        std::vector<int> redo;
+        HCB_TRY(t_compress_sketched<T>(ctx, cnt, dense + c0, ld, out + c0, prm, redo));
+        if (!redo.empty()) {  // spectrum too flat for the sketch: full SVD for those tiles
+            std::vector<const T *> rd(redo.size());
+            std::vector<hcb_tile> ro(redo.size());
+            for (size_t i = 0; i < redo.size(); ++i) { rd[i] = dense[c0 + redo[i]]; ro[i] = out[c0 + redo[i]]; }
+            HCB_TRY(t_compress_full<T>(ctx, (int64_t) redo.size(), rd.data(), ld, ro.data(), prm, d_info));
+            HCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
     }
     return HCB_OK;
 }

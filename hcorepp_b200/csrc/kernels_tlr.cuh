@@ -728,7 +728,30 @@ struct CompressProb {
     const T *Us; const T *Vs; const T *sigma;
     T *U; T *V; int *rank_ptr; int *info;
     int m, n, s, a, transposed, max_rank;
+    int ld_us, ld_vs;  // leading dimensions of Us / Vs
+    int tail_check;    // > 0 (sketched SVD): accept only if sigma[s - tail_check] is far below the threshold, else
+                       // *info = 8 and the tile is left untouched (the caller re-does it with the full SVD)
 };
+
+// Uniform(-1, 1) test matrix for the range finder (counter-based: splitmix64 of the element index).
+template<typename T>
+__global__ void k_fill_uniform(T *__restrict__ out, size_t n, unsigned long long seed) {
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (i + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        out[i] = (T) ((double) (z >> 11) * (2.0 / 9007199254740992.0) - 1.0);
+    }
+}
+
+// Q_explicit start: [I_k ; 0] (m x k, ld m), one CTA per problem
+template<typename T>
+__global__ void k_eye_batched(T *const *__restrict__ mats, const int *__restrict__ ms, int k) {
+    T *A = mats[blockIdx.x];
+    const int m = ms[blockIdx.x];
+    for (size_t idx = threadIdx.x; idx < (size_t) m * k; idx += blockDim.x) A[idx] = (idx % m == idx / m) ? T(1) : T(0);
+}
 
 template<typename T>
 __global__ void __launch_bounds__(256) k_compress_finalize(const CompressProb<T> *__restrict__ probs, T accuracy,
@@ -741,29 +764,36 @@ __global__ void __launch_bounds__(256) k_compress_finalize(const CompressProb<T>
         else rk = new_rank_rule(p.sigma, p.s, accuracy, truncated);
         if (rk < 1) rk = 1;
         if (rk > p.max_rank) rk = p.max_rank;  // Compressed.cpp:117-119 (silent clamp)
+        if (p.tail_check > 0) {  // sketched SVD: the captured spectrum must have decayed well below the threshold
+            const T thr = T(0.01) * accuracy * (truncated ? p.sigma[0] : T(1));
+            const bool ok = rk + p.tail_check <= p.s && p.sigma[p.s - p.tail_check] <= thr;
+            if (p.info) *p.info = ok ? 0 : 8;
+            if (!ok) rk = -1;
+        }
         s_rk = rk;
-        *p.rank_ptr = rk;
+        if (rk > 0) *p.rank_ptr = rk;
     }
     __syncthreads();
     const int rk = s_rk;
+    if (rk < 0) return;
     if (!p.transposed) {  // A = Us S V^T : U = Us[:, :rk], V = (V S)^T = Vs^T
         for (int idx = threadIdx.x; idx < p.m * rk; idx += blockDim.x) {
             const int i = idx % p.m, c = idx / p.m;
-            p.U[(size_t) i + (size_t) c * p.m] = p.Us[(size_t) i + (size_t) c * p.a];
+            p.U[(size_t) i + (size_t) c * p.m] = p.Us[(size_t) i + (size_t) c * p.ld_us];
         }
         for (int idx = threadIdx.x; idx < rk * p.n; idx += blockDim.x) {
             const int c = idx % rk, j = idx / rk;
-            p.V[(size_t) c + (size_t) j * rk] = p.Vs[(size_t) j + (size_t) c * p.s];
+            p.V[(size_t) c + (size_t) j * rk] = p.Vs[(size_t) j + (size_t) c * p.ld_vs];
         }
     } else {  // A^T = Us S V^T -> A = V S Us^T : U = Vs / sigma (m x rk), V = sigma * Us^T (rk x n)
         for (int idx = threadIdx.x; idx < p.m * rk; idx += blockDim.x) {
             const int i = idx % p.m, c = idx / p.m;
             const T sg = p.sigma[c];
-            p.U[(size_t) i + (size_t) c * p.m] = sg > T(0) ? p.Vs[(size_t) i + (size_t) c * p.s] / sg : T(0);
+            p.U[(size_t) i + (size_t) c * p.m] = sg > T(0) ? p.Vs[(size_t) i + (size_t) c * p.ld_vs] / sg : T(0);
         }
         for (int idx = threadIdx.x; idx < rk * p.n; idx += blockDim.x) {
             const int c = idx % rk, j = idx / rk;
-            p.V[(size_t) c + (size_t) j * rk] = p.sigma[c] * p.Us[(size_t) j + (size_t) c * p.a];
+            p.V[(size_t) c + (size_t) j * rk] = p.sigma[c] * p.Us[(size_t) j + (size_t) c * p.ld_us];
         }
     }
 }

@@ -314,6 +314,48 @@ def test_compress_vs_reference_fixture(hc, ctx, dt, name):
     assert np.max(np.abs(U.T @ U - np.eye(U.shape[1]))) < (1e-10 if dt == np.float64 else 1e-3)  # U orthonormal, S in V
 
 
+@pytest.mark.parametrize("shape", [(512, 512), (1024, 700), (600, 1024), (1024, 1024)], ids=lambda s: f"{s[0]}x{s[1]}")
+def test_sketched_compression_vs_oracle(hc, ctx, shape):
+    """Large fp64 tiles take the sketched constructor (range finder + small SVD): same rank and factors as the
+    reference's full SVD (Compressed.cpp:75-146) on the generator's spectrum law, U orthonormal."""
+    m, n = shape
+    acc = 1e-8
+    rng = np.random.default_rng(m * 7 + n)
+    k = min(m, n)
+    qu, _ = np.linalg.qr(rng.standard_normal((m, k)))
+    qv, _ = np.linalg.qr(rng.standard_normal((n, k)))
+    A = (qu * O.latms_spectrum(k)) @ qv.T
+    t = hc.CompressedTile.compress(A, hc.CompressionParameters(acc), ctx)
+    o = O.CompressedTile.compress(A, O.CompressionParameters(acc))
+    assert t.max_rank == o.max_rank
+    assert abs(t.GetTileRank() - o.rank) <= 1, (t.GetTileRank(), o.rank)
+    assert relerr(t.to_dense(), o.to_dense()) <= 10 * acc
+    U = t.GetUMatrix()
+    assert np.max(np.abs(U.T @ U - np.eye(U.shape[1]))) < 1e-10
+
+
+def test_sketched_compression_falls_back_on_flat_spectrum(hc, ctx):
+    """A spectrum that has not decayed within the sketch width is detected on the device and the tile is redone with
+    the full SVD; a batch mixing both kinds gives each tile what it gives alone (the reference clamps at maxRank)."""
+    acc, nb = 1e-8, 512
+    rng = np.random.default_rng(99)
+
+    def tile(sig):
+        qu, _ = np.linalg.qr(rng.standard_normal((nb, nb)))
+        qv, _ = np.linalg.qr(rng.standard_normal((nb, nb)))
+        return (qu * sig) @ qv.T
+    flat = tile(0.95 ** np.arange(nb))            # rank at 1e-8 is ~360 > maxRank = 170: clamped
+    steep = tile(O.latms_spectrum(nb))            # rank 44
+    raw = np.concatenate([flat, steep, flat * 0.5], axis=1)
+    tm = hc.TileMatrix.from_dense(raw, nb, nb, ctx, hc.CompressionParameters(acc))
+    for i, A in enumerate([flat, steep, flat * 0.5]):
+        o = O.CompressedTile.compress(A, O.CompressionParameters(acc))
+        g = tm.GetTile(0, i)
+        assert abs(g.GetTileRank() - o.rank) <= 1, (i, g.GetTileRank(), o.rank)
+        # clamped tiles: both keep the leading maxRank triplets; compare the reconstructions
+        assert relerr(g.to_dense(), o.to_dense()) <= (1e-6 if i != 1 else 10 * acc)
+
+
 # ------------------------------------------------------------------------------------------------ live vs the oracle
 def oracle_tile(kind, D, UV, dt):
     return O.DenseTile(np.asfortranarray(D.astype(dt))) if kind == "D" else O.CompressedTile.from_uv(UV[0].astype(dt), UV[1].astype(dt))
