@@ -1042,66 +1042,80 @@ constexpr int SKETCH_K = 96, SKETCH_TAIL = 8;
 template<typename T>
 int t_compress_sketched(hcb_ctx *ctx, int cnt, const T *const *dense, int64_t ld, const hcb_tile *out,
                         const hcb_compress_params *prm, std::vector<int> &redo) {
+    // A ~ Qx Qx^T A, Qx = orth(A Omega) (m x k1).  B^T = A^T Qx = Qb Rb (n x k1 panel QR), Rb^T = Ub S Z^T (k1 x k1 Jacobi:
+    // LEFT vectors Ub to high relative accuracy), so A ~ (Qx Ub) S (Qb Z)^T:  U = Qx Ub,  V^T = Qb [Z S ; 0].
     const int k1 = SKETCH_K, nblk = cdiv(k1, NBQ);
     int m = 0, n = 0;
     for (int t = 0; t < cnt; ++t) { m = std::max(m, out[t].m); n = std::max(n, out[t].n); }
-    const SvdJobLayout<T> L(n, k1);
-    // per tile scratch (elements): Y | VC | Qx | Uq (m x k1 each) | B (k1 x n) | Us (n x k1) | Vs | tau | sigma | TB | WB
-    const size_t eMK = align_up((size_t) m * k1, 32), eKN = align_up((size_t) k1 * n, 32), eKK = align_up((size_t) k1 * k1, 32),
+    const SvdJobLayout<T> L(k1, k1);
+    const size_t eMK = align_up((size_t) m * k1, 32), eNK = align_up((size_t) n * k1, 32), eKK = align_up((size_t) k1 * k1, 32),
                  eK = align_up((size_t) k1, 32), eTB = align_up((size_t) NBQ * NBQ * nblk, 32), eWB = align_up((size_t) 2 * NBQ * k1, 32);
-    const size_t slab = 4 * eMK + 2 * eKN + eKK + 2 * eK + eTB + eWB + L.slab;
-    const size_t nsj = (size_t) nblk * cnt;  // strip jobs of the explicit Q
-    const size_t desc = svd_jobs_desc_bytes<T>(cnt, n, k1) + align_up(sizeof(CompressProb<T>) * cnt, 256) +
-                        3 * align_up(sizeof(GemmProb<T>) * cnt, 256) + align_up(sizeof(PanelDesc<T>) * cnt, 256) +
-                        qr_block_desc_bytes<T>(cnt, k1) + align_up(sizeof(StripJob) * nsj, 256) +
-                        align_up(sizeof(T *) * cnt, 256) + 2 * align_up(sizeof(int) * cnt, 256) + 1024;
+    // per tile: Y VC Qx Uq (m x k1) | Bt VCb Vn (n x k1) | Mr Us Vs (k1 x k1) | tau taub sigma | TB TBb | WB WBb
+    const size_t per = 4 * eMK + 3 * eNK + 3 * eKK + 3 * eK + 2 * eTB + 2 * eWB;
+    const size_t nsj = (size_t) nblk * cnt;
+    const size_t desc = svd_jobs_desc_bytes<T>(cnt, k1, k1) + align_up(sizeof(CompressProb<T>) * cnt, 256) +
+                        3 * align_up(sizeof(GemmProb<T>) * cnt, 256) + 2 * align_up(sizeof(PanelDesc<T>) * cnt, 256) +
+                        2 * qr_block_desc_bytes<T>(cnt, k1) + 2 * align_up(sizeof(StripJob) * nsj, 256) +
+                        2 * align_up(sizeof(SketchGlue<T>) * cnt, 256) + align_up(sizeof(T *) * cnt, 256) +
+                        2 * align_up(sizeof(int) * cnt, 256) + 1024;
     const size_t eOm = align_up((size_t) n * k1, 32);
-    HCB_TRY(ensure_ws(ctx, desc + (slab * cnt + eOm) * sizeof(T) + 512));
+    HCB_TRY(ensure_ws(ctx, desc + ((L.slab + per) * cnt + eOm) * sizeof(T) + 512));
     char *base = reinterpret_cast<char *>(ctx->ws);
-    char *pd = base + svd_jobs_desc_bytes<T>(cnt, n, k1);
+    char *pd = base + svd_jobs_desc_bytes<T>(cnt, k1, k1);
     auto carve = [&](size_t bytes) { char *q = pd; pd += align_up(bytes, 256); return q; };
     auto *d_fp = reinterpret_cast<CompressProb<T> *>(carve(sizeof(CompressProb<T>) * cnt));
     auto *d_gy = reinterpret_cast<GemmProb<T> *>(carve(sizeof(GemmProb<T>) * cnt));
     auto *d_gb = reinterpret_cast<GemmProb<T> *>(carve(sizeof(GemmProb<T>) * cnt));
     auto *d_gu = reinterpret_cast<GemmProb<T> *>(carve(sizeof(GemmProb<T>) * cnt));
     auto *d_pan = reinterpret_cast<PanelDesc<T> *>(carve(sizeof(PanelDesc<T>) * cnt));
+    auto *d_panb = reinterpret_cast<PanelDesc<T> *>(carve(sizeof(PanelDesc<T>) * cnt));
     char *d_qrb = carve(qr_block_desc_bytes<T>(cnt, k1));
+    char *d_qrbb = carve(qr_block_desc_bytes<T>(cnt, k1));
     auto *d_sj = reinterpret_cast<StripJob *>(carve(sizeof(StripJob) * nsj));
+    auto *d_sjb = reinterpret_cast<StripJob *>(carve(sizeof(StripJob) * nsj));
+    auto *d_g0 = reinterpret_cast<SketchGlue<T> *>(carve(sizeof(SketchGlue<T>) * cnt));
+    auto *d_g1 = reinterpret_cast<SketchGlue<T> *>(carve(sizeof(SketchGlue<T>) * cnt));
     auto *d_qx = reinterpret_cast<T **>(carve(sizeof(T *) * cnt));
     auto *d_ms = reinterpret_cast<int *>(carve(sizeof(int) * cnt));
     auto *d_flags = reinterpret_cast<int *>(carve(sizeof(int) * cnt));
     T *ws = reinterpret_cast<T *>(base + align_up(desc, 256));
-    T *Om = ws + slab * cnt;
+    T *svd_ws = ws, *blk0 = ws + (size_t) cnt * L.slab, *Om = blk0 + per * cnt;
     k_fill_uniform<T><<<148, 256, 0, ctx->stream>>>(Om, (size_t) n * k1, 0x5EEDull);
     HCB_LAUNCH_CHECK("k_fill_uniform");
 
     std::vector<CompressProb<T>> fp(cnt);
     std::vector<GemmProb<T>> gy(cnt), gb(cnt), gu(cnt);
-    std::vector<PanelDesc<T>> pan(cnt);
-    std::vector<StripJob> sj(nsj);
+    std::vector<PanelDesc<T>> pan(cnt), panb(cnt);
+    std::vector<StripJob> sj(nsj), sjb(nsj);
+    std::vector<SketchGlue<T>> g0(cnt), g1(cnt);
     std::vector<SvdJob<T>> jobs(cnt);
     std::vector<T *> qx(cnt);
     std::vector<int> ms(cnt);
-    T *svd_ws = ws;  // cnt * L.slab for the SVD pipeline, then the per-tile blocks
-    T *blk0 = ws + (size_t) cnt * L.slab;
-    const size_t per = slab - L.slab;
     for (int t = 0; t < cnt; ++t) {
         const hcb_tile &o = out[t];
         const int tm = o.m, tn = o.n;
-        T *Y = blk0 + (size_t) t * per, *VC = Y + eMK, *Qx = VC + eMK, *Uq = Qx + eMK, *B = Uq + eMK, *Us = B + eKN,
-          *Vs = Us + eKN, *tau = Vs + eKK, *sg = tau + eK, *TB = sg + eK, *WB = TB + eTB;
+        T *Y = blk0 + (size_t) t * per, *VC = Y + eMK, *Qx = VC + eMK, *Uq = Qx + eMK, *Bt = Uq + eMK, *VCb = Bt + eNK,
+          *Vn = VCb + eNK, *Mr = Vn + eNK, *Us = Mr + eKK, *Vs = Us + eKK, *tau = Vs + eKK, *taub = tau + eK, *sg = taub + eK,
+          *TB = sg + eK, *TBb = TB + eTB, *WB = TBb + eTB, *WBb = WB + eWB;
         gy[t] = GemmProb<T>{dense[t], Om, Y, tm, k1, tn, (int) ld, n, tm, 0, 0, T(1), T(0)};      // Y = A Omega
         pan[t] = PanelDesc<T>{Y, tau, VC, TB, WB, tm, k1, k1, 1};
-        for (int st = 0; st < nblk; ++st)  // Qx = Q [I; 0]: every 32-column strip takes the blocks last to first
+        gb[t] = GemmProb<T>{dense[t], Qx, Bt, tn, k1, tm, (int) ld, tm, tn, 1, 0, T(1), T(0)};     // B^T = A^T Qx
+        panb[t] = PanelDesc<T>{Bt, taub, VCb, TBb, WBb, tn, k1, k1, 1};
+        for (int st = 0; st < nblk; ++st) {  // explicit Q [X; 0]: every 32-column strip takes the blocks last to first
+            const int nc = std::min(NBQ, k1 - st * NBQ);
             sj[(size_t) t * nblk + st] = StripJob{reinterpret_cast<double *>(Qx) + (size_t) st * NBQ * tm,
                                                   reinterpret_cast<const double *>(VC), reinterpret_cast<const double *>(TB), tm, tm,
-                                                  tm, std::min(NBQ, k1 - st * NBQ), std::min(tm, k1), nblk - 1, nblk, -1, 0};
-        gb[t] = GemmProb<T>{Qx, dense[t], B, k1, tn, tm, tm, (int) ld, k1, 1, 0, T(1), T(0)};      // B = Qx^T A
-        jobs[t] = SvdJob<T>{B, k1, 1, tn, k1, Us, Vs, sg};                                       // M = B^T (n x k1)
-        gu[t] = GemmProb<T>{Qx, Vs, Uq, tm, k1, k1, tm, k1, tm, 0, 0, T(1), T(0)};                // Uq = Qx (U_B Sigma)
+                                                  tm, nc, std::min(tm, k1), nblk - 1, nblk, -1, 0};
+            sjb[(size_t) t * nblk + st] = StripJob{reinterpret_cast<double *>(Vn) + (size_t) st * NBQ * tn,
+                                                   reinterpret_cast<const double *>(VCb), reinterpret_cast<const double *>(TBb), tn,
+                                                   tn, tn, nc, std::min(tn, k1), nblk - 1, nblk, -1, 0};
+        }
+        g0[t] = SketchGlue<T>{Bt, Mr, k1, k1, tn};   // Mr = Rb^T
+        jobs[t] = SvdJob<T>{Mr, k1, 0, k1, k1, Us, Vs, sg};  // Rb^T = Ub S Z^T: Us = Ub, Vs = Z S
+        g1[t] = SketchGlue<T>{Vs, Vn, tn, k1, k1};   // Vn = [Z S ; 0]
+        gu[t] = GemmProb<T>{Qx, Us, Uq, tm, k1, k1, tm, k1, tm, 0, 0, T(1), T(0)};                 // Uq = Qx Ub
         T *U = reinterpret_cast<T *>(o.d_data), *V = U + (size_t) tm * o.max_rank;
-        // A = (Qx U_B) Sigma W^T: the "transposed" branch of the finalize kernel with Vs := Uq (ld m), Us := W (ld n)
-        fp[t] = CompressProb<T>{Us, Uq, sg, U, V, o.d_rank, d_flags + t, tm, tn, k1, tn, 1, o.max_rank, tn, tm, SKETCH_TAIL};
+        fp[t] = CompressProb<T>{Uq, Vn, sg, U, V, o.d_rank, d_flags + t, tm, tn, k1, tm, 0, o.max_rank, tm, tn, SKETCH_TAIL};
         qx[t] = Qx;
         ms[t] = tm;
     }
@@ -1110,17 +1124,27 @@ int t_compress_sketched(hcb_ctx *ctx, int cnt, const T *const *dense, int64_t ld
     HCB_TRY(stage_array(ctx, gb, d_gb));
     HCB_TRY(stage_array(ctx, gu, d_gu));
     HCB_TRY(stage_array(ctx, pan, d_pan));
+    HCB_TRY(stage_array(ctx, panb, d_panb));
     HCB_TRY(stage_array(ctx, sj, d_sj));
+    HCB_TRY(stage_array(ctx, sjb, d_sjb));
+    HCB_TRY(stage_array(ctx, g0, d_g0));
+    HCB_TRY(stage_array(ctx, g1, d_g1));
     HCB_TRY(stage_array(ctx, qx, d_qx));
     HCB_TRY(stage_array(ctx, ms, d_ms));
-    HCB_TRY(launch_gemm<T>(ctx, d_gy, cnt, m, k1));
-    HCB_TRY(run_blocked_qr<T>(ctx, d_pan, cnt, m, k1, d_qrb));
+    HCB_TRY(launch_gemm<T>(ctx, d_gy, cnt, m, k1));                       // Y = A Omega
+    HCB_TRY(run_blocked_qr<T>(ctx, d_pan, cnt, m, k1, d_qrb));            // Y = Qx R
     k_eye_batched<T><<<cnt, 256, 0, ctx->stream>>>(d_qx, d_ms, k1);
     HCB_LAUNCH_CHECK("k_eye_batched");
-    HCB_TRY(launch_strips(ctx, d_sj, (int) nsj, m));
-    HCB_TRY(launch_gemm<T>(ctx, d_gb, cnt, k1, n));
-    HCB_TRY(run_svd_jobs<T>(ctx, jobs, n, k1, svd_ws, base));
-    HCB_TRY(launch_gemm<T>(ctx, d_gu, cnt, m, k1));
+    HCB_TRY(launch_strips(ctx, d_sj, (int) nsj, m));                      // Qx explicit
+    HCB_TRY(launch_gemm<T>(ctx, d_gb, cnt, n, k1));                       // B^T = A^T Qx
+    HCB_TRY(run_blocked_qr<T>(ctx, d_panb, cnt, n, k1, d_qrbb));          // B^T = Qb Rb
+    k_sketch_glue<T><<<cnt, 256, 0, ctx->stream>>>(d_g0, 0);
+    HCB_LAUNCH_CHECK("k_sketch_glue");
+    HCB_TRY(run_svd_jobs<T>(ctx, jobs, k1, k1, svd_ws, base));            // Rb^T = Ub S Z^T
+    k_sketch_glue<T><<<cnt, 256, 0, ctx->stream>>>(d_g1, 1);
+    HCB_LAUNCH_CHECK("k_sketch_glue");
+    HCB_TRY(launch_strips(ctx, d_sjb, (int) nsj, n));                     // Vn = Qb [Z S ; 0]
+    HCB_TRY(launch_gemm<T>(ctx, d_gu, cnt, m, k1));                       // Uq = Qx Ub
     k_compress_finalize<T><<<cnt, 256, 0, ctx->stream>>>(d_fp, (T) prm->accuracy, prm->truncated_svd, 0);
     HCB_LAUNCH_CHECK("k_compress_finalize");
     std::vector<int> flags(cnt);
@@ -1147,7 +1171,7 @@ int t_compress_batched(hcb_ctx *ctx, int64_t n64, const T *const *dense, int64_t
     }
     // sketch when it pays (both dimensions well above the sketch width) and the strip kernels apply
     const bool sketch = std::is_same<T, double>::value && prm->fixed_rank <= 0 && mn_min >= 3 * SKETCH_K &&
-                        strip_path_ok(ctx, m) && !getenv("HCB_COMPRESS_FULL_SVD");
+                        strip_path_ok(ctx, std::max(m, n)) && !getenv("HCB_COMPRESS_FULL_SVD");
     if (!sketch) return t_compress_full<T>(ctx, n64, dense, ld, out, prm, d_info);
     const int64_t chunk = 512;
     for (int64_t c0 = 0; c0 < n64; c0 += chunk) {

@@ -745,6 +745,30 @@ __global__ void k_fill_uniform(T *__restrict__ out, size_t n, unsigned long long
     }
 }
 
+// Sketched compression glue, one CTA per problem.  mode 0: Mr = R^T (k x k lower triangle) from the QR-factored B^T
+// panel (R in its upper triangle, reflectors below); mode 1: Vn = [Vs ; 0] (n x k, ld n) from Vs (k x k).
+template<typename T>
+struct SketchGlue {
+    const T *src;
+    T *dst;
+    int rows, k, ld_src;
+};
+template<typename T>
+__global__ void k_sketch_glue(const SketchGlue<T> *__restrict__ gs, int mode) {
+    const SketchGlue<T> g = gs[blockIdx.x];
+    if (mode == 0) {
+        for (int idx = threadIdx.x; idx < g.k * g.k; idx += blockDim.x) {
+            const int i = idx % g.k, j = idx / g.k;  // Mr(i, j) = R(j, i) for j <= i
+            g.dst[idx] = (j <= i) ? g.src[(size_t) j + (size_t) i * g.ld_src] : T(0);
+        }
+    } else {
+        for (size_t idx = threadIdx.x; idx < (size_t) g.rows * g.k; idx += blockDim.x) {
+            const int i = (int) (idx % g.rows), c = (int) (idx / g.rows);
+            g.dst[idx] = i < g.k ? g.src[(size_t) i + (size_t) c * g.ld_src] : T(0);
+        }
+    }
+}
+
 // Q_explicit start: [I_k ; 0] (m x k, ld m), one CTA per problem
 template<typename T>
 __global__ void k_eye_batched(T *const *__restrict__ mats, const int *__restrict__ ms, int k) {
