@@ -48,7 +48,7 @@ def parse():
                     help="rank bound used to size scratch for C tiles (0: calibrate with one untimed pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
-    ap.add_argument("--compress-tiles", type=int, default=8,
+    ap.add_argument("--compress-tiles", type=int, default=64,
                     help="initial-compression leg (SURVEY.md 8d: reported separately): dense tiles compressed (0: skip)")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     return ap.parse_args()
@@ -478,8 +478,8 @@ def run_cpu_baseline(args, torch, hc, ctx, A, B, Cm, Ua, Va, Ub, Vb, krank, prm)
 
 def run_compression(args, torch, hc, ctx, prm, with_reference):
     """Initial compression (the compressing constructor, Compressed.cpp:75-146; TileMatrix.cpp:150-171) of dense nb x nb
-    tiles that follow the reference generator's full spectrum law: ONE batched device call (LQ-preconditioned one-sided
-    Jacobi SVD + rank rule on the device).  Reported separately from the GEMM metric; the reference's own
+    tiles that follow the reference generator's full spectrum law: ONE batched device call (sketched range finder + small
+    Jacobi SVD + rank rule on the device; full SVD fallback for flat spectra).  Reported separately from the GEMM metric; the reference's own
     constructor is timed on a 2-tile sample of the same tiles and its ranks / reconstruction compared."""
     nb, n = args.nb, args.compress_tiles
     dev = ctx.device
