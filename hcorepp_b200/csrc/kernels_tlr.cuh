@@ -274,7 +274,8 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
 // construction); then T1J = T1^T * J.  Everything lives in shared memory; if it does not fit, J = I (no
 // preconditioning, same product).
 template<typename T>
-__global__ void __launch_bounds__(1024) k_precond_product(const PrecondProb<T> *__restrict__ probs, int smem_elems) {
+__global__ void __launch_bounds__(1024) k_precond_product(const PrecondProb<T> *__restrict__ probs, int smem_elems,
+                                                           int max_sweeps) {
     extern __shared__ __align__(16) unsigned char smem_raw_pc[];
     T *sm = reinterpret_cast<T *>(smem_raw_pc);
     const PrecondProb<T> p = probs[blockIdx.x];
@@ -327,42 +328,58 @@ __global__ void __launch_bounds__(1024) k_precond_product(const PrecondProb<T> *
     }
     __syncthreads();
     // J only has to be a good preconditioner (ANY orthogonal J gives the same product), so the sweeps stop at a loose
-    // relative orthogonality of sqrt(eps), ignore columns at rounding level, and are capped at 8.
-    const T tol = t_sqrt(Eps<T>::v());
+    // relative orthogonality of sqrt(eps), ignore columns at rounding level, and are capped (max_sweeps).
+    // Instruction diet (the ncu capture showed 364 instructions per rotation, issue-bound): round-robin indices without
+    // integer division, squared-threshold test without square roots, cached squared norms (one warp sum per rotation
+    // instead of three, refreshed every sweep, recomputed when the update cancels).
+    const T tol = t_sqrt(Eps<T>::v()), tol2 = tol * tol;
     T t1max = T(0);
     for (int idx = lane; idx < ka * kb; idx += 32) t1max = t_abs(N[idx]) > t1max ? t_abs(N[idx]) : t1max;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { const T other = __shfl_xor_sync(0xffffffffu, t1max, o); t1max = other > t1max ? other : t1max; }
     const T noise2 = (Eps<T>::v() * t1max) * (Eps<T>::v() * t1max) * (T) kb;
-    const int nb2 = (ka + 1) & ~1;
-    bool converged = ka < 2;
-    for (int sweep = 0; sweep < 8 && !converged; ++sweep) {
+    const int nb2 = (ka + 1) & ~1, mod = nb2 - 1;
+    __shared__ T nrm[256];                     // cached squared column norms of N
+    bool converged = ka < 2 || ka > 256;       // (wider product terms keep J = I: no preconditioning, same product)
+    for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
         __syncthreads();
         if (tid == 0) s_rot = 0;
+        for (int c = w; c < ka; c += nw) {  // refresh the cached squared norms
+            const T *nc = N + (size_t) c * kb;
+            T ss = T(0);
+            for (int i = lane; i < kb; i += 32) ss = fma(nc[i], nc[i], ss);
+            ss = warp_sum(ss);
+            if (lane == 0) nrm[c] = ss;
+        }
         __syncthreads();
         for (int round = 0; round < nb2 - 1; ++round) {
             for (int slot = w; slot < nb2 / 2; slot += nw) {
                 int x, y;
-                const int mod = nb2 - 1;
-                if (slot == 0) { x = mod; y = round % mod; } else { x = (round + slot) % mod; y = (round - slot + mod) % mod; }
+                if (slot == 0) { x = mod; y = round; }
+                else {
+                    x = round + slot; if (x >= mod) x -= mod;
+                    y = round - slot; if (y < 0) y += mod;
+                }
                 if (x > y) { const int tt = x; x = y; y = tt; }
                 if (y >= ka) continue;
                 T *nx = N + (size_t) x * kb, *ny = N + (size_t) y * kb;
-                T alpha = T(0), beta = T(0), gamma = T(0);
-                for (int i = lane; i < kb; i += 32) {
-                    const T u = nx[i], v = ny[i];
-                    alpha = fma(u, u, alpha); beta = fma(v, v, beta); gamma = fma(u, v, gamma);
-                }
-                alpha = warp_sum(alpha); beta = warp_sum(beta); gamma = warp_sum(gamma);
-                if (!(t_abs(gamma) > tol * t_sqrt(alpha) * t_sqrt(beta)) || gamma == T(0)) continue;
+                T gamma = T(0);
+                for (int i = lane; i < kb; i += 32) gamma = fma(nx[i], ny[i], gamma);
+                gamma = warp_sum(gamma);
+                const T alpha = nrm[x], beta = nrm[y];
+                if (!(gamma * gamma > tol2 * alpha * beta)) continue;
                 if (!(alpha > noise2) || !(beta > noise2)) continue;
                 if (lane == 0) s_rot = 1;
                 const T t = rx_tangent(beta - alpha, gamma + gamma);
                 const T c = t_rsqrt(fma(t, t, T(1))), sn = c * t;
+                T na = T(0), nb = T(0);
                 for (int i = lane; i < kb; i += 32) {
                     const T u = nx[i], v = ny[i];
-                    nx[i] = fma(-sn, v, c * u);
-                    ny[i] = fma(sn, u, c * v);
+                    const T u2 = fma(-sn, v, c * u), v2 = fma(sn, u, c * v);
+                    nx[i] = u2;
+                    ny[i] = v2;
+                    na = fma(u2, u2, na);
+                    nb = fma(v2, v2, nb);
                 }
                 T *jx = J + (size_t) x * ka, *jy = J + (size_t) y * ka;
                 for (int i = lane; i < ka; i += 32) {
@@ -370,6 +387,10 @@ __global__ void __launch_bounds__(1024) k_precond_product(const PrecondProb<T> *
                     jx[i] = fma(-sn, v, c * u);
                     jy[i] = fma(sn, u, c * v);
                 }
+                const T tg = t * gamma;
+                T a2 = alpha - tg, b2 = beta + tg;
+                if (a2 < T(0.01) * alpha || b2 < T(0.01) * beta) { a2 = warp_sum(na); b2 = warp_sum(nb); }
+                if (lane == 0) { nrm[x] = a2; nrm[y] = b2; }
             }
             __syncthreads();
         }
