@@ -144,10 +144,11 @@ __global__ void __launch_bounds__(SKR, 1) k_strip_reflect(const StripJob *__rest
     // ---- prologue: strip, V_0 (and V_1) in flight; T_0 in registers
     copy_cols(Sb, jb_.S, jb_.lds, ncols, pgr < m, pgr + 1 < m);
     load_v(0);
-    if (P > 1) load_v(1);
+    cp_async_commit();
+    if (P > 1) load_v(1);  // not needed before window 2: it keeps flying through windows 0 and 1
     cp_async_commit();
     if (grp == 0) fetch_t(0);
-    cp_async_wait_all();
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
     __syncthreads();
     // the warp's 64 x 16 piece of its half strip as DMMA accumulator fragments (rows 64 wg .. 64 wg + 63)
     double sacc[8][2][2];
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(SKR, 1) k_strip_reflect(const StripJob *__rest
                 }
             }
         }
-        cp_async_wait_all();
+        if (n & 1) cp_async_wait_all();  // V blocks are first read in even windows (phase 1 of group A)
         cluster_sync_pull();
     }
     // ---- strip back to global memory
