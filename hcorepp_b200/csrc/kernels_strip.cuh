@@ -257,16 +257,25 @@ __global__ void __launch_bounds__(SKR, 1) k_strip_reflect(const StripJob *__rest
 #pragma unroll
             for (int c = 0; c < 4; ++c) Wfg[lane * SK_HP + 4 * wg + c] = wsum[c];
             group_bar();  // (group A: op(T_b) is complete; both: nobody still reads the K-split scratch)
-            double o[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-            for (int k = 0; k < NBQ; ++k) {
-                const double tv = Ts[k * NBQ + lane];
+            // 4 outputs per lane, each a 32-term dot product: four partial chains per output (16 independent FMA chains of
+            // 8) instead of one chain of 32 -- this stretch is latency-bound and sits on the window's critical path
+            double o[4][4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) o[c] = fma(tv, Wfg[k * SK_HP + 4 * wg + c], o[c]);
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) o[q][c] = 0.0;
+#pragma unroll
+            for (int k = 0; k < NBQ; k += 4) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double tv = Ts[(k + q) * NBQ + lane];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) o[q][c] = fma(tv, Wfg[(k + q) * SK_HP + 4 * wg + c], o[q][c]);
+                }
             }
             __syncwarp();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) Wfg[lane * SK_HP + 4 * wg + c] = -o[c];
+            for (int c = 0; c < 4; ++c) Wfg[lane * SK_HP + 4 * wg + c] = -((o[0][c] + o[1][c]) + (o[2][c] + o[3][c]));
             group_bar();
             // phase 3: S_half += V_loc (-W2); warp wg owns rows 64 wg .. 64 wg + 63 (two 32-row groups)
             if (cta_active(p)) {
