@@ -383,6 +383,16 @@ __global__ void __launch_bounds__(PQ_ROWS) k_panel_qr_cluster(const QrProb<T> *_
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int PR_THREADS = 256, PR_ROWS = 512, PR_MAXCS = 8;
 
+// reciprocal square root to ~1 ulp without the library's special-case path (arguments are screened by the caller)
+__device__ __forceinline__ double pq_rsqrt(double q) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q));
+    y = fma(0.5 * y, fma(-q * y, y, 1.0), y);  // 2^-22 -> 2^-43
+    y = fma(0.5 * y, fma(-q * y, y, 1.0), y);  //       -> rounding level
+    return y;
+}
+__device__ __forceinline__ float pq_rsqrt(float q) { return rsqrtf(q); }
+
 template<typename T>
 __device__ __forceinline__ T warp_reduce_16(T (&pr)[16], int lane) {  // lane l returns the total of index (l >> 1) & 15
 #pragma unroll
@@ -485,21 +495,36 @@ __global__ void __launch_bounds__(PR_THREADS, 1) k_panel_qr_regs(const QrProb<T>
             }
         }
         cluster.sync();
-        if (t < NBQ) {
-            T sacc = T(0);
-            for (int src = 0; src < CS; ++src)
+        if (t < NBQ) {  // four independent partial sums: this stretch is on the critical path of every column
+            T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+            for (int src = 0; src < CS; ++src) {
+                const T *zp = zpart + ((par * PR_MAXCS + src) * NW) * NBQ + t;
 #pragma unroll
-                for (int ww = 0; ww < NW; ++ww) sacc += zpart[((par * PR_MAXCS + src) * NW + ww) * NBQ + t];
-            zsum[t] = sacc;
+                for (int ww = 0; ww < NW; ww += 4) {
+                    s0 += zp[(ww + 0) * NBQ]; s1 += zp[(ww + 1) * NBQ]; s2 += zp[(ww + 2) * NBQ]; s3 += zp[(ww + 3) * NBQ];
+                }
+            }
+            zsum[t] = (s0 + s1) + (s2 + s3);
         }
         __syncthreads();
         const T ss = zsum[0], alpha = zrow[par * NBQ];
         T tau = T(0), scale = T(0), beta = alpha;
         if (ss != T(0)) {
-            const T nrm = t_sqrt(fma(alpha, alpha, ss));
-            beta = alpha >= T(0) ? -nrm : nrm;
-            tau = (beta - alpha) / beta;
-            scale = T(1) / (alpha - beta);
+            const T h = fma(alpha, alpha, ss);
+            if (h > T(1e-30) && h < T(1e30)) {
+                // one reciprocal square root gives both the norm and 1/beta; 1/(alpha - beta) = sign / (|alpha| + norm) from a
+                // second one (the library sqrt + two divisions were ~500 cycles of dependent instructions per column)
+                const T rs = pq_rsqrt(h), nrm = h * rs;
+                beta = alpha >= T(0) ? -nrm : nrm;
+                tau = (beta - alpha) * (alpha >= T(0) ? -rs : rs);
+                const T rx = pq_rsqrt(t_abs(alpha) + nrm);
+                scale = alpha >= T(0) ? rx * rx : -(rx * rx);
+            } else {
+                const T nrm = t_sqrt(h);
+                beta = alpha >= T(0) ? -nrm : nrm;
+                tau = (beta - alpha) / beta;
+                scale = T(1) / (alpha - beta);
+            }
         }
         // reflector entries of my rows (unit diagonal, zeros above) -> shared memory; trailing update + slot shift
         const T v0 = (gr0 > j) ? x0 * scale : (gr0 == j ? T(1) : T(0));
