@@ -517,7 +517,8 @@ def test_full_size_tile_properties(hc, ctx):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dims", [(1000, 900, 500, 50, 50, 60), (257, 300, 128, 40, 40, 50), (999, 513, 256, 45, 45, 40),
-                                  (130, 700, 96, 30, 40, 45), (1024, 1024, 1024, 44, 44, 240)],
+                                  (130, 700, 96, 30, 40, 45), (1024, 1024, 1024, 44, 44, 240),
+                                  (2048, 2048, 2048, 64, 64, 100), (2048, 1500, 700, 40, 50, 90)],
                          ids=lambda d: "x".join(map(str, d)))
 def test_blocked_recompression_ragged_vs_oracle(hc, ctx, dims):
     """Stacked rank > 64: the compact-WY path -- register panel QR clusters, strip-resident reflector clusters of 1 / 2 / 4
