@@ -166,7 +166,7 @@ int launch_svd(hcb_ctx *ctx, const SvdProb<T> *d_probs, int n_probs, int a_bound
     const size_t pitch = (size_t) cdiv(a_bound, 64) * 64;
     size_t want = (pitch * b_bound + (size_t) b_bound) * sizeof(T);
     const size_t cap = ctx->smem_optin > 2048 ? ctx->smem_optin - 1024 : 0;
-    if (a_bound > 128 && a_bound <= 64 * RX_MAX_NI && want + (size_t) b_bound * sizeof(T) > cap) {
+    if (a_bound > 128 && a_bound <= 64 * RX_MAX_NI_TALL && want + (size_t) b_bound * sizeof(T) > cap) {
         // does not fit shared memory as a whole: block Jacobi with the pivot block in registers
         const size_t rx = align_up(rx_smem_bytes<T>(cdiv(a_bound, 64), b_bound), 16);
         if (rx <= cap) {

@@ -22,7 +22,8 @@ namespace hcb {
 // staging per rotation outweighs the latency hiding.)
 constexpr int RX_THREADS = 512;
 constexpr int RX_BW = RX_THREADS / 16;  // block width (columns)
-constexpr int RX_MAX_NI = 6;
+constexpr int RX_MAX_NI = 6;        // two columns per warp up to 64 * 6 = 384 rows
+constexpr int RX_MAX_NI_TALL = 12;  // one column per warp up to 768 rows
 
 // per-column metadata in shared memory: squared norm (true), scale d, 1/d
 // t = 2 gamma / (d + sign(d) sqrt(d^2 + 4 gamma^2)) needs sqrt and a reciprocal; both from the MUFU approximations
@@ -142,12 +143,52 @@ __device__ __forceinline__ int rx_duo(Vec2<T> (&xa)[NI], int ixa, Vec2<T> (&ya)[
     return (brot ? 1 : 0) | (bbig ? 2 : 0);
 }
 
+// One pair (x, y), every lane computes the scalars (used by the one-column-per-warp geometry of tall problems).
+template<typename T, int NI>
+__device__ __forceinline__ int rx_solo(Vec2<T> (&x)[NI], int ix, Vec2<T> (&y)[NI], int iy, const RxMeta<T> &mt, int lane, T tol2,
+                                       T big2) {
+    T g = T(0), g2a = T(0);
+#pragma unroll
+    for (int i = 0; i < NI; ++i) { g = fma(x[i].x, y[i].x, g); g2a = fma(x[i].y, y[i].y, g2a); }
+    g = warp_sum(g + g2a);
+    const T alpha = mt.n2[ix], beta = mt.n2[iy];
+    const T dx = mt.d[ix], dy = mt.d[iy], idx = mt.id[ix], idy = mt.id[iy];
+    const T gam = g * dx * dy, gg = gam * gam, ab = alpha * beta;
+    if (!(gg > tol2 * ab)) return 0;
+    const int ret = (gg > big2 * ab) ? 3 : 1;
+    const T t = rx_tangent(beta - alpha, gam + gam);
+    const T q = fma(t, t, T(1));
+    const T c = rx_rsqrt(q);
+    const T fx = t * dy * idx, fy = t * dx * idy;
+    const T tg = t * gam, rc = q * c;
+    T a2 = alpha - tg, b2 = beta + tg;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const T ux = x[i].x, uy = x[i].y;
+        x[i].x = fma(-fx, y[i].x, ux); x[i].y = fma(-fx, y[i].y, uy);
+        y[i].x = fma(fy, ux, y[i].x);  y[i].y = fma(fy, uy, y[i].y);
+    }
+    const T ndx = c * dx, ndy = c * dy;
+    if (a2 < T(0.01) * alpha || b2 < T(0.01) * beta) {  // rare: recompute the true squared norms
+        a2 = ndx * ndx * rx_sumsq<T, NI>(x);
+        b2 = ndy * ndy * rx_sumsq<T, NI>(y);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        mt.n2[ix] = a2; mt.n2[iy] = b2;
+        mt.d[ix] = ndx; mt.d[iy] = ndy;
+        mt.id[ix] = rc * idx; mt.id[iy] = rc * idy;
+    }
+    __syncwarp();
+    return ret;
+}
+
 // ONE sweep over all column pairs of problem p (the rotated copy lives in p.J between sweeps; `first` makes it from
 // p.M).  Returns bit 0: something rotated, bit 1: some pair was above the predictive-stop level.  When `last_allowed`
 // or the sweep converged, the epilogue (sigma, sort, scatter of the left factor, info) runs too and bit 2 is set.
-template<typename T, int NI>
+template<typename T, int NI, int XPW>  // XPW: register-resident columns per warp (2; 1 for tall problems, NI > 6)
 __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sweeps) {
-    constexpr int P = 64 * NI, BW = RX_BW;
+    constexpr int P = 64 * NI, BW = (RX_THREADS / 32) * XPW;
     __shared__ int s_rot, s_big;
     const int a = p.a, b = p.b;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -241,12 +282,12 @@ __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sw
                 __syncthreads();
                 continue;
             }
-            // ---- block I -> registers: warp w owns columns 2w, 2w+1
-            Vec2<T> x0[NI], x1[NI];
+            // ---- block I -> registers: warp w owns columns XPW w .. XPW w + XPW - 1
+            Vec2<T> x0[NI], x1[XPW == 2 ? NI : 1];
 #pragma unroll
             for (int i = 0; i < NI; ++i) {
-                x0[i] = *reinterpret_cast<const Vec2<T> *>(R0 + (size_t) (2 * w + 0) * P + 64 * i + 2 * lane);
-                x1[i] = *reinterpret_cast<const Vec2<T> *>(R0 + (size_t) (2 * w + 1) * P + 64 * i + 2 * lane);
+                x0[i] = *reinterpret_cast<const Vec2<T> *>(R0 + (size_t) (XPW * w + 0) * P + 64 * i + 2 * lane);
+                if constexpr (XPW == 2) x1[i] = *reinterpret_cast<const Vec2<T> *>(R0 + (size_t) (2 * w + 1) * P + 64 * i + 2 * lane);
             }
             __syncthreads();  // R0 is free from here on
             int any = 0;
@@ -261,38 +302,53 @@ __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sw
                 if (bj + 1 < nblk) stage_async(other, cj0 + BW, min(BW, b - cj0 - BW));  // flies during this pass
                 init_meta(BB, BW);
                 __syncthreads();
-                for (int s = 0; s < BW / 2; ++s) {
-                    const int q = (w + s) & (BW / 2 - 1), ja = 2 * q, jb = 2 * q + 1;
-                    Vec2<T> ya[NI], yb[NI];
-                    T *pa = BB + (size_t) ja * P + 2 * lane, *pb = BB + (size_t) jb * P + 2 * lane;
+                if constexpr (XPW == 2) {
+                    for (int s = 0; s < BW / 2; ++s) {
+                        const int q = (w + s) & (BW / 2 - 1), ja = 2 * q, jb = 2 * q + 1;
+                        Vec2<T> ya[NI], yb[NI];
+                        T *pa = BB + (size_t) ja * P + 2 * lane, *pb = BB + (size_t) jb * P + 2 * lane;
 #pragma unroll
-                    for (int i = 0; i < NI; ++i) {
-                        ya[i] = *reinterpret_cast<const Vec2<T> *>(pa + 64 * i);
-                        yb[i] = *reinterpret_cast<const Vec2<T> *>(pb + 64 * i);
-                    }
-                    const int ix = 2 * w, iya = BW + ja, iyb = BW + jb;
-                    any |= rx_duo<T, NI>(x0, ix + 0, ya, iya, x1, ix + 1, yb, iyb, mt, lane, tol2, big2);
-                    any |= rx_duo<T, NI>(x1, ix + 1, ya, iya, x0, ix + 0, yb, iyb, mt, lane, tol2, big2);
+                        for (int i = 0; i < NI; ++i) {
+                            ya[i] = *reinterpret_cast<const Vec2<T> *>(pa + 64 * i);
+                            yb[i] = *reinterpret_cast<const Vec2<T> *>(pb + 64 * i);
+                        }
+                        const int ix = 2 * w, iya = BW + ja, iyb = BW + jb;
+                        any |= rx_duo<T, NI>(x0, ix + 0, ya, iya, x1, ix + 1, yb, iyb, mt, lane, tol2, big2);
+                        any |= rx_duo<T, NI>(x1, ix + 1, ya, iya, x0, ix + 0, yb, iyb, mt, lane, tol2, big2);
 #pragma unroll
-                    for (int i = 0; i < NI; ++i) {
-                        *reinterpret_cast<Vec2<T> *>(pa + 64 * i) = ya[i];
-                        *reinterpret_cast<Vec2<T> *>(pb + 64 * i) = yb[i];
+                        for (int i = 0; i < NI; ++i) {
+                            *reinterpret_cast<Vec2<T> *>(pa + 64 * i) = ya[i];
+                            *reinterpret_cast<Vec2<T> *>(pb + 64 * i) = yb[i];
+                        }
+                        // (a per-pair hand-off between neighbouring warps -- mbarriers, then ticket counters -- was tried in
+                        // place of this block barrier: correct with monotone tickets, but the polling warps cost more issue
+                        // slots than the barrier stalls they removed: 176 ms vs 162 ms per step)
+                        __syncthreads();
                     }
-                    // (a per-pair hand-off between neighbouring warps -- mbarriers, then ticket counters -- was tried in
-                    // place of this block barrier: correct with monotone tickets, but the polling warps cost more issue
-                    // slots than the barrier stalls they removed: 176 ms vs 162 ms per step)
-                    __syncthreads();
+                } else {
+                    for (int s = 0; s < BW; ++s) {  // one x column per warp, one y column per round
+                        const int j = (w + s) & (BW - 1);
+                        Vec2<T> y[NI];
+                        T *py = BB + (size_t) j * P + 2 * lane;
+#pragma unroll
+                        for (int i = 0; i < NI; ++i) y[i] = *reinterpret_cast<const Vec2<T> *>(py + 64 * i);
+                        any |= rx_solo<T, NI>(x0, w, y, BW + j, mt, lane, tol2, big2);
+#pragma unroll
+                        for (int i = 0; i < NI; ++i) *reinterpret_cast<Vec2<T> *>(py + 64 * i) = y[i];
+                        __syncthreads();
+                    }
                 }
                 unstage(BB, cj0, wj, BW);
                 // fold the x scales so that they cannot drift far from 1
                 {
-                    const T d0 = mt.d[2 * w], d1 = mt.d[2 * w + 1];
+                    const T d0 = mt.d[XPW * w], d1 = mt.d[XPW * w + XPW - 1];
 #pragma unroll
                     for (int i = 0; i < NI; ++i) {
-                        x0[i].x *= d0; x0[i].y *= d0; x1[i].x *= d1; x1[i].y *= d1;
+                        x0[i].x *= d0; x0[i].y *= d0;
+                        if constexpr (XPW == 2) { x1[i].x *= d1; x1[i].y *= d1; }
                     }
                     __syncwarp();
-                    if (lane < 2) { mt.d[2 * w + lane] = T(1); mt.id[2 * w + lane] = T(1); }
+                    if (lane < XPW) { mt.d[XPW * w + lane] = T(1); mt.id[XPW * w + lane] = T(1); }
                 }
                 __syncthreads();
             }
@@ -310,7 +366,8 @@ __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sw
                         if (r + 1 < a) dst[r + 1] = x[i].y;
                     }
                 };
-                put(x0, 2 * w); put(x1, 2 * w + 1);
+                put(x0, XPW * w);
+                if constexpr (XPW == 2) put(x1, 2 * w + 1);
             }
             __syncthreads();
         }
@@ -328,8 +385,9 @@ __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sw
 }
 
 template<typename T>
-constexpr size_t rx_smem_bytes(int ni, int b_bound) {
-    return sizeof(T) * ((size_t) 2 * 64 * ni * RX_BW + (size_t) b_bound + 6 * RX_BW);
+constexpr size_t rx_smem_bytes(int ni, int b_bound) {  // two block regions (32 columns up to 384 rows, 16 columns above)
+    const size_t wide = (size_t) 2 * 64 * (ni < RX_MAX_NI ? ni : RX_MAX_NI) * RX_BW, tall = ni > RX_MAX_NI ? (size_t) 2 * 64 * ni * (RX_BW / 2) : 0;
+    return sizeof(T) * ((wide > tall ? wide : tall) + (size_t) b_bound + 6 * RX_BW);
 }
 
 // Persistent kernel: grid = min(n_probs, resident CTAs) CTAs of 512 threads; a <= 384.  Work items are (sweep, problem)
@@ -376,12 +434,18 @@ __global__ void __launch_bounds__(RX_THREADS, 1) k_jacobi_svd_rx(const SvdProb<T
         int flags = 4;
         if (p.a > 0 && p.b > 0) {
             switch ((p.a + 63) / 64) {
-                case 1: flags = jacobi_sweep_rx<T, 1>(sm, p, sw, max_sweeps); break;
-                case 2: flags = jacobi_sweep_rx<T, 2>(sm, p, sw, max_sweeps); break;
-                case 3: flags = jacobi_sweep_rx<T, 3>(sm, p, sw, max_sweeps); break;
-                case 4: flags = jacobi_sweep_rx<T, 4>(sm, p, sw, max_sweeps); break;
-                case 5: flags = jacobi_sweep_rx<T, 5>(sm, p, sw, max_sweeps); break;
-                default: flags = jacobi_sweep_rx<T, 6>(sm, p, sw, max_sweeps); break;
+                case 1: flags = jacobi_sweep_rx<T, 1, 2>(sm, p, sw, max_sweeps); break;
+                case 2: flags = jacobi_sweep_rx<T, 2, 2>(sm, p, sw, max_sweeps); break;
+                case 3: flags = jacobi_sweep_rx<T, 3, 2>(sm, p, sw, max_sweeps); break;
+                case 4: flags = jacobi_sweep_rx<T, 4, 2>(sm, p, sw, max_sweeps); break;
+                case 5: flags = jacobi_sweep_rx<T, 5, 2>(sm, p, sw, max_sweeps); break;
+                case 6: flags = jacobi_sweep_rx<T, 6, 2>(sm, p, sw, max_sweeps); break;
+                case 7: flags = jacobi_sweep_rx<T, 7, 1>(sm, p, sw, max_sweeps); break;
+                case 8: flags = jacobi_sweep_rx<T, 8, 1>(sm, p, sw, max_sweeps); break;
+                case 9: flags = jacobi_sweep_rx<T, 9, 1>(sm, p, sw, max_sweeps); break;
+                case 10: flags = jacobi_sweep_rx<T, 10, 1>(sm, p, sw, max_sweeps); break;
+                case 11: flags = jacobi_sweep_rx<T, 11, 1>(sm, p, sw, max_sweeps); break;
+                default: flags = jacobi_sweep_rx<T, 12, 1>(sm, p, sw, max_sweeps); break;
             }
         }
         __syncthreads();

@@ -181,7 +181,7 @@ def test_geqrf_ungqr_unmqr_vs_lapack(ctx, dt, shape):
 
 @pytest.mark.parametrize("dt", DT)
 @pytest.mark.parametrize("shape", [(9, 9), (71, 71), (130, 130), (64, 20), (20, 64), (7, 1), (1, 5), (200, 200),
-                                   (357, 357), (700, 300), (300, 421)])
+                                   (357, 357), (700, 300), (300, 421), (600, 600), (768, 400), (769, 390)])
 def test_svd_vs_lapack(ctx, dt, shape):
     m, n = shape
     rng = np.random.default_rng(m * 7 + n)
