@@ -391,6 +391,10 @@ def main():
                 "recompression_gflops": float(fr.sum()) / t_rec / 1e9,
                 "contraction_gflops": float(fc.sum()) / max(t_con, 1e-9) / 1e9,
                 "c_rank_final_mean": float(rk_all[-1].mean()), "c_rank_max": float(rk_all.max()),
+                # the three FP64-bound recompression phases against the measured FP64 peak (algorithmic flops, true ranks)
+                "phase_fp64_tflops": {n: float(alg_flops[n]) / (phases[n]["ms_per_step"] * 1e-3) / 1e12 for n in alg_flops},
+                "phase_fp64_frac_of_peak": {n: float(alg_flops[n]) / (phases[n]["ms_per_step"] * 1e-3) / 1e12 / fp64_peak()[0]
+                                            for n in alg_flops},
             }
         # ---- end-to-end: same pass through the public API with HOST buffers (pinned), H2D + D2H inside the timing
         if world == 1 and not args.no_e2e:
