@@ -169,8 +169,9 @@ def cpu_reference_sample(args, Uc_A, Vc_A, Uc_B, Vc_B, rank, budget_s, want_outp
     T, nb = args.tiles, args.nb
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, R.lib().hcref_max_threads()))
-    # ~15 ms per tile-GEMM per core at nb = 1024: size the sample for the budget, whole columns
-    est_per_gemm = 15e-3 * (nb / 1024.0) ** 1.2
+    # ~60 ms per tile-GEMM per core at nb = 1024 with race-free inputs (C ranks grow to ~313; measured: 4096 tile-GEMMs in
+    # 15.5 s on 16 cores): size the sample for the budget, whole block-columns
+    est_per_gemm = 60e-3 * (nb / 1024.0) ** 1.2
     cols = int(max(1, min(T, budget_s * threads / (est_per_gemm * T * T))))
     p = R.Params(args.acc)
     tileA = lambda j, k: R.RefTile.from_uv(Uc_A[j + k * T].T, Vc_A[j + k * T].T)
