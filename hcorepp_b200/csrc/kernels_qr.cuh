@@ -207,173 +207,10 @@ __global__ void __launch_bounds__(256) k_larft_extract(const LarftProb<T> *__res
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// On-chip panel factorisation: one thread-block CLUSTER per NBQ-column block.
-//
-// k_geqrf_batched + k_larft_extract work on the panel through L2 (8 + 4 MB of traffic per 1024 x 32 block; at
-// r = 357 they were 45 % of the blocked-QR time and ran at the L2 bandwidth limit, ncu launch list r01).  Here the
-// block lives in shared memory for the whole factorisation: each CTA of the cluster owns 512 rows x 32 columns
-// (128 KB fp64), one row per thread.  Per column step every thread forms its row's 32 products x_j[row] * P[row][c],
-// a transposed warp butterfly + one shared-memory pass reduce them per CTA, and the CTAs exchange their 32 partial
-// sums (+ the pivot row) through DISTRIBUTED SHARED MEMORY (cluster.map_shared_rank) -- one vector per step instead of
-// streaming the trailing columns through L2.  The same sums give ||x||^2 (c == j), the trailing-update dots (c > j)
-// and V_prev^T v_j for the dlarft recurrence (c < j), so T_b and the clean V_b copy come out of the same kernel.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int PQ_ROWS = 512;  // rows (= threads) per CTA
-
-// sum over the warp of pr[k] for every k in [0, 32); lane l returns the total for index l (31 shuffle steps)
-template<typename T>
-__device__ __forceinline__ T warp_reduce_32(T (&pr)[32], int lane) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const bool up = lane & 16;
-        const T send = up ? pr[k] : pr[k + 16];
-        const T keep = up ? pr[k + 16] : pr[k];
-        pr[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const bool up = lane & 8;
-        const T send = up ? pr[k] : pr[k + 8];
-        const T keep = up ? pr[k + 8] : pr[k];
-        pr[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const bool up = lane & 4;
-        const T send = up ? pr[k] : pr[k + 4];
-        const T keep = up ? pr[k + 4] : pr[k];
-        pr[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const bool up = lane & 2;
-        const T send = up ? pr[k] : pr[k + 2];
-        const T keep = up ? pr[k + 2] : pr[k];
-        pr[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    {
-        const bool up = lane & 1;
-        const T send = up ? pr[0] : pr[1];
-        const T keep = up ? pr[1] : pr[0];
-        pr[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-    }
-    return pr[0];
-}
-
-// grid.x = cluster_size * n_panels, cluster dims (cluster_size, 1, 1), block = PQ_ROWS threads,
-// dynamic shared memory = NBQ * PQ_ROWS * sizeof(T).
-template<typename T>
-__global__ void __launch_bounds__(PQ_ROWS) k_panel_qr_cluster(const QrProb<T> *__restrict__ qps,
-                                                              const LarftProb<T> *__restrict__ lps) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int CS = (int) cluster.num_blocks(), crank = (int) cluster.block_rank();
-    const int panel = blockIdx.x / CS;
-    const QrProb<T> q = qps[panel];
-    const LarftProb<T> lp = lps[panel];
-    const int m = q.m, jb = q.n < m ? q.n : m, lda = q.lda;
-    if (m <= 0 || jb <= 0) return;  // uniform over the cluster (same descriptor)
-    extern __shared__ __align__(16) unsigned char smem_raw_pq[];
-    T *P = reinterpret_cast<T *>(smem_raw_pq);  // P[c * PQ_ROWS + t]: column c, local row t
-    __shared__ T zpart[PQ_ROWS / 32][NBQ];
-    __shared__ T zloc[2 * NBQ + 1];  // [0,32): partial dots; [32,64): pivot row (CTA 0 only); [64]: unused
-    __shared__ T zsum[2 * NBQ];
-    __shared__ T Ts[NBQ][NBQ + 1];
-    __shared__ T tcol[NBQ];
-    __shared__ T s_tau[NBQ];
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const int gr = crank * PQ_ROWS + t;  // row inside the block
-    const bool have = gr < m;
-    for (int c = 0; c < NBQ; ++c) P[c * PQ_ROWS + t] = (have && c < jb) ? q.A[(size_t) gr + (size_t) c * lda] : T(0);
-    for (int idx = t; idx < NBQ * (NBQ + 1); idx += PQ_ROWS) (&Ts[0][0])[idx] = T(0);
-    __syncthreads();
-
-    for (int j = 0; j < jb; ++j) {
-        // ---- partial sums z[c] = sum_{rows > j} x_j[row] * P[row][c]
-        const T xv = (have && gr > j) ? P[j * PQ_ROWS + t] : T(0);
-        T pr[NBQ];
-#pragma unroll
-        for (int c = 0; c < NBQ; ++c) pr[c] = xv * P[c * PQ_ROWS + t];
-        const T mine = warp_reduce_32<T>(pr, lane);
-        zpart[w][lane] = mine;
-        __syncthreads();
-        if (t < NBQ) {
-            T sacc = T(0);
-#pragma unroll
-            for (int ww = 0; ww < PQ_ROWS / 32; ++ww) sacc += zpart[ww][t];
-            zloc[t] = sacc;
-            zloc[NBQ + t] = (crank == 0) ? P[t * PQ_ROWS + j] : T(0);  // pivot row j lives in CTA 0 (j < 32 <= PQ_ROWS)
-        }
-        if (CS > 1) {
-            cluster.sync();
-            if (t < 2 * NBQ) {
-                T sacc = T(0);
-                for (int rk = 0; rk < CS; ++rk) sacc += cluster.map_shared_rank(zloc, rk)[t];
-                zsum[t] = sacc;
-            }
-            cluster.sync();  // everybody has read zloc before the next step overwrites it
-        } else {
-            __syncthreads();
-            if (t < 2 * NBQ) zsum[t] = zloc[t];
-            __syncthreads();
-        }
-        // ---- Householder scalars (every thread, from shared broadcasts)
-        const T ss = zsum[j], alpha = zsum[NBQ + j];
-        T tau = T(0), scale = T(0), beta = alpha;
-        if (ss != T(0)) {
-            const T nrm = t_sqrt(fma(alpha, alpha, ss));
-            beta = alpha >= T(0) ? -nrm : nrm;
-            tau = (beta - alpha) / beta;
-            scale = T(1) / (alpha - beta);
-        }
-        // ---- update my row: reflector entry + trailing columns
-        if (tau != T(0)) {
-            if (have && gr > j) {
-                const T v = xv * scale;
-                P[j * PQ_ROWS + t] = v;
-                const T tv = tau * v;
-                for (int c = j + 1; c < jb; ++c) {
-                    const T wc = fma(scale, zsum[c], zsum[NBQ + c]);  // v^T A[:, c]
-                    P[c * PQ_ROWS + t] = fma(-tv, wc, P[c * PQ_ROWS + t]);
-                }
-            } else if (have && gr == j) {
-                P[j * PQ_ROWS + t] = beta;
-                for (int c = j + 1; c < jb; ++c) {
-                    const T wc = fma(scale, zsum[c], zsum[NBQ + c]);
-                    P[c * PQ_ROWS + t] = fma(-tau, wc, P[c * PQ_ROWS + t]);
-                }
-            }
-        }
-        // ---- dlarft recurrence for column j of T (warp 0 of every CTA, only CTA 0 stores it)
-        if (w == 0) {
-            if (lane == 0) s_tau[j] = tau;
-            if (lane < j) tcol[lane] = -tau * fma(scale, zsum[lane], zsum[NBQ + lane]);  // -tau * (V_prev^T v_j)
-            __syncwarp();
-            T acc = T(0);
-            if (lane < j)
-                for (int c = lane; c < j; ++c) acc = fma(Ts[lane][c], tcol[c], acc);
-            __syncwarp();
-            if (lane < j) Ts[lane][j] = acc;
-            if (lane == j) Ts[j][j] = tau;
-        }
-        __syncthreads();
-    }
-    // ---- write back: factored block, tau, clean V_b, T_b
-    if (have) {
-        for (int c = 0; c < jb; ++c) {
-            const T val = P[c * PQ_ROWS + t];
-            q.A[(size_t) gr + (size_t) c * lda] = val;
-            lp.Vc[(size_t) gr + (size_t) c * lp.ldvc] = (gr < c) ? T(0) : (gr == c ? T(1) : val);
-        }
-    }
-    if (crank == 0) {
-        if (t < jb) q.tau[t] = s_tau[t];
-        for (int idx = t; idx < NBQ * NBQ; idx += PQ_ROWS) lp.Tm[idx] = Ts[idx % NBQ][idx / NBQ];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// k_panel_qr_regs: same job as k_panel_qr_cluster with the block in REGISTERS.  256 threads per CTA, two rows per
+// k_panel_qr_regs: on-chip panel factorisation, one thread-block CLUSTER per NBQ-column block, the block in REGISTERS.
+// (k_geqrf_batched + k_larft_extract work on the panel through L2: 8 + 4 MB of traffic per 1024 x 32 block, 1731 us per
+// 512-panel launch at r = 357; a first on-chip version kept the block in shared memory -- 879 us; this one: ~650 us.)
+//  256 threads per CTA, two rows per
 // thread (local rows t and t + 256), 64 doubles of row data per thread.  The pivot column is always register slot 0:
 // the trailing update writes column c into slot c-1, so the loop over the 32 columns stays a rolled loop with
 // compile-time register indices.  Per step: 64 FMAs form the thread's products, two 16-value transposed butterflies
