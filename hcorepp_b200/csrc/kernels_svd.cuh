@@ -115,6 +115,7 @@ __device__ __forceinline__ int jacobi_rotate_reg(T *__restrict__ mx, T *__restri
         a2 = warp_sum(na);
         b2 = warp_sum(nb);
     }
+    __syncwarp();  // every lane has read the cached norms before lane 0 replaces them (racecheck: write-after-read)
     if (lane == 0) { *nx2 = a2; *ny2 = b2; }
     return ret;
 }

@@ -390,6 +390,7 @@ __global__ void __launch_bounds__(1024) k_precond_product(const PrecondProb<T> *
                 const T tg = t * gamma;
                 T a2 = alpha - tg, b2 = beta + tg;
                 if (a2 < T(0.01) * alpha || b2 < T(0.01) * beta) { a2 = warp_sum(na); b2 = warp_sum(nb); }
+                __syncwarp();  // all lanes have read nrm[x], nrm[y]
                 if (lane == 0) { nrm[x] = a2; nrm[y] = b2; }
             }
             __syncthreads();
