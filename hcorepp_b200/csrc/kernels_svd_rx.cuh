@@ -111,6 +111,7 @@ __device__ __forceinline__ int rx_duo(Vec2<T> (&xa)[NI], int ixa, Vec2<T> (&ya)[
         mt.d[ix] = c * dx; mt.d[iy] = c * dy;
         mt.id[ix] = rc * idx; mt.id[iy] = rc * idy;
     }
+    __syncwarp();  // lanes 0 / 16 wrote the metadata that lane 0 may re-read in the (rare) redo path below
     const unsigned brot = __ballot_sync(0xffffffffu, rot), bredo = __ballot_sync(0xffffffffu, redo);
     const unsigned bbig = __ballot_sync(0xffffffffu, big);
     const T fxa = __shfl_sync(0xffffffffu, fx, 0), fya = __shfl_sync(0xffffffffu, fy, 0);
