@@ -207,7 +207,7 @@ __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sw
     const T tol2 = tol * tol;
     // Predictive stop: the sweep after one in which every pair was already below cos = sqrt(tol) would only verify
     // (quadratic convergence leaves residual cosines ~ tol), so it is skipped.
-    const T big2 = tol;
+    const T big2 = T(16) * tol;  // cos < 4 sqrt(tol) = 2.5e-7: the residual after that sweep is ~6e-14 (measured: same parity, fewer sweeps)
     const int nblk = (b + BW - 1) / BW;
 
     // asynchronous staging of columns [c0, c0 + wc) into dst (pitch P, zero padded rows and columns)
