@@ -214,7 +214,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: hcorepp_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # (the version banner would be a second stdout line next to the JSON)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner / debug lines go to stderr: stdout is the ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     P, Q = grid_shape(world)
     pr, pc = rank_env // Q, rank_env % Q
