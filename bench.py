@@ -34,6 +34,9 @@ UNIT = "tile-GEMM/s"
 
 
 # --------------------------------------------------------------------------------------------------------------------
+_JSON_OUT = None  # private copy of the process's stdout, see main()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -193,6 +196,12 @@ def cpu_reference_sample(args, Uc_A, Vc_A, Uc_B, Vc_B, rank, budget_s, want_outp
 # --------------------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    # stdout carries exactly ONE line (the JSON): everything any library writes to fd 1 (NCCL prints its version banner
+    # there when NCCL_DEBUG is set in the environment) is sent to stderr; the JSON goes to a private copy of fd 1.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank_env = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -418,7 +427,7 @@ def main():
                                                                                 krank, prm)
                 except Exception as e:  # the baseline is reported, never required for the GPU number
                     result["cpu_baseline"] = {"error": repr(e)}
-        print(json.dumps(result))
+        print(json.dumps(result), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -602,7 +611,7 @@ def run_reference_arm(args, krank):
             T * nb, T * nb, nb, args.acc)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0}), file=_JSON_OUT, flush=True)
 
 
 def setup_distributed(args, hc, ctx, dist, torch, synth, krank, cap_in, P, Q, pr, pc, prm):
