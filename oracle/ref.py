@@ -58,6 +58,12 @@ def _declare(L):
         f("gemm").restype = C.c_int
         f("gemm").argtypes = [ct, vp, C.c_int, vp, C.c_int, ct, vp, C.c_double, C.c_int, C.c_int, C.c_int, i64,
                               C.c_int, vp]
+        f("potrf").restype = C.c_int
+        f("potrf").argtypes = [vp, C.c_int]
+        f("trsm").restype = C.c_int
+        f("trsm").argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, ct, vp, vp]
+        f("syrk").restype = C.c_int
+        f("syrk").argtypes = [ct, vp, C.c_int, C.c_int, ct, vp]
         f("matmul").restype = C.c_int
         f("matmul").argtypes = [i64, i64, i64, vp, vp, vp, ct, ct, C.c_double, C.c_int, C.c_int, C.c_int, i64,
                                 C.c_int, C.c_int, vp, vp]
@@ -187,6 +193,25 @@ def gemm(alpha, A: RefTile, opA: bool, B: RefTile, opB: bool, beta, Ct: RefTile,
     if rc != 0:
         raise RuntimeError("reference HCore::Gemm threw")
     return int(flops.value)
+
+
+# ---- TLR Cholesky pieces: no driver and no enabled tests in the reference; pinned here only
+def potrf(A: RefTile, uplo: str = "L"):
+    """HCore<T>::Potrf (HCore.cpp:586-621): dense tiles only, in place."""
+    if fn("potrf", A.dtype)(A.h, ord(uplo)) != 0:
+        raise RuntimeError("reference HCore::Potrf threw")
+
+
+def trsm(side: str, uplo: str, trans: bool, diag: str, alpha, A: RefTile, B: RefTile):
+    """HCore<T>::Trsm (HCore.cpp:624-647): A dense triangular, B compressed; the solve is applied to B's V buffer."""
+    if fn("trsm", B.dtype)(ord(side), ord(uplo), int(trans), ord(diag), _CT[B.dtype](alpha), A.h, B.h) != 0:
+        raise RuntimeError("reference HCore::Trsm threw")
+
+
+def syrk(alpha, A: RefTile, opA: bool, uplo: str, beta, Ct: RefTile):
+    """HCore<T>::Syrk (HCore.cpp:484-583)."""
+    if fn("syrk", Ct.dtype)(_CT[Ct.dtype](alpha), A.h, int(opA), ord(uplo), _CT[Ct.dtype](beta), Ct.h) != 0:
+        raise RuntimeError("reference HCore::Syrk threw")
 
 
 def matmul(A, B, Cg, alpha, beta, p: Params, nthreads: int = 0):

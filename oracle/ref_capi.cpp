@@ -124,6 +124,47 @@ int tile_gemm(T alpha, void *a, int opa, void *b, int opb, T beta, void *c, cons
     }
 }
 
+// TLR Cholesky pieces (HCore.cpp:482-647).  The reference has no driver and no enabled tests for
+// them, so these wrappers are the only pin for that row.  uplo: 'L' / 'U'; side 'L' / 'R'; diag 'N' / 'U'.
+template<typename T>
+int tile_potrf(void *a, int uplo) {
+    try {
+        dataunits::MemoryUnit<T> unit(ctx());
+        size_t flops = 0;
+        api::HCore<T>::Potrf(*static_cast<Tile<T> *>(a), (blas::Uplo) uplo, ctx(), flops, unit);
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "hcref potrf: %s\n", e.what());
+        return 1;
+    }
+}
+template<typename T>
+int tile_trsm(int side, int uplo, int trans, int diag, T alpha, void *a, void *b) {
+    try {
+        dataunits::MemoryUnit<T> unit(ctx());
+        size_t flops = 0;
+        api::HCore<T>::Trsm((blas::Side) side, (blas::Uplo) uplo, trans ? blas::Op::Trans : blas::Op::NoTrans, (blas::Diag) diag,
+                            alpha, *static_cast<Tile<T> *>(a), *static_cast<Tile<T> *>(b), ctx(), flops, unit);
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "hcref trsm: %s\n", e.what());
+        return 1;
+    }
+}
+template<typename T>
+int tile_syrk(T alpha, void *a, int opa, int uplo, T beta, void *c) {
+    try {
+        dataunits::MemoryUnit<T> unit(ctx());
+        size_t flops = 0;
+        api::HCore<T>::Syrk(alpha, *static_cast<Tile<T> *>(a), opa ? blas::Op::Trans : blas::Op::NoTrans, (blas::Uplo) uplo, beta,
+                            *static_cast<Tile<T> *>(c), ctx(), flops, unit);
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "hcref syrk: %s\n", e.what());
+        return 1;
+    }
+}
+
 // The tile loop of examples/matrix_multiplication/omp_main.cpp:112-126: C(j,i) += A(j,k) B(k,i) for k = 0..kt-1,
 // OMP-parallel over the independent C tiles, one MemoryUnit per thread. Tile arrays are column-major grids:
 // A[j + k*mt], B[k + i*kt], C[j + i*mt].
@@ -195,6 +236,13 @@ void latms_law(int64_t m, int64_t n, int64_t tile_size, int64_t *seed, T *out, i
                                    int64_t *flops) {                                                                 \
         return tile_gemm<T>(alpha, a, opa, b, opb, beta, c,                                                          \
                             make_params(acc, use_trmm, use_ungqr, trunc, fixed_rank, svd), flops);                   \
+    }                                                                                                                \
+    extern "C" int hcref_##P##potrf(void *a, int uplo) { return tile_potrf<T>(a, uplo); }                            \
+    extern "C" int hcref_##P##trsm(int side, int uplo, int trans, int diag, T alpha, void *a, void *b) {             \
+        return tile_trsm<T>(side, uplo, trans, diag, alpha, a, b);                                                   \
+    }                                                                                                                \
+    extern "C" int hcref_##P##syrk(T alpha, void *a, int opa, int uplo, T beta, void *c) {                           \
+        return tile_syrk<T>(alpha, a, opa, uplo, beta, c);                                                           \
     }                                                                                                                \
     extern "C" int hcref_##P##matmul(int64_t mt, int64_t nt, int64_t kt, void **A, void **B, void **C, T alpha,      \
                                      T beta, double acc, int use_trmm, int use_ungqr, int trunc,                     \

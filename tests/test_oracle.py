@@ -225,3 +225,42 @@ def test_live_multitile_matches_and_example_line():
     Co = np.block([[t.to_dense() for t in r] for r in oC])
     assert np.linalg.norm(Cr - Co) <= 1e-12 * np.linalg.norm(Cr)
     assert np.linalg.norm(Cr - A @ B) <= 10 * acc * np.linalg.norm(A @ B)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# TLR Cholesky pieces of the reference (NOT built on the GPU side yet): the reference has no driver
+# and no enabled tests for them, so what it actually does is recorded here against the compiled reference.
+# ------------------------------------------------------------------------------------------------------------------
+@needs_ref
+def test_reference_cholesky_pieces_semantics():
+    from oracle import ref as R
+    rng = np.random.default_rng(0)
+    n, k = 64, 8
+    M = rng.standard_normal((n, n))
+    S = M @ M.T + n * np.eye(n)
+    # Potrf (HCore.cpp:586-621): dense tiles only, LAPACK potrf in place (the other triangle is left alone)
+    t = R.RefTile.dense(np.asfortranarray(S.copy()))
+    R.potrf(t, "L")
+    L = t.to_dense()
+    assert np.allclose(np.tril(L), np.linalg.cholesky(S)) and np.allclose(np.triu(L, 1), np.triu(S, 1))
+    # Syrk with a dense A (HCore.cpp:576-582): k is taken from C's column count, i.e. A must be a square tile
+    A = rng.standard_normal((n, n))
+    C0 = rng.standard_normal((n, n))
+    C0 = C0 + C0.T
+    ta, tc = R.RefTile.dense(np.asfortranarray(A.copy())), R.RefTile.dense(np.asfortranarray(C0.copy()))
+    R.syrk(-1.0, ta, False, "L", 1.0, tc)
+    assert np.allclose(np.tril(tc.to_dense()), np.tril(C0 - A @ A.T))
+    # Trsm (HCore.cpp:624-647): B must be compressed; the solve runs on B's V buffer viewed as (rows(B) x rank) with the
+    # tile's leading dimension; with side = Right only the leading rank x rank block of A is used.  U is untouched.
+    Lm = np.tril(rng.standard_normal((n, n))) + n * np.eye(n)
+    U, V = rng.standard_normal((n, k)), rng.standard_normal((k, n))
+    tA = R.RefTile.dense(np.asfortranarray(Lm.copy()))
+    tB = R.RefTile.from_uv(np.asfortranarray(U.copy()), np.asfortranarray(V.copy()))
+    R.trsm("R", "L", True, "N", 1.0, tA, tB)
+    U2, V2 = tB.read()
+    assert np.allclose(U2, U)
+    Vn = V.reshape(-1, order="F").reshape((n, k), order="F")
+    got = V2.reshape(-1, order="F").reshape((n, k), order="F")
+    assert np.allclose(got, Vn @ np.linalg.inv(Lm[:k, :k]).T)
+    with pytest.raises(RuntimeError):
+        R.potrf(tB, "L")  # "Potrf works only with dense tiles"
