@@ -16,6 +16,8 @@
 #include <cstdint>
 #include <functional>
 #include <memory>
+#include <cmath>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -554,4 +556,136 @@ public:
     }
 };
 }  // namespace api
+
+namespace helpers {  // include/hcorepp/helpers/{RawMatrix,TileMatrix}.hpp -- the multi-tile container and the driver loop
+
+/// Host column-major matrix (RawMatrix.hpp:27-160, the part the drivers use; generators / LAPACK helpers stay in the
+/// reference's test harness).
+template<typename T>
+class RawMatrix {
+public:
+    RawMatrix(size_t aM, size_t aN) : mM(aM), mN(aN), mData(aM * aN, T(0)) {}
+    RawMatrix(size_t aM, size_t aN, const T *apData) : mM(aM), mN(aN), mData(apData, apData + aM * aN) {}
+    T *GetData() { return mData.data(); }
+    const T *GetData() const { return mData.data(); }
+    size_t GetM() const { return mM; }
+    size_t GetN() const { return mN; }
+    /// Frobenius norm
+    double Norm() const {
+        double s = 0;
+        for (const T &v : mData) s += (double) v * (double) v;
+        return std::sqrt(s);
+    }
+    /// this -= aReference (RawMatrix.hpp ReferenceDifference)
+    void ReferenceDifference(const RawMatrix<T> &aReference) {
+        if (aReference.mM != mM || aReference.mN != mN) throw std::runtime_error("Reference Matrix Is Not The Same Size");
+        for (size_t i = 0; i < mData.size(); ++i) mData[i] -= aReference.mData[i];
+    }
+private:
+    size_t mM, mN;
+    std::vector<T> mData;
+};
+
+/// TileMatrix.hpp:27-196: mt x nt grid of tiles (tile (row, col) at [col][row]); dense or compressed on construction.
+template<typename T>
+class TileMatrix {
+public:
+    TileMatrix(const RawMatrix<T> &aRawMatrix, size_t aRowTileSize, size_t aColumnTileSize, kernels::RunContext &aContext)
+        : TileMatrix(aRawMatrix, aRowTileSize, aColumnTileSize, nullptr, aContext) {}
+    TileMatrix(const RawMatrix<T> &aRawMatrix, size_t aRowTileSize, size_t aColumnTileSize,
+               const operators::CompressionParameters &aParameters, kernels::RunContext &aContext)
+        : TileMatrix(aRawMatrix, aRowTileSize, aColumnTileSize, &aParameters, aContext) {}
+    TileMatrix(const TileMatrix &) = delete;
+    ~TileMatrix() {
+        for (auto &col : mMatrixTiles)
+            for (auto *t : col) delete t;
+    }
+    operators::Tile<T> *GetTile(size_t aRowIndex, size_t aColIndex) { return mMatrixTiles[aColIndex][aRowIndex]; }
+    size_t GetRowTileCount() const { return mRowTileCount; }
+    size_t GetColTileCount() const { return mColTileCount; }
+    size_t GetRowTileSize() const { return mRowTileSize; }
+    size_t GetColTileSize() const { return mColTileSize; }
+    size_t GetM() const { return mM; }
+    size_t GetN() const { return mN; }
+    /// U*V per tile, assembled on the host (TileMatrix.cpp:187-252)
+    RawMatrix<T> ToRawMatrix(kernels::RunContext &aContext) {
+        RawMatrix<T> out(mM, mN);
+        for (size_t c = 0; c < mColTileCount; ++c)
+            for (size_t r = 0; r < mRowTileCount; ++r) {
+                operators::Tile<T> *t = mMatrixTiles[c][r];
+                const size_t tm = t->GetNumOfRows(), tn = t->GetNumOfCols();
+                std::vector<T> d(tm * tn, T(0));
+                if (t->isDense()) {
+                    memory::Memcpy<T>(d.data(), t->GetTileSubMatrix(0), tm * tn, aContext, memory::MemoryTransfer::DEVICE_TO_HOST);
+                    aContext.Sync();
+                } else {
+                    auto *ct = static_cast<operators::CompressedTile<T> *>(t);
+                    const size_t rk = ct->GetTileRank();
+                    std::vector<T> U(tm * rk), V(rk * tn);
+                    memory::Memcpy<T>(U.data(), ct->GetUMatrix(), tm * rk, aContext, memory::MemoryTransfer::DEVICE_TO_HOST);
+                    memory::Memcpy<T>(V.data(), ct->GetVMatrix(), rk * tn, aContext, memory::MemoryTransfer::DEVICE_TO_HOST);
+                    aContext.Sync();
+                    for (size_t j = 0; j < tn; ++j)
+                        for (size_t l = 0; l < rk; ++l)
+                            for (size_t i = 0; i < tm; ++i) d[i + j * tm] += U[i + l * tm] * V[l + j * rk];
+                }
+                for (size_t j = 0; j < tn; ++j)
+                    std::memcpy(out.GetData() + (r * mRowTileSize) + (c * mColTileSize + j) * mM, d.data() + j * tm, tm * sizeof(T));
+            }
+        return out;
+    }
+    /// bytes held by the tiles (TileMatrix.cpp:254-266: compressed tiles count (m + n) * rank elements)
+    size_t GetMemoryFootprint() {
+        size_t bytes = 0;
+        for (auto &col : mMatrixTiles)
+            for (auto *t : col)
+                bytes += sizeof(T) * (t->isDense() ? t->GetNumOfRows() * t->GetNumOfCols()
+                                                   : (t->GetNumOfRows() + t->GetNumOfCols()) * t->GetTileRank());
+        return bytes;
+    }
+private:
+    TileMatrix(const RawMatrix<T> &aRaw, size_t aTm, size_t aTn, const operators::CompressionParameters *apParams,
+               kernels::RunContext &aContext)
+        : mRowTileSize(aTm), mColTileSize(aTn), mM(aRaw.GetM()), mN(aRaw.GetN()) {
+        mRowTileCount = (mM + aTm - 1) / aTm;
+        mColTileCount = (mN + aTn - 1) / aTn;
+        mMatrixTiles.resize(mColTileCount);
+        for (size_t c = 0; c < mColTileCount; ++c) {
+            mMatrixTiles[c].resize(mRowTileCount, nullptr);
+            for (size_t r = 0; r < mRowTileCount; ++r) {
+                const size_t tm = std::min(aTm, mM - r * aTm), tn = std::min(aTn, mN - c * aTn);
+                T *src = const_cast<T *>(aRaw.GetData()) + r * aTm + c * aTn * mM;  // sub-matrix view, ld = M
+                if (apParams)
+                    mMatrixTiles[c][r] = new operators::CompressedTile<T>(tm, tn, src, mM, *apParams, blas::Layout::ColMajor, aContext);
+                else
+                    mMatrixTiles[c][r] = new operators::DenseTile<T>(tm, tn, src, mM, blas::Layout::ColMajor, aContext);
+            }
+        }
+    }
+    std::vector<std::vector<operators::Tile<T> *>> mMatrixTiles;
+    size_t mRowTileCount = 0, mColTileCount = 0, mRowTileSize, mColTileSize, mM, mN;
+};
+
+/// The drivers' triple loop (examples/matrix_multiplication/omp_main.cpp:112-126): C(j,i) = alpha * sum_k A(j,k) B(k,i) +
+/// beta * C(j,i), here ONE batched device call per k over all C tiles (hcb_?tlr_matmul), nothing synchronises.
+template<typename T>
+void TileMatrixMultiplication(TileMatrix<T> &aA, TileMatrix<T> &aB, TileMatrix<T> &aC, T aAlpha, T aBeta,
+                              const operators::CompressionParameters &aParameters, const kernels::RunContext &aContext) {
+    const size_t mt = aC.GetRowTileCount(), nt = aC.GetColTileCount(), kt = aA.GetColTileCount();
+    if (aA.GetRowTileCount() != mt || aB.GetColTileCount() != nt || aB.GetRowTileCount() != kt)
+        throw std::invalid_argument("TileMatrixMultiplication: tile grids do not conform");
+    std::vector<hcb_tile> a(mt * kt), b(kt * nt), c(mt * nt);
+    for (size_t k = 0; k < kt; ++k)
+        for (size_t j = 0; j < mt; ++j) a[j + k * mt] = aA.GetTile(j, k)->Descriptor();
+    for (size_t i = 0; i < nt; ++i)
+        for (size_t k = 0; k < kt; ++k) b[k + i * kt] = aB.GetTile(k, i)->Descriptor();
+    for (size_t i = 0; i < nt; ++i)
+        for (size_t j = 0; j < mt; ++j) c[j + i * mt] = aC.GetTile(j, i)->Descriptor();
+    const hcb_compress_params p = aParameters.ToC();
+    detail::check(detail::abi<T>::tlr_matmul(aContext.Handle(), (int64_t) mt, (int64_t) nt, (int64_t) kt, a.data(), b.data(), c.data(),
+                                             nullptr, 0, 0, (int64_t) kt, aAlpha, aBeta, &p, nullptr),
+                  "TileMatrixMultiplication");
+}
+
+}  // namespace helpers
 }  // namespace hcorepp

@@ -170,6 +170,47 @@ static void run(const char *type) {
         report("invalid sub-matrix index throws", type, threw);
         delete A;
     }
+    {  // multi-tile container + driver loop (TileMatrix.hpp, omp_main.cpp:112-126): 3 x 2 x 2 tiles of 48, rank-5 tiles
+        const size_t nb = 48, mt = 3, nt = 2, kt = 2, rk = 5;
+        auto lowrank = [&](size_t M, size_t N, size_t tm, size_t tn, unsigned seed) {
+            helpers::RawMatrix<T> raw(M, N);
+            unsigned s = seed;
+            auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (double) (s >> 8) / (1 << 24) - 0.5; };
+            for (size_t bc = 0; bc < N / tn; ++bc)
+                for (size_t br = 0; br < M / tm; ++br) {
+                    std::vector<double> U(tm * rk), V(rk * tn);
+                    for (auto &v : U) v = rnd();
+                    for (auto &v : V) v = rnd();
+                    for (size_t j = 0; j < tn; ++j)
+                        for (size_t i = 0; i < tm; ++i) {
+                            double acc = 0;
+                            for (size_t l = 0; l < rk; ++l) acc += U[i + l * tm] * V[l + j * rk] * std::pow(0.5, (double) l);
+                            raw.GetData()[(br * tm + i) + (bc * tn + j) * M] = (T) acc;
+                        }
+                }
+            return raw;
+        };
+        helpers::RawMatrix<T> rA = lowrank(mt * nb, kt * nb, nb, nb, 11), rB = lowrank(kt * nb, nt * nb, nb, nb, 23);
+        helpers::RawMatrix<T> rC(mt * nb, nt * nb);
+        const double acc = sizeof(T) == 8 ? 1e-8 : 1e-4;
+        CompressionParameters prm(acc);
+        RunContext &mctx = const_cast<RunContext &>(ctx);
+        helpers::TileMatrix<T> tA(rA, nb, nb, prm, mctx), tB(rB, nb, nb, prm, mctx), tC(rC, nb, nb, prm, mctx);
+        helpers::TileMatrixMultiplication<T>(tA, tB, tC, (T) 1, (T) 1, prm, ctx);
+        helpers::RawMatrix<T> got = tC.ToRawMatrix(mctx);
+        helpers::RawMatrix<T> want(mt * nb, nt * nb);
+        for (size_t j = 0; j < nt * nb; ++j)
+            for (size_t l = 0; l < kt * nb; ++l)
+                for (size_t i = 0; i < mt * nb; ++i)
+                    want.GetData()[i + j * mt * nb] += rA.GetData()[i + l * mt * nb] * rB.GetData()[l + j * kt * nb];
+        const double nrm = want.Norm();
+        got.ReferenceDifference(want);
+        bool ranks_ok = true;
+        for (size_t i = 0; i < nt; ++i)
+            for (size_t j = 0; j < mt; ++j) ranks_ok = ranks_ok && tC.GetTile(j, i)->GetTileRank() <= 2 * rk;
+        report("TileMatrix + driver loop", type, got.Norm() <= 10 * acc * nrm && ranks_ok && tA.GetTile(0, 0)->GetTileRank() == rk &&
+                                                     tC.GetMemoryFootprint() > 0);
+    }
     (void) flops;
 }
 
