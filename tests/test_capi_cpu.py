@@ -57,3 +57,27 @@ def test_product_never_imports_the_oracle():
                     assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
                     assert "libhcorepp_ref" not in text and "tlr_oracle" not in text and "oracle/" not in text, f
                     assert "scipy" not in text, f
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path, no GPU involved) prints exactly one JSON line on stdout with
+    the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "libhcorepp_ref.so")):
+        import pytest
+        pytest.skip("oracle/_ref not built")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--tiles", "2", "--nb", "256",
+                          "--steps", "1", "--warmup", "1", "--cpu-budget-s", "5"], capture_output=True, text=True, timeout=600,
+                         cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "tile-GEMM/s" and d["value"] > 0 and d["higher_is_better"] is True
+    for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
