@@ -159,7 +159,7 @@ int launch_refl(hcb_ctx *ctx, const ReflProb<T> *d_probs, int n_probs, int nvec_
 }
 
 template<typename T>
-int launch_svd(hcb_ctx *ctx, const SvdProb<T> *d_probs, int n_probs, int a_bound, int b_bound) {
+int launch_svd(hcb_ctx *ctx, const SvdProb<T> *d_probs, int n_probs, int a_bound, int b_bound, double stop2 = 0.0) {
     if (n_probs <= 0) return HCB_OK;
     // shared memory: enough for the whole bound-sized problem (zero-padded column pitch of 64 rows), capped at the
     // opt-in limit; the kernel decides per problem (from its true a, b) which regime applies.
@@ -184,7 +184,7 @@ int launch_svd(hcb_ctx *ctx, const SvdProb<T> *d_probs, int n_probs, int a_bound
             int per_sm = 1;
             HCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jacobi_svd_rx<T>, RX_THREADS, rx));
             const int grid = std::max(1, std::min(n_probs, ctx->sm_count * std::max(per_sm, 1)));
-            k_jacobi_svd_rx<T><<<grid, RX_THREADS, rx, ctx->stream>>>(d_probs, n_probs, 40, ctx->svd_sched);
+            k_jacobi_svd_rx<T><<<grid, RX_THREADS, rx, ctx->stream>>>(d_probs, n_probs, 40, ctx->svd_sched, (T) stop2);
             HCB_LAUNCH_CHECK("k_jacobi_svd_rx");
             return HCB_OK;
         }
@@ -920,7 +920,10 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     }
     {
         PhaseScope ph(ctx, 7);
-        HCB_TRY(launch_svd<T>(ctx, sa.svd, n, L.pq_b, L.pq_b));
+        // opt-in (HCB_JACOBI_ACC_STOP=1, not validated on the GPU in round 1): stop the Jacobi sweeps once the remaining
+        // non-orthogonality is far below the compression accuracy instead of at machine precision
+        static const bool acc_stop = getenv("HCB_JACOBI_ACC_STOP") && atoi(getenv("HCB_JACOBI_ACC_STOP")) > 0;
+        HCB_TRY(launch_svd<T>(ctx, sa.svd, n, L.pq_b, L.pq_b, acc_stop ? prm->accuracy : 0.0));
     }
     {
         PhaseScope ph(ctx, 8);

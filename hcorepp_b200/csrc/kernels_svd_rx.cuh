@@ -188,7 +188,7 @@ __device__ __forceinline__ int rx_solo(Vec2<T> (&x)[NI], int ix, Vec2<T> (&y)[NI
 // p.M).  Returns bit 0: something rotated, bit 1: some pair was above the predictive-stop level.  When `last_allowed`
 // or the sweep converged, the epilogue (sigma, sort, scatter of the left factor, info) runs too and bit 2 is set.
 template<typename T, int NI, int XPW>  // XPW: register-resident columns per warp (2; 1 for tall problems, NI > 6)
-__device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sweeps) {
+__device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sweeps, T stop2) {
     constexpr int P = 64 * NI, BW = (RX_THREADS / 32) * XPW;
     __shared__ int s_rot, s_big;
     const int a = p.a, b = p.b;
@@ -207,7 +207,9 @@ __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sw
     const T tol2 = tol * tol;
     // Predictive stop: the sweep after one in which every pair was already below cos = sqrt(tol) would only verify
     // (quadratic convergence leaves residual cosines ~ tol), so it is skipped.
-    const T big2 = T(16) * tol;  // cos < 4 sqrt(tol) = 2.5e-7: the residual after that sweep is ~6e-14 (measured: same parity, fewer sweeps)
+    // stop2 > 0 (fused path, opt-in): accuracy-aware stop -- end after the sweep whose max cos^2 is below the requested
+    // compression accuracy (residual non-orthogonality ~0.05 * accuracy; see NOTES_NEXT_ROUND.md).  0: machine precision.
+    const T big2 = stop2 > T(16) * tol ? stop2 : T(16) * tol;  // cos < 4 sqrt(tol) = 2.5e-7: the residual after that sweep is ~6e-14
     const int nblk = (b + BW - 1) / BW;
 
     // asynchronous staging of columns [c0, c0 + wc) into dst (pitch P, zero padded rows and columns)
@@ -400,7 +402,7 @@ constexpr size_t rx_smem_bytes(int ni, int b_bound) {  // two block regions (32 
 // Dynamic shared memory: rx_smem_bytes(ceil(a_bound / 64), b_bound).  sched must be zeroed before the launch.
 template<typename T>
 __global__ void __launch_bounds__(RX_THREADS, 1) k_jacobi_svd_rx(const SvdProb<T> *__restrict__ probs, int n_probs,
-                                                                 int max_sweeps, int *__restrict__ sched) {
+                                                                 int max_sweeps, int *__restrict__ sched, T stop2) {
     extern __shared__ __align__(16) unsigned char smem_raw_rx[];
     T *sm = reinterpret_cast<T *>(smem_raw_rx);
     __shared__ int s_item, s_state;
@@ -435,18 +437,18 @@ __global__ void __launch_bounds__(RX_THREADS, 1) k_jacobi_svd_rx(const SvdProb<T
         int flags = 4;
         if (p.a > 0 && p.b > 0) {
             switch ((p.a + 63) / 64) {
-                case 1: flags = jacobi_sweep_rx<T, 1, 2>(sm, p, sw, max_sweeps); break;
-                case 2: flags = jacobi_sweep_rx<T, 2, 2>(sm, p, sw, max_sweeps); break;
-                case 3: flags = jacobi_sweep_rx<T, 3, 2>(sm, p, sw, max_sweeps); break;
-                case 4: flags = jacobi_sweep_rx<T, 4, 2>(sm, p, sw, max_sweeps); break;
-                case 5: flags = jacobi_sweep_rx<T, 5, 2>(sm, p, sw, max_sweeps); break;
-                case 6: flags = jacobi_sweep_rx<T, 6, 2>(sm, p, sw, max_sweeps); break;
-                case 7: flags = jacobi_sweep_rx<T, 7, 1>(sm, p, sw, max_sweeps); break;
-                case 8: flags = jacobi_sweep_rx<T, 8, 1>(sm, p, sw, max_sweeps); break;
-                case 9: flags = jacobi_sweep_rx<T, 9, 1>(sm, p, sw, max_sweeps); break;
-                case 10: flags = jacobi_sweep_rx<T, 10, 1>(sm, p, sw, max_sweeps); break;
-                case 11: flags = jacobi_sweep_rx<T, 11, 1>(sm, p, sw, max_sweeps); break;
-                default: flags = jacobi_sweep_rx<T, 12, 1>(sm, p, sw, max_sweeps); break;
+                case 1: flags = jacobi_sweep_rx<T, 1, 2>(sm, p, sw, max_sweeps, stop2); break;
+                case 2: flags = jacobi_sweep_rx<T, 2, 2>(sm, p, sw, max_sweeps, stop2); break;
+                case 3: flags = jacobi_sweep_rx<T, 3, 2>(sm, p, sw, max_sweeps, stop2); break;
+                case 4: flags = jacobi_sweep_rx<T, 4, 2>(sm, p, sw, max_sweeps, stop2); break;
+                case 5: flags = jacobi_sweep_rx<T, 5, 2>(sm, p, sw, max_sweeps, stop2); break;
+                case 6: flags = jacobi_sweep_rx<T, 6, 2>(sm, p, sw, max_sweeps, stop2); break;
+                case 7: flags = jacobi_sweep_rx<T, 7, 1>(sm, p, sw, max_sweeps, stop2); break;
+                case 8: flags = jacobi_sweep_rx<T, 8, 1>(sm, p, sw, max_sweeps, stop2); break;
+                case 9: flags = jacobi_sweep_rx<T, 9, 1>(sm, p, sw, max_sweeps, stop2); break;
+                case 10: flags = jacobi_sweep_rx<T, 10, 1>(sm, p, sw, max_sweeps, stop2); break;
+                case 11: flags = jacobi_sweep_rx<T, 11, 1>(sm, p, sw, max_sweeps, stop2); break;
+                default: flags = jacobi_sweep_rx<T, 12, 1>(sm, p, sw, max_sweeps, stop2); break;
             }
         }
         __syncthreads();
