@@ -128,6 +128,8 @@ typedef struct hcb_tile {
     int hcb_##P##tlr_gemm_batched(hcb_ctx *, int64_t n_tiles, const hcb_tile *A, int opA, const hcb_tile *B, int opB,   \
                                   const hcb_tile *C, T alpha, T beta, const hcb_compress_params *p, int32_t *d_info);   \
     /* Compressing constructor, batched (Compressed.cpp:75-146): dense tile t (m x n, ld) -> out[t] (U, V, *d_rank) */  \
+    /* fp64 tiles >= 288 on both sides and <= 2048 rows: sketched (range finder + small SVD), tiles whose spectrum   */  \
+    /* is too flat for the sketch are detected on the device and redone with the full SVD (one stream sync per call). */  \
     int hcb_##P##compress_batched(hcb_ctx *, int64_t n_tiles, const T *const *dense_ptrs_host, int64_t ld,              \
                                   const hcb_tile *out, const hcb_compress_params *p, int32_t *d_info);                 \
     /* Multi-tile driver (examples/matrix_multiplication/omp_main.cpp:112-126) on one GPU:                           */  \
