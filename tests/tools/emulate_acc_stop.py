@@ -2,7 +2,7 @@
 parity over a whole k-sum?  The oracle's recompression is run twice on the same seeded tiles -- once with LAPACK's SVD
 (the reference's algorithm), once with a round-robin one-sided Jacobi that stops after the first sweep whose largest
 |cos| satisfies cos^2 < accuracy, V Sigma derived as M^T U like the CUDA path -- and the final C tiles are compared.
-usage: python scripts/emulate_acc_stop.py [nb] [rank] [ksteps] [acc]"""
+usage: python tests/tools/emulate_acc_stop.py [nb] [rank] [ksteps] [acc]"""
 import sys
 
 import numpy as np
