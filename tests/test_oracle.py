@@ -264,3 +264,35 @@ def test_reference_cholesky_pieces_semantics():
     assert np.allclose(got, Vn @ np.linalg.inv(Lm[:k, :k]).T)
     with pytest.raises(RuntimeError):
         R.potrf(tB, "L")  # "Potrf works only with dense tiles"
+
+
+@needs_ref
+def test_cholesky_pieces_restatement_matches_reference():
+    """oracle restatement of Potrf / Syrk(dense) / Trsm == the compiled reference (groundwork for SURVEY 8f row 1)."""
+    from oracle import ref as R
+    rng = np.random.default_rng(5)
+    n, k = 48, 6
+    M = rng.standard_normal((n, n))
+    S = M @ M.T + n * np.eye(n)
+    t, o = R.RefTile.dense(np.asfortranarray(S.copy())), O.DenseTile(np.asfortranarray(S.copy()))
+    R.potrf(t, "L")
+    O.hcore_potrf(o, "L")
+    assert np.allclose(t.to_dense(), o.data, rtol=1e-12, atol=1e-12)
+    A = rng.standard_normal((n, n))
+    C0 = rng.standard_normal((n, n))
+    for uplo in ("L", "U"):
+        ta, tc = R.RefTile.dense(np.asfortranarray(A.copy())), R.RefTile.dense(np.asfortranarray(C0.copy()))
+        oc = O.DenseTile(np.asfortranarray(C0.copy()))
+        R.syrk(-1.0, ta, False, uplo, 0.5, tc)
+        O.hcore_syrk_dense(-1.0, O.DenseTile(np.asfortranarray(A.copy())), False, uplo, 0.5, oc)
+        assert np.allclose(tc.to_dense(), oc.data, rtol=1e-12, atol=1e-12), uplo
+    Lm = np.tril(rng.standard_normal((n, n))) + n * np.eye(n)
+    U, V = rng.standard_normal((n, k)), rng.standard_normal((k, n))
+    for side, trans in (("R", True), ("R", False), ("L", False), ("L", True)):
+        tA = R.RefTile.dense(np.asfortranarray(Lm.copy()))
+        tB = R.RefTile.from_uv(np.asfortranarray(U.copy()), np.asfortranarray(V.copy()))
+        oB = O.CompressedTile.from_uv(U.copy(), V.copy())
+        R.trsm(side, "L", trans, "N", 2.0, tA, tB)
+        O.hcore_trsm(side, "L", trans, "N", 2.0, O.DenseTile(np.asfortranarray(Lm.copy())), oB)
+        U2, V2 = tB.read()
+        assert np.allclose(U2, oB.U) and np.allclose(V2, oB.V, rtol=1e-10, atol=1e-12), (side, trans)
