@@ -26,7 +26,7 @@ i32, i64, vp, sz = C.c_int32, C.c_int64, C.c_void_p, C.c_size_t
 class hcb_tile(C.Structure):
     """Mirror of `struct hcb_tile` (include/hcore_b200.h) == operators::TileMetadata + buffer (Tile.hpp:30-52)."""
     _fields_ = [("type", i32), ("m", i32), ("n", i32), ("ld", i32), ("max_rank", i32), ("rank_bound", i32),
-                ("d_rank", vp), ("d_data", vp)]
+                ("d_rank", vp), ("d_data", vp), ("d_state", vp), ("fixed_rank", i32), ("reserved", i32)]
 
 
 class hcb_compress_params(C.Structure):
@@ -36,6 +36,8 @@ class hcb_compress_params(C.Structure):
 
 
 TILE_DENSE, TILE_COMPRESSED = 0, 1
+STATE_ORTHO_U = 1
+EBOUND = 6
 
 # ---- context / memory -------------------------------------------------------------------------------------------
 lib.hcb_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
@@ -88,6 +90,7 @@ def _declare(p, ct):
     f("tlr_gemm_batched").argtypes = [vp, i64, _PT, C.c_int, _PT, C.c_int, _PT, ct, ct, _PP, vp]
     f("compress_batched").argtypes = [vp, i64, C.POINTER(vp), i64, _PT, _PP, vp]
     f("tlr_matmul").argtypes = [vp, i64, i64, i64, _PT, _PT, _PT, C.POINTER(i64), i64, i64, i64, ct, ct, _PP, vp]
+    f("tlr_matmul_panel_step").argtypes = [vp, i64, i64, vp, vp, _PT, ct, ct, _PP, vp, C.c_int]
     f("tlr_gemm_workspace").argtypes = [i64, i64, i64, i64, i64]
     f("tlr_gemm_workspace").restype = sz
 

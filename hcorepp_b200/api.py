@@ -113,7 +113,7 @@ class DenseTile:
         return self.n
 
     def desc(self) -> hcb_tile:
-        return hcb_tile(TILE_DENSE, self.m, self.n, self.m, 0, 0, None, self.t.data_ptr())
+        return hcb_tile(TILE_DENSE, self.m, self.n, self.m, 0, 0, None, self.t.data_ptr(), None, 0, 0)
 
     def to_numpy(self) -> np.ndarray:
         return np.asfortranarray(self.t.t().cpu().numpy())
@@ -126,12 +126,17 @@ class CompressedTile:
 
     dense = False
 
-    def __init__(self, m, n, max_rank, dtype, ctx: RunContext, buf=None, rank=None, rank_bound=0):
+    def __init__(self, m, n, max_rank, dtype, ctx: RunContext, buf=None, rank=None, rank_bound=0, state=None,
+                 fixed_rank=0):
         self.ctx, self.m, self.n, self.max_rank, self.dtype = ctx, int(m), int(n), int(max_rank), dtype
         self.rank_bound = int(rank_bound)
+        self.fixed_rank = int(fixed_rank)
         self.buf = buf if buf is not None else torch.zeros(self.m * self.max_rank + self.max_rank * self.n,
                                                           dtype=dtype, device=ctx.device)
         self.rank = rank if rank is not None else torch.ones(1, dtype=torch.int32, device=ctx.device)
+        # device state word kept by the library next to the rank (bit 0: "U has orthonormal columns"); a new / externally
+        # written tile starts at 0 = unknown
+        self.state = state if state is not None else torch.zeros(1, dtype=torch.int32, device=ctx.device)
 
     # -- constructors mirroring Compressed.hpp:67-151
     @classmethod
@@ -185,7 +190,11 @@ class CompressedTile:
 
     def desc(self) -> hcb_tile:
         return hcb_tile(TILE_COMPRESSED, self.m, self.n, 0, self.max_rank, self.rank_bound, self.rank.data_ptr(),
-                        self.buf.data_ptr())
+                        self.buf.data_ptr(), self.state.data_ptr(), self.fixed_rank, 0)
+
+    def invalidate(self):
+        """Call after writing the factors through `buf` directly: the library may no longer assume an orthonormal U."""
+        self.state.zero_()
 
     def factors(self):
         rk = self.GetTileRank()
@@ -252,12 +261,13 @@ class TileMatrix:
         self.tile_elems = (tm * self.max_rank + self.max_rank * tn) if compressed else tm * tn
         self.buf = torch.zeros(mt * nt * self.tile_elems, dtype=dtype, device=ctx.device)
         self.ranks = torch.ones(mt * nt, dtype=torch.int32, device=ctx.device)
+        self.state = torch.zeros(mt * nt, dtype=torch.int32, device=ctx.device)  # per-tile state words (see hcb_tile.d_state)
         self._build_descs()
 
     def _build_descs(self):
         n = self.mt * self.nt
         esz = self.buf.element_size()
-        base, rbase = self.buf.data_ptr(), self.ranks.data_ptr()
+        base, rbase, sbase = self.buf.data_ptr(), self.ranks.data_ptr(), self.state.data_ptr()
         self.descs = (hcb_tile * n)()
         for lin in range(n):  # column-major grid: lin = j + i*mt  (TileMatrix.hpp:78-80)
             d = self.descs[lin]
@@ -265,12 +275,21 @@ class TileMatrix:
             d.m, d.n, d.ld = self.tm, self.tn, self.tm
             d.max_rank, d.rank_bound = self.max_rank, self.rank_bound
             d.d_rank = rbase + 4 * lin if self.compressed else None
+            d.d_state = sbase + 4 * lin if self.compressed else None
+            d.fixed_rank = 0
             d.d_data = base + esz * self.tile_elems * lin
 
     def set_rank_bound(self, bound: int):
         self.rank_bound = int(bound)
         for d in self.descs:
             d.rank_bound = self.rank_bound
+
+    def set_fixed_ranks(self, table):
+        """Per-tile fixed ranks for the replay drivers (par_fixed_rank_streams_main.cpp:465-477): table[row][col] > 0
+        makes the recompression of C(row, col) keep exactly that rank, 0 / None restores truncation by accuracy."""
+        for col in range(self.nt):
+            for row in range(self.mt):
+                self.descs[self.lin(row, col)].fixed_rank = 0 if table is None else int(table[row][col])
 
     def lin(self, row, col):
         return row + col * self.mt
@@ -284,7 +303,8 @@ class TileMatrix:
         lin = self.lin(row, col)
         if self.compressed:
             return CompressedTile(self.tm, self.tn, self.max_rank, self.dtype, self.ctx, buf=self.tile_buf(row, col),
-                                  rank=self.ranks[lin: lin + 1], rank_bound=self.rank_bound)
+                                  rank=self.ranks[lin: lin + 1], rank_bound=self.rank_bound,
+                                  state=self.state[lin: lin + 1])
         t = DenseTile.__new__(DenseTile)
         t.ctx, t.t, t.m, t.n, t.dtype = self.ctx, self.tile_buf(row, col).view(self.tn, self.tm), self.tm, self.tn, self.dtype
         return t
@@ -328,6 +348,7 @@ class TileMatrix:
         v[:, : self.tm].zero_()
         v[:, self.tm * self.max_rank: self.tm * self.max_rank + self.tn].zero_()
         self.ranks.fill_(1)
+        self.state.zero_()
 
     def load_factors(self, U: torch.Tensor, V: torch.Tensor, rank: int):
         """Fill every tile from compact factor stacks: U (ntiles, rank, tm) [= column-major tm x rank], V (ntiles, tn,
@@ -337,6 +358,7 @@ class TileMatrix:
         v[:, self.tm * self.max_rank: self.tm * self.max_rank + rank * self.tn].copy_(
             V.reshape(self.mt * self.nt, -1), non_blocking=True)
         self.ranks.fill_(rank)
+        self.state.zero_()
 
     def rank_table(self) -> np.ndarray:
         return self.ranks.cpu().numpy().reshape(self.nt, self.mt).T.copy()

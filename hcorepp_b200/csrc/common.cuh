@@ -75,6 +75,20 @@ __device__ __forceinline__ T block_sum(T v, T *red) {
     return red[32];
 }
 
+// d_info word of the fused path: low byte = sticky flags (OR), bits 8..15 = Jacobi sweeps (MAXIMUM over the steps that
+// shared the word, e.g. the k loop of tlr_matmul)
+__device__ __forceinline__ void info_max_sweeps(int *info, int sweeps) {
+    int old = *reinterpret_cast<volatile int *>(info);
+    for (;;) {
+        const int cur = (old >> 8) & 0xff;
+        if (cur >= sweeps) return;
+        const int want = (old & ~0xff00) | ((sweeps & 0xff) << 8);
+        const int seen = atomicCAS(info, old, want);
+        if (seen == old) return;
+        old = seen;
+    }
+}
+
 template<typename T> struct Eps;
 template<> struct Eps<double> { static __host__ __device__ constexpr double v() { return 2.220446049250313e-16; } };
 template<> struct Eps<float> { static __host__ __device__ constexpr float v() { return 1.1920929e-07f; } };
@@ -151,9 +165,15 @@ struct LqProb {   // LQ preconditioning: L = R^T of the QR-factored transpose (s
 // context
 // ---------------------------------------------------------------------------------------------------------------
 struct ParamRing {  // pinned host staging + device mirror for small descriptor uploads
+    // Four segments, one event each: a segment is re-used only after the copies issued from it on the previous lap have
+    // completed (event wait, normally long satisfied) -- never a stream synchronise in steady state.
+    static constexpr int NSEG = 4;
     char *h = nullptr;
     char *d = nullptr;
     size_t cap = 0, off = 0;
+    int seg = 0;
+    cudaEvent_t ev[NSEG] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_pending[NSEG] = {false, false, false, false};
 };
 
 }  // namespace hcb
@@ -169,6 +189,8 @@ struct hcb_ctx {
     int *svd_sched = nullptr;  // work counters of the persistent Jacobi kernel (2 + problems ints, grow-only)
     size_t svd_sched_n = 0;
     hcb::ParamRing ring;
+    int *d_err = nullptr;      // device-side sticky error word of the fused path (bit 2: a rank exceeded its bound)
+    int *h_err = nullptr;      // pinned mirror read by hcb_ctx_sync
     // optional per-phase device timing of the fused path (CUDA events on this stream; see hcb_ctx_phase_timing)
     bool timing = false;
     std::vector<cudaEvent_t> ev_pool;

@@ -34,19 +34,32 @@ int ensure_ws(hcb_ctx *ctx, size_t bytes) {
 int ring_upload(hcb_ctx *ctx, const void *host, size_t bytes, void **d_out) {
     ParamRing &r = ctx->ring;
     const size_t need = align_up(bytes, 256);
-    if (need > r.cap) {
+    if (need * ParamRing::NSEG > r.cap) {  // (re)allocate: a segment must hold the largest upload
         HCB_CUDA(cudaStreamSynchronize(ctx->stream));
         if (r.h) HCB_CUDA(cudaFreeHost(r.h));
         if (r.d) HCB_CUDA(cudaFree(r.d));
-        r.cap = align_up(std::max(need * 4, (size_t) 1 << 20), 4096);
+        r.cap = align_up(std::max(need * 2, (size_t) 1 << 20), 4096) * ParamRing::NSEG;
         r.off = 0;
+        r.seg = 0;
         HCB_CUDA(cudaMallocHost((void **) &r.h, r.cap));
         HCB_CUDA(cudaMalloc((void **) &r.d, r.cap));
+        for (int i = 0; i < ParamRing::NSEG; ++i) {
+            if (!r.ev[i]) HCB_CUDA(cudaEventCreateWithFlags(&r.ev[i], cudaEventDisableTiming));
+            r.ev_pending[i] = false;
+        }
     }
-    if (r.off + need > r.cap) {
-        // wrap: earlier slots may still be in flight -> wait for the stream once per lap
-        HCB_CUDA(cudaStreamSynchronize(ctx->stream));
-        r.off = 0;
+    const size_t seg_bytes = r.cap / ParamRing::NSEG;
+    if (r.off + need > (size_t) (r.seg + 1) * seg_bytes) {
+        // leave this segment: everything issued from it so far is covered by its event; enter the next one once ITS
+        // previous lap has drained
+        HCB_CUDA(cudaEventRecord(r.ev[r.seg], ctx->stream));
+        r.ev_pending[r.seg] = true;
+        r.seg = (r.seg + 1) % ParamRing::NSEG;
+        r.off = (size_t) r.seg * seg_bytes;
+        if (r.ev_pending[r.seg]) {
+            HCB_CUDA(cudaEventSynchronize(r.ev[r.seg]));
+            r.ev_pending[r.seg] = false;
+        }
     }
     std::memcpy(r.h + r.off, host, bytes);
     HCB_CUDA(cudaMemcpyAsync(r.d + r.off, r.h + r.off, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -639,8 +652,9 @@ template<typename T>
 struct Layout {
     size_t slab = 0, o_w1 = 0, o_w2 = 0, o_uw = 0, o_vw = 0, o_tauu = 0, o_tauv = 0, o_m = 0, o_j = 0, o_us = 0,
            o_vs = 0, o_sig = 0, o_vn = 0, o_vcu = 0, o_vcv = 0, o_tbu = 0, o_tbv = 0, o_wbu = 0, o_wbv = 0, o_mt = 0,
-           o_taum = 0, o_lb = 0, o_vcm = 0, o_tbm = 0, o_wbm = 0, o_pj = 0, o_pos = 0;
-    int r_b = 0, pq_b = 0, wcols = 0, nblk = 0;
+           o_taum = 0, o_lb = 0, o_vcm = 0, o_tbm = 0, o_wbm = 0, o_pj = 0, o_pos = 0, o_gu = 0, o_gu2 = 0, o_q2 = 0,
+           o_tu = 0;
+    int r_b = 0, pq_b = 0, wcols = 0, nblk = 0, kp_b = 0;
 };
 
 template<typename T>
@@ -694,6 +708,12 @@ Layout<T> make_layout(const BatchShape &s) {
         L.o_wbm = take((size_t) 2 * NBQ * L.wcols);
         L.o_pj = take((size_t) s.kA * s.kA);
         L.o_pos = take((size_t) L.r_b);  // r_b ints in T-sized slots
+        // incremental U side: Gram-Schmidt coefficients, [clean reflectors | explicit Q2] of the new columns, rebuilt CU
+        L.kp_b = kp;
+        L.o_gu = take((size_t) s.kC * kp);
+        L.o_gu2 = take((size_t) s.kC * kp);
+        L.o_q2 = take((size_t) 2 * s.m * kp);
+        L.o_tu = take((size_t) s.m * std::min(L.pq_b, std::max(s.maxrankC, 1)));
     }
     L.slab = off;
     return L;
@@ -704,8 +724,9 @@ struct DescArrays {  // device arrays living at the front of the scratch arena
     size_t bytes = 0;
     size_t o_g1, o_g2, o_g3, o_gv, o_gc, o_cp, o_qr, o_rf, o_svd, o_rc, o_rk, o_tiles;
     size_t o_bqr = 0, o_blf = 0, o_bgw = 0, o_bgw2 = 0, o_bgup = 0, o_agw = 0, o_agw2 = 0, o_agup = 0;
-    size_t o_pds = 0, o_pdc = 0, o_qrc = 0, o_lq = 0, o_pc = 0, o_asj = 0;
-    explicit DescArrays(int n, int nblk = 0, int qr_cols = 0, int rk_bound = 0) {
+    size_t o_pds = 0, o_pdc = 0, o_qrc = 0, o_lq = 0, o_pc = 0, o_asj = 0, o_gi = 0, o_isj = 0, o_gru = 0;
+    int nst_inc = 0;
+    explicit DescArrays(int n, int nblk = 0, int qr_cols = 0, int rk_bound = 0, int kp_b = 0) {
         size_t off = 0;
         auto take = [&](size_t b) { size_t o = off; off += align_up(b, 256); return o; };
         o_g1 = take(sizeof(GemmProb<T>) * n);
@@ -720,14 +741,18 @@ struct DescArrays {  // device arrays living at the front of the scratch arena
         o_rc = take(sizeof(RecompProb<T>) * n);
         o_rk = take(sizeof(int) * n);
         o_tiles = take(sizeof(hcb_tile) * 3 * n);
-        o_pds = take(sizeof(PanelDesc<T>) * 2 * n);
+        o_pds = take(sizeof(PanelDesc<T>) * 3 * n);  // U stack, V stack per tile, then one incremental P panel per tile
         o_pdc = take(sizeof(PanelDesc<T>) * n);
+        o_gi = take(sizeof(GemmProb<T>) * 4 * n);
+        o_gru = take(sizeof(GemmProb<T>) * 2 * n);
+        nst_inc = std::max(1, cdiv(std::max(kp_b, 1), NBQ));
+        o_isj = take(sizeof(StripJob) * (size_t) nst_inc * n);
         o_qrc = take(sizeof(QrProb<T>) * n);
         o_lq = take(sizeof(LqProb<T>) * n);
         o_pc = take(sizeof(PrecondProb<T>) * n);
         if (nblk > 0) {
             const size_t nb = (size_t) nblk * 2 * n;
-            o_bqr = take(qr_block_desc_bytes<T>(2 * n, qr_cols));
+            o_bqr = take(qr_block_desc_bytes<T>(3 * n, qr_cols));
             o_asj = take(sizeof(StripJob) * (size_t) cdiv(std::max(rk_bound, 1), NBQ) * 2 * n);
             o_agw = take(sizeof(GemmProb<T>) * nb);
             o_agw2 = take(sizeof(GemmProb<T>) * nb);
@@ -770,7 +795,8 @@ static int classify(const hcb_tile *A, const hcb_tile *B, const hcb_tile *C, int
 
 template<typename T>
 int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, const hcb_tile *B, int opB,
-                       const hcb_tile *C, T alpha, T beta, const hcb_compress_params *prm, int32_t *d_info) {
+                       const hcb_tile *C, T alpha, T beta, const hcb_compress_params *prm, int32_t *d_info,
+                       bool reset_info = true) {
     HCB_TRY(check_ctx(ctx));
     if (n64 <= 0) return HCB_OK;
     if (!A || !B || !C || !prm) return fail(HCB_EINVAL, "tlr_gemm_batched: null argument");
@@ -781,7 +807,10 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     const Layout<T> L = make_layout<T>(s);
     const bool blocked = L.r_b > 2 * NBQ;  // compact-WY path once the stacked rank spans more than two blocks
     const int rk_bound = std::max(1, std::min(L.pq_b, s.maxrankC));
-    const DescArrays<T> D(n, blocked ? L.nblk : 0, std::max(L.r_b, L.pq_b), rk_bound);
+    const DescArrays<T> D(n, blocked ? L.nblk : 0, std::max(L.r_b, L.pq_b), rk_bound, L.kp_b);
+    // incremental U side (tiles whose state says "U orthonormal"): needs the blocked fp64 strip machinery
+    const bool inc_enabled = blocked && std::is_same<T, double>::value && strip_path_ok(ctx, std::max(s.m, s.n)) &&
+                             !getenv("HCB_NO_INCREMENTAL");
     const size_t total = D.bytes + L.slab * sizeof(T) * (size_t) n + 256;
     HCB_TRY(ensure_ws(ctx, total));
     char *base = reinterpret_cast<char *>(ctx->ws);
@@ -829,6 +858,15 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     sa.rf = reinterpret_cast<ReflProb<T> *>(base + D.o_rf);
     sa.svd = reinterpret_cast<SvdProb<T> *>(base + D.o_svd);
     sa.rc = reinterpret_cast<RecompProb<T> *>(base + D.o_rc);
+    sa.inc_enabled = inc_enabled ? 1 : 0;
+    sa.o_gu = L.o_gu; sa.o_gu2 = L.o_gu2; sa.o_q2 = L.o_q2; sa.o_tu = L.o_tu;
+    sa.gi = reinterpret_cast<GemmProb<T> *>(base + D.o_gi);
+    sa.pd_inc = sa.pd_stack + 2 * (size_t) n;
+    sa.inc_sj = reinterpret_cast<StripJob *>(base + D.o_isj);
+    sa.nst_inc = D.nst_inc; sa.kp_b = L.kp_b;
+    sa.inc_refresh = getenv("HCB_INC_REFRESH") ? std::max(1, atoi(getenv("HCB_INC_REFRESH"))) : 16;
+    sa.err_flag = ctx->d_err;
+    if (d_info && reset_info) HCB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t) * (size_t) n, ctx->stream));
     {
         PhaseScope ph(ctx, 0);
         k_setup_tlr<T><<<cdiv(n, 128), 128, 0, ctx->stream>>>(sa);
@@ -895,7 +933,23 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     {
         PhaseScope ph(ctx, 3);
         if (!blocked) HCB_TRY(launch_qr<T>(ctx, sa.qr, 2 * n));
-        else HCB_TRY(run_blocked_qr<T>(ctx, sa.pd_stack, npan, std::max(s.m, s.n), L.r_b, blk_store));
+        else {
+            if (inc_enabled) {
+                // block classical Gram-Schmidt (twice) of the new U columns against the orthonormal CU
+                HCB_TRY(launch_gemm<T>(ctx, sa.gi + 0 * (size_t) n, n, s.kC, L.kp_b));
+                HCB_TRY(launch_gemm<T>(ctx, sa.gi + 1 * (size_t) n, n, s.m, L.kp_b));
+                HCB_TRY(launch_gemm<T>(ctx, sa.gi + 2 * (size_t) n, n, s.kC, L.kp_b));
+                HCB_TRY(launch_gemm<T>(ctx, sa.gi + 3 * (size_t) n, n, s.m, L.kp_b));
+            }
+            // one pass over 3n panels: the two stacks of every tile (U stack inactive when incremental) + the P panels
+            HCB_TRY(run_blocked_qr<T>(ctx, sa.pd_stack, inc_enabled ? 3 * n : npan, std::max(s.m, s.n), L.r_b, blk_store));
+            if (inc_enabled) {
+                dim3 ge(std::max(1, std::min(64, cdiv((long long) s.m * L.kp_b, 2048))), n);
+                k_inc_eye<T><<<ge, 256, 0, ctx->stream>>>(sa.rc);
+                HCB_LAUNCH_CHECK("k_inc_eye");
+                HCB_TRY(launch_strips(ctx, sa.inc_sj, D.nst_inc * n, s.m));   // explicit Q2
+            }
+        }
     }
     {
         PhaseScope ph(ctx, 4);
@@ -920,9 +974,10 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     }
     {
         PhaseScope ph(ctx, 7);
-        // opt-in (HCB_JACOBI_ACC_STOP=1, not validated on the GPU in round 1): stop the Jacobi sweeps once the remaining
-        // non-orthogonality is far below the compression accuracy instead of at machine precision
-        static const bool acc_stop = getenv("HCB_JACOBI_ACC_STOP") && atoi(getenv("HCB_JACOBI_ACC_STOP")) > 0;
+        // accuracy-aware stop (default since round 2: full GPU suite green, 442 -> 426 ms per step; HCB_JACOBI_ACC_STOP=0
+        // restores machine precision): the sweeps end once the remaining non-orthogonality is far below the compression
+        // accuracy
+        static const bool acc_stop = !(getenv("HCB_JACOBI_ACC_STOP") && atoi(getenv("HCB_JACOBI_ACC_STOP")) == 0);
         HCB_TRY(launch_svd<T>(ctx, sa.svd, n, L.pq_b, L.pq_b, acc_stop ? prm->accuracy : 0.0));
     }
     {
@@ -939,9 +994,14 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
         PhaseScope ph(ctx, 5);
         StripJob *sj = reinterpret_cast<StripJob *>(base + D.o_asj);
         const int nstrips = cdiv(rk_bound, NBQ);
-        k_setup_apply_strips<T><<<cdiv(nstrips * npan, 128), 128, 0, ctx->stream>>>(sa.rc, sj, nstrips, npan);
+        GemmProb<T> *gru = reinterpret_cast<GemmProb<T> *>(base + D.o_gru);
+        k_setup_apply_strips<T><<<cdiv(nstrips * npan, 128), 128, 0, ctx->stream>>>(sa.rc, sj, nstrips, npan, gru);
         HCB_LAUNCH_CHECK("k_setup_apply_strips");
         HCB_TRY(launch_strips(ctx, sj, nstrips * npan, std::max(s.m, s.n)));
+        if (inc_enabled) {  // CU' = [CU | Q2] * Us for the incremental tiles (two GEMMs into TU)
+            HCB_TRY(launch_gemm<T>(ctx, gru, n, s.m, rk_bound));
+            HCB_TRY(launch_gemm<T>(ctx, gru + n, n, s.m, rk_bound));
+        }
     } else {
         // blocked rebuild C := Q [X;0]: blocks last-to-first, three batched GEMMs per block, rank read on the device
         PhaseScope ph(ctx, 5);
@@ -985,9 +1045,28 @@ int t_tlr_matmul(hcb_ctx *ctx, int64_t mt, int64_t nt, int64_t kt, const hcb_til
             b[q] = B[k + i * kt];
             c[q] = C[lin];
         }
-        HCB_TRY(t_tlr_gemm_batched<T>(ctx, total, a.data(), 0, b.data(), 0, c.data(), alpha, beta, prm, d_info));
+        // d_info flags are sticky over the k loop: zeroed once, OR-ed by every step (sweep count: maximum)
+        HCB_TRY(t_tlr_gemm_batched<T>(ctx, total, a.data(), 0, b.data(), 0, c.data(), alpha, beta, prm, d_info, k == k_begin));
     }
     return HCB_OK;
+}
+
+// One k-step of the multi-tile product on this context's tiles: C(j, i) += alpha * Apan[j] * Bpan[i] for all j < mt,
+// i < nt -- the local step of the distributed driver (hcorepp_b200/distributed.py): Apan / Bpan are the broadcast panels.
+template<typename T>
+int t_tlr_matmul_panel_step(hcb_ctx *ctx, int64_t mt, int64_t nt, const hcb_tile *Apan, const hcb_tile *Bpan,
+                            const hcb_tile *C, T alpha, T beta, const hcb_compress_params *prm, int32_t *d_info, int first) {
+    HCB_TRY(check_ctx(ctx));
+    if (mt <= 0 || nt <= 0) return HCB_OK;
+    if (!Apan || !Bpan || !C) return fail(HCB_EINVAL, "tlr_matmul_panel_step: null argument");
+    const int64_t total = mt * nt;
+    std::vector<hcb_tile> a(total), b(total);
+    for (int64_t i = 0; i < nt; ++i)
+        for (int64_t j = 0; j < mt; ++j) {
+            a[j + i * mt] = Apan[j];
+            b[j + i * mt] = Bpan[i];
+        }
+    return t_tlr_gemm_batched<T>(ctx, total, a.data(), 0, b.data(), 0, C, alpha, beta, prm, d_info, first != 0);
 }
 
 template<typename T>
@@ -1236,6 +1315,10 @@ static int ctx_init(int device, cudaStream_t stream, bool own, hcb_ctx **out) {
     HCB_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
+    HCB_CUDA(cudaMalloc((void **) &c->d_err, sizeof(int)));
+    HCB_CUDA(cudaMemset(c->d_err, 0, sizeof(int)));
+    HCB_CUDA(cudaMallocHost((void **) &c->h_err, sizeof(int)));
+    *c->h_err = 0;
     if (own) {
         HCB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
@@ -1255,7 +1338,10 @@ int hcb_ctx_destroy(hcb_ctx *c) {
     cudaStreamSynchronize(c->stream);
     if (c->ws) cudaFree(c->ws);
     if (c->svd_sched) cudaFree(c->svd_sched);
+    if (c->d_err) cudaFree(c->d_err);
+    if (c->h_err) cudaFreeHost(c->h_err);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
+    for (auto e : c->ring.ev) if (e) cudaEventDestroy(e);
     if (c->ring.h) cudaFreeHost(c->ring.h);
     if (c->ring.d) cudaFree(c->ring.d);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -1289,7 +1375,17 @@ const char *hcb_phase_name(int phase) {
 
 int hcb_ctx_sync(hcb_ctx *c) {
     HCB_TRY(check_ctx(c));
+    // the fused path reports a violated rank bound (tile left untouched) here even when the caller passed no d_info
+    HCB_CUDA(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     HCB_CUDA(cudaStreamSynchronize(c->stream));
+    if (*c->h_err) {
+        const int e = *c->h_err;
+        *c->h_err = 0;
+        HCB_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
+        if (e & 4)
+            return fail(HCB_EBOUND, "a tile's rank exceeded its rank_bound in a fused call since the last sync: that "
+                                    "tile's update was NOT applied (raise rank_bound, or leave it 0 = max_rank)");
+    }
     return HCB_OK;
 }
 void *hcb_ctx_stream(hcb_ctx *c) { return c ? (void *) c->stream : nullptr; }
@@ -1390,6 +1486,11 @@ int hcb_memset(hcb_ctx *c, void *dst, int value, size_t bytes) {
                             const hcb_tile *C, const int64_t *owned, int64_t n_owned, int64_t k_begin,                \
                             int64_t k_end, T alpha, T beta, const hcb_compress_params *p, int32_t *info) {            \
         return t_tlr_matmul<T>(c, mt, nt, kt, A, B, C, owned, n_owned, k_begin, k_end, alpha, beta, p, info);        \
+    }                                                                                                                 \
+    int hcb_##P##tlr_matmul_panel_step(hcb_ctx *c, int64_t mt, int64_t nt, const hcb_tile *Apan, const hcb_tile *Bpan, \
+                                       const hcb_tile *C, T alpha, T beta, const hcb_compress_params *p, int32_t *info, \
+                                       int first) {                                                                   \
+        return t_tlr_matmul_panel_step<T>(c, mt, nt, Apan, Bpan, C, alpha, beta, p, info, first);                    \
     }                                                                                                                 \
     size_t hcb_##P##tlr_gemm_workspace(int64_t n_tiles, int64_t m, int64_t n, int64_t k, int64_t r_bound) {            \
         return t_workspace<T>(n_tiles, m, n, k, r_bound);                                                            \

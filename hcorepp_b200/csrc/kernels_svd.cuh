@@ -307,7 +307,7 @@ __device__ void jacobi_sweeps(T *sm, const SvdProb<T> &p, int smem_elems, int ma
     }
     if (p.info && tid == 0) {
         if (!converged) atomicOr(p.info, 1);
-        atomicOr(p.info, sweeps_used << 8);  // diagnostics: number of Jacobi sweeps in bits 8..15
+        info_max_sweeps(p.info, sweeps_used);  // diagnostics: number of Jacobi sweeps in bits 8..15
     }
     __syncthreads();
 

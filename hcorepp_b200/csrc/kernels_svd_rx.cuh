@@ -380,7 +380,7 @@ __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sw
     if (!converged && sweep + 1 < max_sweeps) return flags;
     if (p.info && tid == 0) {
         if (!converged) atomicOr(p.info, 1);
-        atomicOr(p.info, (b < 2 ? 0 : sweep + 1) << 8);
+        info_max_sweeps(p.info, b < 2 ? 0 : sweep + 1);
     }
     __syncthreads();
     jacobi_finish<T, true>(M, a, sig, p);

@@ -39,6 +39,18 @@ struct RecompProb {
     // gathered into UW / VW sorted by decreasing V-stack column norm; pos[c] = destination column of stack column c
     T *SU0, *SV0;
     int *pos;
+    // Incremental U side (round 2): when the tile's state says "CU has orthonormal columns" (it does after every
+    // recompression, Compressed.cpp:558-560) only the kp NEW columns P are orthogonalised against CU (block classical
+    // Gram-Schmidt, twice) and QR-factored:  [CU | P] = [CU | Q2] * [[I, G], [0, R2]].  The 2 m r^2 Householder QR of
+    // the U stack becomes 8 m kc kp GEMM flops + a kp-column panel, and the rebuild CU' = [CU | Q2] * Us is one GEMM.
+    int inc;            // 1: U side incremental
+    int kc, kp;         // old rank / new columns (r = kc + kp)
+    T *Pn;              // P (m x kp, ld m): orthogonalised in place against CU, then QR-factored in place
+    T *Gu, *Gu2;        // first / second pass coefficients CU^T P (kc x kp, ld kc)
+    T *Q2;              // explicit Q2 (m x kp, ld m)
+    T *TU;              // rebuild target [CU | Q2] * Us[:, :rk] (m x rk, ld m), copied into CU by k_finalize
+    int *state;         // C tile's device state word (may be null)
+    int fixed_rank;     // per-tile fixed rank (0: batch value)
 };
 
 // Preconditioning of the product term (CCC): an orthogonal J (ka x ka) that makes the rows of J^T (T1 * BR) mutually
@@ -92,6 +104,15 @@ struct SetupArgs {
     ReflProb<T> *rf;            // 2 per tile
     SvdProb<T> *svd;
     RecompProb<T> *rc;
+    // incremental U side
+    int inc_enabled;            // host: blocked fp64 strip path in use
+    size_t o_gu, o_gu2, o_q2, o_tu;   // scratch offsets: Gu, Gu2 (kC_b x kp_b), [VCp | Q2] (2 m kp_b), TU (m x rank bound)
+    GemmProb<T> *gi;            // 4 per tile, arrays of n: gi + q*n_tiles, q = 0..3 (G = CU^T P, P -= CU G, twice)
+    PanelDesc<T> *pd_inc;       // 1 per tile: QR of the orthogonalised P
+    StripJob *inc_sj;           // nst_inc per tile: explicit Q2 = H_0 .. H_{kp-1} [I; 0]
+    int nst_inc, kp_b;
+    int inc_refresh;            // consecutive incremental updates allowed before one full re-factorisation
+    int *err_flag;              // context-level sticky error word (bit 2: a rank exceeded its bound)
 };
 
 template<typename T>
@@ -156,6 +177,10 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
     memset(&pc, 0, sizeof(pc));
     const T one = T(1), zero = T(0);
     int kp = 0;  // rank of the product term entering the recompression
+    GemmProb<T> gi0 = g1, gi1 = g1, gi2 = g1, gi3 = g1;
+    PanelDesc<T> pdi;
+    memset(&pdi, 0, sizeof(pdi));
+    int inc = 0;
 
     if (!bad) {
         switch (s.mix) {
@@ -238,6 +263,32 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
                 // rebuild (Compressed.cpp:551-560, 611-628): CU = Q_U [Unew;0], VN = Q_V [Vfac;0], rank read on device
                 r0 = ReflProb<T>{UW, rc.tauU, CU, m, p, m, m, 0, m, 0, 0, rc.rk_new};
                 r1 = ReflProb<T>{VW, rc.tauV, rc.VN, n, q, n, n, 0, n, 0, 0, rc.rk_new};
+                rc.state = C.d_state;
+                rc.fixed_rank = C.fixed_rank;
+                rc.kc = kc; rc.kp = kp;
+                // incremental U side: CU is known to be orthonormal, the new columns fit (r <= m, kp within the scratch)
+                // (bits 8.. of the state word count the consecutive incremental updates: every s.inc_refresh-th update
+                // takes the full path, so that the loss of orthogonality of CU -- it adds up, ~0.05 * accuracy per
+                // update with the accuracy-aware Jacobi stop -- is reset)
+                const int st_word = C.d_state ? *C.d_state : 0;
+                inc = s.inc_enabled && (st_word & HCB_STATE_ORTHO_U) && (st_word >> 8) < s.inc_refresh && kc >= 1 &&
+                      kp >= 1 && r <= m && r <= n && kp <= s.kp_b;
+                if (inc) {
+                    rc.inc = 1;
+                    rc.Pn = SU0 + (size_t) m * kc;
+                    rc.Gu = slab + s.o_gu; rc.Gu2 = slab + s.o_gu2;
+                    T *VCp = slab + s.o_q2;
+                    rc.Q2 = VCp + (size_t) m * s.kp_b;
+                    rc.TU = slab + s.o_tu;
+                    c0.rows = 0;          // CU is read in place
+                    pdu.active = 0;       // no Householder QR of the U stack
+                    q0.m = 0;
+                    gi0 = mk_gemm<T>(CU, m, 1, rc.Pn, m, 0, rc.Gu, kc, kc, kp, m, one, zero);     // G  = CU^T P
+                    gi1 = mk_gemm<T>(CU, m, 0, rc.Gu, kc, 0, rc.Pn, m, m, kp, kc, -one, one);     // P -= CU G
+                    gi2 = mk_gemm<T>(CU, m, 1, rc.Pn, m, 0, rc.Gu2, kc, kc, kp, m, one, zero);    // G2 = CU^T P
+                    gi3 = mk_gemm<T>(CU, m, 0, rc.Gu2, kc, 0, rc.Pn, m, m, kp, kc, -one, one);    // P -= CU G2
+                    pdi = PanelDesc<T>{rc.Pn, rc.tauU, VCp, rc.TB[0], rc.WB[0], m, kp, s.wcols, 1};
+                }
             }
         }
     }
@@ -252,9 +303,27 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
         pc.active = 0;
         qm.m = qm.n = 0;
         lq.a = lq.b = 0;
-        if (s.info) s.info[t] = 4;  // rank exceeded the bound the scratch was sized for: tile left untouched
-    } else if (s.info) {
-        s.info[t] = 0;
+        gi0.m = gi1.m = gi2.m = gi3.m = 0;
+        pdi.active = 0;
+        inc = 0;
+        rc.inc = 0;
+        // rank exceeded the bound the scratch was sized for: tile left untouched.  Sticky in d_info (flags are OR-ed, the
+        // caller of the entry point zeroes them) AND in the context's error word, so that a caller without an info buffer
+        // still hears about it at the next hcb_ctx_sync.
+        if (s.info) atomicOr(s.info + t, 4);
+        if (s.err_flag) atomicOr(s.err_flag, 4);
+    }
+    for (int q = 0; q < 4; ++q) s.gi[(size_t) q * s.n_tiles + t] = q == 0 ? gi0 : (q == 1 ? gi1 : (q == 2 ? gi2 : gi3));
+    s.pd_inc[t] = pdi;
+    if constexpr (std::is_same<T, double>::value) {
+        for (int st = 0; st < s.nst_inc; ++st) {  // explicit Q2: strip st of [I; 0] takes the panel's blocks last to first
+            StripJob j{nullptr, nullptr, nullptr, 1, 1, 0, 0, 0, 0, 0, -1, 0};
+            if (inc && st * NBQ < kp) {
+                const int nbp = (kp + NBQ - 1) / NBQ, nc = (kp - st * NBQ) < NBQ ? (kp - st * NBQ) : NBQ;
+                j = StripJob{rc.Q2 + (size_t) st * NBQ * m, pdi.VC, pdi.TB, m, m, m, nc, kp, nbp - 1, nbp, -1, 0};
+            }
+            s.inc_sj[(size_t) t * s.nst_inc + st] = j;
+        }
     }
     s.g1[t] = g1; s.g2[t] = g2; s.g3[t] = g3; s.gv[t] = gv; s.gc[t] = gc;
     s.cp[4 * t + 0] = c0; s.cp[4 * t + 1] = c1; s.cp[4 * t + 2] = c2; s.cp[4 * t + 3] = c3;
@@ -455,6 +524,7 @@ __global__ void __launch_bounds__(256) k_permute_stacks(const RecompProb<T> *__r
     const RecompProb<T> p = probs[blockIdx.y >> 1];
     if (!p.active) return;
     const int side = blockIdx.y & 1;
+    if (p.inc && side == 0) return;  // incremental U side: CU is used in place, P stays where the contraction wrote it
     const int rows = side ? p.n : p.m;
     const T *src = side ? p.SV0 : p.SU0;
     T *dst = side ? p.VW : p.UW;
@@ -531,8 +601,22 @@ struct ApplyBlockArrays {
 
 // Strip jobs of the rebuild: strip s (32 columns) of CU / VN, all reflector blocks last-to-first (Q).
 template<typename T>
-__global__ void k_setup_apply_strips(const RecompProb<T> *__restrict__ rcs, StripJob *__restrict__ out, int nstrips, int npan) {
+__global__ void k_setup_apply_strips(const RecompProb<T> *__restrict__ rcs, StripJob *__restrict__ out, int nstrips, int npan,
+                                     GemmProb<T> *__restrict__ gru) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < npan / 2) {
+        // incremental U side: CU' = [CU | Q2] * Us[:, :rk] as two GEMMs into TU (the rank was just chosen on the device)
+        const RecompProb<T> rc = rcs[idx];
+        GemmProb<T> ga = mk_gemm<T>(nullptr, 1, 0, nullptr, 1, 0, nullptr, 1, 0, 0, 0, T(0), T(0)), gb = ga;
+        if (rc.active && rc.inc) {
+            int rk = *rc.rk_new;
+            if (rk > rc.wcols) rk = 0;
+            ga = mk_gemm<T>(rc.CU, rc.m, 0, rc.Us, rc.a, 0, rc.TU, rc.m, rc.m, rk, rc.kc, T(1), T(0));
+            gb = mk_gemm<T>(rc.Q2, rc.m, 0, rc.Us + rc.kc, rc.a, 0, rc.TU, rc.m, rc.m, rk, rc.kp, T(1), T(1));
+        }
+        gru[idx] = ga;
+        gru[npan / 2 + idx] = gb;
+    }
     if (idx >= nstrips * npan) return;
     // the strips of one panel are neighbours in the grid: they run at the same time and share the panel's reflector
     // blocks through L2 (strip-major order re-read them from HBM: 10 GB per launch in the ncu capture)
@@ -540,7 +624,7 @@ __global__ void k_setup_apply_strips(const RecompProb<T> *__restrict__ rcs, Stri
     const RecompProb<T> rc = rcs[pan >> 1];
     StripJob j{nullptr, nullptr, nullptr, 1, 1, 0, 0, 0, 0, 0, -1, 0};
     if constexpr (std::is_same<T, double>::value) {
-        if (rc.active) {
+        if (rc.active && !(rc.inc && side == 0)) {
             const int m = side ? rc.n : rc.m, r = rc.r, kmax = m < r ? m : r;
             int rk = *rc.rk_new;
             if (rk > rc.wcols) rk = 0;
@@ -622,7 +706,19 @@ __global__ void __launch_bounds__(256) k_extract_r(const RecompProb<T> *__restri
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         if (idx < nu) {
             const int i = idx % p.p, l = idx / p.p;
-            p.MT[idx] = i <= l ? p.UW[(size_t) i + (size_t) l * p.m] : T(0);
+            if (p.inc) {
+                // RU = [[I, G], [0, R2]] (r x r) in the column order of the sorted V stack: column l goes to pos[l]
+                T v;
+                if (l < p.kc) v = (i == l) ? T(1) : T(0);
+                else {
+                    const int c = l - p.kc;
+                    if (i < p.kc) v = p.Gu[(size_t) i + (size_t) c * p.kc] + p.Gu2[(size_t) i + (size_t) c * p.kc];
+                    else v = (i - p.kc <= c) ? p.Pn[(size_t) (i - p.kc) + (size_t) c * p.m] : T(0);
+                }
+                p.MT[(size_t) i + (size_t) p.pos[l] * p.p] = v;
+            } else {
+                p.MT[idx] = i <= l ? p.UW[(size_t) i + (size_t) l * p.m] : T(0);
+            }
         } else {
             const int e = idx - nu, j = e % p.q, l = e / p.q;
             p.Lb[e] = j <= l ? p.VW[(size_t) j + (size_t) l * p.n] : T(0);
@@ -655,7 +751,8 @@ __global__ void __launch_bounds__(256) k_truncate(const RecompProb<T> *__restric
     __shared__ int s_rk;
     if (threadIdx.x == 0) {
         int rk;
-        if (fixed_rank > 0) rk = fixed_rank < p.r ? fixed_rank : p.r;
+        const int fr = p.fixed_rank > 0 ? p.fixed_rank : fixed_rank;  // per-tile replay rank overrides the batch value
+        if (fr > 0) rk = fr < p.r ? fr : p.r;
         else rk = new_rank_rule(p.sigma, p.b, accuracy, truncated);
         if (rk > p.b) rk = p.b;  // only b = min(m, n, r) singular triplets exist
         if (rk < 1) rk = 1;
@@ -672,7 +769,8 @@ __global__ void __launch_bounds__(256) k_truncate(const RecompProb<T> *__restric
     // not transposed (M = core)  : Ufac = Us (p x b),            Vfac*S = Vs (q x b)
     // transposed (M = core^T)    : core = (Vs/S) S Us^T -> Ufac = Vs / sigma (p x b, b == p), Vfac*S = Us * sigma (q x b)
     if (!p.transposed) {
-        for (int idx = threadIdx.x; idx < p.m * rk; idx += blockDim.x) {
+        // (incremental U side: Us is consumed by the rebuild GEMMs [CU | Q2] * Us, CU must stay intact until then)
+        for (int idx = threadIdx.x; idx < (p.inc ? 0 : p.m * rk); idx += blockDim.x) {
             const int i = idx % p.m, c = idx / p.m;
             p.CU[(size_t) i + (size_t) c * p.m] = (i < p.p) ? p.Us[(size_t) i + (size_t) c * p.a] : T(0);
         }
@@ -716,7 +814,30 @@ __global__ void __launch_bounds__(256) k_finalize(const RecompProb<T> *__restric
         }
         __syncthreads();
     }
-    if (blockIdx.x == 0 && tx == 0 && ty == 0) *p.rank_ptr = rk;
+    if (p.inc) {  // incremental U side: the rebuilt factor sits in TU
+        const int nthr = 256, tid = ty * 32 + tx;
+        for (size_t idx = (size_t) blockIdx.x * nthr + tid; idx < (size_t) p.m * rk; idx += (size_t) gridDim.x * nthr)
+            p.CU[idx] = p.TU[idx];
+    }
+    if (blockIdx.x == 0 && tx == 0 && ty == 0) {
+        *p.rank_ptr = rk;
+        // U = Q_U * (normalised left vectors of the core): orthonormal columns unless a kept singular value vanished
+        if (p.state) {
+            const bool ortho = !p.transposed && p.sigma[rk - 1] > T(1e-30) * p.sigma[0] && p.sigma[0] > T(0);
+            const int count = p.inc ? ((*p.state >> 8) + 1) : 0;  // consecutive incremental updates so far
+            *p.state = ortho ? (HCB_STATE_ORTHO_U | (count << 8)) : 0;
+        }
+    }
+}
+
+// [I; 0] in the explicit-Q2 buffers of the incremental tiles.  grid = (chunks, n_tiles)
+template<typename T>
+__global__ void __launch_bounds__(256) k_inc_eye(const RecompProb<T> *__restrict__ probs) {
+    const RecompProb<T> p = probs[blockIdx.y];
+    if (!p.active || !p.inc) return;
+    const size_t total = (size_t) p.m * p.kp;
+    for (size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t) gridDim.x * blockDim.x)
+        p.Q2[idx] = (idx % p.m == idx / p.m) ? T(1) : T(0);
 }
 
 // DDC epilogue (HCore.cpp:291-298 -> CompressedTile::ReadjustTile, Compressed.cpp:696-734): C becomes full rank,
@@ -740,7 +861,10 @@ __global__ void __launch_bounds__(256) k_ddc_finalize(const hcb_tile *__restrict
         for (int idx = g0; idx < m * rank; idx += gstride) CU[idx] = (idx % m == idx / m) ? T(1) : T(0);
         for (int idx = g0; idx < rank * n; idx += gstride) CV[idx] = W[idx];  // V = T (rank == m, ld m)
     }
-    if (g0 == 0) *C.d_rank = rank;
+    if (g0 == 0) {
+        *C.d_rank = rank;
+        if (C.d_state) *C.d_state = 0;  // (U = T, V = I) is not an orthonormal-U representation
+    }
 }
 
 // Initial compression epilogue (Compressed.cpp:103-135): rank rule, U = Uf[:, :rk], V = diag(sigma) Vf[:, :rk]^T.

@@ -34,6 +34,7 @@ extern "C" {
 #define HCB_ENODEVICE 3 /* no CUDA device: there is no CPU fallback */
 #define HCB_ENOMEM 4
 #define HCB_EUNSUPPORTED 5
+#define HCB_EBOUND 6    /* hcb_ctx_sync: a rank exceeded its rank_bound in a fused call (that tile was left untouched) */
 
 typedef struct hcb_ctx hcb_ctx;
 
@@ -90,7 +91,19 @@ typedef struct hcb_tile {
     int32_t rank_bound; /* host-known upper bound on *d_rank used to size grids/scratch (0 -> max_rank) */
     int32_t *d_rank;    /* compressed: DEVICE int32 holding the current rank (the device owns rank truth) */
     void *d_data;       /* DEVICE buffer: dense m x n (ld) or [U (m x max_rank) | V (max_rank x n)] */
+    /* compressed, optional (NULL = unknown): DEVICE int32 of state bits the library keeps next to the rank.
+     * bit 0 (HCB_STATE_ORTHO_U): "U has orthonormal columns" -- set by the library at the end of every recompression /
+     * compression (Compressed.cpp:558-560 guarantees it: U = Q_U * Unew), and what lets the next update orthogonalise
+     * only the NEW columns against U instead of re-factoring the whole stack.  Whoever writes the factors through
+     * d_data directly must clear it (the host mirrors do so in every constructor / PackTile / load).
+     * bits 8..: number of consecutive incremental updates (the library re-factors the whole stack every 16th time). */
+    int32_t *d_state;
+    /* compressed C tiles: per-tile fixed rank for the replay drivers (par_fixed_rank_streams_main.cpp:465-477,540-541;
+     * Compressed.cpp:510-515): > 0 overrides hcb_compress_params.fixed_rank for this tile, 0 = use the batch value */
+    int32_t fixed_rank;
+    int32_t reserved;
 } hcb_tile;
+#define HCB_STATE_ORTHO_U 1
 
 /* ---- (2) fine-grained kernel table : one symbol per HCoreKernels<T> entry (kernels.hpp:27-129) --------------- */
 /* trans: 0 NoTrans, 1 Trans.  type for lacpy/laset: 'G','U','L' (common::MatrixType).  side 'L'/'R'. */
@@ -124,7 +137,9 @@ typedef struct hcb_tile {
     /* HCore<T>::Gemm (HCore.cpp:36-313; the batch must be mix-homogeneous), recompression included, ranks on the   */  \
     /* device.  A,B,C are HOST arrays of descriptors.  d_info (device int32[n_tiles], may be NULL): low byte flags  */  \
     /* 0 ok | 1 Jacobi not converged | 2 rank clipped to max_rank | 4 a rank exceeded its rank_bound (tile left     */  \
-    /* untouched); bits 8..15 = Jacobi sweeps used (diagnostics).  Asynchronous.                                    */  \
+    /* untouched -- also reported by the next hcb_ctx_sync as HCB_EBOUND); bits 8..15 = Jacobi sweeps used.  The    */  \
+    /* call zeroes d_info first; flags are OR-ed, the sweep count is a maximum.  hcb_?tlr_matmul zeroes it once and   */  \
+    /* keeps it sticky over its k loop.  Asynchronous.                                                              */  \
     int hcb_##P##tlr_gemm_batched(hcb_ctx *, int64_t n_tiles, const hcb_tile *A, int opA, const hcb_tile *B, int opB,   \
                                   const hcb_tile *C, T alpha, T beta, const hcb_compress_params *p, int32_t *d_info);   \
     /* Compressing constructor, batched (Compressed.cpp:75-146): dense tile t (m x n, ld) -> out[t] (U, V, *d_rank) */  \
@@ -140,6 +155,14 @@ typedef struct hcb_tile {
     int hcb_##P##tlr_matmul(hcb_ctx *, int64_t mt, int64_t nt, int64_t kt, const hcb_tile *A, const hcb_tile *B,        \
                             const hcb_tile *C, const int64_t *owned, int64_t n_owned, int64_t k_begin, int64_t k_end,   \
                             T alpha, T beta, const hcb_compress_params *p, int32_t *d_info);                                            \
+    /* Local step of the multi-GPU driver (one process per GPU, C tiles 2D block-cyclic over a P x Q grid, SURVEY   */  \
+    /* 8e / BASELINE configs[3]): C(j,i) += alpha*Apan[j]*Bpan[i] + (beta-1)*C for all j < mt, i < nt of THIS rank,   */  \
+    /* where Apan / Bpan are the k-th row-panel of A / column-panel of B after the NCCL broadcast (the host layer     */  \
+    /* hcorepp_b200/distributed.py moves them on a side stream, double buffered).  d_info as above, sticky over k:  */  \
+    /* first != 0 zeroes it before the step.                                                                        */  \
+    int hcb_##P##tlr_matmul_panel_step(hcb_ctx *, int64_t mt, int64_t nt, const hcb_tile *Apan, const hcb_tile *Bpan,   \
+                                       const hcb_tile *C, T alpha, T beta, const hcb_compress_params *p,               \
+                                       int32_t *d_info, int first);                                                    \
     /* scratch bytes the fused path needs for a batch of n_tiles (m x n) tiles with rank bound r = kc+ka            */  \
     /* (replaces HCore<T>::CalculateMemoryPoolSize, HCore.cpp:417-480)                                              */  \
     size_t hcb_##P##tlr_gemm_workspace(int64_t n_tiles, int64_t m, int64_t n, int64_t k, int64_t r_bound);

@@ -24,8 +24,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_capi.hcb_tile) == 40
+    assert C.sizeof(_capi.hcb_tile) == 56
     assert _capi.hcb_tile.d_rank.offset == 24 and _capi.hcb_tile.d_data.offset == 32
+    assert _capi.hcb_tile.d_state.offset == 40 and _capi.hcb_tile.fixed_rank.offset == 48
     assert C.sizeof(_capi.hcb_compress_params) == 40
 
 

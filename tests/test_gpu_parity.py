@@ -464,8 +464,92 @@ def test_batched_equals_one_by_one_and_info(hc, ctx):
     As[0].rank_bound = 2
     info1 = torch.zeros(1, dtype=torch.int32, device="cuda")
     hc.gemm_batched(1.0, As[:1], False, Bs[:1], False, 1.0, C1[:1], ctx, p, info=info1)
-    ctx.Sync()
+    from hcorepp_b200._capi import HcbError
+    with pytest.raises(HcbError, match="rank_bound"):  # sticky context error: heard even without an info buffer
+        ctx.Sync()
+    ctx.Sync()                                          # ... once
     assert int(info1.item()) & 0xff == 4 and np.array_equal(C1[0].to_dense(), before)
+    hc.gemm_batched(1.0, As[:1], False, Bs[:1], False, 1.0, C1[:1], ctx, p)   # same violation, no info buffer
+    with pytest.raises(HcbError, match="rank_bound"):
+        ctx.Sync()
+    assert np.array_equal(C1[0].to_dense(), before)
+
+
+def test_incremental_u_side_ksum_vs_oracle(hc, ctx):
+    """Round 2: a C tile that carries the state bit "U orthonormal" takes the incremental U path (block Gram-Schmidt of
+    the new columns against CU + a kp-column panel QR + GEMM rebuild).  An 8-step k-sum against the oracle (<= 10*acc,
+    ranks +/-1), against the full-QR path (HCB_NO_INCREMENTAL=1), U stays orthonormal, info flags are sticky over k."""
+    nb, k, acc, kt = 512, 30, 1e-8, 8
+    p, po = hc.CompressionParameters(acc), O.CompressionParameters(acc)
+    tiles = [(O.synth_compressed_tile(nb, k, 7000 + i), O.synth_compressed_tile(nb, k, 8000 + i)) for i in range(kt)]
+    oC = O.CompressedTile(np.zeros((nb, 1), order="F"), np.zeros((1, nb), order="F"), nb // 3)
+    oranks = []
+    for a, b in tiles:
+        O.hcore_gemm(1.0, a, False, b, False, 1.0, oC, po)
+        oranks.append(oC.rank)
+    ref = oC.to_dense()
+    res = {}
+    for mode in ("incremental", "full"):
+        if mode == "full":
+            os.environ["HCB_NO_INCREMENTAL"] = "1"
+        try:
+            Ct = hc.CompressedTile(nb, nb, nb // 3, torch.float64, ctx)
+            ranks, states = [], []
+            for a, b in tiles:
+                A = hc.CompressedTile.from_uv(a.U, a.V, ctx)
+                B = hc.CompressedTile.from_uv(b.U, b.V, ctx)
+                hc.HCore.Gemm(1.0, A, False, B, False, 1.0, Ct, ctx, p)
+                ranks.append(Ct.GetTileRank())
+                states.append(int(Ct.state.item()))
+            res[mode] = (Ct.to_dense(), ranks, states, Ct.factors()[0])
+        finally:
+            os.environ.pop("HCB_NO_INCREMENTAL", None)
+    for mode, (d, ranks, states, U) in res.items():
+        assert relerr(d, ref) <= 10 * acc, mode
+        assert max(abs(a - b) for a, b in zip(ranks, oranks)) <= 1, (mode, ranks, oranks)
+        assert all(s & 1 for s in states), (mode, states)
+        assert [s >> 8 for s in states] == ([0] + list(range(1, kt)) if mode == "incremental" else [0] * kt), (mode, states)
+        # accuracy-aware Jacobi stop: the left vectors are orthogonal to ~0.05 * accuracy per update (adds up over the
+        # incremental updates until the periodic full re-factorisation)
+        orth = torch.linalg.norm(U.t() @ U - torch.eye(U.shape[1], dtype=torch.float64, device="cuda")).item()
+        assert orth < 0.5 * acc, (mode, orth)
+    assert relerr(res["incremental"][0], res["full"][0]) <= 1e-9
+    # a tile written behind the library's back: invalidate() clears the bit and the next update takes the full path
+    Ct = hc.CompressedTile.from_uv(tiles[0][0].U * 3.0, tiles[0][0].V, ctx, max_rank=nb // 3)  # U NOT orthonormal
+    assert int(Ct.state.item()) == 0
+    A, B = hc.CompressedTile.from_uv(tiles[1][0].U, tiles[1][0].V, ctx), hc.CompressedTile.from_uv(tiles[1][1].U, tiles[1][1].V, ctx)
+    o = O.CompressedTile.from_uv(tiles[0][0].U * 3.0, tiles[0][0].V)
+    o.max_rank = nb // 3
+    hc.HCore.Gemm(1.0, A, False, B, False, 1.0, Ct, ctx, p)
+    O.hcore_gemm(1.0, tiles[1][0], False, tiles[1][1], False, 1.0, o, po)
+    assert relerr(Ct.to_dense(), o.to_dense()) <= 10 * acc and abs(Ct.GetTileRank() - o.rank) <= 1
+
+
+def test_matmul_info_is_sticky_over_k(hc, ctx):
+    """hcb_?tlr_matmul passes one d_info to every k-step -- flags are OR-ed, the sweep count is the maximum."""
+    nb, T, k, acc = 128, 2, 12, 1e-8
+    A = hc.TileMatrix(T, T, nb, nb, torch.float64, ctx, compressed=True)
+    B = hc.TileMatrix(T, T, nb, nb, torch.float64, ctx, compressed=True)
+    Cm = hc.TileMatrix.zeros_compressed(T, T, nb, nb, torch.float64, ctx)
+    for tm, seed in ((A, 1), (B, 2)):
+        for j in range(T):
+            for i in range(T):
+                t = O.synth_compressed_tile(nb, k, seed * 100 + j * 10 + i)
+                g = tm.GetTile(j, i)
+                g.buf[: nb * k] = dev(t.U)
+                g.buf[nb * tm.max_rank: nb * tm.max_rank + k * nb] = dev(t.V)
+                g.rank.fill_(k)
+    # the bound is violated in the FIRST k-step only: the A(:, 0) tiles claim a bound below their rank
+    A.descs[0].rank_bound = 3
+    A.descs[1].rank_bound = 3
+    info = torch.full((T * T,), -1, dtype=torch.int32, device="cuda")
+    hc.tile_matrix_multiplication(A, B, Cm, 1.0, 1.0, ctx, hc.CompressionParameters(acc), info=info)
+    from hcorepp_b200._capi import HcbError
+    with pytest.raises(HcbError):
+        ctx.Sync()
+    h = info.cpu().numpy()
+    assert np.all((h & 0xff) == 4)            # every C tile lost its k = 0 update: the flag survived the k = 1 step
+    assert np.all(((h >> 8) & 0xff) >= 1)     # ... whose Jacobi sweeps are reported as the maximum over k
 
 
 def test_full_size_tile_properties(hc, ctx):
@@ -570,8 +654,7 @@ def test_cpp_host_layer_replays_reference_tests():
     operator/API known answers (tests/cpp/test_api.cpp), built by __graft_entry__.build() with plain g++."""
     import subprocess
     exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "test_api")
-    if not os.path.exists(exe):
-        pytest.skip("tests/cpp/test_api not built (run __graft_entry__.build())")
+    assert os.path.exists(exe), "tests/cpp/test_api not built (run __graft_entry__.build()): the C++ replay must not be skipped"
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "0 failure(s)" in r.stdout
