@@ -96,6 +96,31 @@ class DistTileMatrix:
         return self.local.buf[p_local * n * e:(p_local + 1) * n * e], self.local.ranks[p_local * n:(p_local + 1) * n]
 
 
+def exchange_panels(g: Grid2D, k: int, a_slab, b_slab, pan_a, pan_b, have_rows=True, have_cols=True):
+    """The data-path collective of step k (device-agnostic: NCCL on the GPUs, gloo in the CPU tests).  a_slab(kl) /
+    b_slab(kl) return this rank's (factor slab, rank slab) of its kl-th local A column panel / B row panel; pan_a /
+    pan_b = (buffer, ranks) receive the panels of step k: A(rows of this grid row, k) from grid column k mod Q along the
+    grid row, B(k, columns of this grid column) from grid row k mod P along the grid column."""
+    dist = g.dist
+    src_c, src_r = k % g.Q, k % g.P
+    if have_rows:
+        if src_c == g.pc:
+            buf, rk = a_slab(k // g.Q)
+            pan_a[0].copy_(buf, non_blocking=True)
+            pan_a[1].copy_(rk, non_blocking=True)
+        if g.Q > 1:
+            dist.broadcast(pan_a[0], src=g.pr * g.Q + src_c, group=g.row_group)
+            dist.broadcast(pan_a[1], src=g.pr * g.Q + src_c, group=g.row_group)
+    if have_cols:
+        if src_r == g.pr:
+            buf, rk = b_slab(k // g.P)
+            pan_b[0].copy_(buf, non_blocking=True)
+            pan_b[1].copy_(rk, non_blocking=True)
+        if g.P > 1:
+            dist.broadcast(pan_b[0], src=src_r * g.Q + g.pc, group=g.col_group)
+            dist.broadcast(pan_b[1], src=src_r * g.Q + g.pc, group=g.col_group)
+
+
 class MatmulPlan:
     """Buffers, streams and descriptor arrays of C = alpha * A * B + beta * C on a grid; reusable across calls."""
 
@@ -120,26 +145,10 @@ class MatmulPlan:
         self.fn = getattr(lib, f"hcb_{_PFX[Cm.dtype]}tlr_matmul_panel_step")
 
     def _fetch(self, k: int, b: int):
-        g, dist = self.grid, self.grid.dist
         with torch.cuda.stream(self.comm):
             self.comm.wait_event(self.done[b])
-            src_c, src_r = k % g.Q, k % g.P
-            if self.mt_l:
-                if src_c == g.pc:
-                    buf, rk = self.A.panel_slab(k // g.Q)
-                    self.panA[b].buf.copy_(buf, non_blocking=True)
-                    self.panA[b].ranks.copy_(rk, non_blocking=True)
-                if g.Q > 1:
-                    dist.broadcast(self.panA[b].buf, src=g.pr * g.Q + src_c, group=g.row_group)
-                    dist.broadcast(self.panA[b].ranks, src=g.pr * g.Q + src_c, group=g.row_group)
-            if self.nt_l:
-                if src_r == g.pr:
-                    buf, rk = self.B.panel_slab(k // g.P)
-                    self.panB[b].buf.copy_(buf, non_blocking=True)
-                    self.panB[b].ranks.copy_(rk, non_blocking=True)
-                if g.P > 1:
-                    dist.broadcast(self.panB[b].buf, src=src_r * g.Q + g.pc, group=g.col_group)
-                    dist.broadcast(self.panB[b].ranks, src=src_r * g.Q + g.pc, group=g.col_group)
+            exchange_panels(self.grid, k, self.A.panel_slab, self.B.panel_slab, (self.panA[b].buf, self.panA[b].ranks),
+                            (self.panB[b].buf, self.panB[b].ranks), self.mt_l > 0, self.nt_l > 0)
             self.ready[b].record(self.comm)
 
     def run(self, alpha, beta, params: CompressionParameters, info: torch.Tensor | None = None, k_range=None):

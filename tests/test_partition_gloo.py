@@ -81,3 +81,41 @@ def test_panel_broadcast_schedule_gloo(world):
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, 3, 2, 5, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world)) and len(out) == world
+
+
+def _worker_lib(rank, world, port, mt, nt, kt, out):
+    """The LIBRARY's exchange step (hcorepp_b200.distributed.Grid2D + exchange_panels, the code bench.py and
+    tlr_matmul_distributed run with NCCL) under gloo on CPU tensors: a 'tile' is two floats (payload id, rank id); after
+    step k every rank must hold A(j, k) for its C rows and B(k, i) for its C columns, in local order."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hcorepp_b200 import distributed as D
+    g = D.Grid2D()
+    assert (g.P, g.Q) == part.grid_shape(world) and g.rank == rank
+    rows, cols = part.owned_indices(mt, g.P, g.pr), part.owned_indices(nt, g.Q, g.pc)
+    kA, kB = part.owned_indices(kt, g.Q, g.pc), part.owned_indices(kt, g.P, g.pr)
+    a_id = lambda j, k: 1000.0 * j + k
+    b_id = lambda k, i: -(1000.0 * k + i) - 1
+    A_buf = [torch.tensor([a_id(j, k) for j in rows], dtype=torch.float64) for k in kA]
+    A_rk = [torch.tensor([int(a_id(j, k)) % 97 for j in rows], dtype=torch.int32) for k in kA]
+    B_buf = [torch.tensor([b_id(k, i) for i in cols], dtype=torch.float64) for k in kB]
+    B_rk = [torch.tensor([int(-b_id(k, i)) % 89 for i in cols], dtype=torch.int32) for k in kB]
+    pan_a = (torch.zeros(len(rows), dtype=torch.float64), torch.zeros(len(rows), dtype=torch.int32))
+    pan_b = (torch.zeros(len(cols), dtype=torch.float64), torch.zeros(len(cols), dtype=torch.int32))
+    ok = True
+    for k in range(kt):
+        D.exchange_panels(g, k, lambda kl: (A_buf[kl], A_rk[kl]), lambda kl: (B_buf[kl], B_rk[kl]), pan_a, pan_b,
+                          len(rows) > 0, len(cols) > 0)
+        ok &= pan_a[0].tolist() == [a_id(j, k) for j in rows] and pan_a[1].tolist() == [int(a_id(j, k)) % 97 for j in rows]
+        ok &= pan_b[0].tolist() == [b_id(k, i) for i in cols] and pan_b[1].tolist() == [int(-b_id(k, i)) % 89 for i in cols]
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape", [(2, (5, 4, 7)), (4, (6, 7, 5)), (4, (3, 8, 9))])
+def test_library_panel_exchange_gloo(world, shape):
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_lib, args=(world, port, *shape, out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world)) and len(out) == world
