@@ -110,6 +110,9 @@ struct GemmProb {  // C = alpha*op(A)*op(B) + beta*C ; m == 0 means "skip"
     int lda, ldb, ldc;
     int ta, tb;
     T alpha, beta;
+    // optional second A segment: op(A) = [A | A2] along k, split at k1 (ta == 0 only; A2 == nullptr: none)
+    const T *A2;
+    int k1, lda2;
 };
 
 template<typename T>

@@ -112,7 +112,7 @@ int launch_gemm(hcb_ctx *ctx, const GemmProb<T> *d_probs, int n_probs, int m_bou
             continue;
         }
         if constexpr (std::is_same<T, double>::value) {
-            // FP64: tensor pipe (DMMA). Tile shape follows the skinny dimension.
+            // FP64: tensor pipe (DMMA); row-contiguous operands arrive by TMA bulk copies. Tile shape follows the skinny side.
             if (m_bound <= 32) {
                 dim3 grid(std::max(1, cdiv(n_bound, 128)), cnt);
                 k_gemm_dmma<1, 4><<<grid, 128, 0, ctx->stream>>>(d_probs + off);
@@ -700,9 +700,9 @@ Layout<T> make_layout(const BatchShape &s) {
         L.o_wbu = take((size_t) 2 * NBQ * L.wcols);
         L.o_wbv = take((size_t) 2 * NBQ * L.wcols);
         // LQ preconditioning of the core
-        L.o_mt = take((size_t) L.pq_b * L.r_b);  // M^T for the LQ path, or RU (p x r) for the GEMM core
+        L.o_mt = take((size_t) (L.pq_b + 1) * L.r_b);  // M^T for the LQ path, or RU (p x r, even ld) for the GEMM core
         L.o_taum = take(L.pq_b);
-        L.o_lb = take((size_t) L.pq_b * L.r_b);  // L for the LQ path, or RV (q x r)
+        L.o_lb = take((size_t) (L.pq_b + 1) * L.r_b);  // L for the LQ path, or RV (q x r, even ld)
         L.o_vcm = take(sq);
         L.o_tbm = take((size_t) NBQ * NBQ * L.nblk);
         L.o_wbm = take((size_t) 2 * NBQ * L.wcols);
@@ -1000,7 +1000,7 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
         HCB_TRY(launch_strips(ctx, sj, nstrips * npan, std::max(s.m, s.n)));
         if (inc_enabled) {  // CU' = [CU | Q2] * Us for the incremental tiles (two GEMMs into TU)
             HCB_TRY(launch_gemm<T>(ctx, gru, n, s.m, rk_bound));
-            HCB_TRY(launch_gemm<T>(ctx, gru + n, n, s.m, rk_bound));
+            if (!std::is_same<T, double>::value) HCB_TRY(launch_gemm<T>(ctx, gru + n, n, s.m, rk_bound));
         }
     } else {
         // blocked rebuild C := Q [X;0]: blocks last-to-first, three batched GEMMs per block, rank read on the device

@@ -49,6 +49,8 @@ struct RecompProb {
     T *Gu, *Gu2;        // first / second pass coefficients CU^T P (kc x kp, ld kc)
     T *Q2;              // explicit Q2 (m x kp, ld m)
     T *TU;              // rebuild target [CU | Q2] * Us[:, :rk] (m x rk, ld m), copied into CU by k_finalize
+    int lp, lq;         // leading dimensions of the extracted triangles MT (p x r) / Lb (q x r): p, q rounded up to even
+                        // so that the core GEMM's row-contiguous operands qualify for TMA bulk copies
     int *state;         // C tile's device state word (may be null)
     int fixed_rank;     // per-tile fixed rank (0: batch value)
 };
@@ -121,6 +123,7 @@ __device__ __forceinline__ GemmProb<T> mk_gemm(const T *A, int lda, int ta, cons
     GemmProb<T> g;
     g.A = A; g.B = B; g.C = C; g.m = m; g.n = n; g.k = k; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
     g.ta = ta; g.tb = tb; g.alpha = alpha; g.beta = beta;
+    g.A2 = nullptr; g.k1 = k; g.lda2 = 1;
     return g;
 }
 
@@ -258,8 +261,10 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
                 lq = LqProb<T>{rc.MT, rc.Lb, rc.a, rc.b};
                 gv = mk_gemm<T>(rc.M, rc.a, 1, rc.Us, rc.a, 0, rc.Vs, rc.b, rc.b, rc.b, rc.a, one, zero);
                 // core from the extracted triangles RU (p x r, ld p, in MT) and RV (q x r, ld q, in Lb)
-                if (rc.transposed) gc = mk_gemm<T>(rc.Lb, q, 0, rc.MT, p, 1, rc.M, rc.a, q, p, r, one, zero);
-                else gc = mk_gemm<T>(rc.MT, p, 0, rc.Lb, q, 1, rc.M, rc.a, p, q, r, one, zero);
+                rc.lp = s.use_lq ? p : ((p + 1) & ~1);
+                rc.lq = s.use_lq ? q : ((q + 1) & ~1);
+                if (rc.transposed) gc = mk_gemm<T>(rc.Lb, rc.lq, 0, rc.MT, rc.lp, 1, rc.M, rc.a, q, p, r, one, zero);
+                else gc = mk_gemm<T>(rc.MT, rc.lp, 0, rc.Lb, rc.lq, 1, rc.M, rc.a, p, q, r, one, zero);
                 // rebuild (Compressed.cpp:551-560, 611-628): CU = Q_U [Unew;0], VN = Q_V [Vfac;0], rank read on device
                 r0 = ReflProb<T>{UW, rc.tauU, CU, m, p, m, m, 0, m, 0, 0, rc.rk_new};
                 r1 = ReflProb<T>{VW, rc.tauV, rc.VN, n, q, n, n, 0, n, 0, 0, rc.rk_new};
@@ -611,8 +616,13 @@ __global__ void k_setup_apply_strips(const RecompProb<T> *__restrict__ rcs, Stri
         if (rc.active && rc.inc) {
             int rk = *rc.rk_new;
             if (rk > rc.wcols) rk = 0;
-            ga = mk_gemm<T>(rc.CU, rc.m, 0, rc.Us, rc.a, 0, rc.TU, rc.m, rc.m, rk, rc.kc, T(1), T(0));
-            gb = mk_gemm<T>(rc.Q2, rc.m, 0, rc.Us + rc.kc, rc.a, 0, rc.TU, rc.m, rc.m, rk, rc.kp, T(1), T(1));
+            if (std::is_same<T, double>::value) {  // one pass: op(A) = [CU | Q2] (two-segment A of k_gemm_dmma)
+                ga = mk_gemm<T>(rc.CU, rc.m, 0, rc.Us, rc.a, 0, rc.TU, rc.m, rc.m, rk, rc.kc + rc.kp, T(1), T(0));
+                ga.A2 = rc.Q2; ga.k1 = rc.kc; ga.lda2 = rc.m;
+            } else {
+                ga = mk_gemm<T>(rc.CU, rc.m, 0, rc.Us, rc.a, 0, rc.TU, rc.m, rc.m, rk, rc.kc, T(1), T(0));
+                gb = mk_gemm<T>(rc.Q2, rc.m, 0, rc.Us + rc.kc, rc.a, 0, rc.TU, rc.m, rc.m, rk, rc.kp, T(1), T(1));
+            }
         }
         gru[idx] = ga;
         gru[npan / 2 + idx] = gb;
@@ -715,13 +725,13 @@ __global__ void __launch_bounds__(256) k_extract_r(const RecompProb<T> *__restri
                     if (i < p.kc) v = p.Gu[(size_t) i + (size_t) c * p.kc] + p.Gu2[(size_t) i + (size_t) c * p.kc];
                     else v = (i - p.kc <= c) ? p.Pn[(size_t) (i - p.kc) + (size_t) c * p.m] : T(0);
                 }
-                p.MT[(size_t) i + (size_t) p.pos[l] * p.p] = v;
+                p.MT[(size_t) i + (size_t) p.pos[l] * p.lp] = v;
             } else {
-                p.MT[idx] = i <= l ? p.UW[(size_t) i + (size_t) l * p.m] : T(0);
+                p.MT[(size_t) i + (size_t) l * p.lp] = i <= l ? p.UW[(size_t) i + (size_t) l * p.m] : T(0);
             }
         } else {
             const int e = idx - nu, j = e % p.q, l = e / p.q;
-            p.Lb[e] = j <= l ? p.VW[(size_t) j + (size_t) l * p.n] : T(0);
+            p.Lb[(size_t) j + (size_t) l * p.lq] = j <= l ? p.VW[(size_t) j + (size_t) l * p.n] : T(0);
         }
     }
 }
