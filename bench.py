@@ -55,6 +55,10 @@ def parse():
                     help="initial-compression leg (SURVEY.md 8d: reported separately): dense tiles compressed (0: skip)")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (BASELINE configs[3])")
+    ap.add_argument("--no-cholesky", action="store_true", help="skip the TLR Cholesky leg (BASELINE configs[4], N=1 only)")
+    ap.add_argument("--chol-tiles", type=int, default=32)
+    ap.add_argument("--chol-nb", type=int, default=1024)
+    ap.add_argument("--chol-acc", type=float, default=1e-8)
     ap.add_argument("--strong-tiles", type=int, default=32)
     ap.add_argument("--strong-nb", type=int, default=2048)
     ap.add_argument("--strong-acc", type=float, default=1e-6)
@@ -403,6 +407,12 @@ def main():
     if rank_env == 0 and strong is not None:
         result["strong_scaling"] = strong
         result["config"]["strong_workload"] = strong.get("workload")
+    if world == 1 and not args.no_cholesky:
+        try:
+            result["cholesky"] = run_cholesky_leg(args, torch, hc, ctx)
+        except Exception as e:
+            result["cholesky"] = {"error": repr(e)}
+        torch.cuda.empty_cache()
     if rank_env == 0:
         result["clocks"] = clocks
         phases = {}
@@ -805,6 +815,89 @@ def run_e2e_dist(leg, steps):
     h2d = sum(x.numel() * x.element_size() for x in (hUa, hVa, hUb, hVb))
     d2h = h_ranks.numel() * 4 + (hU.numel() + hV.numel()) * 8
     return float(t.item()), h2d, d2h
+
+
+def run_cholesky_leg(args, torch, hc, ctx):
+    """BASELINE.json configs[4]: tile Cholesky of a synthetic covariance matrix (32768 points in the unit square along a
+    Morton curve, Matern-5/2 kernel, nugget 1e-2), tile 1024, accuracy 1e-8: dense diagonal tiles, compressed tiles below
+    (compressed on the device, untimed), factorised by hcb_dtlr_potrf (potrf / panel trsm / syrk / one batched recompressing
+    GEMM per step).  Timed with CUDA events; checked through the size-independent property A = L L^T on sampled tiles."""
+    nt, nb, acc = args.chol_tiles, args.chol_nb, args.chol_acc
+    dev, dt = ctx.device, torch.float64
+    g = torch.Generator(device=dev)
+    g.manual_seed(77)
+    pts = torch.rand(nt * nb, 2, generator=g, dtype=dt, device=dev)
+    q = (pts * 65535).to(torch.int64)
+
+    def spread(v):
+        v = (v | (v << 8)) & 0x00FF00FF
+        v = (v | (v << 4)) & 0x0F0F0F0F
+        v = (v | (v << 2)) & 0x33333333
+        return (v | (v << 1)) & 0x55555555
+    pts = pts[torch.argsort(spread(q[:, 0]) | (spread(q[:, 1]) << 1), stable=True)]
+    ell, nugget = 0.1, 1e-2
+
+    def tile(i, j):
+        a, b = pts[i * nb:(i + 1) * nb], pts[j * nb:(j + 1) * nb]
+        z = math.sqrt(5.0) * torch.cdist(a, b) / ell
+        t = (1 + z + z * z / 3.0) * torch.exp(-z)
+        if i == j:
+            t = t + nugget * torch.eye(nb, dtype=dt, device=dev)
+        return t
+    prm = hc.CompressionParameters(acc)
+    t0 = time.time()
+    S = hc.SymTileMatrix.from_tiles(tile, nt, nb, dt, ctx, prm)
+    torch.cuda.synchronize()
+    t_build = time.time() - t0
+    ranks0 = S.low.rank_table()
+    low_mask = np.tril(np.ones((nt, nt), dtype=bool), -1)
+    keep = (S.diag.clone(), S.low.buf.clone(), S.low.ranks.clone(), S.low.state.clone())
+    pinfo = torch.zeros(nt, dtype=torch.int32, device=dev)
+
+    def restore():
+        S.diag.copy_(keep[0]); S.low.buf.copy_(keep[1]); S.low.ranks.copy_(keep[2]); S.low.state.copy_(keep[3])
+    hc.tlr_cholesky(S, ctx, prm, potrf_info=pinfo)   # warm-up (scratch arena)
+    ctx.Sync()
+    ms = []
+    for _ in range(2):
+        restore()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        hc.tlr_cholesky(S, ctx, prm, potrf_info=pinfo)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    ms = min(ms)
+    ranks1 = S.low.rank_table()
+    # property check on sampled tiles: (L L^T)(i, j) = sum_{k <= j} L(i, k) L(j, k)^T against the generated block
+    def Lt(i, k):
+        if i == k:
+            return torch.tril(S.diag[k].view(nb, nb).t())
+        U, V = S.low.GetTile(i, k).factors()
+        return U @ V
+    num = den = 0.0
+    samples = [(nt - 1, nt - 1), (nt - 1, 0), (nt // 2, nt // 2 - 1), (nt - 1, nt - 2), (nt // 3, nt // 3)]
+    for (i, j) in samples:
+        acc_t = torch.zeros(nb, nb, dtype=dt, device=dev)
+        for k in range(j + 1):
+            acc_t += Lt(i, k) @ Lt(j, k).t()
+        ref = tile(i, j)
+        num += float(torch.linalg.norm(acc_t - ref) ** 2)
+        den += float(torch.linalg.norm(ref) ** 2)
+    err = math.sqrt(num / den)
+    n_updates = sum((nt - k - 1) * (nt - k - 2) // 2 for k in range(nt))
+    return {"workload": "TLR Cholesky %dx%d f64, tile %d, acc %.0e, Matern-5/2 covariance (ell %.2f, nugget %.0e), dense diagonal + "
+                        "compressed lower tiles" % (nt * nb, nt * nb, nb, acc, ell, nugget),
+            "baseline_config": "BASELINE.json configs[4]" if (nt, nb, acc) == (32, 1024, 1e-8) else "custom",
+            "ms": ms, "tile_updates": n_updates, "tile_updates_per_s": n_updates / (ms * 1e-3),
+            "dense_equivalent_tflops": (nt * nb) ** 3 / 3.0 / (ms * 1e-3) / 1e12,
+            "build_and_compress_s": t_build, "rank_in_mean": float(ranks0[low_mask].mean()), "rank_in_max": int(ranks0[low_mask].max()),
+            "rank_out_mean": float(ranks1[low_mask].mean()), "rank_out_max": int(ranks1[low_mask].max()),
+            "potrf_info_max": int(pinfo.abs().max().item()),
+            "check": {"rel_fro_err_LLt_vs_A_sampled_tiles": err, "tiles": len(samples), "tolerance": 10 * acc,
+                      "pass": bool(err <= 10 * acc and int(pinfo.abs().max().item()) == 0)},
+            "driver": "hcorepp_b200.tlr_cholesky (hcb_dtlr_potrf)"}
 
 
 def run_strong_leg(args, torch, hc, ctx, grid, rank_env):

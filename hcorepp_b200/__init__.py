@@ -7,7 +7,7 @@ Importing this package requires the built CUDA library (no CPU fallback).
 """
 from . import _capi  # noqa: F401  (raises ImportError when libhcore_b200.so is missing)
 from .api import (RunContext, CompressionParameters, DenseTile, CompressedTile, HCore, TileMatrix,  # noqa: F401
-                  tile_matrix_multiplication, gemm_batched)
+                  tile_matrix_multiplication, gemm_batched, SymTileMatrix, tlr_cholesky)
 
 __all__ = ["RunContext", "CompressionParameters", "DenseTile", "CompressedTile", "HCore", "TileMatrix",
-           "tile_matrix_multiplication", "gemm_batched"]
+           "tile_matrix_multiplication", "gemm_batched", "SymTileMatrix", "tlr_cholesky"]

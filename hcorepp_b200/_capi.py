@@ -90,6 +90,14 @@ def _declare(p, ct):
     f("tlr_gemm_batched").argtypes = [vp, i64, _PT, C.c_int, _PT, C.c_int, _PT, ct, ct, _PP, vp]
     f("compress_batched").argtypes = [vp, i64, C.POINTER(vp), i64, _PT, _PP, vp]
     f("tlr_matmul").argtypes = [vp, i64, i64, i64, _PT, _PT, _PT, C.POINTER(i64), i64, i64, i64, ct, ct, _PP, vp]
+    f("potrf").argtypes = [vp, C.c_int, i64, vp, i64, vp]
+    f("trsm").argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, i64, i64, ct, vp, i64, vp, i64]
+    f("syrk").argtypes = [vp, C.c_int, C.c_int, i64, i64, ct, vp, i64, ct, vp, i64]
+    f("fill_triangle").argtypes = [vp, C.c_int, i64, vp, i64, ct]
+    f("symmetrize").argtypes = [vp, C.c_int, i64, vp, i64]
+    f("tlr_trsm_batched").argtypes = [vp, i64, _PT, C.POINTER(vp), C.POINTER(i64)]
+    f("tlr_syrk_batched").argtypes = [vp, i64, _PT, C.POINTER(vp), C.POINTER(i64), ct, ct]
+    f("tlr_potrf").argtypes = [vp, i64, i64, C.POINTER(vp), i64, _PT, _PP, vp, vp]
     f("tlr_matmul_panel_step").argtypes = [vp, i64, i64, vp, vp, _PT, ct, ct, _PP, vp, C.c_int]
     f("tlr_gemm_workspace").argtypes = [i64, i64, i64, i64, i64]
     f("tlr_gemm_workspace").restype = sz

@@ -249,6 +249,45 @@ class HCore:
         gemm_batched(alpha, [A], opA, [B], opB, beta, [Ct], ctx, params)
 
 
+def _chr(x):
+    return ord(x) if isinstance(x, str) else int(x)
+
+
+def _potrf(A: "DenseTile", uplo, ctx: RunContext):
+    info = torch.zeros(1, dtype=torch.int32, device=ctx.device)
+    check(_fn("potrf", A.dtype)(ctx.h, _chr(uplo), A.m, A.t.data_ptr(), A.m, info.data_ptr()))
+    return info
+
+
+def _hcore_potrf(A, uplo, ctx: RunContext):
+    """HCore<T>::Potrf (HCore.cpp:586-621): dense tiles only, LAPACK potrf semantics in place (the other triangle is left
+    as it was).  Returns LAPACK's info (0 = success) -- read from the device, so this synchronises."""
+    if not A.dense:
+        raise RuntimeError(" Potrf works only with dense tiles")
+    return int(_potrf(A, uplo, ctx).item())
+
+
+def _hcore_trsm(side, uplo, trans, diag, alpha, A, B, ctx: RunContext):
+    """HCore<T>::Trsm (HCore.cpp:624-647): A dense triangular, B compressed; blas::trsm with m = rows(B), n = rank(B) on
+    B's V buffer viewed as an (m x rank) matrix -- the reference's Cholesky convention stores V as n x k; U is not touched."""
+    if B.dense:
+        raise RuntimeError(" TRSM: Tile B must be compressed ")
+    rk = B.GetTileRank()
+    vptr = B.buf.data_ptr() + B.buf.element_size() * B.m * B.max_rank
+    check(_fn("trsm", B.dtype)(ctx.h, _chr(side), _chr(uplo), int(bool(trans)), _chr(diag), B.m, rk, _CT[B.dtype](alpha),
+                               A.t.data_ptr(), A.m, vptr, B.m))
+
+
+def _hcore_syrk(alpha, A, opA, uplo, beta, Ct, ctx: RunContext):
+    """HCore<T>::Syrk (HCore.cpp:484-583) with a dense A: blas::syrk with n = rows(C), k = cols(C); only the `uplo` triangle
+    of C is referenced.  (A compressed A goes through tlr_syrk_batched / the Cholesky driver in this library's V = rank x n
+    convention; the reference's own compressed branch is unpinned)"""
+    if not A.dense or not Ct.dense:
+        raise RuntimeError(" Syrk: dense tiles only in the reference-convention mirror (see tlr_cholesky for compressed A)")
+    check(_fn("syrk", Ct.dtype)(ctx.h, _chr(uplo), int(bool(opA)), Ct.m, Ct.n, _CT[Ct.dtype](alpha), A.t.data_ptr(), A.m,
+                                _CT[Ct.dtype](beta), Ct.t.data_ptr(), Ct.m))
+
+
 class TileMatrix:
     """helpers::TileMatrix<T>: an mt x nt grid of tiles in ONE pooled device buffer (+ a device rank table and a
     pre-built descriptor array), so that a whole k-step is a single batched call with no per-tile host work."""
@@ -395,3 +434,68 @@ def tile_matrix_multiplication(A: TileMatrix, B: TileMatrix, Cm: TileMatrix, alp
     k0, k1 = k_range if k_range is not None else (0, A.nt)
     check(_fn("tlr_matmul", Cm.dtype)(ctx.h, Cm.mt, Cm.nt, A.nt, A.descs, B.descs, Cm.descs, o_ptr, n_owned, k0, k1,
                                       ct(alpha), ct(beta), C.byref(prm), None if info is None else info.data_ptr()))
+
+
+HCore.Potrf = staticmethod(_hcore_potrf)
+HCore.Trsm = staticmethod(_hcore_trsm)
+HCore.Syrk = staticmethod(_hcore_syrk)
+
+
+class SymTileMatrix:
+    """A symmetric positive definite matrix in tile-low-rank form for the Cholesky driver (BASELINE.json configs[4]):
+    nt dense nb x nb DIAGONAL tiles (one pooled buffer, column-major each) + compressed tiles strictly BELOW the diagonal
+    (a pooled nt x nt TileMatrix of which the entries i > j are used).  The reference has the tile routines but neither
+    this container nor a driver."""
+
+    def __init__(self, nt, nb, dtype, ctx: RunContext, max_rank=None, rank_bound=0):
+        self.nt, self.nb, self.dtype, self.ctx = nt, nb, dtype, ctx
+        self.diag = torch.zeros(nt, nb * nb, dtype=dtype, device=ctx.device)
+        self.low = TileMatrix(nt, nt, nb, nb, dtype, ctx, compressed=True, max_rank=max_rank, rank_bound=rank_bound)
+
+    @classmethod
+    def from_tiles(cls, tile_fn, nt, nb, dtype, ctx: RunContext, params: CompressionParameters, chunk=64, max_rank=None):
+        """tile_fn(i, j) -> dense nb x nb block (torch tensor on the device or numpy, A[i-block, j-block]); diagonal blocks
+        are stored dense, blocks below the diagonal are compressed on the device in batches (hcb_?compress_batched)."""
+        S = cls(nt, nb, dtype, ctx, max_rank=max_rank)
+        dev = ctx.device
+        as_t = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(dev).to(dtype)
+        for k in range(nt):
+            S.diag[k] = as_t(tile_fn(k, k)).t().contiguous().reshape(-1)
+        pairs = [(i, j) for j in range(nt) for i in range(j + 1, nt)]
+        prm = params.c()
+        for c0 in range(0, len(pairs), chunk):
+            part = pairs[c0:c0 + chunk]
+            dense = torch.stack([as_t(tile_fn(i, j)).t().contiguous() for (i, j) in part])  # column-major tiles
+            n = len(part)
+            ptrs = (C.c_void_p * n)(*[dense.data_ptr() + dense.element_size() * nb * nb * q for q in range(n)])
+            descs = (hcb_tile * n)(*[S.low.descs[S.low.lin(i, j)] for (i, j) in part])
+            check(_fn("compress_batched", dtype)(ctx.h, n, ptrs, nb, descs, C.byref(prm), None))
+            ctx.Sync()
+        return S
+
+    def lower_factor_dense(self) -> np.ndarray:
+        """the lower-triangular factor L (after tlr_cholesky) / the lower triangle of A (before) as one dense matrix"""
+        nt, nb = self.nt, self.nb
+        out = np.zeros((nt * nb, nt * nb))
+        d = self.diag.cpu().numpy()
+        for k in range(nt):
+            out[k * nb:(k + 1) * nb, k * nb:(k + 1) * nb] = np.tril(d[k].reshape(nb, nb).T)
+        for j in range(nt):
+            for i in range(j + 1, nt):
+                out[i * nb:(i + 1) * nb, j * nb:(j + 1) * nb] = self.low.GetTile(i, j).to_dense()
+        return out
+
+
+def tlr_cholesky(S: SymTileMatrix, ctx: RunContext, params: CompressionParameters, info: torch.Tensor | None = None,
+                 potrf_info: torch.Tensor | None = None):
+    """Right-looking tile Cholesky A = L L^T in place (hcb_?tlr_potrf): per step k -- potrf of the dense diagonal tile, the
+    panel solve A(i,k) := A(i,k) L_kk^-T on the V factors of the block column, the symmetric updates of the diagonal
+    tiles, and ONE batched recompressing update A(i,j) -= A(i,k) A(j,k)^T for all i > j > k (HCore::Gemm with
+    opB = Trans).  Asynchronous; potrf_info (int32[nt], optional) receives LAPACK's info per diagonal tile."""
+    nt, nb = S.nt, S.nb
+    esz = S.diag.element_size()
+    dptr = (C.c_void_p * nt)(*[S.diag.data_ptr() + esz * nb * nb * k for k in range(nt)])
+    prm = params.c()
+    check(_fn("tlr_potrf", S.dtype)(ctx.h, nt, nb, dptr, nb, S.low.descs, C.byref(prm),
+                                    None if info is None else info.data_ptr(),
+                                    None if potrf_info is None else potrf_info.data_ptr()))

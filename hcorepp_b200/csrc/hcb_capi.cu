@@ -8,6 +8,7 @@
 #include "kernels_svd.cuh"
 #include "kernels_svd_rx.cuh"
 #include "kernels_tlr.cuh"
+#include "kernels_chol.cuh"
 
 #include <algorithm>
 #include <type_traits>
@@ -1120,14 +1121,14 @@ int t_compress_full(hcb_ctx *ctx, int64_t n64, const T *const *dense, int64_t ld
 // the small factor B = Q^T A (k1 x n) goes through the batched SVD pipeline, U = Q U_B, V = Sigma W^T.  A tile whose
 // captured spectrum has not decayed two decades below the truncation threshold within k1 - 8 values is flagged on the
 // device and re-done with the full SVD.  ~0.5 GFLOP of GEMM-shaped work per 1024^2 tile instead of a 40 GFLOP Jacobi.
-constexpr int SKETCH_K = 96, SKETCH_TAIL = 8;
+constexpr int SKETCH_K = 96, SKETCH_K2 = 288, SKETCH_TAIL = 8;  // second, wider sketch for the tiles the first one rejects
 
 template<typename T>
 int t_compress_sketched(hcb_ctx *ctx, int cnt, const T *const *dense, int64_t ld, const hcb_tile *out,
-                        const hcb_compress_params *prm, std::vector<int> &redo) {
+                        const hcb_compress_params *prm, std::vector<int> &redo, int sketch_k = SKETCH_K) {
     // A ~ Qx Qx^T A, Qx = orth(A Omega) (m x k1).  B^T = A^T Qx = Qb Rb (n x k1 panel QR), Rb^T = Ub S Z^T (k1 x k1 Jacobi:
     // LEFT vectors Ub to high relative accuracy), so A ~ (Qx Ub) S (Qb Z)^T:  U = Qx Ub,  V^T = Qb [Z S ; 0].
-    const int k1 = SKETCH_K, nblk = cdiv(k1, NBQ);
+    const int k1 = sketch_k, nblk = cdiv(k1, NBQ);
     int m = 0, n = 0;
     for (int t = 0; t < cnt; ++t) { m = std::max(m, out[t].m); n = std::max(n, out[t].n); }
     const SvdJobLayout<T> L(k1, k1);
@@ -1261,12 +1262,251 @@ int t_compress_batched(hcb_ctx *ctx, int64_t n64, const T *const *dense, int64_t
         const int cnt = (int) std::min<int64_t>(chunk, n64 - c0);
         std::vector<int> redo;
         HCB_TRY(t_compress_sketched<T>(ctx, cnt, dense + c0, ld, out + c0, prm, redo));
-        if (!redo.empty()) {  // spectrum too flat for the sketch: full SVD for those tiles
+        if (!redo.empty() && mn_min >= 3 * SKETCH_K2) {
+            // rank beyond the first sketch (e.g. neighbouring clusters of a covariance matrix: ranks 100-200 at nb = 1024):
+            // a second, 288-column sketch before giving up on sketching
+            std::vector<const T *> rd(redo.size());
+            std::vector<hcb_tile> ro(redo.size());
+            for (size_t i = 0; i < redo.size(); ++i) { rd[i] = dense[c0 + redo[i]]; ro[i] = out[c0 + redo[i]]; }
+            std::vector<int> redo2, again;
+            for (size_t b0 = 0; b0 < rd.size(); b0 += 128) {
+                const int bc = (int) std::min<size_t>(128, rd.size() - b0);
+                redo2.clear();
+                HCB_TRY(t_compress_sketched<T>(ctx, bc, rd.data() + b0, ld, ro.data() + b0, prm, redo2, SKETCH_K2));
+                for (int r : redo2) again.push_back(redo[b0 + r]);
+            }
+            redo.swap(again);
+        }
+        if (!redo.empty()) {  // spectrum too flat for the sketches: full SVD for those tiles
             std::vector<const T *> rd(redo.size());
             std::vector<hcb_tile> ro(redo.size());
             for (size_t i = 0; i < redo.size(); ++i) { rd[i] = dense[c0 + redo[i]]; ro[i] = out[c0 + redo[i]]; }
             HCB_TRY(t_compress_full<T>(ctx, (int64_t) redo.size(), rd.data(), ld, ro.data(), prm, d_info));
             HCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return HCB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TLR Cholesky pieces: dense potrf / trsm / syrk of the kernel table + the batched tile forms
+// ---------------------------------------------------------------------------------------------------------------
+template<typename T>
+int t_potrf_lower(hcb_ctx *ctx, int64_t n64, T *A, int64_t lda, int32_t *d_info, T *D) {
+    const int n = (int) n64;
+    k_diag_upper<T><<<cdiv(n, 256), 256, 0, ctx->stream>>>(0, n, A, (int) lda, D);
+    HCB_LAUNCH_CHECK("k_diag_upper");
+    for (int j0 = 0; j0 < n; j0 += CH_NB) {
+        const int jb = std::min(CH_NB, n - j0);
+        if (j0 > 0) {  // left-looking update of block column j0 (all rows from j0 down) with the columns to its left
+            GemmProb<T> g{A + j0, A + j0, A + j0 + (size_t) j0 * lda, n - j0, jb, j0, (int) lda, (int) lda, (int) lda, 0, 1, T(-1), T(1)};
+            const GemmProb<T> *d;
+            HCB_TRY(upload_one(ctx, g, &d));
+            HCB_TRY(launch_gemm<T>(ctx, d, 1, n - j0, jb));
+        }
+        k_potrf_panel<T><<<1 + cdiv(std::max(0, n - j0 - jb), 256), 256, 0, ctx->stream>>>(A, n, (int) lda, j0, jb, d_info);
+        HCB_LAUNCH_CHECK("k_potrf_panel");
+    }
+    k_diag_upper<T><<<cdiv(n, 256), 256, 0, ctx->stream>>>(1, n, A, (int) lda, D);
+    HCB_LAUNCH_CHECK("k_diag_upper");
+    return HCB_OK;
+}
+
+template<typename T>
+int t_potrf(hcb_ctx *ctx, int uplo, int64_t n, T *A, int64_t lda, int32_t *d_info) {
+    HCB_TRY(check_ctx(ctx));
+    if (n <= 0) return HCB_OK;
+    if (lda < n) return fail(HCB_EINVAL, "potrf: lda < n");
+    const bool upper = (uplo == 'U' || uplo == 'u' || uplo == 1);
+    const size_t eD = align_up((size_t) n * CH_NB, 32), eS = upper ? (size_t) n * n : 0;
+    HCB_TRY(ensure_ws(ctx, (eD + 2 * eS) * sizeof(T) + 1024));  // (once, up front: growing the arena frees the old one)
+    T *D = reinterpret_cast<T *>(ctx->ws), *S = D + eD;
+    if (d_info) HCB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), ctx->stream));
+    if (!upper) return t_potrf_lower<T>(ctx, n, A, lda, d_info, D);
+    // A = U^T U with the upper triangle stored: factor the transposed triangle as a lower problem, transpose back
+    HCB_TRY(t_copy<T>(ctx, A, (int) lda, S, (int) n, (int) n, (int) n, 1, T(1)));      // S = A^T (lower of S = upper of A)
+    HCB_TRY(t_potrf_lower<T>(ctx, n, S, n, d_info, D));
+    // write back only the upper triangle (incl. diagonal) of A := (lower of S)^T
+    T *S2 = S + eS;
+    HCB_TRY(t_copy<T>(ctx, S, (int) n, S2, (int) n, (int) n, (int) n, 1, T(1)));       // S2 = S^T
+    return t_lacpy<T>(ctx, 'U', n, n, S2, n, A, lda);
+}
+
+template<typename T>
+int t_trsm(hcb_ctx *ctx, int side, int uplo, int trans, int diag, int64_t m, int64_t n, T alpha, const T *A, int64_t lda,
+           T *B, int64_t ldb) {
+    HCB_TRY(check_ctx(ctx));
+    if (m <= 0 || n <= 0) return HCB_OK;
+    const int right = (side == 'R' || side == 'r' || side == 1), upper = (uplo == 'U' || uplo == 'u' || uplo == 1);
+    const int tr = (trans != 0 && trans != 'N' && trans != 'n'), unit = (diag == 'U' || diag == 'u' || diag == 1);
+    const int nrhs = (int) (right ? m : n);
+    k_trsm_generic<T><<<cdiv(nrhs, 64), 64, 0, ctx->stream>>>(right, upper, tr, unit, (int) m, (int) n, alpha, A, (int) lda, B, (int) ldb);
+    HCB_LAUNCH_CHECK("k_trsm_generic");
+    return HCB_OK;
+}
+
+template<typename T>
+int t_syrk(hcb_ctx *ctx, int uplo, int trans, int64_t n, int64_t k, T alpha, const T *A, int64_t lda, T beta, T *Cm, int64_t ldc) {
+    HCB_TRY(check_ctx(ctx));
+    if (n <= 0) return HCB_OK;
+    const int upper = (uplo == 'U' || uplo == 'u' || uplo == 1), tr = (trans != 0 && trans != 'N' && trans != 'n');
+    HCB_TRY(ensure_ws(ctx, (size_t) n * n * sizeof(T) + 1024));
+    T *W = reinterpret_cast<T *>(ctx->ws);
+    // W = op(A) op(A)^T : NoTrans -> A (n x k) A^T ; Trans -> A^T (n x k) A with A stored k x n
+    GemmProb<T> g{A, A, W, (int) n, (int) n, (int) k, (int) lda, (int) lda, (int) n, tr, tr ? 0 : 1, T(1), T(0)};
+    const GemmProb<T> *d;
+    HCB_TRY(upload_one(ctx, g, &d));
+    HCB_TRY(launch_gemm<T>(ctx, d, 1, (int) n, (int) n));
+    dim3 block(32, 8), grid(cdiv(n, 32), cdiv(n, 8));
+    k_syrk_combine<T><<<grid, block, 0, ctx->stream>>>(upper, (int) n, alpha, W, beta, Cm, (int) ldc);
+    HCB_LAUNCH_CHECK("k_syrk_combine");
+    return HCB_OK;
+}
+
+template<typename T>
+int t_fill_triangle(hcb_ctx *ctx, int uplo, int64_t n, T *A, int64_t lda, T value) {
+    HCB_TRY(check_ctx(ctx));
+    if (n <= 0) return HCB_OK;
+    dim3 block(32, 8), grid(cdiv(n, 32), cdiv(n, 8));
+    k_fill_triangle<T><<<grid, block, 0, ctx->stream>>>((uplo == 'U' || uplo == 'u' || uplo == 1) ? 1 : 0, (int) n, A, (int) lda, value);
+    HCB_LAUNCH_CHECK("k_fill_triangle");
+    return HCB_OK;
+}
+
+template<typename T>
+int t_symmetrize(hcb_ctx *ctx, int uplo, int64_t n, T *A, int64_t lda) {
+    HCB_TRY(check_ctx(ctx));
+    if (n <= 0) return HCB_OK;
+    dim3 block(32, 8), grid(cdiv(n, 32), cdiv(n, 8));
+    k_symmetrize<T><<<grid, block, 0, ctx->stream>>>((uplo == 'U' || uplo == 'u' || uplo == 1) ? 1 : 0, (int) n, A, (int) lda);
+    HCB_LAUNCH_CHECK("k_symmetrize");
+    return HCB_OK;
+}
+
+// V := V L^-T for a batch of compressed tiles X (the tile-Cholesky panel solve A(i,k) := A(i,k) L_kk^-T acts on the
+// right factor only), L = lower Cholesky factors (one per tile; usually the same diagonal tile for a whole block column)
+template<typename T>
+int t_tlr_trsm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *X, const T *const *dL, const int64_t *ldl) {
+    HCB_TRY(check_ctx(ctx));
+    if (n64 <= 0) return HCB_OK;
+    if (!X || !dL || !ldl) return fail(HCB_EINVAL, "tlr_trsm_batched: null argument");
+    const int n = (int) n64;
+    int cols = 0, rkb = 0;
+    std::vector<int> lds(n);
+    for (int t = 0; t < n; ++t) {
+        if (X[t].type != HCB_TILE_COMPRESSED || !X[t].d_rank || !X[t].d_data || !dL[t])
+            return fail(HCB_EINVAL, "tlr_trsm_batched: X must be compressed tiles, L non-null");
+        cols = std::max(cols, X[t].n);
+        rkb = std::max(rkb, bound_of(X[t]));
+        lds[t] = (int) ldl[t];
+    }
+    const int nsteps = cdiv(cols, CH_NB);
+    const size_t bG = align_up(sizeof(GemmProb<T>) * (size_t) nsteps * n, 256), bT = align_up(sizeof(TrsmProb<T>) * n, 256),
+                 bX = align_up(sizeof(hcb_tile) * n, 256), bL = align_up(sizeof(T *) * n, 256), bI = align_up(sizeof(int) * n, 256);
+    HCB_TRY(ensure_ws(ctx, bG + bT + bX + bL + bI + 256));
+    char *base = reinterpret_cast<char *>(ctx->ws);
+    auto *d_g = reinterpret_cast<GemmProb<T> *>(base);
+    auto *d_t = reinterpret_cast<TrsmProb<T> *>(base + bG);
+    auto *d_x = reinterpret_cast<hcb_tile *>(base + bG + bT);
+    auto *d_l = reinterpret_cast<const T **>(base + bG + bT + bX);
+    auto *d_i = reinterpret_cast<int *>(base + bG + bT + bX + bL);
+    std::vector<hcb_tile> xs(X, X + n);
+    std::vector<const T *> ls(dL, dL + n);
+    HCB_TRY(stage_array(ctx, xs, d_x));
+    HCB_TRY(stage_array(ctx, ls, d_l));
+    HCB_TRY(stage_array(ctx, lds, d_i));
+    k_setup_trsm_tiles<T><<<cdiv(nsteps * n, 128), 128, 0, ctx->stream>>>(d_x, d_l, d_i, n, nsteps, d_g, d_t);
+    HCB_LAUNCH_CHECK("k_setup_trsm_tiles");
+    for (int step = 0; step < nsteps; ++step) {
+        if (step > 0) HCB_TRY(launch_gemm<T>(ctx, d_g + (size_t) step * n, n, rkb, CH_NB));
+        dim3 grid(std::max(1, cdiv(rkb, 128)), n);
+        k_trsm_rlt_block<T><<<grid, 128, 0, ctx->stream>>>(d_t, step * CH_NB, CH_NB);
+        HCB_LAUNCH_CHECK("k_trsm_rlt_block");
+    }
+    return HCB_OK;
+}
+
+// C[t] := beta C[t] + alpha A[t] A[t]^T for compressed A[t] = U V and dense C[t] (m x m): HCore<T>::Syrk with a compressed
+// operand (HCore.cpp:484-575) without the triangle fill (the caller keeps C symmetric / reads one triangle)
+template<typename T>
+int t_tlr_syrk_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, T *const *dC, const int64_t *ldc, T alpha, T beta) {
+    HCB_TRY(check_ctx(ctx));
+    if (n64 <= 0) return HCB_OK;
+    if (!A || !dC || !ldc) return fail(HCB_EINVAL, "tlr_syrk_batched: null argument");
+    const int n = (int) n64;
+    int m = 0, cols = 0, rkb = 0, cap = 0;
+    std::vector<int> lds(n);
+    for (int t = 0; t < n; ++t) {
+        if (A[t].type != HCB_TILE_COMPRESSED || !A[t].d_rank || !A[t].d_data || !dC[t])
+            return fail(HCB_EINVAL, "tlr_syrk_batched: A must be compressed tiles, C non-null");
+        m = std::max(m, A[t].m); cols = std::max(cols, A[t].n);
+        rkb = std::max(rkb, bound_of(A[t])); cap = std::max(cap, A[t].max_rank);
+        lds[t] = (int) ldc[t];
+    }
+    const size_t slab = align_up((size_t) cap * cap, 32) + align_up((size_t) m * cap, 32);
+    const size_t bG = align_up(sizeof(GemmProb<T>) * n, 256), bX = align_up(sizeof(hcb_tile) * n, 256),
+                 bC = align_up(sizeof(T *) * n, 256), bI = align_up(sizeof(int) * n, 256);
+    HCB_TRY(ensure_ws(ctx, 3 * bG + bX + bC + bI + slab * sizeof(T) * n + 512));
+    char *base = reinterpret_cast<char *>(ctx->ws);
+    auto *g1 = reinterpret_cast<GemmProb<T> *>(base), *g2 = reinterpret_cast<GemmProb<T> *>(base + bG),
+         *g3 = reinterpret_cast<GemmProb<T> *>(base + 2 * bG);
+    auto *d_x = reinterpret_cast<hcb_tile *>(base + 3 * bG);
+    auto *d_c = reinterpret_cast<T **>(base + 3 * bG + bX);
+    auto *d_i = reinterpret_cast<int *>(base + 3 * bG + bX + bC);
+    T *ws = reinterpret_cast<T *>(base + align_up(3 * bG + bX + bC + bI, 256));
+    std::vector<hcb_tile> xs(A, A + n);
+    std::vector<T *> cs(dC, dC + n);
+    HCB_TRY(stage_array(ctx, xs, d_x));
+    HCB_TRY(stage_array(ctx, cs, d_c));
+    HCB_TRY(stage_array(ctx, lds, d_i));
+    k_setup_syrk_tiles<T><<<cdiv(n, 128), 128, 0, ctx->stream>>>(d_x, d_c, d_i, n, ws, slab, alpha, beta, g1, g2, g3);
+    HCB_LAUNCH_CHECK("k_setup_syrk_tiles");
+    HCB_TRY(launch_gemm<T>(ctx, g1, n, rkb, rkb));
+    HCB_TRY(launch_gemm<T>(ctx, g2, n, m, rkb));
+    return launch_gemm<T>(ctx, g3, n, m, m);
+}
+
+// Right-looking tile Cholesky A = L L^T of a symmetric positive definite matrix held as dense diagonal tiles + compressed
+// tiles below the diagonal (the reference has the tile routines HCore<T>::Potrf / Trsm / Syrk / Gemm(aCholesky) but no
+// driver):  for k:  L_kk = potrf(A_kk);  A_ik := A_ik L_kk^-T (i > k);  A_ii -= A_ik A_ik^T;
+// A_ij -= A_ik A_jk^T (i > j > k, ONE batched recompressing call).  low = nt x nt column-major grid, entries i > j used.
+template<typename T>
+int t_tlr_potrf(hcb_ctx *ctx, int64_t nt, int64_t nb, T *const *diag, int64_t ldd, const hcb_tile *low,
+                const hcb_compress_params *prm, int32_t *d_info, int32_t *d_potrf_info) {
+    HCB_TRY(check_ctx(ctx));
+    if (nt <= 0) return HCB_OK;
+    if (!diag || !low || !prm || nb <= 0 || ldd < nb) return fail(HCB_EINVAL, "tlr_potrf: bad argument");
+    if (d_info) HCB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t) * (size_t) (nt * nt), ctx->stream));
+    if (d_potrf_info) HCB_CUDA(cudaMemsetAsync(d_potrf_info, 0, sizeof(int32_t) * (size_t) nt, ctx->stream));
+    std::vector<hcb_tile> col, a, b, c;
+    std::vector<const T *> ls;
+    std::vector<T *> cs;
+    std::vector<int64_t> lds;
+    for (int64_t k = 0; k < nt; ++k) {
+        HCB_TRY(ensure_ws(ctx, align_up((size_t) nb * CH_NB, 32) * sizeof(T) + 1024));
+        HCB_TRY(t_potrf_lower<T>(ctx, nb, diag[k], ldd, d_potrf_info ? d_potrf_info + k : nullptr, reinterpret_cast<T *>(ctx->ws)));
+        const int64_t cnt = nt - k - 1;
+        if (cnt <= 0) break;
+        col.assign(cnt, hcb_tile{});
+        ls.assign(cnt, diag[k]);
+        lds.assign(cnt, ldd);
+        cs.resize(cnt);
+        for (int64_t i = k + 1; i < nt; ++i) {
+            col[i - k - 1] = low[i + k * nt];
+            cs[i - k - 1] = diag[i];
+        }
+        HCB_TRY(t_tlr_trsm_batched<T>(ctx, cnt, col.data(), ls.data(), lds.data()));
+        HCB_TRY(t_tlr_syrk_batched<T>(ctx, cnt, col.data(), cs.data(), lds.data(), T(-1), T(1)));
+        a.clear(); b.clear(); c.clear();
+        for (int64_t j = k + 1; j < nt; ++j)
+            for (int64_t i = j + 1; i < nt; ++i) {
+                a.push_back(low[i + k * nt]);
+                b.push_back(low[j + k * nt]);
+                c.push_back(low[i + j * nt]);
+            }
+        if (!a.empty()) {
+            // d_info: sticky over the steps, indexed by the position of the C tile in the step's batch (diagnostics)
+            HCB_TRY(t_tlr_gemm_batched<T>(ctx, (int64_t) a.size(), a.data(), 0, b.data(), 1, c.data(), T(-1), T(1), prm, d_info, false));
         }
     }
     return HCB_OK;
@@ -1486,6 +1726,34 @@ int hcb_memset(hcb_ctx *c, void *dst, int value, size_t bytes) {
                             const hcb_tile *C, const int64_t *owned, int64_t n_owned, int64_t k_begin,                \
                             int64_t k_end, T alpha, T beta, const hcb_compress_params *p, int32_t *info) {            \
         return t_tlr_matmul<T>(c, mt, nt, kt, A, B, C, owned, n_owned, k_begin, k_end, alpha, beta, p, info);        \
+    }                                                                                                                 \
+    int hcb_##P##potrf(hcb_ctx *c, int uplo, int64_t n, T *A, int64_t lda, int32_t *d_info) {                          \
+        return t_potrf<T>(c, uplo, n, A, lda, d_info);                                                               \
+    }                                                                                                                 \
+    int hcb_##P##trsm(hcb_ctx *c, int side, int uplo, int trans, int diag, int64_t m, int64_t n, T alpha, const T *A,  \
+                      int64_t lda, T *B, int64_t ldb) {                                                               \
+        return t_trsm<T>(c, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb);                                   \
+    }                                                                                                                 \
+    int hcb_##P##syrk(hcb_ctx *c, int uplo, int trans, int64_t n, int64_t k, T alpha, const T *A, int64_t lda, T beta,  \
+                      T *Cm, int64_t ldc) {                                                                           \
+        return t_syrk<T>(c, uplo, trans, n, k, alpha, A, lda, beta, Cm, ldc);                                        \
+    }                                                                                                                 \
+    int hcb_##P##fill_triangle(hcb_ctx *c, int uplo, int64_t n, T *A, int64_t lda, T value) {                          \
+        return t_fill_triangle<T>(c, uplo, n, A, lda, value);                                                        \
+    }                                                                                                                 \
+    int hcb_##P##symmetrize(hcb_ctx *c, int uplo, int64_t n, T *A, int64_t lda) {                                      \
+        return t_symmetrize<T>(c, uplo, n, A, lda);                                                                  \
+    }                                                                                                                 \
+    int hcb_##P##tlr_trsm_batched(hcb_ctx *c, int64_t n, const hcb_tile *X, const T *const *dL, const int64_t *ldl) {  \
+        return t_tlr_trsm_batched<T>(c, n, X, dL, ldl);                                                              \
+    }                                                                                                                 \
+    int hcb_##P##tlr_syrk_batched(hcb_ctx *c, int64_t n, const hcb_tile *A, T *const *dC, const int64_t *ldc, T alpha,  \
+                                  T beta) {                                                                           \
+        return t_tlr_syrk_batched<T>(c, n, A, dC, ldc, alpha, beta);                                                 \
+    }                                                                                                                 \
+    int hcb_##P##tlr_potrf(hcb_ctx *c, int64_t nt, int64_t nb, T *const *diag, int64_t ldd, const hcb_tile *low,       \
+                           const hcb_compress_params *p, int32_t *info, int32_t *potrf_info) {                        \
+        return t_tlr_potrf<T>(c, nt, nb, diag, ldd, low, p, info, potrf_info);                                       \
     }                                                                                                                 \
     int hcb_##P##tlr_matmul_panel_step(hcb_ctx *c, int64_t mt, int64_t nt, const hcb_tile *Apan, const hcb_tile *Bpan, \
                                        const hcb_tile *C, T alpha, T beta, const hcb_compress_params *p, int32_t *info, \

@@ -132,6 +132,33 @@ typedef struct hcb_tile {
                      int64_t ldvt); /* SomeVec/SomeVec; dA destroyed */                                                \
     int hcb_##P##trmm(hcb_ctx *, int side, int uplo, int trans, int diag, int64_t m, int64_t n, T alpha, const T *dA,   \
                       int64_t lda, T *dB, int64_t ldb);                                                                \
+    /* ---- TLR Cholesky pieces of the kernel table (kernels.hpp potrf / trsm / syrk / FillMatrixTriangle /          */  \
+    /* Symmetrize; src/kernels/omp/kernels.cpp:234-303).  uplo 'L'/'U', side 'L'/'R', trans 0/'N' or 1/'T', diag      */  \
+    /* 'N'/'U'.  potrf: in place, the other triangle is left as it was; d_info (device int32, may be NULL) receives  */  \
+    /* LAPACK's info (0, or 1-based index of the first non-positive pivot).                                          */  \
+    int hcb_##P##potrf(hcb_ctx *, int uplo, int64_t n, T *dA, int64_t lda, int32_t *d_info);                            \
+    int hcb_##P##trsm(hcb_ctx *, int side, int uplo, int trans, int diag, int64_t m, int64_t n, T alpha, const T *dA,   \
+                      int64_t lda, T *dB, int64_t ldb);                                                                \
+    int hcb_##P##syrk(hcb_ctx *, int uplo, int trans, int64_t n, int64_t k, T alpha, const T *dA, int64_t lda, T beta,   \
+                      T *dC, int64_t ldc);                                                                             \
+    int hcb_##P##fill_triangle(hcb_ctx *, int uplo, int64_t n, T *dA, int64_t lda, T value); /* strict triangle */      \
+    int hcb_##P##symmetrize(hcb_ctx *, int uplo, int64_t n, T *dA, int64_t lda);           /* copy uplo onto the other */ \
+    /* Batched tile forms for the Cholesky driver (HOST arrays of descriptors / device pointers):                    */  \
+    /*   tlr_trsm_batched: X[t] := X[t] * L[t]^-T for compressed X (acts on the V factor only; HCore<T>::Trsm,        */  \
+    /*                     HCore.cpp:624-647, in this library's V = rank x n convention)                             */  \
+    /*   tlr_syrk_batched: C[t] := beta*C[t] + alpha*A[t]*A[t]^T, A compressed, C dense m x m (HCore<T>::Syrk with a  */  \
+    /*                     compressed operand, HCore.cpp:484-575; both triangles are updated)                        */  \
+    /*   tlr_potrf:        right-looking tile Cholesky of an SPD matrix: nt dense nb x nb diagonal tiles (diag[k], ldd)*/  \
+    /*                     + compressed tiles below the diagonal (low: nt x nt column-major grid, entries i > j):     */  \
+    /*                     potrf / trsm panel / syrk / ONE batched recompressing GEMM (opB = Trans) per step.  The    */  \
+    /*                     reference has no such driver.  d_potrf_info: device int32[nt] or NULL;      */  \
+    /*                     d_info: device int32[nt*nt] or NULL, flags of the recompressing updates, sticky over the  */  \
+    /*                     steps, indexed by the tile's position in its step's batch (diagnostics).                  */  \
+    int hcb_##P##tlr_trsm_batched(hcb_ctx *, int64_t n_tiles, const hcb_tile *X, const T *const *dL, const int64_t *ldl); \
+    int hcb_##P##tlr_syrk_batched(hcb_ctx *, int64_t n_tiles, const hcb_tile *A, T *const *dC, const int64_t *ldc,      \
+                                  T alpha, T beta);                                                                    \
+    int hcb_##P##tlr_potrf(hcb_ctx *, int64_t nt, int64_t nb, T *const *diag, int64_t ldd, const hcb_tile *low,         \
+                           const hcb_compress_params *p, int32_t *d_info, int32_t *d_potrf_info);                      \
     /* ---- (3) fused batched fast path -------------------------------------------------------------------------- */  \
     /* C[t] = alpha*op(A[t])*op(B[t]) + beta*C[t] for t < n_tiles, all eight Dense/Compressed operand mixes of      */  \
     /* HCore<T>::Gemm (HCore.cpp:36-313; the batch must be mix-homogeneous), recompression included, ranks on the   */  \

@@ -4,7 +4,7 @@
 OUT=${1:-launches_step}
 mkdir -p gpurun_out
 timeout 2000 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 40000 --csv --log-file gpurun_out/$OUT.csv \
-    python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --compress-tiles 0 --no-strong > gpurun_out/$OUT.log 2>&1
+    python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --compress-tiles 0 --no-strong --no-cholesky > gpurun_out/$OUT.log 2>&1
 echo "ncu rc=$?"
 N=$(grep -c gpu__time_duration gpurun_out/$OUT.csv)
 echo "launches: $N"

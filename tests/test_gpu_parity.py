@@ -658,3 +658,131 @@ def test_cpp_host_layer_replays_reference_tests():
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "0 failure(s)" in r.stdout
+
+
+# ------------------------------------------------------------------------------------------------ TLR Cholesky (8f row 1)
+def _spd(rng, n, dt=np.float64):
+    a = rng.standard_normal((n, n))
+    return np.asfortranarray((a @ a.T / n + np.eye(n)).astype(dt))
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("n", [1, 31, 64, 300, 1024])
+def test_potrf_vs_oracle(hc, ctx, n, dt):
+    """hcb_?potrf == HCore<T>::Potrf (HCore.cpp:586-621 -> lapack::potrf): in place, the other triangle untouched, both uplo."""
+    rng = np.random.default_rng(n)
+    A = _spd(rng, n, dt)
+    tol = 1e-11 if dt == np.float64 else 2e-4
+    for uplo in ("L", "U"):
+        t = hc.DenseTile(A.copy(), ctx)
+        assert hc.HCore.Potrf(t, uplo, ctx) == 0
+        o = O.DenseTile(np.asfortranarray(A.copy()))
+        O.hcore_potrf(o, uplo)
+        assert relerr(t.to_numpy(), o.data) < tol * max(1, n / 64), (uplo, n)
+    with pytest.raises(RuntimeError, match="dense"):
+        hc.HCore.Potrf(hc.CompressedTile.from_uv(np.ones((4, 1)), np.ones((1, 4)), ctx), "L", ctx)
+    if n >= 31:  # LAPACK's info: 1-based index of the first non-positive pivot
+        bad = A.copy()
+        bad[17, 17] = -5.0
+        assert hc.HCore.Potrf(hc.DenseTile(bad, ctx), "L", ctx) == 18
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_trsm_syrk_triangle_helpers_vs_oracle(hc, ctx, dt):
+    """hcb_?trsm (all side / uplo / trans / diag combinations), hcb_?syrk, fill_triangle, symmetrize and the HCore::Trsm /
+    Syrk mirrors against the oracle (scipy / numpy restatements pinned against the compiled reference in test_oracle.py)."""
+    import scipy.linalg as sl
+    rng = np.random.default_rng(5)
+    m, n = 70, 45
+    tol = 1e-11 if dt == np.float64 else 5e-4
+    for side in "LR":
+        na = m if side == "L" else n
+        Tm = (0.1 * rng.standard_normal((na, na)) + 4 * np.eye(na)).astype(dt)  # (well conditioned with a unit diagonal too)
+        for uplo in "LU":
+            for trans in (0, 1):
+                for diag in "NU":
+                    B = rng.standard_normal((m, n)).astype(dt)
+                    dA, dB = dev(Tm), dev(B)
+                    ok(fn("trsm", dt)(ctx.h, ord(side), ord(uplo), trans, ord(diag), m, n, ct(dt)(1.5), dA.data_ptr(), na,
+                                      dB.data_ptr(), m))
+                    tri = np.tril(Tm) if uplo == "L" else np.triu(Tm)
+                    if diag == "U":
+                        tri = tri - np.diag(np.diag(tri)) + np.eye(na)
+                    op = (tri.T if trans else tri).astype(np.float64)
+                    ref = 1.5 * (np.linalg.solve(op, B.astype(np.float64)) if side == "L"
+                                 else np.linalg.solve(op.T, B.astype(np.float64).T).T)
+                    assert relerr(host(dB, (m, n)), ref) < tol, (side, uplo, trans, diag)
+    # syrk: only the uplo triangle is touched
+    nn, kk = 60, 60
+    A, Cm = rng.standard_normal((nn, kk)).astype(dt), rng.standard_normal((nn, nn)).astype(dt)
+    for uplo in "LU":
+        for ta in (False, True):
+            tc = hc.DenseTile(Cm.copy(), ctx)
+            hc.HCore.Syrk(-1.0, hc.DenseTile(A.copy(), ctx), ta, uplo, 0.5, tc, ctx)
+            oc = O.DenseTile(np.asfortranarray(Cm.copy()))
+            O.hcore_syrk_dense(dt(-1.0), O.DenseTile(np.asfortranarray(A.copy())), ta, uplo, dt(0.5), oc)
+            assert relerr(tc.to_numpy(), oc.data) < tol, (uplo, ta)
+    # FillMatrixTriangle / Symmetrize (omp/kernels.cpp:245-262, 283-303)
+    for uplo in "LU":
+        d = dev(Cm)
+        ok(fn("fill_triangle", dt)(ctx.h, ord(uplo), nn, d.data_ptr(), nn, ct(dt)(0.0)))
+        ref = np.tril(Cm) if uplo == "U" else np.triu(Cm)
+        assert np.array_equal(host(d, (nn, nn)), ref)
+        d = dev(Cm)
+        ok(fn("symmetrize", dt)(ctx.h, ord(uplo), nn, d.data_ptr(), nn))
+        tri = np.triu(Cm) if uplo == "U" else np.tril(Cm)
+        assert np.array_equal(host(d, (nn, nn)), tri + tri.T - np.diag(np.diag(Cm)))
+    # HCore::Trsm mirror: reference semantics (solve on B's V buffer viewed m x rank)
+    Lm = np.asfortranarray((np.tril(rng.standard_normal((m, m))) + 4 * np.eye(m)).astype(dt))
+    U, V = lowrank(rng, m, m, 9, dt)
+    for side, trans in (("L", False), ("L", True)):
+        tB = hc.CompressedTile.from_uv(U, V, ctx)
+        hc.HCore.Trsm(side, "L", trans, "N", 2.0, hc.DenseTile(Lm.copy(), ctx), tB, ctx)
+        oB = O.CompressedTile.from_uv(U, V)
+        O.hcore_trsm(side, "L", trans, "N", dt(2.0), O.DenseTile(np.asfortranarray(Lm.copy())), oB)
+        assert relerr(tB.GetVMatrix(), oB.V) < tol and relerr(tB.GetUMatrix(), oB.U) == 0.0
+    with pytest.raises(RuntimeError, match="compressed"):
+        hc.HCore.Trsm("L", "L", False, "N", 1.0, hc.DenseTile(Lm, ctx), hc.DenseTile(Lm, ctx), ctx)
+
+
+@pytest.mark.parametrize("nt,nb,acc", [(4, 256, 1e-8), (5, 128, 1e-5), (3, 512, 1e-8)])
+def test_tlr_cholesky_vs_oracle(hc, ctx, nt, nb, acc):
+    """Tile Cholesky driver (hcb_dtlr_potrf) on a synthetic Matern covariance matrix against the oracle's loop over the
+    reference's tile routines (oracle.tile_cholesky): factor L within 10*acc (relative Frobenius), tile ranks +/-1, and the
+    size-independent property ||A - L L^T|| / ||A|| <= 10*acc."""
+    pts, tile = O.covariance_tiles(nt, nb, ell=0.1, nugget=1e-2, seed=nt)
+    p, po = hc.CompressionParameters(acc), O.CompressionParameters(acc)
+    S = hc.SymTileMatrix.from_tiles(tile, nt, nb, torch.float64, ctx, p)
+    diag = [tile(k, k) for k in range(nt)]
+    low = {(i, j): O.CompressedTile.compress(tile(i, j), po) for j in range(nt) for i in range(j + 1, nt)}
+    for (i, j), t in low.items():  # same compressed inputs on both sides (the compressing constructor has its own test)
+        assert abs(S.low.GetTile(i, j).GetTileRank() - t.rank) <= 1
+    pinfo = torch.full((nt,), -1, dtype=torch.int32, device="cuda")
+    hc.tlr_cholesky(S, ctx, p, potrf_info=pinfo)
+    ctx.Sync()
+    assert int(pinfo.abs().max().item()) == 0
+    O.tile_cholesky(diag, low, po)
+    Lg = S.lower_factor_dense()
+    Lo = np.zeros_like(Lg)
+    for k in range(nt):
+        Lo[k * nb:(k + 1) * nb, k * nb:(k + 1) * nb] = np.tril(diag[k])
+    for (i, j), t in low.items():
+        Lo[i * nb:(i + 1) * nb, j * nb:(j + 1) * nb] = t.to_dense()
+        assert abs(S.low.GetTile(i, j).GetTileRank() - t.rank) <= 1, (i, j)
+    assert relerr(Lg, Lo) <= 10 * acc
+    A = np.block([[tile(i, j) for j in range(nt)] for i in range(nt)])
+    assert relerr(Lg @ Lg.T, A) <= 10 * acc
+
+
+def test_sketched_compression_second_sketch_for_ranks_beyond_96(hc, ctx):
+    """Ranks between the first sketch (96 columns) and the second (288): the tile is rejected by the first range finder on
+    the device and accepted by the wider one -- same rank and product as the reference's full SVD (oracle)."""
+    rng = np.random.default_rng(11)
+    nb, acc = 1024, 1e-8
+    U, _ = np.linalg.qr(rng.standard_normal((nb, 260)))
+    V, _ = np.linalg.qr(rng.standard_normal((nb, 260)))
+    A = np.asfortranarray((U * (0.9 ** np.arange(260))) @ V.T)     # sigma_i = 0.9^i: rank 175 at 1e-8
+    t = hc.CompressedTile.compress(A, hc.CompressionParameters(acc), ctx)
+    o = O.CompressedTile.compress(A, O.CompressionParameters(acc))
+    assert 120 < o.rank < 280 and abs(t.GetTileRank() - o.rank) <= 1
+    assert relerr(t.to_dense(), o.to_dense()) <= 10 * acc

@@ -296,3 +296,40 @@ def test_cholesky_pieces_restatement_matches_reference():
         O.hcore_trsm(side, "L", trans, "N", 2.0, O.DenseTile(np.asfortranarray(Lm.copy())), oB)
         U2, V2 = tB.read()
         assert np.allclose(U2, oB.U) and np.allclose(V2, oB.V, rtol=1e-10, atol=1e-12), (side, trans)
+
+
+def test_tile_cholesky_driver_composition_vs_compiled_reference():
+    """The Cholesky driver loop of the oracle (the reference has tile routines but no driver) with its
+    recompressing update done (a) by the numpy restatement and (b) by the COMPILED reference's HCore::Gemm (opB = Trans):
+    same factor, same ranks; and the factor reproduces the covariance matrix to the compression accuracy."""
+    from oracle import ref as R
+    nt, nb, acc = 4, 96, 1e-6
+    pts, tile = O.covariance_tiles(nt, nb, ell=0.2, nugget=1e-2, seed=3)
+    p = O.CompressionParameters(acc)
+
+    def build():
+        return ([tile(k, k) for k in range(nt)],
+                {(i, j): O.CompressedTile.compress(tile(i, j), p) for j in range(nt) for i in range(j + 1, nt)})
+    d1, l1 = O.tile_cholesky(*build(), p)
+
+    def ref_gemm(a, b, c):
+        # the compiled reference returns NaN for a TRANSPOSED compressed operand outside its aCholesky mode (HCore.cpp:57-110
+        # reads the factors with the wrong shapes), so B^T is handed over as the explicit tile (BV^T)(BU^T), NoTrans
+        ta, tb = R.RefTile.from_uv(a.U, a.V), R.RefTile.from_uv(np.asfortranarray(b.V.T), np.asfortranarray(b.U.T))
+        tc = R.RefTile.from_uv_cap(c.U, c.V, c.max_rank)
+        R.gemm(-1.0, ta, False, tb, False, 1.0, tc, R.Params(acc))
+        u, v = tc.read()
+        c.U, c.V = np.asfortranarray(u), np.asfortranarray(v)
+    d2, l2 = O.tile_cholesky(*build(), p, gemm=ref_gemm)
+    A = np.block([[tile(i, j) for j in range(nt)] for i in range(nt)])
+    for dd, ll in ((d1, l1), (d2, l2)):
+        L = np.zeros_like(A)
+        for k in range(nt):
+            L[k * nb:(k + 1) * nb, k * nb:(k + 1) * nb] = np.tril(dd[k])
+        for (i, j), t in ll.items():
+            L[i * nb:(i + 1) * nb, j * nb:(j + 1) * nb] = t.to_dense()
+        assert np.linalg.norm(A - L @ L.T) / np.linalg.norm(A) <= 10 * acc
+    for key in l1:
+        assert l1[key].rank == l2[key].rank
+        assert np.linalg.norm(l1[key].to_dense() - l2[key].to_dense()) <= 10 * acc * max(1.0, np.linalg.norm(l2[key].to_dense()))
+    assert np.all(np.linalg.eigvalsh(A) > 0)
