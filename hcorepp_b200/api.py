@@ -410,6 +410,65 @@ class TileMatrix:
                 out[j * self.tm:(j + 1) * self.tm, i * self.tn:(i + 1) * self.tn] = self.GetTile(j, i).to_dense()
         return out
 
+    # -- wire / on-disk format: per tile the reference's TileMetadata (Tile.hpp:30-52) + the packed
+    #    buffer UnPackTile hands out (Compressed.cpp:769-779), frozen here as a JSON manifest + one little-endian binary
+    def save(self, path: str):
+        """Persist the matrix for parity runs: `path`.json (manifest: grid, dtype, one TileMetadata record per tile with its
+        byte offset) + `path`.bin (per compressed tile the LIVE factors [U (m x rank) | V (rank x n, ld = rank)] column-major,
+        per dense tile the m x n block)."""
+        import json
+        ranks = self.ranks.cpu().numpy()
+        esz = self.buf.element_size()
+        tiles, off = [], 0
+        with open(path + ".bin", "wb") as f:
+            for lin in range(self.mt * self.nt):
+                o = lin * self.tile_elems
+                if self.compressed:
+                    rk = int(ranks[lin])
+                    u = self.buf[o: o + self.tm * rk]
+                    v = self.buf[o + self.tm * self.max_rank: o + self.tm * self.max_rank + rk * self.tn]
+                    blob = torch.cat([u, v]).cpu().numpy().tobytes()
+                    meta = dict(mNumOfRows=self.tm, mNumOfCols=self.tn, mMatrixRank=rk, mMaxRank=self.max_rank,
+                                mLeadingDimension=self.tm, mLayout="C", mType="COMPRESSED")
+                else:
+                    blob = self.buf[o: o + self.tile_elems].cpu().numpy().tobytes()
+                    meta = dict(mNumOfRows=self.tm, mNumOfCols=self.tn, mMatrixRank=0, mMaxRank=0, mLeadingDimension=self.tm,
+                                mLayout="C", mType="DENSE")
+                f.write(blob)
+                tiles.append(dict(row=lin % self.mt, col=lin // self.mt, offset=off, nbytes=len(blob), metadata=meta))
+                off += len(blob)
+        manifest = dict(format="hcorepp-b200 tile manifest v1", dtype={8: "f64", 4: "f32"}[esz], byteorder="little",
+                        mt=self.mt, nt=self.nt, tile_rows=self.tm, tile_cols=self.tn, compressed=bool(self.compressed),
+                        max_rank=self.max_rank, tiles=tiles)
+        with open(path + ".json", "w") as f:
+            json.dump(manifest, f)
+
+    @classmethod
+    def load(cls, path: str, ctx: RunContext):
+        """Inverse of save(): every tile is re-packed from its (metadata, buffer) record (PackTile, Compressed.cpp:780-805)."""
+        import json
+        man = json.load(open(path + ".json"))
+        assert man["format"].startswith("hcorepp-b200 tile manifest")
+        dtype = torch.float64 if man["dtype"] == "f64" else torch.float32
+        npdt = np.float64 if man["dtype"] == "f64" else np.float32
+        tm = cls(man["mt"], man["nt"], man["tile_rows"], man["tile_cols"], dtype, ctx, compressed=man["compressed"],
+                 max_rank=man["max_rank"] or None)
+        raw = np.fromfile(path + ".bin", dtype=np.uint8)
+        for t in man["tiles"]:
+            lin = t["row"] + t["col"] * tm.mt
+            a = torch.from_numpy(raw[t["offset"]: t["offset"] + t["nbytes"]].view(npdt).copy()).to(ctx.device)
+            o = lin * tm.tile_elems
+            md = t["metadata"]
+            if md["mType"] == "COMPRESSED":
+                rk, m, n = md["mMatrixRank"], md["mNumOfRows"], md["mNumOfCols"]
+                tm.buf[o: o + m * rk] = a[: m * rk]
+                tm.buf[o + m * tm.max_rank: o + m * tm.max_rank + rk * n] = a[m * rk:]
+                tm.ranks[lin] = rk
+            else:
+                tm.buf[o: o + tm.tile_elems] = a
+        tm.state.zero_()
+        return tm
+
     def GetMemoryFootprint(self) -> int:
         """bytes actually holding data (TileMatrix.cpp:176-184)."""
         esz = self.buf.element_size()

@@ -66,6 +66,14 @@ template<typename T> struct abi;  // maps T to the hcb_{d,s}* symbols
         static constexpr auto compress_batched = hcb_##P##compress_batched;                                             \
         static constexpr auto tlr_matmul = hcb_##P##tlr_matmul;                                                         \
         static constexpr auto tlr_gemm_workspace = hcb_##P##tlr_gemm_workspace;                                         \
+        static constexpr auto potrf = hcb_##P##potrf;                                                                   \
+        static constexpr auto trsm = hcb_##P##trsm;                                                                     \
+        static constexpr auto syrk = hcb_##P##syrk;                                                                     \
+        static constexpr auto fill_triangle = hcb_##P##fill_triangle;                                                   \
+        static constexpr auto symmetrize = hcb_##P##symmetrize;                                                         \
+        static constexpr auto tlr_trsm_batched = hcb_##P##tlr_trsm_batched;                                             \
+        static constexpr auto tlr_syrk_batched = hcb_##P##tlr_syrk_batched;                                             \
+        static constexpr auto tlr_potrf = hcb_##P##tlr_potrf;                                                           \
     };
 HCOREPP_B200_ABI(d, double)
 HCOREPP_B200_ABI(s, float)
@@ -290,6 +298,10 @@ public:
     virtual int64_t GetNumOfSubMatrices() const = 0;
     virtual TileType GetTileType() = 0;
     virtual hcb_tile Descriptor() const = 0;  // what crosses the C ABI
+    /// Tile.hpp:214,231 -- the (metadata, buffer) wire format: UnPackTile hands out a NEW TileMetadata (the caller deletes
+    /// it) and a BORROWED data pointer; PackTile adopts a buffer without taking ownership (Compressed.cpp:769-805).
+    virtual std::pair<TileMetadata *, T *> UnPackTile(const kernels::RunContext &aContext) = 0;
+    virtual void PackTile(TileMetadata aMetadata, T *aDataArray, const kernels::RunContext &aContext) = 0;
 protected:
     blas::Layout mLayout = blas::Layout::ColMajor;
     size_t mLeadingDim = 0, mNumOfRows = 0, mNumOfCols = 0, mRank = 0, mMaxRank = 0;
@@ -307,6 +319,7 @@ public:
         this->mLeadingDim = this->mpDataArray->GetLeadingDim();
     }
     DenseTile(size_t m, size_t n, T *d, size_t ld, const kernels::RunContext &c) : DenseTile(m, n, d, ld, blas::Layout::ColMajor, c) {}
+    DenseTile() = default;  // for TilePacker::PackTile (Dense.hpp default constructor)
     ~DenseTile() override { delete this->mpDataArray; }
     T *GetTileSubMatrix(size_t aIndex) const override {
         if (aIndex != 0) throw std::invalid_argument("GetTileSubMatrix ::Index out of range, should be 0 in case of dense tile.\n");
@@ -324,9 +337,17 @@ public:
         return hcb_tile{HCB_TILE_DENSE, (int32_t) this->mNumOfRows, (int32_t) this->mNumOfCols,
                         (int32_t) this->mpDataArray->GetLeadingDim(), 0, 0, nullptr, this->mpDataArray->GetData()};
     }
-    std::pair<TileMetadata *, T *> UnPackTile(const kernels::RunContext &) {
+    std::pair<TileMetadata *, T *> UnPackTile(const kernels::RunContext &) override {
         return {new TileMetadata(this->mNumOfRows, this->mNumOfCols, 0, 0, this->mLeadingDim, this->mLayout, DENSE),
                 this->mpDataArray->GetData()};
+    }
+    /// Dense.cpp:137-143: adopt a DEVICE buffer (no ownership) described by the metadata
+    void PackTile(TileMetadata aMetadata, T *aDataArray, const kernels::RunContext &aContext) override {
+        if (aMetadata.mLayout != blas::Layout::ColMajor) throw std::invalid_argument("DenseTile: only ColMajor tiles are supported");
+        delete this->mpDataArray;
+        this->mLayout = aMetadata.mLayout; this->mLeadingDim = aMetadata.mLeadingDimension;
+        this->mNumOfRows = aMetadata.mNumOfRows; this->mNumOfCols = aMetadata.mNumOfCols; this->mRank = aMetadata.mMatrixRank;
+        this->mpDataArray = new dataunits::DataHolder<T>(this->mNumOfRows, this->mNumOfCols, this->mLeadingDim, aDataArray, aContext, false);
     }
 };
 
@@ -337,7 +358,7 @@ class CompressedTile : public Tile<T> {  // Compressed.hpp:67-151 ; buffer = [U 
 public:
     /// (m, n, U, V, ld, rank, layout, ctx): maxRank = rank  (Compressed.cpp:20-47)
     CompressedTile(size_t aNumOfRows, size_t aNumOfCols, T *apDataU, T *apDataV, size_t aLeadingDim, size_t aRank,
-                   blas::Layout aLayout, const kernels::RunContext &aContext) : mContext(aContext) {
+                   blas::Layout aLayout, const kernels::RunContext &aContext) : mpContext(&aContext) {
         Init(aNumOfRows, aNumOfCols, aLeadingDim, aRank, std::max<size_t>(aRank, 1), aLayout);
         memory::Memcpy<T>(GetUMatrix(), apDataU, aNumOfRows * aRank, aContext, memory::MemoryTransfer::AUTOMATIC);
         memory::Memcpy<T>(GetVMatrix(), apDataV, aRank * aNumOfCols, aContext, memory::MemoryTransfer::AUTOMATIC);
@@ -345,7 +366,7 @@ public:
     }
     /// (m, n, UV, ld, rank[, layout], ctx): UV = [U | V] packed, maxRank = rank  (Compressed.cpp:49-73)
     CompressedTile(size_t aNumOfRows, size_t aNumOfCols, T *apData, size_t aLeadingDim, size_t aRank, blas::Layout aLayout,
-                   const kernels::RunContext &aContext) : mContext(aContext) {
+                   const kernels::RunContext &aContext) : mpContext(&aContext) {
         Init(aNumOfRows, aNumOfCols, aLeadingDim, aRank, std::max<size_t>(aRank, 1), aLayout);
         if (apData) {
             memory::Memcpy<T>(GetUMatrix(), apData, aNumOfRows * aRank, aContext, memory::MemoryTransfer::AUTOMATIC);
@@ -357,7 +378,7 @@ public:
         : CompressedTile(m, n, d, ld, rank, blas::Layout::ColMajor, c) {}
     /// compressing constructor: SVD + truncation on the device, maxRank = max(min(m,n)/3, 1)  (Compressed.cpp:75-146)
     CompressedTile(size_t aNumOfRows, size_t aNumOfCols, T *apData, size_t aLeadingDim, const CompressionParameters &aParameters,
-                   blas::Layout aLayout, const kernels::RunContext &aContext) : mContext(aContext) {
+                   blas::Layout aLayout, const kernels::RunContext &aContext) : mpContext(&aContext) {
         const size_t maxRank = std::max<size_t>(std::min(aNumOfRows, aNumOfCols) / HCOREPP_B200_MAX_RANK_RATIO, 1);
         Init(aNumOfRows, aNumOfCols, aLeadingDim, maxRank, maxRank, aLayout);
         if (apData) {
@@ -370,10 +391,11 @@ public:
             aContext.Sync();
         }
     }
+    CompressedTile() = default;  // for TilePacker::PackTile (Compressed.hpp default constructor)
     CompressedTile(const CompressedTile &) = delete;
     ~CompressedTile() override {
         delete this->mpDataArray;
-        if (mpRank) hcb_free(mContext.Handle(), mpRank);
+        if (mpRank && mpContext) hcb_free(mpContext->Handle(), mpRank);
     }
     T *GetUMatrix() const { return this->mpDataArray->GetData(); }
     T *GetVMatrix() const { return this->mpDataArray->GetData() + this->mNumOfRows * this->mMaxRank; }  // Compressed.cpp:180-185
@@ -389,9 +411,18 @@ public:
     /// CalculateNewRank does per GEMM, CudaKernels.cu:656-697 -- here only when somebody asks).
     size_t GetTileRank() const override {
         int32_t r = 0;
-        detail::check(hcb_memcpy(mContext.Handle(), &r, mpRank, sizeof(r), 2), "GetTileRank");
-        mContext.Sync();
+        detail::check(hcb_memcpy(mpContext->Handle(), &r, mpRank, sizeof(r), 2), "GetTileRank");
+        mpContext->Sync();
         return (size_t) r;
+    }
+    /// Per-tile fixed rank of the replay drivers (par_fixed_rank_streams_main.cpp:465-477,540-541; Compressed.cpp:510-515):
+    /// > 0 makes every recompression of THIS tile keep exactly that rank, 0 restores truncation by accuracy.
+    void SetFixedRank(size_t aRank) { mFixedRank = (int32_t) aRank; }
+    /// The library keeps a state word next to the rank (hcb_tile.d_state: "U has orthonormal columns"); whoever writes the
+    /// factors through GetUMatrix() / GetVMatrix() directly must call this.
+    void InvalidateState() {
+        const int32_t z = 0;
+        detail::check(hcb_memcpy(mpContext->Handle(), mpRank + 1, &z, sizeof(z), 0), "InvalidateState");
     }
     size_t GetMaxRank() const { return this->mMaxRank; }
     size_t GetULeadingDim() const { return this->mNumOfRows; }
@@ -402,40 +433,74 @@ public:
     TileType GetTileType() override { return COMPRESSED; }
     hcb_tile Descriptor() const override {
         return hcb_tile{HCB_TILE_COMPRESSED, (int32_t) this->mNumOfRows, (int32_t) this->mNumOfCols, 0, (int32_t) this->mMaxRank, 0,
-                        mpRank, this->mpDataArray->GetData()};
+                        mpRank, this->mpDataArray->GetData(), mpRank + 1, mFixedRank, 0};
     }
     /// Dense*Dense -> Compressed makes the tile full rank (HCore.cpp:291-298): grow the buffer like DataHolder::Resize.
     void EnsureCapacity(size_t aMaxRank) {
         if (aMaxRank <= this->mMaxRank) return;
         const size_t m = this->mNumOfRows, n = this->mNumOfCols, rk = GetTileRank();
-        auto *fresh = new dataunits::DataHolder<T>(m * aMaxRank + aMaxRank * n, 1, m * aMaxRank + aMaxRank * n, nullptr, mContext);
-        memory::Memcpy<T>(fresh->GetData(), GetUMatrix(), m * rk, mContext);
-        memory::Memcpy<T>(fresh->GetData() + m * aMaxRank, GetVMatrix(), rk * n, mContext);
-        mContext.Sync();
+        auto *fresh = new dataunits::DataHolder<T>(m * aMaxRank + aMaxRank * n, 1, m * aMaxRank + aMaxRank * n, nullptr, *mpContext);
+        memory::Memcpy<T>(fresh->GetData(), GetUMatrix(), m * rk, *mpContext);
+        memory::Memcpy<T>(fresh->GetData() + m * aMaxRank, GetVMatrix(), rk * n, *mpContext);
+        mpContext->Sync();
         delete this->mpDataArray;
         this->mpDataArray = fresh;
         this->mMaxRank = aMaxRank;
     }
-    std::pair<TileMetadata *, T *> UnPackTile(const kernels::RunContext &) {
+    std::pair<TileMetadata *, T *> UnPackTile(const kernels::RunContext &) override {
         return {new TileMetadata(this->mNumOfRows, this->mNumOfCols, GetTileRank(), this->mMaxRank, this->mLeadingDim,
                                  this->mLayout, COMPRESSED), this->mpDataArray->GetData()};
     }
+    /// Compressed.cpp:780-805: adopt a DEVICE buffer [U (m x maxRank) | V (maxRank x n), ld = rank] without ownership; the
+    /// rank of the metadata goes to the device-resident rank word, the state word starts at "unknown".
+    void PackTile(TileMetadata aMetadata, T *aDataArray, const kernels::RunContext &aContext) override {
+        if (aMetadata.mLayout != blas::Layout::ColMajor) throw std::invalid_argument("CompressedTile: only ColMajor tiles are supported");
+        delete this->mpDataArray;
+        if (mpRank && mpContext) hcb_free(mpContext->Handle(), mpRank);
+        mpContext = &aContext;
+        this->mLayout = aMetadata.mLayout; this->mRank = aMetadata.mMatrixRank; this->mLeadingDim = aMetadata.mLeadingDimension;
+        this->mNumOfRows = aMetadata.mNumOfRows; this->mNumOfCols = aMetadata.mNumOfCols; this->mMaxRank = aMetadata.mMaxRank;
+        const size_t elems = this->mNumOfRows * this->mMaxRank + this->mMaxRank * this->mNumOfCols;
+        this->mpDataArray = new dataunits::DataHolder<T>(elems, 1, elems, aDataArray, aContext, false);
+        AllocRankWord((int32_t) aMetadata.mMatrixRank);
+    }
 private:
+    void AllocRankWord(int32_t aRank) {
+        void *p = nullptr;
+        detail::check(hcb_malloc(mpContext->Handle(), 2 * sizeof(int32_t), &p), "CompressedTile");
+        mpRank = static_cast<int32_t *>(p);
+        const int32_t init[2] = {aRank, 0};  // {rank, state: unknown}
+        detail::check(hcb_memcpy(mpContext->Handle(), mpRank, init, sizeof(init), 0), "CompressedTile");
+        mpContext->Sync();
+    }
     void Init(size_t m, size_t n, size_t ld, size_t rank, size_t maxRank, blas::Layout layout) {
         if (layout != blas::Layout::ColMajor) throw std::invalid_argument("CompressedTile: only ColMajor tiles are supported");
         this->mLayout = layout; this->mNumOfRows = m; this->mNumOfCols = n; this->mLeadingDim = ld;
         this->mRank = rank; this->mMaxRank = maxRank;
         const size_t elems = m * maxRank + maxRank * n;
-        this->mpDataArray = new dataunits::DataHolder<T>(elems, 1, elems, nullptr, mContext);
-        void *p = nullptr;
-        detail::check(hcb_malloc(mContext.Handle(), sizeof(int32_t), &p), "CompressedTile");
-        mpRank = static_cast<int32_t *>(p);
-        const int32_t r = (int32_t) rank;
-        detail::check(hcb_memcpy(mContext.Handle(), mpRank, &r, sizeof(r), 0), "CompressedTile");
-        mContext.Sync();
+        this->mpDataArray = new dataunits::DataHolder<T>(elems, 1, elems, nullptr, *mpContext);
+        AllocRankWord((int32_t) rank);
     }
-    const kernels::RunContext &mContext;
-    int32_t *mpRank = nullptr;  // device-resident rank
+    const kernels::RunContext *mpContext = nullptr;
+    int32_t *mpRank = nullptr;  // device-resident {rank, state}
+    int32_t mFixedRank = 0;
+};
+
+/// TilePacker (include/hcorepp/operators/interface/TilePacker.hpp:18-60, src/operators/TilePacker.cpp:4-26)
+template<typename T>
+class TilePacker {
+public:
+    virtual ~TilePacker() = default;
+    static std::pair<TileMetadata *, T *> UnPackTile(Tile<T> &aTile, const kernels::RunContext &aContext) {
+        return aTile.UnPackTile(aContext);
+    }
+    static Tile<T> *PackTile(TileMetadata aMetadata, T *apDataArray, const kernels::RunContext &aContext) {
+        Tile<T> *tile;
+        if (aMetadata.mType == DENSE) tile = new DenseTile<T>();
+        else tile = new CompressedTile<T>();
+        tile->PackTile(aMetadata, apDataArray, aContext);
+        return tile;
+    }
 };
 }  // namespace operators
 
@@ -502,6 +567,41 @@ public:
     static void ungqr(size_t aM, size_t aN, size_t aK, T *apA, size_t aLdA, T *apTau, T *, size_t, const RunContext &c) {
         detail::check(A::ungqr(c.Handle(), aM, aN, aK, apA, aLdA, apTau), "ungqr");
     }
+    /// kernels.hpp:103-129 -- the Cholesky pieces of the table (src/kernels/omp/kernels.cpp:234-303)
+    static int potrf(blas::Uplo aUplo, T *, size_t, size_t, size_t aMatrixOrder, T *apMatrix, size_t aLeadingDim, blas::Layout,
+                     const RunContext &c) {
+        int32_t *d_info = nullptr;
+        detail::check(hcb_malloc(c.Handle(), sizeof(int32_t), (void **) &d_info), "potrf");
+        detail::check(A::potrf(c.Handle(), (int) aUplo, aMatrixOrder, apMatrix, aLeadingDim, d_info), "potrf");
+        int32_t info = 0;
+        detail::check(hcb_memcpy(c.Handle(), &info, d_info, sizeof(info), 2), "potrf");
+        c.Sync();
+        hcb_free(c.Handle(), d_info);
+        return info;
+    }
+    static void trsm(blas::Layout, blas::Side aSide, blas::Uplo aUplo, blas::Op aTrans, blas::Diag aDiag, size_t aRows, size_t aCols,
+                     T aAlpha, const T *apMatrixA, size_t aLeadingDimA, T *apMatrixB, size_t aLeadingDimB, const RunContext &c) {
+        detail::check(A::trsm(c.Handle(), (int) aSide, (int) aUplo, op(aTrans), (int) aDiag, aRows, aCols, aAlpha, apMatrixA,
+                              aLeadingDimA, apMatrixB, aLeadingDimB), "trsm");
+    }
+    static void syrk(blas::Layout, blas::Uplo aUplo, blas::Op aTrans, size_t aRows, size_t aCols, T aAlpha, const T *apMatrixA,
+                     size_t aLeadingDimA, T aBeta, T *apMatrixB, size_t aLeadingDimB, const RunContext &c) {
+        detail::check(A::syrk(c.Handle(), (int) aUplo, op(aTrans), aRows, aCols, aAlpha, apMatrixA, aLeadingDimA, aBeta, apMatrixB,
+                              aLeadingDimB), "syrk");
+    }
+    static void FillMatrixTriangle(blas::Uplo aUplo, size_t aRows, size_t aCols, T *apMatrix, blas::Layout, size_t aValue,
+                                   const RunContext &c) {
+        if (aRows != aCols) return;
+        detail::check(A::fill_triangle(c.Handle(), (int) aUplo, aRows, apMatrix, aRows, (T) aValue), "FillMatrixTriangle");
+    }
+    static void Symmetrize(blas::Layout, T *apMatrixA, size_t aRows, size_t aCols, blas::Uplo aUplo, const RunContext &c) {
+        if (aRows != aCols) return;
+        detail::check(A::symmetrize(c.Handle(), (int) aUplo, aRows, apMatrixA, aRows), "Symmetrize");
+    }
+    static size_t CalculatePotrfWorkspaceSize(T *, blas::Uplo, size_t, size_t, size_t &aHostSize, const RunContext &) {
+        aHostSize = 0;
+        return 0;
+    }
     static size_t CalculateGemmWorkspaceSize(size_t, size_t, size_t, size_t, size_t, const operators::CompressionParameters &,
                                              size_t &aHostSize, const RunContext &) {
         aHostSize = 0;  // scratch lives in the context's arena; callers need not provide any
@@ -517,13 +617,17 @@ class HCore {
 public:
     /// HCore<T>::Gemm (HCore.hpp:41-46): C = alpha*op(A)*op(B) + beta*C on Dense / Compressed tiles, recompression
     /// included; one fused device call, nothing synchronises.  aFlops receives the reference's dense-equivalent model
-    /// for the contraction (2mnk); aCholesky is not supported on this path.
+    /// for the contraction (2mnk).
     static void Gemm(T aAlpha, operators::Tile<T> const &aA, blas::Op const &aAOp, operators::Tile<T> const &aB,
                      blas::Op const &aBOp, T aBeta, operators::Tile<T> &aC, const kernels::RunContext &aContext, size_t &aFlops,
                      dataunits::MemoryUnit<T> &aMemoryUnit, const operators::CompressionParameters &aSVDArguments = {1e-9},
                      bool aCholesky = false) {
         (void) aMemoryUnit;
-        if (aCholesky) throw std::runtime_error("HCore::Gemm: the Cholesky variant is not part of the B200 TLR-GEMM path");
+        // aCholesky (HCore.cpp:160-174): the reference's Cholesky variant is C += alpha * A * B^T on compressed tiles whose V
+        // factors it keeps as n x k.  Here every tile keeps the one layout of this library (V = rank x n), so the variant is the
+        // plain transposed product -- it only checks what the reference's branch requires.
+        if (aCholesky && !(aA.isCompressed() && aB.isCompressed() && aAOp == blas::Op::NoTrans && aBOp == blas::Op::Trans))
+            throw std::runtime_error("HCore::Gemm: the Cholesky variant takes compressed A, B with (NoTrans, Trans)");
         if (aA.isDense() && aB.isDense() && aC.isCompressed())
             static_cast<operators::CompressedTile<T> &>(aC).EnsureCapacity(std::min(aC.GetNumOfRows(), aC.GetNumOfCols()));
         const hcb_tile a = aA.Descriptor(), b = aB.Descriptor(), c = aC.Descriptor();
@@ -545,6 +649,44 @@ public:
         detail::check(detail::abi<T>::tlr_gemm_batched(aContext.Handle(), (int64_t) n, a.data(), aAOp == blas::Op::NoTrans ? 0 : 1,
                                                        b.data(), aBOp == blas::Op::NoTrans ? 0 : 1, c.data(), aAlpha, aBeta, &p, nullptr),
                       "HCore::GemmBatched");
+    }
+    /// HCore<T>::Potrf (HCore.cpp:586-621): dense tiles only, in place; the other triangle is left as it was.
+    static void Potrf(operators::Tile<T> &aA, const blas::Uplo aUplo, const kernels::RunContext &aContext, size_t &aFlops,
+                      dataunits::MemoryUnit<T> &) {
+        if (aA.GetNumOfSubMatrices() != 1) throw std::runtime_error(" Potrf works only with dense tiles");
+        auto &dh = aA.GetDataHolder().get();
+        kernels::HCoreKernels<T>::potrf(aUplo, nullptr, 0, 0, aA.GetNumOfRows(), dh.GetData(), dh.GetLeadingDim(), aA.GetLayout(), aContext);
+        aFlops += aA.GetNumOfRows() * aA.GetNumOfRows() * aA.GetNumOfRows() / 3;
+    }
+    /// HCore<T>::Trsm (HCore.cpp:624-647): A dense triangular, B compressed; blas::trsm with m = rows(B), n = rank(B) on B's V
+    /// buffer with the tile's leading dimension (the reference's Cholesky convention stores V as n x k); U is not touched.
+    static void Trsm(blas::Side aSide, blas::Uplo aUplo, blas::Op aTrans, blas::Diag aDiag, T aAlpha, operators::Tile<T> &aA,
+                     operators::Tile<T> &aB, const kernels::RunContext &aContext, size_t &, dataunits::MemoryUnit<T> &) {
+        if (aB.GetNumOfSubMatrices() != 2) throw std::runtime_error(" TRSM: Tile B must be compressed ");
+        auto &b = static_cast<operators::CompressedTile<T> &>(aB);
+        auto &dh = aA.GetDataHolder().get();
+        kernels::HCoreKernels<T>::trsm(aB.GetLayout(), aSide, aUplo, aTrans, aDiag, aB.GetNumOfRows(), b.GetTileRank(), aAlpha,
+                                       dh.GetData(), dh.GetLeadingDim(), b.GetVMatrix(), aB.GetNumOfRows(), aContext);
+    }
+    /// HCore<T>::Syrk (HCore.cpp:484-583).  Dense A: blas::syrk with n = rows(C), k = cols(C) on the `uplo` triangle.
+    /// Compressed A (= U V in this library's layout): C := beta C - (U (V V^T)) U^T and the other strict triangle zeroed --
+    /// the reference's compressed branch (alpha is hard-coded to -1 there, HCore.cpp:546).
+    static void Syrk(T aAlpha, const operators::Tile<T> &aA, const blas::Op &aAOp, const blas::Uplo aUplo, T aBeta,
+                     operators::Tile<T> &aC, const kernels::RunContext &aContext, size_t &, dataunits::MemoryUnit<T> &) {
+        auto &cd = aC.GetDataHolder().get();
+        if (aA.GetNumOfSubMatrices() == 1) {
+            auto &ad = aA.GetDataHolder().get();
+            kernels::HCoreKernels<T>::syrk(aC.GetLayout(), aUplo, aAOp, aC.GetNumOfRows(), aC.GetNumOfCols(), aAlpha, ad.GetData(),
+                                           ad.GetLeadingDim(), aBeta, cd.GetData(), cd.GetLeadingDim(), aContext);
+            return;
+        }
+        if (!aC.isDense()) throw std::runtime_error("HCore::Syrk: compressed A needs a dense C");
+        const hcb_tile a = aA.Descriptor();
+        T *cptr[1] = {cd.GetData()};
+        const int64_t ldc[1] = {(int64_t) cd.GetLeadingDim()};
+        detail::check(detail::abi<T>::tlr_syrk_batched(aContext.Handle(), 1, &a, cptr, ldc, T(-1), aBeta), "HCore::Syrk");
+        kernels::HCoreKernels<T>::FillMatrixTriangle(aUplo == blas::Uplo::Lower ? blas::Uplo::Upper : blas::Uplo::Lower, aC.GetNumOfRows(),
+                                                     aC.GetNumOfCols(), cd.GetData(), aC.GetLayout(), 0, aContext);
     }
     /// HCore.hpp:59-63 -- in ELEMENTS, like the reference; what one fused call needs for these tiles.
     static size_t CalculateMemoryPoolSize(const operators::Tile<T> &aA, const operators::Tile<T> &aB, const operators::Tile<T> &aC,

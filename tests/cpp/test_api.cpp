@@ -211,6 +211,77 @@ static void run(const char *type) {
         report("TileMatrix + driver loop", type, got.Norm() <= 10 * acc * nrm && ranks_ok && tA.GetTile(0, 0)->GetTileRank() == rk &&
                                                      tC.GetMemoryFootprint() > 0);
     }
+    {  // wire format (Tile.hpp:30-52, Compressed.cpp:769-805, TilePacker.cpp:4-26): UnPackTile -> (metadata, buffer) -> PackTile
+        auto *A = dense({{1, 2}, {3, 4}, {5, 6}});
+        const std::vector<T> u = colmajor<T>({{1, 0}, {0, 1}, {1, 1}}), v = colmajor<T>({{1, 2, 3, 4}, {0, 1, 0, 1}});
+        std::vector<T> uh = u, vh = v;
+        CompressedTile<T> Ct(3, 4, uh.data(), vh.data(), 3, 2, blas::Layout::ColMajor, ctx);
+        auto pc = TilePacker<T>::UnPackTile(Ct, ctx);
+        auto pd = TilePacker<T>::UnPackTile(*A, ctx);
+        bool meta_ok = pc.first->mType == COMPRESSED && pc.first->mMatrixRank == 2 && pc.first->mMaxRank == 2 && pc.first->mNumOfRows == 3 &&
+                       pc.first->mNumOfCols == 4 && pd.first->mType == DENSE && pd.first->mNumOfRows == 3 && pd.first->mNumOfCols == 2;
+        Tile<T> *rc = TilePacker<T>::PackTile(*pc.first, pc.second, ctx);   // views over the same device buffers
+        Tile<T> *rd = TilePacker<T>::PackTile(*pd.first, pd.second, ctx);
+        bool same = rc->isCompressed() && rd->isDense() && rc->GetTileRank() == 2 && dense_of(*rc, ctx) == dense_of(Ct, ctx) &&
+                    dense_of(*rd, ctx) == dense_of(*A, ctx) && rc->GetTileSubMatrix(0) == Ct.GetUMatrix();
+        // the re-packed view is a full citizen: use it as an operand
+        auto *C = zeros_c(3, 2, 2);
+        auto *B = dense({{1, 0}, {0, 1}, {1, 1}, {2, 0}});
+        HCore<T>::Gemm(1, *rc, blas::Op::NoTrans, *B, blas::Op::NoTrans, 1, *C, ctx, flops, unit, eps_params);
+        report("PackTile / UnPackTile / TilePacker", type, meta_ok && same && approx(dense_of(*C, ctx), {{12, 5}, {2, 1}, {14, 6}}));
+        delete pc.first; delete pd.first; delete rc; delete rd; delete A; delete B; delete C;
+    }
+    {  // per-tile fixed rank (par_fixed_rank_streams_main.cpp:465-477,540-541; Compressed.cpp:510-515)
+        const size_t n = 24;
+        Mat<double> ma(n, std::vector<double>(n)), mb(n, std::vector<double>(n));
+        for (size_t i = 0; i < n; ++i)
+            for (size_t j = 0; j < n; ++j) {
+                ma[i][j] = std::sin(0.31 * i + 0.1) * std::cos(0.17 * j) + 0.3 * std::cos(0.05 * i * j);
+                mb[i][j] = std::cos(0.23 * i) * std::sin(0.19 * j + 0.4) + 0.2 * std::sin(0.07 * i * j);
+            }
+        auto ha = colmajor<T>(ma), hb = colmajor<T>(mb);
+        const double acc = sizeof(T) == 8 ? 1e-9 : 1e-4;
+        CompressedTile<T> A(n, n, ha.data(), n, CompressionParameters(acc), blas::Layout::ColMajor, ctx);
+        CompressedTile<T> B(n, n, hb.data(), n, CompressionParameters(acc), blas::Layout::ColMajor, ctx);
+        auto *C1 = zeros_c(n, n, 8);
+        HCore<T>::Gemm(1, A, blas::Op::NoTrans, B, blas::Op::NoTrans, 1, *C1, ctx, flops, unit, CompressionParameters(acc));
+        const size_t free_rank = C1->GetTileRank();
+        auto *C2 = zeros_c(n, n, 8);
+        static_cast<CompressedTile<T> *>(C2)->SetFixedRank(3);
+        HCore<T>::Gemm(1, A, blas::Op::NoTrans, B, blas::Op::NoTrans, 1, *C2, ctx, flops, unit, CompressionParameters(acc));
+        report("per-tile fixed rank", type, free_rank > 3 && C2->GetTileRank() == 3);
+        delete C1; delete C2;
+    }
+    {  // Cholesky pieces (HCore.cpp:482-647): Potrf on a dense tile, Syrk, Trsm on the V buffer, the aCholesky product
+        auto *A = dense({{4, 99, 99}, {2, 5, 99}, {2, 3, 6}});   // lower triangle of an SPD matrix, junk above
+        HCore<T>::Potrf(*A, blas::Uplo::Lower, ctx, flops, unit);
+        const double l22 = std::sqrt(6.0 - 1.0 - 1.0);
+        bool potrf_ok = approx(dense_of(*A, ctx), {{2, 99, 99}, {1, 2, 99}, {1, 1, l22}}, 1e-5);
+        bool threw = false;
+        auto *Cc = zeros_c(3, 3, 1);
+        try { HCore<T>::Potrf(*Cc, blas::Uplo::Lower, ctx, flops, unit); } catch (const std::runtime_error &) { threw = true; }
+        // Syrk, dense A: C := -A A^T + C on the lower triangle only
+        auto *S = dense({{1, 2}, {3, 4}});
+        auto *Cs = dense({{10, 7}, {10, 10}});
+        HCore<T>::Syrk(-1, *S, blas::Op::NoTrans, blas::Uplo::Lower, 1, *Cs, ctx, flops, unit);
+        bool syrk_ok = approx(dense_of(*Cs, ctx), {{5, 7}, {-1, -15}}, 1e-5);
+        // Trsm: L X = V on the V buffer of a compressed tile (viewed m x rank)
+        const std::vector<T> u = colmajor<T>({{1}, {1}, {1}}), v = colmajor<T>({{2, 4, 6}});
+        std::vector<T> uh = u, vh = v;
+        CompressedTile<T> Bt(3, 3, uh.data(), vh.data(), 3, 1, blas::Layout::ColMajor, ctx);
+        auto *L = dense({{2, 0, 0}, {1, 1, 0}, {0, 1, 2}});
+        HCore<T>::Trsm(blas::Side::Left, blas::Uplo::Lower, blas::Op::NoTrans, blas::Diag::NonUnit, 1, *L, Bt, ctx, flops, unit);
+        auto vb = to_host<T>(Bt.GetVMatrix(), 3, ctx);   // x = L^-1 (2,4,6)^T = (1, 3, 1.5)
+        bool trsm_ok = std::fabs(vb[0] - 1) < 1e-5 && std::fabs(vb[1] - 3) < 1e-5 && std::fabs(vb[2] - 1.5) < 1e-5;
+        // aCholesky product: C += alpha A B^T on compressed tiles
+        std::vector<T> u2 = colmajor<T>({{1}, {0}, {2}}), v2 = colmajor<T>({{1, 1, 0}});
+        CompressedTile<T> X(3, 3, u2.data(), v2.data(), 3, 1, blas::Layout::ColMajor, ctx);
+        auto *Cx = zeros_c(3, 3, 3);
+        HCore<T>::Gemm(-1, X, blas::Op::NoTrans, X, blas::Op::Trans, 1, *Cx, ctx, flops, unit, eps_params, true);
+        bool chol_gemm_ok = approx(dense_of(*Cx, ctx), {{-2, 0, -4}, {0, 0, 0}, {-4, 0, -8}}, 1e-5);
+        report("Potrf / Syrk / Trsm / aCholesky Gemm", type, potrf_ok && threw && syrk_ok && trsm_ok && chol_gemm_ok);
+        delete A; delete Cc; delete S; delete Cs; delete L; delete Cx;
+    }
     (void) flops;
 }
 

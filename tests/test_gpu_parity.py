@@ -786,3 +786,56 @@ def test_sketched_compression_second_sketch_for_ranks_beyond_96(hc, ctx):
     o = O.CompressedTile.compress(A, O.CompressionParameters(acc))
     assert 120 < o.rank < 280 and abs(t.GetTileRank() - o.rank) <= 1
     assert relerr(t.to_dense(), o.to_dense()) <= 10 * acc
+
+
+def test_per_tile_fixed_rank_replay_and_manifest(hc, ctx, tmp_path):
+    """SURVEY.md 8f rows 2-3.  Fixed-rank replay (par_fixed_rank_streams_main.cpp:465-477,540-541): a first product learns
+    the rank of every C tile, the replay pins each tile to ITS rank (hcb_tile.fixed_rank) and must reproduce ranks and
+    products; against the oracle with the same per-tile fixed ranks.  Tile manifest: save -> load round trip is exact."""
+    nb, T, k, acc = 128, 2, 10, 1e-6
+    def fill(tm, og, name):
+        for j in range(T):
+            for i in range(T):
+                t = O.synth_compressed_tile(nb, k + 2 * i + j, seed=ord(name) * 100 + j * 10 + i)   # different ranks per tile
+                og[j][i] = t
+                g = tm.GetTile(j, i)
+                rk = t.U.shape[1]
+                g.buf[: nb * rk] = dev(t.U)
+                g.buf[nb * tm.max_rank: nb * tm.max_rank + rk * nb] = dev(t.V)
+                g.rank.fill_(rk)
+    A = hc.TileMatrix(T, T, nb, nb, torch.float64, ctx, compressed=True)
+    B = hc.TileMatrix(T, T, nb, nb, torch.float64, ctx, compressed=True)
+    oA, oB = [[None] * T for _ in range(T)], [[None] * T for _ in range(T)]
+    fill(A, oA, "A"); fill(B, oB, "B")
+    p = hc.CompressionParameters(acc)
+    C1 = hc.TileMatrix.zeros_compressed(T, T, nb, nb, torch.float64, ctx)
+    hc.tile_matrix_multiplication(A, B, C1, 1.0, 1.0, ctx, p)
+    ctx.Sync()
+    learned = C1.rank_table()
+    forced = np.maximum(learned - np.array([[0, 3], [5, 1]]), 1)      # replay with per-tile ranks (some below the free rank)
+    C2 = hc.TileMatrix.zeros_compressed(T, T, nb, nb, torch.float64, ctx)
+    C2.set_fixed_ranks(forced)
+    hc.tile_matrix_multiplication(A, B, C2, 1.0, 1.0, ctx, p)
+    ctx.Sync()
+    assert np.array_equal(C2.rank_table(), forced)
+    for j in range(T):
+        for i in range(T):
+            oc = O.CompressedTile(np.zeros((nb, 1), order="F"), np.zeros((1, nb), order="F"), nb // 3)
+            pf = O.CompressionParameters(acc, fixed_rank=int(forced[j][i]))
+            for kk in range(T):
+                O.hcore_gemm(1.0, oA[j][kk], False, oB[kk][i], False, 1.0, oc, pf)
+            assert oc.rank == forced[j][i]
+            assert relerr(C2.GetTile(j, i).to_dense(), oc.to_dense()) <= 10 * acc
+    C2.set_fixed_ranks(None)
+    # manifest round trip
+    path = str(tmp_path / "c1")
+    C1.save(path)
+    L = hc.TileMatrix.load(path, ctx)
+    assert np.array_equal(L.rank_table(), learned)
+    assert np.array_equal(L.ToRawMatrix(), C1.ToRawMatrix())
+    import json
+    man = json.load(open(path + ".json"))
+    assert man["tiles"][1]["metadata"]["mType"] == "COMPRESSED" and man["tiles"][1]["metadata"]["mMatrixRank"] == int(learned[1][0])
+    D = hc.TileMatrix.from_dense(np.arange(64.0).reshape(8, 8), 4, 4, ctx)
+    D.save(str(tmp_path / "d"))
+    assert np.array_equal(hc.TileMatrix.load(str(tmp_path / "d"), ctx).ToRawMatrix(), D.ToRawMatrix())
