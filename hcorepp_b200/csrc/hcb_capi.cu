@@ -642,6 +642,7 @@ struct BatchShape {
     int m = 0, n = 0, k = 0;           // maxima over the batch
     int kA = 0, kB = 0, kC = 0, maxrankC = 0;  // rank bounds
     int mix = 0;
+    int r_force = 0;  // > 0: stacked-rank bound given directly (workspace query) instead of kC + kA
 };
 
 static inline int bound_of(const hcb_tile &t) {
@@ -677,7 +678,7 @@ Layout<T> make_layout(const BatchShape &s) {
     const bool recomp = (s.mix == CCC || s.mix == CDC || s.mix == DCC);
     if (recomp) {
         const int kp = (s.mix == DCC) ? s.kB : s.kA;
-        L.r_b = s.kC + kp;
+        L.r_b = s.r_force > 0 ? s.r_force : s.kC + kp;
         const int p_b = std::min(s.m, L.r_b), q_b = std::min(s.n, L.r_b);
         L.pq_b = std::max(p_b, q_b);
         const size_t sq = (size_t) L.pq_b * L.pq_b;
@@ -1516,8 +1517,10 @@ template<typename T>
 size_t t_workspace(int64_t n_tiles, int64_t m, int64_t n, int64_t k, int64_t r_bound) {
     BatchShape s;
     s.m = (int) m; s.n = (int) n; s.k = (int) k; s.mix = CCC;
-    s.kA = s.kB = (int) ((r_bound + 1) / 2);
-    s.kC = (int) (r_bound - s.kA);
+    // r_bound = bound on the stacked rank kc + ka of any tile of the batch; the split is not known here, so every
+    // single rank is bounded by r_bound as well (an upper bound of what a call with these bounds makes the arena grow to)
+    s.kA = s.kB = s.kC = (int) r_bound;
+    s.r_force = (int) r_bound;
     s.maxrankC = (int) std::max<int64_t>(1, std::min(m, n) / 3);
     const Layout<T> L = make_layout<T>(s);
     const DescArrays<T> D((int) n_tiles, L.nblk, std::max(L.r_b, L.pq_b), std::max(1, std::min(L.pq_b, s.maxrankC)));

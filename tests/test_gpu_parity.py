@@ -839,3 +839,145 @@ def test_per_tile_fixed_rank_replay_and_manifest(hc, ctx, tmp_path):
     D = hc.TileMatrix.from_dense(np.arange(64.0).reshape(8, 8), 4, 4, ctx)
     D.save(str(tmp_path / "d"))
     assert np.array_equal(hc.TileMatrix.load(str(tmp_path / "d"), ctx).ToRawMatrix(), D.ToRawMatrix())
+
+
+# ------------------------------------------------------------------------------------------------ round-2 test holes
+def _ref_or_skip():
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built")
+    return R
+
+
+def test_config0_replay_whole_matrix_generator(hc, ctx):
+    """BASELINE.json configs[0] replayed EXACTLY: examples/matrix_multiplication/omp_main.cpp with 4 x 4 tiles of 512,
+    accuracy 1e-8, the reference's WHOLE-MATRIX LATMS generator (A then B drawn from one seed state, omp_main.cpp:232-242),
+    C0 = 0 -- on the GPU through TileMatrix(compressing) + tile_matrix_multiplication, side by side with the compiled
+    reference on the same bytes.  The example prints error 1.067069e-07 and a C footprint of 10624 KB for this case."""
+    R = _ref_or_skip()
+    nb, T, acc = 512, 4, 1e-8
+    A, B = R.latms_law(nb * T, nb * T, np.float64, tile_size=0, reps=2)
+    p, pr = hc.CompressionParameters(acc), R.Params(acc)
+    tA = hc.TileMatrix.from_dense(A, nb, nb, ctx, p)
+    tB = hc.TileMatrix.from_dense(B, nb, nb, ctx, p)
+    tC = hc.TileMatrix.from_dense(np.zeros_like(A), nb, nb, ctx, p)
+    tile = lambda M, j, i: np.asfortranarray(M[j * nb:(j + 1) * nb, i * nb:(i + 1) * nb])
+    rA = [[R.RefTile.compress(tile(A, j, k), pr) for k in range(T)] for j in range(T)]
+    rB = [[R.RefTile.compress(tile(B, j, k), pr) for k in range(T)] for j in range(T)]
+    rC = [[R.RefTile.compress(np.zeros((nb, nb), order="F"), pr) for _ in range(T)] for _ in range(T)]
+    rank = lambda g: np.array([[t.info()["rank"] for t in r] for r in g])
+    assert np.max(np.abs(tA.rank_table() - rank(rA))) <= 1 and np.max(np.abs(tB.rank_table() - rank(rB))) <= 1
+    # "memory(KB)": the footprints TileMatrix records AT CONSTRUCTION (TileMatrix.cpp:176-184) -- C0's rank-1 zero tiles included
+    fp_ref = int(rank(rA).sum() + rank(rB).sum() + rank(rC).sum()) * (nb + nb) * 8
+    fp_gpu = tA.GetMemoryFootprint() + tB.GetMemoryFootprint() + tC.GetMemoryFootprint()
+    hc.tile_matrix_multiplication(tA, tB, tC, 1.0, 1.0, ctx, p)
+    ctx.Sync()
+    R.matmul(rA, rB, rC, 1.0, 1.0, pr, nthreads=4)
+    assert np.max(np.abs(tC.rank_table() - rank(rC))) <= 1, (tC.rank_table(), rank(rC))
+    Cr = np.block([[t.to_dense() for t in r] for r in rC])
+    Cg = tC.ToRawMatrix()
+    assert relerr(Cg, Cr) <= 10 * acc
+    # the example's printed "error" is RawMatrix::Norm() of the difference to the dense product = the INFINITY norm
+    # (RawMatrix.cpp:45-48), its "memory" the footprint of A + B + C in KB (omp_main.cpp:366-377)
+    dense = A @ B
+    inf = lambda X: float(np.abs(X - dense).sum(axis=1).max())
+    err_ref, err_gpu = inf(Cr), inf(Cg)
+    assert abs(err_ref - 1.067069e-07) <= 0.02e-07 and abs(err_gpu - err_ref) <= 0.1 * err_ref, (err_ref, err_gpu)
+    a_inf, b_inf = np.abs(A).sum(axis=1).max(), np.abs(B).sum(axis=1).max()
+    assert err_gpu / ((a_inf + b_inf) * acc * nb * T) < 10        # the example's own pass criterion
+    assert fp_ref == 10624 * 1024                                  # ... and its printed footprint
+    assert abs(fp_gpu - fp_ref) <= 2 * T * T * 2 * nb * 8          # (A / B ranks within +/-1 per tile)
+
+
+@pytest.mark.parametrize("mix", ["CCC", "CDC", "DCC"])
+@pytest.mark.parametrize("ops", [(True, False), (False, True), (True, True)])
+def test_transposed_operands_compressed_output(hc, ctx, mix, ops):
+    """op = Trans with a COMPRESSED C (only dense C was covered).  The reference itself cannot serve as the
+    checker here -- outside its aCholesky branch HCore::Gemm reads a transposed compressed operand with the wrong shapes
+    (NaN from the compiled reference, tests/test_oracle.py) -- so the check is against the dense truth: the recompressed
+    result within 10*acc and its rank = the numerical rank of the truth at that accuracy (+/-1)."""
+    rng = np.random.default_rng(hash((mix, ops)) % 1000)
+    dt, acc = np.float64, 1e-8
+    m, n, k = 160, 140, 96
+    ta, tb = ops
+    AUV = lowrank(rng, k, m, 20, dt) if ta else lowrank(rng, m, k, 20, dt)
+    BUV = lowrank(rng, n, k, 18, dt) if tb else lowrank(rng, k, n, 18, dt)
+    CUV = lowrank(rng, m, n, 25, dt)
+    Ad, Bd, Cd = AUV[0] @ AUV[1], BUV[0] @ BUV[1], CUV[0] @ CUV[1]
+    a = mk_tile(hc, ctx, mix[0], Ad, *AUV, dt)
+    b = mk_tile(hc, ctx, mix[1], Bd, *BUV, dt)
+    c = mk_tile(hc, ctx, "C", None, *CUV, dt, max_rank=min(m, n))
+    for _ in range(2):  # second pass: C carries the orthonormal-U state -> incremental path with transposed operands
+        hc.HCore.Gemm(0.75, a, ta, b, tb, -1.25, c, ctx, hc.CompressionParameters(acc))
+        Cd = 0.75 * (Ad.T if ta else Ad) @ (Bd.T if tb else Bd) - 1.25 * Cd
+        assert relerr(c.to_dense(), Cd) <= 10 * acc
+        s = np.linalg.svd(Cd, compute_uv=False)
+        assert abs(c.GetTileRank() - int(O.k_new_rank(False, s, len(s), acc))) <= 1
+
+
+@pytest.mark.parametrize("dims", [(1000, 900, 500, 50, 50, 60), (257, 300, 128, 40, 40, 50), (1024, 1024, 1024, 44, 44, 120)],
+                         ids=lambda d: "x".join(map(str, d)))
+def test_blocked_recompression_fp32(hc, ctx, dims):
+    """fp32 on the blocked path (stacked rank > 64: GEMM-based blocked QR + shared-memory / register Jacobi) at accuracy
+    1e-4 against the fp32 oracle (all blocked tests were f64)."""
+    m, n, k, ka, kb, kc = dims
+    dt, acc = np.float32, 1e-4
+    rng = np.random.default_rng(sum(dims) + 1)
+    AUV, BUV, CUV = lowrank(rng, m, k, ka, dt, 0.9), lowrank(rng, k, n, kb, dt, 0.9), lowrank(rng, m, n, kc, dt, 0.97)
+    cap = min(m, n)
+    a, b = mk_tile(hc, ctx, "C", None, *AUV, dt), mk_tile(hc, ctx, "C", None, *BUV, dt)
+    c = mk_tile(hc, ctx, "C", None, *CUV, dt, max_rank=cap)
+    oa, ob, oc = (oracle_tile("C", None, x, dt) for x in (AUV, BUV, CUV))
+    oc.max_rank = cap
+    for _ in range(2):
+        hc.HCore.Gemm(1.0, a, False, b, False, 1.0, c, ctx, hc.CompressionParameters(acc))
+        O.hcore_gemm(dt(1.0), oa, False, ob, False, dt(1.0), oc, O.CompressionParameters(acc))
+        ref = oc.to_dense().astype(np.float64)
+        assert np.linalg.norm(c.to_dense().astype(np.float64) - ref) <= 10 * acc * max(np.linalg.norm(ref), 1.0)
+        # fp32 singular values near the threshold carry ~1e-6 * sigma_0 of noise on both sides: ranks within a few
+        assert abs(c.GetTileRank() - oc.rank) <= max(1, int(0.03 * oc.rank)), (c.GetTileRank(), oc.rank)
+
+
+@pytest.mark.parametrize("nb,rank,mixes", [(1024, 128, MIXES), (1024, 256, MIXES), (2048, 256, ["CCC", "CDC", "DCC", "CCD"])],
+                         ids=["nb1024-r128", "nb1024-r256", "nb2048-r256"])
+def test_single_tile_sweep_large_ranks(hc, ctx, nb, rank, mixes):
+    """BASELINE.json configs[1]: the single-tile HCore::Gemm sweep at its upper end -- tile 1024 / 2048, operand ranks 128
+    and 256 (stacked rank up to 512: the one-column-per-warp register Jacobi, 8-CTA strip clusters) -- against the oracle."""
+    dt, acc = np.float64, 1e-8
+    rng = np.random.default_rng(nb + rank)
+    AUV, BUV, CUV = lowrank(rng, nb, nb, rank, dt, 0.93), lowrank(rng, nb, nb, rank, dt, 0.93), lowrank(rng, nb, nb, rank, dt, 0.95)
+    Ad, Bd, Cd = AUV[0] @ AUV[1], BUV[0] @ BUV[1], CUV[0] @ CUV[1]
+    for mix in mixes:
+        a = mk_tile(hc, ctx, mix[0], Ad, *AUV, dt)
+        b = mk_tile(hc, ctx, mix[1], Bd, *BUV, dt)
+        cap = nb if mix == "DDC" else nb // 3 + rank
+        c = mk_tile(hc, ctx, mix[2], Cd, *CUV, dt, max_rank=cap)
+        oa, ob, oc = oracle_tile(mix[0], Ad, AUV, dt), oracle_tile(mix[1], Bd, BUV, dt), oracle_tile(mix[2], Cd, CUV, dt)
+        if mix[2] == "C":
+            oc.max_rank = cap
+        hc.HCore.Gemm(1.0, a, False, b, False, 1.0, c, ctx, hc.CompressionParameters(acc))
+        O.hcore_gemm(1.0, oa, False, ob, False, 1.0, oc, O.CompressionParameters(acc))
+        ref = oc.to_dense() if mix != "DDC" else Ad @ Bd + Cd
+        assert relerr(c.to_dense(), ref) <= 10 * acc, mix
+        if mix[2] == "C" and mix != "DDC":
+            assert abs(c.GetTileRank() - oc.rank) <= 1, (mix, c.GetTileRank(), oc.rank)
+
+
+def test_workspace_formula_covers_the_arena(hc):
+    """a2 / a11: hcb_?tlr_gemm_workspace (the replacement of HCore::CalculateMemoryPoolSize, HCore.cpp:417-480) must be an
+    upper bound of what a fused call actually makes the context's arena grow to (plus the arena's own 12.5 % + 1 MiB slack)."""
+    from hcorepp_b200 import _capi
+    rng = np.random.default_rng(2)
+    ctx2 = hc.RunContext(0)          # fresh, empty arena
+    nb, n_tiles, ka, kc = 512, 6, 30, 70
+    As = [hc.CompressedTile.from_uv(*lowrank(rng, nb, nb, ka, np.float64), ctx2) for _ in range(n_tiles)]
+    Bs = [hc.CompressedTile.from_uv(*lowrank(rng, nb, nb, ka, np.float64), ctx2) for _ in range(n_tiles)]
+    Cs = [hc.CompressedTile.from_uv(*lowrank(rng, nb, nb, kc, np.float64), ctx2, max_rank=nb // 3) for _ in range(n_tiles)]
+    for t in Cs:
+        t.rank_bound = kc + ka
+    assert _capi.lib.hcb_ctx_workspace_bytes(ctx2.h) == 0
+    hc.gemm_batched(1.0, As, False, Bs, False, 1.0, Cs, ctx2, hc.CompressionParameters(1e-8))
+    ctx2.Sync()
+    used = _capi.lib.hcb_ctx_workspace_bytes(ctx2.h)
+    formula = _capi.lib.hcb_dtlr_gemm_workspace(n_tiles, nb, nb, nb, (kc + ka) + ka)   # stacked bound = C's rank bound + ka
+    assert 0 < used <= formula * 1.125 + (2 << 20), (used, formula)
