@@ -655,7 +655,7 @@ struct Layout {
     size_t slab = 0, o_w1 = 0, o_w2 = 0, o_uw = 0, o_vw = 0, o_tauu = 0, o_tauv = 0, o_m = 0, o_j = 0, o_us = 0,
            o_vs = 0, o_sig = 0, o_vn = 0, o_vcu = 0, o_vcv = 0, o_tbu = 0, o_tbv = 0, o_wbu = 0, o_wbv = 0, o_mt = 0,
            o_taum = 0, o_lb = 0, o_vcm = 0, o_tbm = 0, o_wbm = 0, o_pj = 0, o_pos = 0, o_gu = 0, o_gu2 = 0, o_q2 = 0,
-           o_tu = 0;
+           o_tu = 0, o_sig0 = 0, o_hv = 0, o_zv = 0, o_q2v = 0, o_q2vt = 0, o_rvp = 0, o_t1 = 0;
     int r_b = 0, pq_b = 0, wcols = 0, nblk = 0, kp_b = 0;
 };
 
@@ -716,6 +716,14 @@ Layout<T> make_layout(const BatchShape &s) {
         L.o_gu2 = take((size_t) s.kC * kp);
         L.o_q2 = take((size_t) 2 * s.m * kp);
         L.o_tu = take((size_t) s.m * std::min(L.pq_b, std::max(s.maxrankC, 1)));
+        // incremental V side
+        L.o_sig0 = take(s.kC);
+        L.o_hv = take((size_t) s.kC * kp);
+        L.o_zv = take((size_t) s.kC * kp);
+        L.o_q2v = take((size_t) 2 * s.n * kp);
+        L.o_q2vt = take((size_t) s.n * kp);
+        L.o_rvp = take((size_t) L.r_b * L.r_b);
+        L.o_t1 = take((size_t) L.r_b * L.r_b);
     }
     L.slab = off;
     return L;
@@ -726,7 +734,7 @@ struct DescArrays {  // device arrays living at the front of the scratch arena
     size_t bytes = 0;
     size_t o_g1, o_g2, o_g3, o_gv, o_gc, o_cp, o_qr, o_rf, o_svd, o_rc, o_rk, o_tiles;
     size_t o_bqr = 0, o_blf = 0, o_bgw = 0, o_bgw2 = 0, o_bgup = 0, o_agw = 0, o_agw2 = 0, o_agup = 0;
-    size_t o_pds = 0, o_pdc = 0, o_qrc = 0, o_lq = 0, o_pc = 0, o_asj = 0, o_gi = 0, o_isj = 0, o_gru = 0;
+    size_t o_pds = 0, o_pdc = 0, o_qrc = 0, o_lq = 0, o_pc = 0, o_asj = 0, o_gi = 0, o_isj = 0, o_gru = 0, o_giv = 0, o_pvc = 0, o_bqr2 = 0;
     int nst_inc = 0;
     explicit DescArrays(int n, int nblk = 0, int qr_cols = 0, int rk_bound = 0, int kp_b = 0) {
         size_t off = 0;
@@ -743,18 +751,21 @@ struct DescArrays {  // device arrays living at the front of the scratch arena
         o_rc = take(sizeof(RecompProb<T>) * n);
         o_rk = take(sizeof(int) * n);
         o_tiles = take(sizeof(hcb_tile) * 3 * n);
-        o_pds = take(sizeof(PanelDesc<T>) * 3 * n);  // U stack, V stack per tile, then one incremental P panel per tile
+        o_pds = take(sizeof(PanelDesc<T>) * 4 * n);  // U stack, V stack per tile, then the incremental P and Y panels
         o_pdc = take(sizeof(PanelDesc<T>) * n);
         o_gi = take(sizeof(GemmProb<T>) * 4 * n);
-        o_gru = take(sizeof(GemmProb<T>) * 2 * n);
+        o_giv = take(sizeof(GemmProb<T>) * 6 * n);   // 4 Gram-Schmidt GEMMs + T1 + X of the incremental V side
+        o_gru = take(sizeof(GemmProb<T>) * 3 * n);
+        o_pvc = take(sizeof(PanelDesc<T>) * n);
         nst_inc = std::max(1, cdiv(std::max(kp_b, 1), NBQ));
-        o_isj = take(sizeof(StripJob) * (size_t) nst_inc * n);
+        o_isj = take(sizeof(StripJob) * (size_t) nst_inc * 2 * n);
         o_qrc = take(sizeof(QrProb<T>) * n);
         o_lq = take(sizeof(LqProb<T>) * n);
         o_pc = take(sizeof(PrecondProb<T>) * n);
         if (nblk > 0) {
             const size_t nb = (size_t) nblk * 2 * n;
-            o_bqr = take(qr_block_desc_bytes<T>(3 * n, qr_cols));
+            o_bqr = take(qr_block_desc_bytes<T>(4 * n, qr_cols));
+            o_bqr2 = take(qr_block_desc_bytes<T>(n, qr_cols));   // second pass: the r x r panels of the incremental V side
             o_asj = take(sizeof(StripJob) * (size_t) cdiv(std::max(rk_bound, 1), NBQ) * 2 * n);
             o_agw = take(sizeof(GemmProb<T>) * nb);
             o_agw2 = take(sizeof(GemmProb<T>) * nb);
@@ -867,6 +878,16 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     sa.inc_sj = reinterpret_cast<StripJob *>(base + D.o_isj);
     sa.nst_inc = D.nst_inc; sa.kp_b = L.kp_b;
     sa.inc_refresh = getenv("HCB_INC_REFRESH") ? std::max(1, atoi(getenv("HCB_INC_REFRESH"))) : 16;
+    // incremental V side: pays when the tile is much taller than the stacked rank (the R-only QR runs on r x r instead of
+    // n x r); HCB_VINC=0/1 overrides the default (on)
+    const bool vinc_enabled = inc_enabled && !(getenv("HCB_VINC") && atoi(getenv("HCB_VINC")) == 0);
+    sa.vinc_enabled = vinc_enabled ? 1 : 0;
+    sa.o_sig0 = L.o_sig0; sa.o_hv = L.o_hv; sa.o_zv = L.o_zv; sa.o_q2v = L.o_q2v; sa.o_q2vt = L.o_q2vt; sa.o_rvp = L.o_rvp;
+    sa.o_t1 = L.o_t1;
+    sa.giv = reinterpret_cast<GemmProb<T> *>(base + D.o_giv);
+    sa.gt1 = sa.giv + 4 * (size_t) n;
+    sa.gx = sa.giv + 5 * (size_t) n;
+    sa.pd_vcore = reinterpret_cast<PanelDesc<T> *>(base + D.o_pvc);
     sa.err_flag = ctx->d_err;
     if (d_info && reset_info) HCB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t) * (size_t) n, ctx->stream));
     {
@@ -922,6 +943,10 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     {
         PhaseScope ph(ctx, 2);
         HCB_TRY(launch_copy<T>(ctx, sa.cp, 4 * n, std::max(s.m, s.n), std::max(L.r_b, 1)));
+        if (vinc_enabled) {
+            k_vinc_sig0<T><<<n, 256, 0, ctx->stream>>>(sa.rc);
+            HCB_LAUNCH_CHECK("k_vinc_sig0");
+        }
         // sort the stack columns by decreasing V-stack norm (same permutation on both stacks)
         const size_t want = align_up((size_t) std::max(L.r_b, 1) * sizeof(T), 16);
         k_stack_order<T><<<n, 256, want, ctx->stream>>>(sa.rc, (int) (want / sizeof(T)));
@@ -943,13 +968,32 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
                 HCB_TRY(launch_gemm<T>(ctx, sa.gi + 2 * (size_t) n, n, s.kC, L.kp_b));
                 HCB_TRY(launch_gemm<T>(ctx, sa.gi + 3 * (size_t) n, n, s.m, L.kp_b));
             }
-            // one pass over 3n panels: the two stacks of every tile (U stack inactive when incremental) + the P panels
-            HCB_TRY(run_blocked_qr<T>(ctx, sa.pd_stack, inc_enabled ? 3 * n : npan, std::max(s.m, s.n), L.r_b, blk_store));
+            if (vinc_enabled) {
+                // ... and of the new V columns against W = CV^T diag(sigma)^-1 (Zv = S^-2 (CV Y), Y -= CV^T Zv, twice)
+                dim3 gs(std::max(1, std::min(16, cdiv((long long) s.kC * L.kp_b, 256))), n);
+                HCB_TRY(launch_gemm<T>(ctx, sa.giv + 0 * (size_t) n, n, s.kC, L.kp_b));
+                k_vinc_scale<T><<<gs, 256, 0, ctx->stream>>>(sa.rc, 0);
+                HCB_LAUNCH_CHECK("k_vinc_scale");
+                HCB_TRY(launch_gemm<T>(ctx, sa.giv + 1 * (size_t) n, n, s.n, L.kp_b));
+                HCB_TRY(launch_gemm<T>(ctx, sa.giv + 2 * (size_t) n, n, s.kC, L.kp_b));
+                k_vinc_scale<T><<<gs, 256, 0, ctx->stream>>>(sa.rc, 1);
+                HCB_LAUNCH_CHECK("k_vinc_scale");
+                HCB_TRY(launch_gemm<T>(ctx, sa.giv + 3 * (size_t) n, n, s.n, L.kp_b));
+            }
+            // one pass over 4n panels: the two stacks of every tile (inactive where incremental) + the P and Y panels
+            HCB_TRY(run_blocked_qr<T>(ctx, sa.pd_stack, inc_enabled ? 4 * n : npan, std::max(s.m, s.n), L.r_b, blk_store));
             if (inc_enabled) {
-                dim3 ge(std::max(1, std::min(64, cdiv((long long) s.m * L.kp_b, 2048))), n);
+                dim3 ge(std::max(1, std::min(64, cdiv((long long) std::max(s.m, s.n) * L.kp_b, 2048))), 2 * n);
                 k_inc_eye<T><<<ge, 256, 0, ctx->stream>>>(sa.rc);
                 HCB_LAUNCH_CHECK("k_inc_eye");
-                HCB_TRY(launch_strips(ctx, sa.inc_sj, D.nst_inc * n, s.m));   // explicit Q2
+                HCB_TRY(launch_strips(ctx, sa.inc_sj, D.nst_inc * 2 * n, std::max(s.m, s.n)));   // explicit Q2 (U and V side)
+            }
+            if (vinc_enabled) {
+                // R-only Householder QR of the r x r matrices RV * Pi (second pass: it needs R2v from the Y panels)
+                dim3 gb(std::max(1, std::min(64, cdiv((long long) L.r_b * L.r_b, 1024))), n);
+                k_vinc_build_rv<T><<<gb, 256, 0, ctx->stream>>>(sa.rc);
+                HCB_LAUNCH_CHECK("k_vinc_build_rv");
+                HCB_TRY(run_blocked_qr<T>(ctx, sa.pd_vcore, n, L.r_b, L.r_b, base + D.o_bqr2));
             }
         }
     }
@@ -985,6 +1029,10 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     {
         PhaseScope ph(ctx, 8);
         HCB_TRY(launch_gemm<T>(ctx, sa.gv, n, L.pq_b, L.pq_b));
+        if (vinc_enabled) {  // V S' = (RV Pi) ((RU Pi)^T Us) for the incremental tiles
+            HCB_TRY(launch_gemm<T>(ctx, sa.gt1, n, L.pq_b, L.pq_b));
+            HCB_TRY(launch_gemm<T>(ctx, sa.gx, n, L.pq_b, L.pq_b));
+        }
         k_truncate<T><<<n, 256, 0, ctx->stream>>>(sa.rc, (T) prm->accuracy, prm->truncated_svd, (int) prm->fixed_rank);
         HCB_LAUNCH_CHECK("k_truncate");
     }
@@ -1003,6 +1051,12 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
         if (inc_enabled) {  // CU' = [CU | Q2] * Us for the incremental tiles (two GEMMs into TU)
             HCB_TRY(launch_gemm<T>(ctx, gru, n, s.m, rk_bound));
             if (!std::is_same<T, double>::value) HCB_TRY(launch_gemm<T>(ctx, gru + n, n, s.m, rk_bound));
+            if (vinc_enabled) {  // VN = [CV ; Q2v^T]^T * (S^-1-scaled V S')
+                dim3 gt(std::max(1, std::min(64, cdiv(s.n, 32) * cdiv(L.kp_b, 32))), n);
+                k_vinc_transpose_q2<T><<<gt, dim3(32, 8), 0, ctx->stream>>>(sa.rc);
+                HCB_LAUNCH_CHECK("k_vinc_transpose_q2");
+                HCB_TRY(launch_gemm<T>(ctx, gru + 2 * (size_t) n, n, s.n, rk_bound));
+            }
         }
     } else {
         // blocked rebuild C := Q [X;0]: blocks last-to-first, three batched GEMMs per block, rank read on the device

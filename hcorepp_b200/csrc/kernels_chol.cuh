@@ -147,7 +147,10 @@ __global__ void k_setup_trsm_tiles(const hcb_tile *__restrict__ tiles, const T *
     g.lda = rk; g.ldb = ldls[t]; g.ldc = rk; g.ta = 0; g.tb = 1; g.alpha = T(-1); g.beta = T(1);
     g.A2 = nullptr; g.k1 = j0; g.lda2 = 1;
     gp[idx] = g;
-    if (step == 0) tp[t] = TrsmProb<T>{V, Ls[t], rk, n, rk, ldls[t]};
+    if (step == 0) {
+        tp[t] = TrsmProb<T>{V, Ls[t], rk, n, rk, ldls[t]};
+        if (X.d_state) atomicAnd(X.d_state, ~HCB_STATE_ORTHO_V);  // V L^-T no longer has orthogonal rows (U is untouched)
+    }
 }
 
 // Descriptors of the symmetric update of the diagonal tiles by the compressed tiles of a block column (HCore<T>::Syrk

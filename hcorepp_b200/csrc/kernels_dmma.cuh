@@ -44,7 +44,7 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // CTA tile (32*WM) x (32*WN), WM*WN == 4 warps, each warp a 32x32 tile = 4x4 DMMA tiles (32 accumulator doubles).
 // BK = 16: four k-steps of 4 per shared-memory stage (two stages); operands staged k-major with a row pitch of tile+4
 // doubles so that the 8-byte fragment loads of a half-warp hit 16 distinct bank pairs.
-// Optional second A segment (p.A2): op(A) = [A | A2] along k, split at p.k1 (ta == 0 only) -- the rebuild
+// Optional second A segment (p.A2): op(A) = [op(A) | op(A2)] along k, split at p.k1 -- the rebuild
 // CU' = [CU | Q2] * Us reads CU from the tile and Q2 from scratch without a second accumulate pass over C.
 // grid = (tiles_bound, n_problems), grid-stride over output tiles.
 template<int WM, int WN>
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(128, 3) k_gemm_dmma(const GemmProb<double> *__
                     const int gr = row0 + r, gk = k0 + kk;
                     double v = 0.0;
                     if (gr < p.m && gk < p.k) {
-                        if (p.ta != 0) v = p.A[(size_t) gk + (size_t) gr * p.lda];
+                        if (p.ta != 0) v = gk < k1 ? p.A[(size_t) gk + (size_t) gr * p.lda] : p.A2[(size_t) (gk - k1) + (size_t) gr * p.lda2];
                         else v = gk < k1 ? p.A[(size_t) gr + (size_t) gk * p.lda] : p.A2[(size_t) gr + (size_t) (gk - k1) * p.lda2];
                     }
                     ra[q] = v;

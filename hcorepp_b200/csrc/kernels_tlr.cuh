@@ -49,6 +49,21 @@ struct RecompProb {
     T *Gu, *Gu2;        // first / second pass coefficients CU^T P (kc x kp, ld kc)
     T *Q2;              // explicit Q2 (m x kp, ld m)
     T *TU;              // rebuild target [CU | Q2] * Us[:, :rk] (m x rk, ld m), copied into CU by k_finalize
+    // Incremental V side (round 2): when the state says "the rows of CV are mutually orthogonal" (CV = diag(sigma) W^T
+    // after every recompression, Compressed.cpp:598-622) the new right columns Y are orthogonalised against W the same way:
+    //   [beta CV^T | Y] = [W | Q2v] * RV,  RV = [[beta S, Gv], [0, R2v]]  (r x r).
+    // The column-sorted, graded triangular factor the Jacobi sweeps need (5 sweeps instead of ~17) comes from a
+    // Householder QR of the SMALL r x r matrix RV * Pi instead of the n x r stack (R only: no Q is ever applied), and
+    // V' = [W | Q2v] * (RV RU^T Us) is GEMMs.
+    int vinc;           // 1: V side incremental
+    int ldvw;           // leading dimension of the QR-factored V panel k_extract_r reads R from (n, or r when vinc)
+    T *sig0;            // row norms of CV = the old singular values (kc)
+    T *Yn;              // Y (n x kp, ld n): orthogonalised in place against W, then QR-factored in place
+    T *Hv, *Zv;         // Hv = sum over the two passes of CV * Y (kc x kp, ld kc);  Zv = diag(sigma)^-2 * (CV * Y) of the pass
+    T *Q2v, *Q2vT;      // explicit Q2v (n x kp, ld n) and its transpose (kp x n, ld kp)
+    T *RVp;             // copy of RV * Pi (r x r, ld r) kept for V S = RV Pi (RU Pi)^T Us (the QR overwrites its own copy)
+    T *T1;              // (RU Pi)^T Us (r x b, ld r)
+    T beta_c;           // beta of the call (scales the old singular values in RV)
     int lp, lq;         // leading dimensions of the extracted triangles MT (p x r) / Lb (q x r): p, q rounded up to even
                         // so that the core GEMM's row-contiguous operands qualify for TMA bulk copies
     int *state;         // C tile's device state word (may be null)
@@ -114,6 +129,12 @@ struct SetupArgs {
     StripJob *inc_sj;           // nst_inc per tile: explicit Q2 = H_0 .. H_{kp-1} [I; 0]
     int nst_inc, kp_b;
     int inc_refresh;            // consecutive incremental updates allowed before one full re-factorisation
+    // incremental V side
+    int vinc_enabled;
+    size_t o_sig0, o_hv, o_zv, o_q2v, o_q2vt, o_rvp, o_t1;
+    GemmProb<T> *giv;           // 4 arrays of n (Hv = CV Y, Y -= CV^T Zv, twice)
+    GemmProb<T> *gt1, *gx;      // T1 = (RU Pi)^T Us ;  X = (RV Pi) T1  (arrays of n)
+    PanelDesc<T> *pd_vcore;     // 1 per tile: the r x r panel RV * Pi (R-only QR)
     int *err_flag;              // context-level sticky error word (bit 2: a rank exceeded its bound)
 };
 
@@ -181,9 +202,10 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
     const T one = T(1), zero = T(0);
     int kp = 0;  // rank of the product term entering the recompression
     GemmProb<T> gi0 = g1, gi1 = g1, gi2 = g1, gi3 = g1;
-    PanelDesc<T> pdi;
-    memset(&pdi, 0, sizeof(pdi));
-    int inc = 0;
+    GemmProb<T> gv0 = g1, gv1 = g1, gv2 = g1, gv3 = g1, gt1 = g1, gx = g1;
+    PanelDesc<T> pdi, pdiv, pdvc;
+    memset(&pdi, 0, sizeof(pdi)); memset(&pdiv, 0, sizeof(pdiv)); memset(&pdvc, 0, sizeof(pdvc));
+    int inc = 0, vinc = 0;
 
     if (!bad) {
         switch (s.mix) {
@@ -294,6 +316,38 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
                     gi3 = mk_gemm<T>(CU, m, 0, rc.Gu2, kc, 0, rc.Pn, m, m, kp, kc, -one, one);    // P -= CU G2
                     pdi = PanelDesc<T>{rc.Pn, rc.tauU, VCp, rc.TB[0], rc.WB[0], m, kp, s.wcols, 1};
                 }
+                // incremental V side: the rows of CV are known to be orthogonal
+                rc.ldvw = n;
+                rc.beta_c = s.beta;
+                vinc = s.vinc_enabled && (st_word & HCB_STATE_ORTHO_V) && (st_word >> 8) < s.inc_refresh && kc >= 1 && kp >= 1 &&
+                       r <= m && r <= n && kp <= s.kp_b && s.beta != T(0);
+                if (vinc) {
+                    rc.vinc = 1;
+                    rc.ldvw = r;
+                    rc.sig0 = slab + s.o_sig0;
+                    rc.Yn = SV0 + (size_t) n * kc;
+                    rc.Hv = slab + s.o_hv; rc.Zv = slab + s.o_zv;
+                    T *VCy = slab + s.o_q2v;
+                    rc.Q2v = VCy + (size_t) n * s.kp_b;
+                    rc.Q2vT = slab + s.o_q2vt;
+                    rc.RVp = slab + s.o_rvp;
+                    rc.T1 = slab + s.o_t1;
+                    c2.rows = 0;          // CV is read in place
+                    pdv.active = 0;       // no Householder QR of the n x r stack
+                    q1.m = 0;
+                    gv0 = mk_gemm<T>(CV, kc, 0, rc.Yn, n, 0, rc.Hv, kc, kc, kp, n, one, zero);    // Hv  = CV Y
+                    gv1 = mk_gemm<T>(CV, kc, 1, rc.Zv, kc, 0, rc.Yn, n, n, kp, kc, -one, one);    // Y  -= CV^T Zv
+                    gv2 = mk_gemm<T>(CV, kc, 0, rc.Yn, n, 0, rc.Zv, kc, kc, kp, n, one, zero);    // Zv  = CV Y   (second pass)
+                    gv3 = gv1;
+                    pdiv = PanelDesc<T>{rc.Yn, rc.tauV, VCy, rc.TB[1], rc.WB[1], n, kp, s.wcols, 1};
+                    // R-only QR of the r x r matrix RV * Pi, assembled in the (otherwise unused) VW buffer with ld r; its clean
+                    // reflectors / T blocks reuse the V stack's scratch (free once the Y panel has been expanded into Q2v)
+                    pdvc = PanelDesc<T>{VW, slab + s.o_taum, slab + s.o_vcm, slab + s.o_tbm, slab + s.o_wbm, r, r, s.wcols, 1};
+                    // V S' = (RV Pi) (RU Pi)^T Us  instead of  K'^T Us  (K' = K O carries the QR's orthogonal factor on the right)
+                    gv.m = 0;
+                    gt1 = mk_gemm<T>(rc.MT, rc.lp, 1, rc.Us, rc.a, 0, rc.T1, r, r, rc.b, p, one, zero);
+                    gx = mk_gemm<T>(rc.RVp, r, 0, rc.T1, r, 0, rc.Vs, rc.b, r, rc.b, r, one, zero);
+                }
             }
         }
     }
@@ -309,9 +363,10 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
         qm.m = qm.n = 0;
         lq.a = lq.b = 0;
         gi0.m = gi1.m = gi2.m = gi3.m = 0;
-        pdi.active = 0;
-        inc = 0;
-        rc.inc = 0;
+        gv0.m = gv1.m = gv2.m = gv3.m = gt1.m = gx.m = 0;
+        pdi.active = pdiv.active = pdvc.active = 0;
+        inc = vinc = 0;
+        rc.inc = rc.vinc = 0;
         // rank exceeded the bound the scratch was sized for: tile left untouched.  Sticky in d_info (flags are OR-ed, the
         // caller of the entry point zeroes them) AND in the context's error word, so that a caller without an info buffer
         // still hears about it at the next hcb_ctx_sync.
@@ -319,15 +374,27 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
         if (s.err_flag) atomicOr(s.err_flag, 4);
     }
     for (int q = 0; q < 4; ++q) s.gi[(size_t) q * s.n_tiles + t] = q == 0 ? gi0 : (q == 1 ? gi1 : (q == 2 ? gi2 : gi3));
+    for (int q = 0; q < 4; ++q) s.giv[(size_t) q * s.n_tiles + t] = q == 0 ? gv0 : (q == 1 ? gv1 : (q == 2 ? gv2 : gv3));
+    s.gt1[t] = gt1; s.gx[t] = gx;
     s.pd_inc[t] = pdi;
+    s.pd_inc[s.n_tiles + t] = pdiv;
+    s.pd_vcore[t] = pdvc;
     if constexpr (std::is_same<T, double>::value) {
-        for (int st = 0; st < s.nst_inc; ++st) {  // explicit Q2: strip st of [I; 0] takes the panel's blocks last to first
-            StripJob j{nullptr, nullptr, nullptr, 1, 1, 0, 0, 0, 0, 0, -1, 0};
-            if (inc && st * NBQ < kp) {
-                const int nbp = (kp + NBQ - 1) / NBQ, nc = (kp - st * NBQ) < NBQ ? (kp - st * NBQ) : NBQ;
-                j = StripJob{rc.Q2 + (size_t) st * NBQ * m, pdi.VC, pdi.TB, m, m, m, nc, kp, nbp - 1, nbp, -1, 0};
+        // explicit Q2 (U side: jobs [0, n*nst), V side: jobs [n*nst, 2*n*nst)): strip st of [I; 0] takes the panel's blocks
+        // last to first
+        for (int side = 0; side < 2; ++side) {
+            const bool on = side ? vinc : inc;
+            const int rows = side ? n : m;
+            const PanelDesc<T> &pd = side ? pdiv : pdi;
+            T *Q = side ? rc.Q2v : rc.Q2;
+            for (int st = 0; st < s.nst_inc; ++st) {
+                StripJob j{nullptr, nullptr, nullptr, 1, 1, 0, 0, 0, 0, 0, -1, 0};
+                if (on && st * NBQ < kp) {
+                    const int nbp = (kp + NBQ - 1) / NBQ, nc = (kp - st * NBQ) < NBQ ? (kp - st * NBQ) : NBQ;
+                    j = StripJob{Q + (size_t) st * NBQ * rows, pd.VC, pd.TB, rows, rows, rows, nc, kp, nbp - 1, nbp, -1, 0};
+                }
+                s.inc_sj[((size_t) side * s.n_tiles + t) * s.nst_inc + st] = j;
             }
-            s.inc_sj[(size_t) t * s.nst_inc + st] = j;
         }
     }
     s.g1[t] = g1; s.g2[t] = g2; s.g3[t] = g3; s.gv[t] = gv; s.gc[t] = gc;
@@ -503,6 +570,10 @@ __global__ void __launch_bounds__(256) k_stack_order(const RecompProb<T> *__rest
         return;
     }
     for (int c = w; c < r; c += nw) {
+        if (p.vinc && c < p.kc) {  // incremental V side: the old columns are beta * sigma_c * w_c, never assembled
+            if (lane == 0) { const T v = p.beta_c * p.sig0[c]; nrm[c] = v * v; }
+            continue;
+        }
         const T *col = p.SV0 + (size_t) c * n;
         T ss = T(0);
         for (int i = lane; i < n; i += 32) ss = fma(col[i], col[i], ss);
@@ -530,6 +601,7 @@ __global__ void __launch_bounds__(256) k_permute_stacks(const RecompProb<T> *__r
     if (!p.active) return;
     const int side = blockIdx.y & 1;
     if (p.inc && side == 0) return;  // incremental U side: CU is used in place, P stays where the contraction wrote it
+    if (p.vinc && side == 1) return; // incremental V side: likewise for CV and Y
     const int rows = side ? p.n : p.m;
     const T *src = side ? p.SV0 : p.SU0;
     T *dst = side ? p.VW : p.UW;
@@ -626,6 +698,15 @@ __global__ void k_setup_apply_strips(const RecompProb<T> *__restrict__ rcs, Stri
         }
         gru[idx] = ga;
         gru[npan / 2 + idx] = gb;
+        // incremental V side: VN = [CV^T | Q2v] * Vs[:, :rk] = [CV ; Q2v^T]^T * Vs (two-segment transposed A) -> VN (n x rk)
+        GemmProb<T> gn = mk_gemm<T>(nullptr, 1, 0, nullptr, 1, 0, nullptr, 1, 0, 0, 0, T(0), T(0));
+        if (rc.active && rc.vinc) {
+            int rk = *rc.rk_new;
+            if (rk > rc.wcols) rk = 0;
+            gn = mk_gemm<T>(rc.CV, rc.kc, 1, rc.Vs, rc.b, 0, rc.VN, rc.n, rc.n, rk, rc.kc + rc.kp, T(1), T(0));
+            gn.A2 = rc.Q2vT; gn.k1 = rc.kc; gn.lda2 = rc.kp;
+        }
+        gru[2 * (npan / 2) + idx] = gn;
     }
     if (idx >= nstrips * npan) return;
     // the strips of one panel are neighbours in the grid: they run at the same time and share the panel's reflector
@@ -634,7 +715,7 @@ __global__ void k_setup_apply_strips(const RecompProb<T> *__restrict__ rcs, Stri
     const RecompProb<T> rc = rcs[pan >> 1];
     StripJob j{nullptr, nullptr, nullptr, 1, 1, 0, 0, 0, 0, 0, -1, 0};
     if constexpr (std::is_same<T, double>::value) {
-        if (rc.active && !(rc.inc && side == 0)) {
+        if (rc.active && !(rc.inc && side == 0) && !(rc.vinc && side == 1)) {
             const int m = side ? rc.n : rc.m, r = rc.r, kmax = m < r ? m : r;
             int rk = *rc.rk_new;
             if (rk > rc.wcols) rk = 0;
@@ -731,7 +812,7 @@ __global__ void __launch_bounds__(256) k_extract_r(const RecompProb<T> *__restri
             }
         } else {
             const int e = idx - nu, j = e % p.q, l = e / p.q;
-            p.Lb[(size_t) j + (size_t) l * p.lq] = j <= l ? p.VW[(size_t) j + (size_t) l * p.n] : T(0);
+            p.Lb[(size_t) j + (size_t) l * p.lq] = j <= l ? p.VW[(size_t) j + (size_t) l * p.ldvw] : T(0);
         }
     }
 }
@@ -784,7 +865,15 @@ __global__ void __launch_bounds__(256) k_truncate(const RecompProb<T> *__restric
             const int i = idx % p.m, c = idx / p.m;
             p.CU[(size_t) i + (size_t) c * p.m] = (i < p.p) ? p.Us[(size_t) i + (size_t) c * p.a] : T(0);
         }
-        for (int idx = threadIdx.x; idx < p.n * rk; idx += blockDim.x) {
+        // (incremental V side: Vs = V S' in [W | Q2v] coordinates is consumed by the rebuild GEMM; its first kc rows are
+        // divided by the old singular values here because the GEMM multiplies by CV^T = W diag(sigma), not by W)
+        if (p.vinc) {
+            for (int idx = threadIdx.x; idx < p.kc * rk; idx += blockDim.x) {
+                const int i = idx % p.kc, c = idx / p.kc;
+                p.Vs[(size_t) i + (size_t) c * p.b] /= p.sig0[i];
+            }
+        }
+        for (int idx = threadIdx.x; idx < (p.vinc ? 0 : p.n * rk); idx += blockDim.x) {
             const int i = idx % p.n, c = idx / p.n;
             p.VN[(size_t) i + (size_t) c * p.n] = (i < p.q) ? p.Vs[(size_t) i + (size_t) c * p.b] : T(0);
         }
@@ -834,20 +923,110 @@ __global__ void __launch_bounds__(256) k_finalize(const RecompProb<T> *__restric
         // U = Q_U * (normalised left vectors of the core): orthonormal columns unless a kept singular value vanished
         if (p.state) {
             const bool ortho = !p.transposed && p.sigma[rk - 1] > T(1e-30) * p.sigma[0] && p.sigma[0] > T(0);
-            const int count = p.inc ? ((*p.state >> 8) + 1) : 0;  // consecutive incremental updates so far
-            *p.state = ortho ? (HCB_STATE_ORTHO_U | (count << 8)) : 0;
+            const int count = (p.inc || p.vinc) ? ((*p.state >> 8) + 1) : 0;  // consecutive incremental updates so far
+            *p.state = ortho ? (HCB_STATE_ORTHO_U | HCB_STATE_ORTHO_V | (count << 8)) : 0;
         }
     }
 }
 
-// [I; 0] in the explicit-Q2 buffers of the incremental tiles.  grid = (chunks, n_tiles)
+// [I; 0] in the explicit-Q2 buffers of the incremental tiles (U side and V side).  grid = (chunks, 2 * n_tiles)
 template<typename T>
 __global__ void __launch_bounds__(256) k_inc_eye(const RecompProb<T> *__restrict__ probs) {
-    const RecompProb<T> p = probs[blockIdx.y];
-    if (!p.active || !p.inc) return;
-    const size_t total = (size_t) p.m * p.kp;
+    const RecompProb<T> p = probs[blockIdx.y >> 1];
+    const int side = blockIdx.y & 1;
+    if (!p.active || !(side ? p.vinc : p.inc)) return;
+    const int rows = side ? p.n : p.m;
+    T *Q = side ? p.Q2v : p.Q2;
+    const size_t total = (size_t) rows * p.kp;
     for (size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t) gridDim.x * blockDim.x)
-        p.Q2[idx] = (idx % p.m == idx / p.m) ? T(1) : T(0);
+        Q[idx] = (idx % rows == idx / rows) ? T(1) : T(0);
+}
+
+// Incremental V side: sig0[i] = || CV(i, :) ||, the old singular values (CV = diag(sigma) W^T).  One CTA per tile;
+// thread (i, g) of a 32 x 8 block walks row i + 32a over the columns g, g + 8, ... (rows are contiguous in memory).
+template<typename T>
+__global__ void __launch_bounds__(256) k_vinc_sig0(const RecompProb<T> *__restrict__ probs) {
+    const RecompProb<T> p = probs[blockIdx.x];
+    if (!p.active || !p.vinc) return;
+    __shared__ T part[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i0 = 0; i0 < p.kc; i0 += 32) {
+        const int i = i0 + tx;
+        T ss = T(0);
+        if (i < p.kc)
+            for (int j = ty; j < p.n; j += 8) { const T v = p.CV[(size_t) i + (size_t) j * p.kc]; ss = fma(v, v, ss); }
+        part[ty][tx] = ss;
+        __syncthreads();
+        if (ty == 0 && i < p.kc) {
+            T tot = T(0);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) tot += part[g][tx];
+            p.sig0[i] = t_sqrt(tot);
+        }
+        __syncthreads();
+    }
+}
+
+// Incremental V side: Zv = diag(sigma)^-2 * H of the CURRENT pass.  pass 0: H = Hv (first GEMM);  pass 1: the second
+// GEMM left H2 = CV * Y1 in Zv -- it is added to Hv (Gv = S^-1 (H + H2)) and scaled in place.  grid = (chunks, n_tiles)
+template<typename T>
+__global__ void __launch_bounds__(256) k_vinc_scale(const RecompProb<T> *__restrict__ probs, int pass) {
+    const RecompProb<T> p = probs[blockIdx.y];
+    if (!p.active || !p.vinc) return;
+    const int total = p.kc * p.kp;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const T sg = p.sig0[idx % p.kc], s2 = sg * sg;
+        T h;
+        if (pass == 0) h = p.Hv[idx];
+        else { h = p.Zv[idx]; p.Hv[idx] += h; }
+        p.Zv[idx] = h / s2;
+    }
+}
+
+// Incremental V side: RV * Pi (r x r) into the VW buffer (ld r, QR-factored next) and into RVp (kept):
+//   RV = [[beta S, Gv], [0, R2v]],  Gv = S^-1 Hv,  R2v = the triangle of the QR-factored Y panel;  column c goes to pos[c].
+// grid = (chunks, n_tiles)
+template<typename T>
+__global__ void __launch_bounds__(256) k_vinc_build_rv(const RecompProb<T> *__restrict__ probs) {
+    const RecompProb<T> p = probs[blockIdx.y];
+    if (!p.active || !p.vinc) return;
+    const int r = p.r, total = r * r;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int i = idx % r, c = idx / r;
+        T v;
+        if (c < p.kc) v = (i == c) ? p.beta_c * p.sig0[c] : T(0);
+        else {
+            const int l = c - p.kc;
+            if (i < p.kc) v = p.Hv[(size_t) i + (size_t) l * p.kc] / p.sig0[i];
+            else v = (i - p.kc <= l) ? p.Yn[(size_t) (i - p.kc) + (size_t) l * p.n] : T(0);
+        }
+        const size_t o = (size_t) i + (size_t) p.pos[c] * r;
+        p.VW[o] = v;
+        p.RVp[o] = v;
+    }
+}
+
+// Incremental V side: Q2vT (kp x n, ld kp) = Q2v^T, so that [CV ; Q2vT] is one transposed two-segment GEMM operand.
+// grid = (tile chunks, n_tiles), block (32, 8)
+template<typename T>
+__global__ void __launch_bounds__(256) k_vinc_transpose_q2(const RecompProb<T> *__restrict__ probs) {
+    const RecompProb<T> p = probs[blockIdx.y];
+    if (!p.active || !p.vinc) return;
+    __shared__ T tile[32][33];
+    const int tr = (p.n + 31) / 32, tc = (p.kp + 31) / 32, tx = threadIdx.x, ty = threadIdx.y;
+    for (int t = blockIdx.x; t < tr * tc; t += gridDim.x) {
+        const int r0 = (t % tr) * 32, c0 = (t / tr) * 32;  // r: row of Q2v (0..n), c: column (0..kp)
+        for (int j = ty; j < 32; j += 8) {
+            const int r = r0 + tx, c = c0 + j;
+            tile[j][tx] = (r < p.n && c < p.kp) ? p.Q2v[(size_t) r + (size_t) c * p.n] : T(0);
+        }
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8) {
+            const int c = c0 + tx, r = r0 + j;
+            if (r < p.n && c < p.kp) p.Q2vT[(size_t) c + (size_t) r * p.kp] = tile[tx][j];
+        }
+        __syncthreads();
+    }
 }
 
 // DDC epilogue (HCore.cpp:291-298 -> CompressedTile::ReadjustTile, Compressed.cpp:696-734): C becomes full rank,

@@ -104,6 +104,7 @@ typedef struct hcb_tile {
     int32_t reserved;
 } hcb_tile;
 #define HCB_STATE_ORTHO_U 1
+#define HCB_STATE_ORTHO_V 2  /* the rows of V are mutually orthogonal (V = diag(sigma) W^T, Compressed.cpp:598-622) */
 
 /* ---- (2) fine-grained kernel table : one symbol per HCoreKernels<T> entry (kernels.hpp:27-129) --------------- */
 /* trans: 0 NoTrans, 1 Trans.  type for lacpy/laset: 'G','U','L' (common::MatrixType).  side 'L'/'R'. */

@@ -507,7 +507,7 @@ def test_incremental_u_side_ksum_vs_oracle(hc, ctx):
     for mode, (d, ranks, states, U) in res.items():
         assert relerr(d, ref) <= 10 * acc, mode
         assert max(abs(a - b) for a, b in zip(ranks, oranks)) <= 1, (mode, ranks, oranks)
-        assert all(s & 1 for s in states), (mode, states)
+        assert all(s & 3 == 3 for s in states), (mode, states)   # U orthonormal, rows of V orthogonal
         assert [s >> 8 for s in states] == ([0] + list(range(1, kt)) if mode == "incremental" else [0] * kt), (mode, states)
         # accuracy-aware Jacobi stop: the left vectors are orthogonal to ~0.05 * accuracy per update (adds up over the
         # incremental updates until the periodic full re-factorisation)
