@@ -95,6 +95,7 @@ def _declare(p, ct):
     f("syrk").argtypes = [vp, C.c_int, C.c_int, i64, i64, ct, vp, i64, ct, vp, i64]
     f("fill_triangle").argtypes = [vp, C.c_int, i64, vp, i64, ct]
     f("symmetrize").argtypes = [vp, C.c_int, i64, vp, i64]
+    f("transpose").argtypes = [vp, i64, i64, vp, i64, vp, i64]
     f("tlr_trsm_batched").argtypes = [vp, i64, _PT, C.POINTER(vp), C.POINTER(i64)]
     f("tlr_syrk_batched").argtypes = [vp, i64, _PT, C.POINTER(vp), C.POINTER(i64), ct, ct]
     f("tlr_potrf").argtypes = [vp, i64, i64, C.POINTER(vp), i64, _PT, _PP, vp, vp]

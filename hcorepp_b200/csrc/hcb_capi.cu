@@ -1784,6 +1784,11 @@ int hcb_memset(hcb_ctx *c, void *dst, int value, size_t bytes) {
                             int64_t k_end, T alpha, T beta, const hcb_compress_params *p, int32_t *info) {            \
         return t_tlr_matmul<T>(c, mt, nt, kt, A, B, C, owned, n_owned, k_begin, k_end, alpha, beta, p, info);        \
     }                                                                                                                 \
+    int hcb_##P##transpose(hcb_ctx *c, int64_t rows, int64_t cols, const T *A, int64_t lda, T *Out, int64_t ldo) {     \
+        int rc_ = check_ctx(c);                                                                                       \
+        if (rc_ != HCB_OK) return rc_;                                                                                \
+        return t_copy<T>(c, A, (int) lda, Out, (int) ldo, (int) cols, (int) rows, 1, T(1));                          \
+    }                                                                                                                 \
     int hcb_##P##potrf(hcb_ctx *c, int uplo, int64_t n, T *A, int64_t lda, int32_t *d_info) {                          \
         return t_potrf<T>(c, uplo, n, A, lda, d_info);                                                               \
     }                                                                                                                 \

@@ -144,6 +144,8 @@ typedef struct hcb_tile {
                       T *dC, int64_t ldc);                                                                             \
     int hcb_##P##fill_triangle(hcb_ctx *, int uplo, int64_t n, T *dA, int64_t lda, T value); /* strict triangle */      \
     int hcb_##P##symmetrize(hcb_ctx *, int uplo, int64_t n, T *dA, int64_t lda);           /* copy uplo onto the other */ \
+    /* HCoreKernels<T>::transpose (omp/kernels.cpp:305-333): Out (cols x rows, ldo) = A (rows x cols, lda)^T           */  \
+    int hcb_##P##transpose(hcb_ctx *, int64_t rows, int64_t cols, const T *dA, int64_t lda, T *dOut, int64_t ldo);      \
     /* Batched tile forms for the Cholesky driver (HOST arrays of descriptors / device pointers):                    */  \
     /*   tlr_trsm_batched: X[t] := X[t] * L[t]^-T for compressed X (acts on the V factor only; HCore<T>::Trsm,        */  \
     /*                     HCore.cpp:624-647, in this library's V = rank x n convention)                             */  \

@@ -7,6 +7,9 @@
 // is_complex, Gflop, Queue, op2str and the five char enums).  All arithmetic is forwarded to the
 // Fortran BLAS inside the scipy wheel's OpenBLAS (symbols prefixed scipy_, LP64).
 #pragma once
+#ifdef HCB_SHIM_CUDA_QUEUE
+#include <cuda_runtime.h>
+#endif
 #include <complex>
 #include <cstdint>
 #include <cstddef>
@@ -68,12 +71,31 @@ template<typename T> struct is_complex<std::complex<T>> : std::true_type {};
 inline float conj(float x) { return x; }
 inline double conj(double x) { return x; }
 
+#ifdef HCB_SHIM_CUDA_QUEUE
+// drop-in build of the reference's -DUSE_CUDA operator layer (tests/dropin): the queue is what BLAS++ makes it there,
+// a CUDA stream with sync(); no cuBLAS handle behind it (nothing on the new path uses one)
+class Queue {
+public:
+    Queue() : Queue(0, 0) {}
+    Queue(int device, int64_t) {
+        cudaSetDevice(device);
+        cudaStreamCreateWithFlags(&mStream, cudaStreamNonBlocking);
+    }
+    Queue(const Queue &) = delete;
+    ~Queue() { if (mStream) cudaStreamDestroy(mStream); }
+    cudaStream_t stream() const { return mStream; }
+    void sync() { cudaStreamSynchronize(mStream); }
+private:
+    cudaStream_t mStream = nullptr;
+};
+#else
 class Queue {
 public:
     Queue() = default;
     Queue(int, int64_t) {}
     void sync() {}
 };
+#endif
 
 namespace detail {
     inline char flip_uplo(Uplo u) { return u == Uplo::Upper ? 'L' : (u == Uplo::Lower ? 'U' : 'G'); }

@@ -981,3 +981,35 @@ def test_workspace_formula_covers_the_arena(hc):
     used = _capi.lib.hcb_ctx_workspace_bytes(ctx2.h)
     formula = _capi.lib.hcb_dtlr_gemm_workspace(n_tiles, nb, nb, nb, (kc + ka) + ka)   # stacked bound = C's rank bound + ka
     assert 0 < used <= formula * 1.125 + (2 << 20), (used, formula)
+
+
+def test_dropin_reference_operator_layer_on_libhcore_b200(tmp_path):
+    """the reference's UNMODIFIED src/api/HCore.cpp + src/operators/concrete/{Compressed,Dense}.cpp
+    (compiled with -DUSE_CUDA by tests/dropin/Makefile) linked against integration/src/kernels/b200/kernels.cpp, i.e. the
+    kernel table HCoreKernels<T> forwarded to libhcore_b200.so.  The binary replays a TestGemm-style known answer, a Potrf,
+    and a seeded 5-step k-sum through the reference's own tile-at-a-time flow (Geqrf / ungqr / SVD / CalculateNewRank / ...
+    per tile); the result is compared with the oracle on the same bytes: ranks +/-1, relative Frobenius <= 10*acc."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin", "dropin_test")
+    assert os.path.exists(exe), "tests/dropin/dropin_test not built (run __graft_entry__.build() where /root/reference exists)"
+    nb, ka, steps, acc = 192, 16, 5, 1e-8
+    tiles = [(O.synth_compressed_tile(nb, ka, 500 + k), O.synth_compressed_tile(nb, ka, 600 + k)) for k in range(steps)]
+    inp, out = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(inp, "wb") as f:
+        f.write(np.array([nb, ka, steps], dtype=np.int64).tobytes())
+        f.write(np.array([acc], dtype=np.float64).tobytes())
+        for a, b in tiles:
+            for x in (a.U, a.V, b.U, b.V):
+                f.write(np.asfortranarray(x, dtype=np.float64).tobytes(order="F"))
+    r = subprocess.run([exe, inp, out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "0 failure(s)" in r.stdout, r.stdout[-3000:]
+    raw = np.fromfile(out, dtype=np.uint8)
+    ranks = raw[: 8 * steps].view(np.int64)
+    dense = raw[8 * steps:].view(np.float64).reshape((nb, nb), order="F")
+    oC = O.CompressedTile(np.zeros((nb, 1), order="F"), np.zeros((1, nb), order="F"), nb // 3)
+    oranks = []
+    for a, b in tiles:
+        O.hcore_gemm(1.0, a, False, b, False, 1.0, oC, O.CompressionParameters(acc))
+        oranks.append(oC.rank)
+    assert max(abs(int(x) - y) for x, y in zip(ranks, oranks)) <= 1, (ranks, oranks)
+    assert relerr(dense, oC.to_dense()) <= 10 * acc
