@@ -655,7 +655,8 @@ struct Layout {
     size_t slab = 0, o_w1 = 0, o_w2 = 0, o_uw = 0, o_vw = 0, o_tauu = 0, o_tauv = 0, o_m = 0, o_j = 0, o_us = 0,
            o_vs = 0, o_sig = 0, o_vn = 0, o_vcu = 0, o_vcv = 0, o_tbu = 0, o_tbv = 0, o_wbu = 0, o_wbv = 0, o_mt = 0,
            o_taum = 0, o_lb = 0, o_vcm = 0, o_tbm = 0, o_wbm = 0, o_pj = 0, o_pos = 0, o_gu = 0, o_gu2 = 0, o_q2 = 0,
-           o_tu = 0, o_sig0 = 0, o_hv = 0, o_zv = 0, o_q2v = 0, o_q2vt = 0, o_rvp = 0, o_t1 = 0;
+           o_tu = 0, o_sig0 = 0, o_hv = 0, o_zv = 0, o_q2v = 0, o_q2vt = 0, o_rvp = 0, o_t1 = 0, o_xu = 0, o_xv = 0, o_rn = 0,
+           o_t1b = 0;
     int r_b = 0, pq_b = 0, wcols = 0, nblk = 0, kp_b = 0;
 };
 
@@ -724,6 +725,10 @@ Layout<T> make_layout(const BatchShape &s) {
         L.o_q2vt = take((size_t) s.n * kp);
         L.o_rvp = take((size_t) L.r_b * L.r_b);
         L.o_t1 = take((size_t) L.r_b * L.r_b);
+        L.o_xu = take((size_t) L.r_b * kp);
+        L.o_xv = take((size_t) L.r_b * kp);
+        L.o_rn = take((size_t) L.r_b * kp);
+        L.o_t1b = take((size_t) L.r_b * kp);
     }
     L.slab = off;
     return L;
@@ -884,6 +889,7 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     sa.vinc_enabled = vinc_enabled ? 1 : 0;
     sa.o_sig0 = L.o_sig0; sa.o_hv = L.o_hv; sa.o_zv = L.o_zv; sa.o_q2v = L.o_q2v; sa.o_q2vt = L.o_q2vt; sa.o_rvp = L.o_rvp;
     sa.o_t1 = L.o_t1;
+    sa.o_xu = L.o_xu; sa.o_xv = L.o_xv; sa.o_rn = L.o_rn; sa.o_t1b = L.o_t1b;
     sa.giv = reinterpret_cast<GemmProb<T> *>(base + D.o_giv);
     sa.gt1 = sa.giv + 4 * (size_t) n;
     sa.gx = sa.giv + 5 * (size_t) n;
@@ -1005,6 +1011,11 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
             dim3 gx(std::max(1, std::min(128, cdiv((long long) 2 * L.pq_b * L.r_b, 256))), n);
             k_extract_r<T><<<gx, 256, 0, ctx->stream>>>(sa.rc);
             HCB_LAUNCH_CHECK("k_extract_r");
+            if (vinc_enabled) {  // tiles with both sides incremental: gather part of the core (the GEMM below adds the rest)
+                dim3 gk(std::max(1, std::min(64, cdiv(L.pq_b, 32) * cdiv(L.pq_b, 32))), n);
+                k_both_core<T><<<gk, dim3(32, 8), 0, ctx->stream>>>(sa.rc);
+                HCB_LAUNCH_CHECK("k_both_core");
+            }
             HCB_TRY(launch_gemm<T>(ctx, sa.gc, n, L.pq_b, L.pq_b));
         } else {
             k_core_build<T><<<grid, 256, 0, ctx->stream>>>(sa.rc);

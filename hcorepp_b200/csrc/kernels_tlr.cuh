@@ -64,6 +64,14 @@ struct RecompProb {
     T *RVp;             // copy of RV * Pi (r x r, ld r) kept for V S = RV Pi (RU Pi)^T Us (the QR overwrites its own copy)
     T *T1;              // (RU Pi)^T Us (r x b, ld r)
     T beta_c;           // beta of the call (scales the old singular values in RV)
+    // Both sides incremental: K = RU RV^T = diag(beta S, 0) + Xu Xv^T is a rank-kp update of a diagonal matrix, so the
+    // three r^3 GEMMs around the Jacobi kernel collapse to rank-kp ones:
+    //   K' = (RU Pi) R'^T :  row i < kc of K' is column pos[i] of R' (gather), plus  Xu * (R'[:, pos[kc..]])^T
+    //   V S' = RV RU^T Us  =  diag(beta S, 0) Us  +  Xv (Xu^T Us)
+    int both;           // 1: inc && vinc
+    T *Xu, *Xv;         // [Gu ; R2u], [Gv ; R2v]  (r x kp, ld r)
+    T *Rn;              // R'[:, pos[kc + l]], l < kp  (r x kp, ld r)
+    T *T1b;             // Xu^T Us  (kp x b, ld kp)
     int lp, lq;         // leading dimensions of the extracted triangles MT (p x r) / Lb (q x r): p, q rounded up to even
                         // so that the core GEMM's row-contiguous operands qualify for TMA bulk copies
     int *state;         // C tile's device state word (may be null)
@@ -135,6 +143,7 @@ struct SetupArgs {
     GemmProb<T> *giv;           // 4 arrays of n (Hv = CV Y, Y -= CV^T Zv, twice)
     GemmProb<T> *gt1, *gx;      // T1 = (RU Pi)^T Us ;  X = (RV Pi) T1  (arrays of n)
     PanelDesc<T> *pd_vcore;     // 1 per tile: the r x r panel RV * Pi (R-only QR)
+    size_t o_xu, o_xv, o_rn, o_t1b;
     int *err_flag;              // context-level sticky error word (bit 2: a rank exceeded its bound)
 };
 
@@ -347,6 +356,13 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
                     gv.m = 0;
                     gt1 = mk_gemm<T>(rc.MT, rc.lp, 1, rc.Us, rc.a, 0, rc.T1, r, r, rc.b, p, one, zero);
                     gx = mk_gemm<T>(rc.RVp, r, 0, rc.T1, r, 0, rc.Vs, rc.b, r, rc.b, r, one, zero);
+                    if (inc) {  // both sides incremental: rank-kp forms of the core and of V S'
+                        rc.both = 1;
+                        rc.Xu = slab + s.o_xu; rc.Xv = slab + s.o_xv; rc.Rn = slab + s.o_rn; rc.T1b = slab + s.o_t1b;
+                        gc = mk_gemm<T>(rc.Xu, r, 0, rc.Rn, r, 1, rc.M, rc.a, r, r, kp, one, one);          // K' += Xu Rn^T
+                        gt1 = mk_gemm<T>(rc.Xu, r, 1, rc.Us, rc.a, 0, rc.T1b, kp, kp, rc.b, r, one, zero);  // T1b = Xu^T Us
+                        gx = mk_gemm<T>(rc.Xv, r, 0, rc.T1b, kp, 0, rc.Vs, rc.b, r, rc.b, kp, one, zero);   // X   = Xv T1b
+                    }
                 }
             }
         }
@@ -366,7 +382,7 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
         gv0.m = gv1.m = gv2.m = gv3.m = gt1.m = gx.m = 0;
         pdi.active = pdiv.active = pdvc.active = 0;
         inc = vinc = 0;
-        rc.inc = rc.vinc = 0;
+        rc.inc = rc.vinc = rc.both = 0;
         // rank exceeded the bound the scratch was sized for: tile left untouched.  Sticky in d_info (flags are OR-ed, the
         // caller of the entry point zeroes them) AND in the context's error word, so that a caller without an info buffer
         // still hears about it at the next hcb_ctx_sync.
@@ -792,7 +808,7 @@ __global__ void __launch_bounds__(256) k_core_build(const RecompProb<T> *__restr
 template<typename T>
 __global__ void __launch_bounds__(256) k_extract_r(const RecompProb<T> *__restrict__ probs) {
     const RecompProb<T> p = probs[blockIdx.y];
-    if (!p.active) return;
+    if (!p.active || p.both) return;  // (both sides incremental: the core is assembled by k_both_core, no triangles needed)
     const int nu = p.p * p.r, total = nu + p.q * p.r;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         if (idx < nu) {
@@ -870,7 +886,9 @@ __global__ void __launch_bounds__(256) k_truncate(const RecompProb<T> *__restric
         if (p.vinc) {
             for (int idx = threadIdx.x; idx < p.kc * rk; idx += blockDim.x) {
                 const int i = idx % p.kc, c = idx / p.kc;
-                p.Vs[(size_t) i + (size_t) c * p.b] /= p.sig0[i];
+                const size_t o = (size_t) i + (size_t) c * p.b;
+                // (rank-kp form: Vs holds Xv (Xu^T Us) only; the diagonal part beta S Us, divided by S, is beta Us)
+                p.Vs[o] = p.both ? p.Vs[o] / p.sig0[i] + p.beta_c * p.Us[(size_t) i + (size_t) c * p.a] : p.Vs[o] / p.sig0[i];
             }
         }
         for (int idx = threadIdx.x; idx < (p.vinc ? 0 : p.n * rk); idx += blockDim.x) {
@@ -1003,6 +1021,46 @@ __global__ void __launch_bounds__(256) k_vinc_build_rv(const RecompProb<T> *__re
         const size_t o = (size_t) i + (size_t) p.pos[c] * r;
         p.VW[o] = v;
         p.RVp[o] = v;
+        if (p.both && c >= p.kc) {   // Xv = [Gv ; R2v], Xu = [Gu ; R2u]  (r x kp, natural order)
+            const int l = c - p.kc;
+            p.Xv[(size_t) i + (size_t) l * r] = v;
+            T u;
+            if (i < p.kc) u = p.Gu[(size_t) i + (size_t) l * p.kc] + p.Gu2[(size_t) i + (size_t) l * p.kc];
+            else u = (i - p.kc <= l) ? p.Pn[(size_t) (i - p.kc) + (size_t) l * p.m] : T(0);
+            p.Xu[(size_t) i + (size_t) l * r] = u;
+        }
+    }
+}
+
+// Both sides incremental: the part of the core K' = (RU Pi) R'^T that is a pure gather -- row i < kc of K' is column
+// pos[i] of the triangular factor R' (in VW, ld r, reflectors below the diagonal masked), rows >= kc are zero -- and
+// Rn = the kp columns pos[kc + l] of R' for the rank-kp GEMM K' += Xu Rn^T that follows.  32 x 32 tiles through shared
+// memory (coalesced on both sides).  grid = (tile chunks, n_tiles), block (32, 8)
+template<typename T>
+__global__ void __launch_bounds__(256) k_both_core(const RecompProb<T> *__restrict__ probs) {
+    const RecompProb<T> p = probs[blockIdx.y];
+    if (!p.active || !p.both) return;
+    __shared__ T tile[32][33];
+    const int r = p.r, nt = (r + 31) / 32, tx = threadIdx.x, ty = threadIdx.y;
+    for (int t = blockIdx.x; t < nt * nt; t += gridDim.x) {
+        const int i0 = (t % nt) * 32, j0 = (t / nt) * 32;   // block of K' rows [i0, i0+32) x columns [j0, j0+32)
+        for (int q = ty; q < 32; q += 8) {                   // read: column pos[i0 + q] of R', rows j0 + tx
+            const int i = i0 + q, j = j0 + tx;
+            T v = T(0);
+            if (i < p.kc && j < r) { const int c = p.pos[i]; v = j <= c ? p.VW[(size_t) j + (size_t) c * r] : T(0); }
+            tile[q][tx] = v;
+        }
+        __syncthreads();
+        for (int q = ty; q < 32; q += 8) {                   // write: K'(i0 + tx, j0 + q)
+            const int i = i0 + tx, j = j0 + q;
+            if (i < r && j < r) p.M[(size_t) i + (size_t) j * p.a] = tile[tx][q];
+        }
+        __syncthreads();
+    }
+    const int total = r * p.kp;
+    for (int idx = blockIdx.x * 256 + ty * 32 + tx; idx < total; idx += gridDim.x * 256) {
+        const int j = idx % r, l = idx / r, c = p.pos[p.kc + l];
+        p.Rn[idx] = j <= c ? p.VW[(size_t) j + (size_t) c * r] : T(0);
     }
 }
 
