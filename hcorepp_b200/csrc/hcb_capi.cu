@@ -113,17 +113,16 @@ int launch_gemm(hcb_ctx *ctx, const GemmProb<T> *d_probs, int n_probs, int m_bou
             continue;
         }
         if constexpr (std::is_same<T, double>::value) {
-            // FP64: tensor pipe (DMMA); row-contiguous operands arrive by TMA bulk copies. Tile shape follows the skinny side.
-            if (m_bound <= 32) {
-                dim3 grid(std::max(1, cdiv(n_bound, 128)), cnt);
-                k_gemm_dmma<1, 4><<<grid, 128, 0, ctx->stream>>>(d_probs + off);
-            } else if (n_bound <= 32) {
-                dim3 grid(std::max(1, cdiv(m_bound, 128)), cnt);
-                k_gemm_dmma<4, 1><<<grid, 128, 0, ctx->stream>>>(d_probs + off);
-            } else {
-                dim3 grid(std::max(1, cdiv(m_bound, 64) * cdiv(n_bound, 64)), cnt);
-                k_gemm_dmma<2, 2><<<grid, 128, 0, ctx->stream>>>(d_probs + off);
-            }
+            // FP64: tensor pipe (DMMA), three-stage ring fed by TMA bulk copies / cp.async. Tile shape follows the skinny side.
+            auto go = [&](auto kern, size_t smem, int tiles) -> int {
+                HCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+                dim3 grid(std::max(1, tiles), cnt);
+                kern<<<grid, 128, smem, ctx->stream>>>(d_probs + off);
+                return HCB_OK;
+            };
+            if (m_bound <= 32) HCB_TRY(go(k_gemm_dmma<1, 4>, dg_smem_bytes<1, 4>(), cdiv(n_bound, 128)));
+            else if (n_bound <= 32) HCB_TRY(go(k_gemm_dmma<4, 1>, dg_smem_bytes<4, 1>(), cdiv(m_bound, 128)));
+            else HCB_TRY(go(k_gemm_dmma<2, 2>, dg_smem_bytes<2, 2>(), cdiv(m_bound, 64) * cdiv(n_bound, 64)));
             HCB_LAUNCH_CHECK("k_gemm_dmma");
         } else {
             // FP32: FFMA (TF32 tensor MMA would cost ~1e-3 relative error, incompatible with accuracy <= 1e-4)
