@@ -491,6 +491,9 @@ def main():
                 "recompression_gflops": float(fr.sum()) / t_rec / 1e9,
                 "contraction_gflops": float(fc.sum()) / max(t_con, 1e-9) / 1e9,
                 "c_rank_final_mean": float(rk_all[-1].mean()), "c_rank_max": float(rk_all.max()),
+                # Jacobi sweeps per (k-step, tile): histogram over the whole pass and over the last k-step
+                "jacobi_sweep_hist": {str(int(v)): int(c) for v, c in zip(*np.unique(sw_all, return_counts=True))},
+                "jacobi_sweep_hist_last_k": {str(int(v)): int(c) for v, c in zip(*np.unique(sw_all[-1], return_counts=True))},
                 # the three FP64-bound recompression phases against the measured FP64 peak (algorithmic flops, true ranks)
                 "phase_fp64_tflops": {n: float(alg_flops[n]) / (phases[n]["ms_per_step"] * 1e-3) / 1e12 for n in alg_flops},
                 "phase_fp64_frac_of_peak": {n: float(alg_flops[n]) / (phases[n]["ms_per_step"] * 1e-3) / 1e12 / fp64_peak(torch)[0]

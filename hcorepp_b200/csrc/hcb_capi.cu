@@ -343,7 +343,7 @@ struct SvdJobLayout {
     int nblk;
     SvdJobLayout(int a, int b) {
         nblk = cdiv(b, NBQ);
-        eM = align_up((size_t) a * b, 32);
+        eM = align_up((size_t) (a + 1) * b, 32);  // (+1: the Jacobi work copy uses an even leading dimension)
         eTau = align_up((size_t) b, 32);
         eTB = align_up((size_t) NBQ * NBQ * nblk, 32);
         eWB = align_up((size_t) 2 * NBQ * a, 32);
@@ -687,7 +687,7 @@ Layout<T> make_layout(const BatchShape &s) {
         L.o_tauu = take(L.r_b);
         L.o_tauv = take(L.r_b);
         L.o_m = take(sq);
-        L.o_j = take(sq);
+        L.o_j = take(sq + L.pq_b);  // rotated copy of the core with an even leading dimension
         L.o_us = take(sq);
         L.o_vs = take(sq);
         L.o_sig = take(L.pq_b);

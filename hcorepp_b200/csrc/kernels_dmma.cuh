@@ -17,6 +17,7 @@
 // Same device-resident GemmProb descriptors as k_gemm_batched.
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 namespace hcb {
 
@@ -105,6 +106,8 @@ __global__ void __launch_bounds__(128, 3) k_gemm_dmma(const GemmProb<double> *__
         const int row0 = (tile % tiles_m) * BM, col0 = (tile / tiles_m) * BN;
         const int mrem = min(BM, p.m - row0);
         const bool a_bulk = p.ta == 0 && a_16 && ((mrem & 1) == 0);   // whole k columns of the A tile by TMA
+        const int nrem = min(BN, p.n - col0);
+        const int imax = min(4, max(0, (mrem - wm * 32 + 7) >> 3)), jmax = min(4, max(0, (nrem - wn * 32 + 7) >> 3));
         double acc[4][4][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -219,27 +222,43 @@ __global__ void __launch_bounds__(128, 3) k_gemm_dmma(const GemmProb<double> *__
             if (it + S - 1 < nk) issue((it + S - 1) % S, it + S - 1);   // refill the stage read in iteration it-1
             else cp_async_commit();
             const double *as = As + (size_t) st * EA, *bs = Bs + (size_t) st * EB;
+            // Edge tiles: a warp only issues the DMMAs of the 8 x 8 sub-tiles that intersect the matrix (warp-uniform
+            // bounds imax / jmax).  The skinny products of the incremental recompression have n = kp = 44 of BN = 64
+            // columns: the second warp column then issues 2 of its 4 tile columns -- a quarter of the CTA's DMMAs saved.
+            auto mma_stage = [&](auto jm_tag) {
+                constexpr int JM = decltype(jm_tag)::value;
 #pragma unroll
-            for (int ks = 0; ks < BK; ks += 4) {
-                double a[4], b[4];
-                if (p.ta == 0) {
+                for (int ks = 0; ks < BK; ks += 4) {
+                    double a[4], b[JM];
+                    if (p.ta == 0) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) a[i] = as[(ks + c) * PA0 + wm * 32 + i * 8 + g];
-                } else {
+                        for (int i = 0; i < 4; ++i) a[i] = as[(ks + c) * PA0 + wm * 32 + i * 8 + g];
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) a[i] = as[(wm * 32 + i * 8 + g) * PA1 + ks + c];
+                        for (int i = 0; i < 4; ++i) a[i] = as[(wm * 32 + i * 8 + g) * PA1 + ks + c];
+                    }
+                    if (p.tb == 0) {
+#pragma unroll
+                        for (int j = 0; j < JM; ++j) b[j] = bs[(wn * 32 + j * 8 + g) * PB0 + ks + c];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < JM; ++j) b[j] = bs[(ks + c) * PB1 + wn * 32 + j * 8 + g];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (i < imax) {
+#pragma unroll
+                            for (int j = 0; j < JM; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                        }
+                    }
                 }
-                if (p.tb == 0) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) b[j] = bs[(wn * 32 + j * 8 + g) * PB0 + ks + c];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) b[j] = bs[(ks + c) * PB1 + wn * 32 + j * 8 + g];
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            };
+            switch (jmax) {
+                case 4: mma_stage(std::integral_constant<int, 4>{}); break;
+                case 3: mma_stage(std::integral_constant<int, 3>{}); break;
+                case 2: mma_stage(std::integral_constant<int, 2>{}); break;
+                case 1: mma_stage(std::integral_constant<int, 1>{}); break;
+                default: break;
             }
         }
         cp_async_wait<0>();

@@ -6,10 +6,12 @@
 // Here the 32 columns of the pivot block I live in the registers of the 16 warps (2 columns each) for the whole pass
 // over the later blocks J; a warp loads TWO columns of J, rotates them against its two x columns (4 rotations, as two
 // steps of two independent pairs, so two dependency chains are in flight per warp) and stores them back:
-// 4 * 8 * a bytes of shared-memory traffic per 4 rotations.  The rotations are "fast" (scaled) rotations,
-//     x' = x - (t dy/dx) y,   y' = y + (t dx/dy) x,   dx' = c dx,  dy' = c dy,
-// two FMAs per element instead of four; the per-column scales are folded back when a block leaves shared memory /
-// registers.  Block J+1 is prefetched with cp.async into the other shared-memory region while block J is rotated.
+// 4 * 8 * a bytes of shared-memory traffic per 4 rotations.  The rotations are "fast" (scaled) rotations in the
+// SEQUENTIAL (in-place) form
+//     x' = x - (t dy/dx) y,   y' = y + (t c^2 dx/dy) x',   dx' = c dx,  dy' = dy / c,
+// two FMAs per element instead of four and no copy of the old x (the simultaneous form y' = y + (t dx/dy) x_old made
+// the compiler rotate the x registers through a spare slot: one MOV per DFMA, 9 % of the kernel's instructions --
+// ncu source view, round 2); the per-column scales are folded back when a block leaves shared memory / registers.  Block J+1 is prefetched with cp.async into the other shared-memory region while block J is rotated.
 // The pairs INSIDE a block are done once per sweep in shared memory with jacobi_rotate_reg (kernels_svd.cuh).
 #pragma once
 #include "common.cuh"
@@ -102,14 +104,14 @@ __device__ __forceinline__ int rx_duo(Vec2<T> (&xa)[NI], int ixa, Vec2<T> (&ya)[
     const T t = rx_tangent(d, g2);
     const T q = fma(t, t, T(1));
     const T c = rx_rsqrt(q);
-    const T fx = t * dy * idx, fy = t * dx * idy;  // zero when !rot (t == 0)
+    const T fx = t * dy * idx, fy = t * (c * c) * dx * idy;  // zero when !rot (t == 0)
     const T tg = t * gam, a2 = alpha - tg, b2 = beta + tg, rc = q * c;  // rc = 1 / c
     const bool redo = rot && ((a2 < T(0.01) * alpha) || (b2 < T(0.01) * beta));
     __syncwarp();
     if (rot && (lane & 15) == 0) {
         mt.n2[ix] = a2; mt.n2[iy] = b2;
-        mt.d[ix] = c * dx; mt.d[iy] = c * dy;
-        mt.id[ix] = rc * idx; mt.id[iy] = rc * idy;
+        mt.d[ix] = c * dx; mt.d[iy] = rc * dy;
+        mt.id[ix] = rc * idx; mt.id[iy] = c * idy;
     }
     __syncwarp();  // lanes 0 / 16 wrote the metadata that lane 0 may re-read in the (rare) redo path below
     const unsigned brot = __ballot_sync(0xffffffffu, rot), bredo = __ballot_sync(0xffffffffu, redo);
@@ -119,17 +121,15 @@ __device__ __forceinline__ int rx_duo(Vec2<T> (&xa)[NI], int ixa, Vec2<T> (&ya)[
     if (brot & 1u) {
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
-            const T ux = xa[i].x, uy = xa[i].y;
-            xa[i].x = fma(-fxa, ya[i].x, ux); xa[i].y = fma(-fxa, ya[i].y, uy);
-            ya[i].x = fma(fya, ux, ya[i].x);  ya[i].y = fma(fya, uy, ya[i].y);
+            xa[i].x = fma(-fxa, ya[i].x, xa[i].x); xa[i].y = fma(-fxa, ya[i].y, xa[i].y);
+            ya[i].x = fma(fya, xa[i].x, ya[i].x);  ya[i].y = fma(fya, xa[i].y, ya[i].y);
         }
     }
     if (brot & 0x10000u) {
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
-            const T ux = xb[i].x, uy = xb[i].y;
-            xb[i].x = fma(-fxb, yb[i].x, ux); xb[i].y = fma(-fxb, yb[i].y, uy);
-            yb[i].x = fma(fyb, ux, yb[i].x);  yb[i].y = fma(fyb, uy, yb[i].y);
+            xb[i].x = fma(-fxb, yb[i].x, xb[i].x); xb[i].y = fma(-fxb, yb[i].y, xb[i].y);
+            yb[i].x = fma(fyb, xb[i].x, yb[i].x);  yb[i].y = fma(fyb, xb[i].y, yb[i].y);
         }
     }
     if (bredo & 1u) {  // rare: the norm update cancelled -- recompute the true squared norms d^2 * |stored|^2
@@ -160,16 +160,15 @@ __device__ __forceinline__ int rx_solo(Vec2<T> (&x)[NI], int ix, Vec2<T> (&y)[NI
     const T t = rx_tangent(beta - alpha, gam + gam);
     const T q = fma(t, t, T(1));
     const T c = rx_rsqrt(q);
-    const T fx = t * dy * idx, fy = t * dx * idy;
+    const T fx = t * dy * idx, fy = t * (c * c) * dx * idy;
     const T tg = t * gam, rc = q * c;
     T a2 = alpha - tg, b2 = beta + tg;
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
-        const T ux = x[i].x, uy = x[i].y;
-        x[i].x = fma(-fx, y[i].x, ux); x[i].y = fma(-fx, y[i].y, uy);
-        y[i].x = fma(fy, ux, y[i].x);  y[i].y = fma(fy, uy, y[i].y);
+        x[i].x = fma(-fx, y[i].x, x[i].x); x[i].y = fma(-fx, y[i].y, x[i].y);
+        y[i].x = fma(fy, x[i].x, y[i].x);  y[i].y = fma(fy, x[i].y, y[i].y);
     }
-    const T ndx = c * dx, ndy = c * dy;
+    const T ndx = c * dx, ndy = rc * dy;
     if (a2 < T(0.01) * alpha || b2 < T(0.01) * beta) {  // rare: recompute the true squared norms
         a2 = ndx * ndx * rx_sumsq<T, NI>(x);
         b2 = ndy * ndy * rx_sumsq<T, NI>(y);
@@ -178,7 +177,7 @@ __device__ __forceinline__ int rx_solo(Vec2<T> (&x)[NI], int ix, Vec2<T> (&y)[NI
     if (lane == 0) {
         mt.n2[ix] = a2; mt.n2[iy] = b2;
         mt.d[ix] = ndx; mt.d[iy] = ndy;
-        mt.id[ix] = rc * idx; mt.id[iy] = rc * idy;
+        mt.id[ix] = rc * idx; mt.id[iy] = c * idy;
     }
     __syncwarp();
     return ret;
@@ -198,9 +197,15 @@ __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sw
     T *sig = R1 + (size_t) P * BW;               // b singular values
     T *meta = sig + b;                           // 3 x 64 metadata: x columns [0,32), y columns [32,64)
     RxMeta<T> mt{meta, meta + 2 * BW, meta + 4 * BW};
-    T *M = p.J;  // rotated copy (global / L2), ld a
+    T *M = p.J;  // rotated copy (global / L2), EVEN ld: every column starts 16-byte aligned for the cp.async staging
+    const int lda = (a + 1) & ~1;  // (p.J holds (a + 1) * b elements)
     if (sweep == 0) {
-        for (int idx = tid; idx < a * b; idx += RX_THREADS) M[idx] = p.M[(size_t) (idx % a) + (size_t) (idx / a) * p.ldm];
+        for (int idx = tid; idx < a * b; idx += RX_THREADS) {
+            const int i = idx % a, c = idx / a;
+            M[(size_t) c * lda + i] = p.M[(size_t) i + (size_t) c * p.ldm];
+        }
+        if (lda > a)  // the pad row stays zero for the whole solve (nothing writes rows >= a)
+            for (int c = tid; c < b; c += RX_THREADS) M[(size_t) c * lda + a] = T(0);
     }
     __syncthreads();
     const T tol = Eps<T>::v() * t_sqrt((T) a);
@@ -217,14 +222,13 @@ __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sw
         for (int q = tid; q < BW * P / 2; q += RX_THREADS) {
             const int c = q / (P / 2), row = 2 * (q % (P / 2));
             T *d = dst + (size_t) c * P + row;
-            const T *src = M + (size_t) (c0 + c) * a + row;
+            const T *src = M + (size_t) (c0 + c) * lda + row;
             const bool v0 = c < wc && row < a, v1 = c < wc && row + 1 < a;
             if (sizeof(T) == 8) {
-                if (v0 && v1 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) cp_async_16(d, src);
-                else {
-                    d[0] = v0 ? __ldcg(src) : T(0);  // (L2 loads: another SM may have run this problem's last sweep)
-                    d[1] = v1 ? __ldcg(src + 1) : T(0);
-                }
+                // even ld + zero pad row: every row pair of a live column is one aligned 16-byte copy (with ld = a, odd a
+                // sent every other column through synchronous scalar loads: 3 % of the kernel's stall samples)
+                if (v0) cp_async_16(d, src);
+                else { d[0] = T(0); d[1] = T(0); }
             } else {
                 d[0] = v0 ? __ldcg(src) : T(0);
                 d[1] = v1 ? __ldcg(src + 1) : T(0);
@@ -246,7 +250,7 @@ __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sw
     auto unstage = [&](const T *src, int c0, int wc, int m0) {
         for (int idx = tid; idx < P * wc; idx += RX_THREADS) {
             const int i = idx % P, c = idx / P;
-            if (i < a) M[(size_t) (c0 + c) * a + i] = src[idx] * mt.d[m0 + c];
+            if (i < a) M[(size_t) (c0 + c) * lda + i] = src[idx] * mt.d[m0 + c];
         }
     };
 
@@ -361,7 +365,7 @@ __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sw
             {
                 auto put = [&](const Vec2<T> (&x)[NI], int c) {
                     if (c >= wi) return;
-                    T *dst = M + (size_t) (ci0 + c) * a;
+                    T *dst = M + (size_t) (ci0 + c) * lda;
 #pragma unroll
                     for (int i = 0; i < NI; ++i) {
                         const int r = 64 * i + 2 * lane;
@@ -383,7 +387,7 @@ __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sw
         info_max_sweeps(p.info, b < 2 ? 0 : sweep + 1);
     }
     __syncthreads();
-    jacobi_finish<T, true>(M, a, sig, p);
+    jacobi_finish<T, true>(M, lda, sig, p);
     return flags | 4;
 }
 
