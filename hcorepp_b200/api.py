@@ -209,8 +209,16 @@ class CompressedTile:
         return np.asfortranarray(self.factors()[1].cpu().numpy())
 
     def to_dense(self) -> np.ndarray:
-        U, V = self.factors()
-        return np.asfortranarray((U @ V).cpu().numpy())
+        """U * V through the library's own GEMM entry (hcb_?gemm on the packed buffer: U ld m, V ld rank)."""
+        rk = self.GetTileRank()
+        out = torch.empty(self.n, self.m, dtype=self.dtype, device=self.buf.device)   # column-major m x n
+        p = "d" if self.dtype == torch.float64 else "s"
+        es = self.buf.element_size()
+        torch.cuda.synchronize(self.buf.device)  # (buf may have been written on another torch stream)
+        check(getattr(lib, f"hcb_{p}gemm")(self.ctx.h, 0, 0, self.m, self.n, rk, 1.0, self.buf.data_ptr(), self.m,
+                                           self.buf.data_ptr() + es * self.m * self.max_rank, rk, 0.0, out.data_ptr(), self.m))
+        torch.cuda.synchronize(self.buf.device)
+        return np.asfortranarray(out.cpu().numpy().T)
 
 
 def gemm_batched(alpha, A, opA, B, opB, beta, Cs, ctx: RunContext, params: CompressionParameters | None = None,

@@ -184,7 +184,7 @@ int launch_svd(hcb_ctx *ctx, const SvdProb<T> *d_probs, int n_probs, int a_bound
         const size_t rx = align_up(rx_smem_bytes<T>(cdiv(a_bound, 64), b_bound), 16);
         if (rx <= cap) {
             HCB_CUDA(cudaFuncSetAttribute(k_jacobi_svd_rx<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) rx));
-            const size_t need = (size_t) n_probs + 2;
+            const size_t need = (size_t) 2 * n_probs + 2;  // item counter, finished counter, per-problem state, per-problem flags
             if (need > ctx->svd_sched_n) {
                 if (ctx->svd_sched) { HCB_CUDA(cudaStreamSynchronize(ctx->stream)); HCB_CUDA(cudaFree(ctx->svd_sched)); }
                 ctx->svd_sched = nullptr; ctx->svd_sched_n = 0;

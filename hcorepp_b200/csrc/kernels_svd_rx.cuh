@@ -186,8 +186,14 @@ __device__ __forceinline__ int rx_solo(Vec2<T> (&x)[NI], int ix, Vec2<T> (&y)[NI
 // ONE sweep over all column pairs of problem p (the rotated copy lives in p.J between sweeps; `first` makes it from
 // p.M).  Returns bit 0: something rotated, bit 1: some pair was above the predictive-stop level.  When `last_allowed`
 // or the sweep converged, the epilogue (sigma, sort, scatter of the left factor, info) runs too and bit 2 is set.
+// A sweep is cut into RX_PARTS work items (consecutive ranges of pivot blocks with about equal numbers of block pairs).
+// The item's description lives in shared memory (the kernel is at its 128-register cap): part index, the rotated / big
+// flags carried over from the earlier parts of this sweep.  A part that is not the last one returns bit 3 set and the
+// flags so far in bits 0-1.
+constexpr int RX_PARTS = 4;
+struct RxItem { int part, carry, bi_lo, bi_hi; };
 template<typename T, int NI, int XPW>  // XPW: register-resident columns per warp (2; 1 for tall problems, NI > 6)
-__device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sweeps, T stop2) {
+__device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, volatile RxItem *it, int max_sweeps, T stop2) {
     constexpr int P = 64 * NI, BW = (RX_THREADS / 32) * XPW;
     __shared__ int s_rot, s_big;
     const int a = p.a, b = p.b;
@@ -199,7 +205,7 @@ __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sw
     RxMeta<T> mt{meta, meta + 2 * BW, meta + 4 * BW};
     T *M = p.J;  // rotated copy (global / L2), EVEN ld: every column starts 16-byte aligned for the cp.async staging
     const int lda = (a + 1) & ~1;  // (p.J holds (a + 1) * b elements)
-    if (sweep == 0) {
+    if (sweep == 0 && it->part == 0) {
         for (int idx = tid; idx < a * b; idx += RX_THREADS) {
             const int i = idx % a, c = idx / a;
             M[(size_t) c * lda + i] = p.M[(size_t) i + (size_t) c * p.ldm];
@@ -257,9 +263,20 @@ __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sw
     bool converged = (b < 2);
     if (!converged) {
         __syncthreads();
-        if (tid == 0) { s_rot = 0; s_big = 0; }
+        if (tid == 0) {
+            s_rot = it->carry & 1; s_big = (it->carry >> 1) & 1;
+            // pivot blocks of this part: block bi costs (nblk - bi) block passes; the total is cut into RX_PARTS shares
+            const int total = nblk * (nblk + 1) / 2, part = it->part;
+            int acc = 0, q = 0, lo = nblk, hi = 0;
+            for (int bi = 0; bi < nblk; ++bi) {  // block bi belongs to the first part whose share is not yet full
+                while (q + 1 < RX_PARTS && acc * RX_PARTS >= (q + 1) * total) ++q;
+                if (q == part) { lo = bi < lo ? bi : lo; hi = bi + 1; }
+                acc += nblk - bi;
+            }
+            it->bi_lo = lo; it->bi_hi = hi;  // (lo = nblk, hi = 0: empty part)
+        }
         __syncthreads();
-        for (int bi = 0; bi < nblk; ++bi) {
+        for (int bi = it->bi_lo; bi < it->bi_hi; ++bi) {
             const int ci0 = bi * BW, wi = min(BW, b - ci0);
             // block I -> R0 (and block I+1 -> R1 right behind it)
             stage_async(R0, ci0, wi);
@@ -378,7 +395,10 @@ __device__ int jacobi_sweep_rx(T *sm, const SvdProb<T> &p, int sweep, int max_sw
             }
             __syncthreads();
         }
+        if (it->part + 1 < RX_PARTS) return 8 | (s_rot ? 1 : 0) | (s_big ? 2 : 0);  // the sweep goes on in the next part
         converged = (s_rot == 0) || (s_big == 0);
+    } else if (it->part + 1 < RX_PARTS) {
+        return 8;
     }
     const int flags = converged ? 0 : 3;
     if (!converged && sweep + 1 < max_sweeps) return flags;
@@ -397,12 +417,16 @@ constexpr size_t rx_smem_bytes(int ni, int b_bound) {  // two block regions (32 
     return sizeof(T) * ((wide > tall ? wide : tall) + (size_t) b_bound + 6 * RX_BW);
 }
 
-// Persistent kernel: grid = min(n_probs, resident CTAs) CTAs of 512 threads; a <= 384.  Work items are (sweep, problem)
-// pairs handed out sweep-major through an atomic counter, so that the 256 problems of a batch do not run as 1.73
-// "waves" of whole problems on 148 SMs (the second one 73 % full): a CTA that finishes a sweep takes the next item,
-// whichever problem it belongs to.  sched[0] = next item, sched[1] = finished problems, sched[2 + t] = state of problem
-// t: number of completed sweeps, or -1 when finished.  Items are claimed in increasing order and all CTAs are
-// resident, so waiting for a problem's previous sweep (claimed earlier, hence running) cannot deadlock.
+// Persistent kernel: grid = min(n_probs, resident CTAs) CTAs of 512 threads; a <= 384.  Work items are (sweep, part,
+// problem) triples -- a quarter of a sweep of one problem -- handed out (sweep, part)-major through an atomic counter, so
+// that the 256 problems of a batch do not run as 1.73 "waves" of whole problems on 148 SMs (the second one 73 % full): a
+// CTA that finishes an item takes the next one, whichever problem it belongs to.  (Whole sweeps as items, round 1: the
+// last sweep of the ~180 of 256 problems that need it ran as 148 + 32 -- ncu showed 12.9 % of the kernel's warp samples
+// at the scheduler barrier; quarter sweeps make that tail four times shorter.)  sched[0] = next item, sched[1] =
+// finished problems, sched[2 + t] = state of problem t: number of completed parts, or -1 when finished,
+// sched[2 + n_probs + t] = rotated / big flags of the parts of t's current sweep.  Items are claimed in increasing
+// order and only resident CTAs claim, so waiting for a problem's previous part (claimed earlier, hence running or done)
+// cannot deadlock.
 // Dynamic shared memory: rx_smem_bytes(ceil(a_bound / 64), b_bound).  sched must be zeroed before the launch.
 template<typename T>
 __global__ void __launch_bounds__(RX_THREADS, 1) k_jacobi_svd_rx(const SvdProb<T> *__restrict__ probs, int n_probs,
@@ -410,6 +434,7 @@ __global__ void __launch_bounds__(RX_THREADS, 1) k_jacobi_svd_rx(const SvdProb<T
     extern __shared__ __align__(16) unsigned char smem_raw_rx[];
     T *sm = reinterpret_cast<T *>(smem_raw_rx);
     __shared__ int s_item, s_state;
+    __shared__ RxItem s_it;
     const int tid = threadIdx.x;
     for (;;) {
         __syncthreads();
@@ -417,15 +442,17 @@ __global__ void __launch_bounds__(RX_THREADS, 1) k_jacobi_svd_rx(const SvdProb<T
             int item = -1;
             if (*reinterpret_cast<volatile int *>(sched + 1) < n_probs) item = atomicAdd(sched, 1);
             int state = 0;
-            if (item >= 0 && item < n_probs * max_sweeps) {
-                const int pr = item % n_probs, sw = item / n_probs;
+            if (item >= 0 && item < n_probs * max_sweeps * RX_PARTS) {
+                const int pr = item % n_probs, sp = item / n_probs;  // sp = sweep * RX_PARTS + part
                 volatile int *st = reinterpret_cast<volatile int *>(sched + 2 + pr);
                 unsigned spins = 0;
-                while ((state = *st) >= 0 && state < sw) {  // previous sweep still running elsewhere
+                while ((state = *st) >= 0 && state < sp) {  // previous part still running elsewhere
                     __nanosleep(200);
                     if (++spins > (1u << 26)) __trap();  // watchdog (> 10 s): abort instead of hanging the GPU
                 }
                 __threadfence();
+                s_it.part = sp % RX_PARTS;
+                s_it.carry = (sp % RX_PARTS) ? *reinterpret_cast<volatile int *>(sched + 2 + n_probs + pr) : 0;
             } else {
                 item = -1;
             }
@@ -436,23 +463,23 @@ __global__ void __launch_bounds__(RX_THREADS, 1) k_jacobi_svd_rx(const SvdProb<T
         const int item = s_item;
         if (item < 0) break;
         if (s_state < 0) continue;  // problem already finished
-        const int pr = item % n_probs, sw = item / n_probs;
+        const int pr = item % n_probs, sw = item / n_probs / RX_PARTS;
         const SvdProb<T> p = probs[pr];
         int flags = 4;
         if (p.a > 0 && p.b > 0) {
             switch ((p.a + 63) / 64) {
-                case 1: flags = jacobi_sweep_rx<T, 1, 2>(sm, p, sw, max_sweeps, stop2); break;
-                case 2: flags = jacobi_sweep_rx<T, 2, 2>(sm, p, sw, max_sweeps, stop2); break;
-                case 3: flags = jacobi_sweep_rx<T, 3, 2>(sm, p, sw, max_sweeps, stop2); break;
-                case 4: flags = jacobi_sweep_rx<T, 4, 2>(sm, p, sw, max_sweeps, stop2); break;
-                case 5: flags = jacobi_sweep_rx<T, 5, 2>(sm, p, sw, max_sweeps, stop2); break;
-                case 6: flags = jacobi_sweep_rx<T, 6, 2>(sm, p, sw, max_sweeps, stop2); break;
-                case 7: flags = jacobi_sweep_rx<T, 7, 1>(sm, p, sw, max_sweeps, stop2); break;
-                case 8: flags = jacobi_sweep_rx<T, 8, 1>(sm, p, sw, max_sweeps, stop2); break;
-                case 9: flags = jacobi_sweep_rx<T, 9, 1>(sm, p, sw, max_sweeps, stop2); break;
-                case 10: flags = jacobi_sweep_rx<T, 10, 1>(sm, p, sw, max_sweeps, stop2); break;
-                case 11: flags = jacobi_sweep_rx<T, 11, 1>(sm, p, sw, max_sweeps, stop2); break;
-                default: flags = jacobi_sweep_rx<T, 12, 1>(sm, p, sw, max_sweeps, stop2); break;
+                case 1: flags = jacobi_sweep_rx<T, 1, 2>(sm, p, sw, &s_it, max_sweeps, stop2); break;
+                case 2: flags = jacobi_sweep_rx<T, 2, 2>(sm, p, sw, &s_it, max_sweeps, stop2); break;
+                case 3: flags = jacobi_sweep_rx<T, 3, 2>(sm, p, sw, &s_it, max_sweeps, stop2); break;
+                case 4: flags = jacobi_sweep_rx<T, 4, 2>(sm, p, sw, &s_it, max_sweeps, stop2); break;
+                case 5: flags = jacobi_sweep_rx<T, 5, 2>(sm, p, sw, &s_it, max_sweeps, stop2); break;
+                case 6: flags = jacobi_sweep_rx<T, 6, 2>(sm, p, sw, &s_it, max_sweeps, stop2); break;
+                case 7: flags = jacobi_sweep_rx<T, 7, 1>(sm, p, sw, &s_it, max_sweeps, stop2); break;
+                case 8: flags = jacobi_sweep_rx<T, 8, 1>(sm, p, sw, &s_it, max_sweeps, stop2); break;
+                case 9: flags = jacobi_sweep_rx<T, 9, 1>(sm, p, sw, &s_it, max_sweeps, stop2); break;
+                case 10: flags = jacobi_sweep_rx<T, 10, 1>(sm, p, sw, &s_it, max_sweeps, stop2); break;
+                case 11: flags = jacobi_sweep_rx<T, 11, 1>(sm, p, sw, &s_it, max_sweeps, stop2); break;
+                default: flags = jacobi_sweep_rx<T, 12, 1>(sm, p, sw, &s_it, max_sweeps, stop2); break;
             }
         }
         __syncthreads();
@@ -462,7 +489,11 @@ __global__ void __launch_bounds__(RX_THREADS, 1) k_jacobi_svd_rx(const SvdProb<T
                 *reinterpret_cast<volatile int *>(sched + 2 + pr) = -1;
                 atomicAdd(sched + 1, 1);
             } else {
-                *reinterpret_cast<volatile int *>(sched + 2 + pr) = sw + 1;
+                if (flags & 8) {
+                    *reinterpret_cast<volatile int *>(sched + 2 + n_probs + pr) = flags & 3;
+                    __threadfence();
+                }
+                *reinterpret_cast<volatile int *>(sched + 2 + pr) = item / n_probs + 1;
             }
         }
     }
