@@ -946,7 +946,15 @@ def run_strong_leg(args, torch, hc, ctx, grid, rank_env):
     krank = rank_for_accuracy(nb, acc)
     leg = DistLeg(torch, hc, ctx, grid, T, T, T, nb, acc, krank)
     bound = leg.calibrate()
+    import ctypes as C
+    from hcorepp_b200 import _capi
+    ph_ms, ph_n = (C.c_double * _capi.N_PHASES)(), (C.c_uint64 * _capi.N_PHASES)()
+    _capi.check(_capi.lib.hcb_ctx_phase_times(ctx.h, ph_ms, ph_n))   # flush
+    ph_ms, ph_n = (C.c_double * _capi.N_PHASES)(), (C.c_uint64 * _capi.N_PHASES)()
+    _capi.check(_capi.lib.hcb_ctx_phase_timing(ctx.h, 1))
     ms = leg.timed(args.strong_steps, 1)
+    _capi.check(_capi.lib.hcb_ctx_phase_times(ctx.h, ph_ms, ph_n))
+    _capi.check(_capi.lib.hcb_ctx_phase_timing(ctx.h, 0))
     bad, sweeps = leg.flags()
     total = T ** 3
     out = {"workload": "TLR GEMM %dx%d f64, tile %d, acc %.0e, compressed A,B,C, %d tile-GEMMs/step, 2D block-cyclic %dx%d%s" % (
@@ -956,7 +964,10 @@ def run_strong_leg(args, torch, hc, ctx, grid, rank_env):
            "steps": args.strong_steps, "warmup": 1, "c_rank_bound": bound, "jacobi_or_bound_flags": bad,
            "jacobi_sweeps_max": sweeps, "input_rank": krank,
            "dense_equivalent_tflops": 2.0 * (T * nb) ** 3 / (ms * 1e-3) / 1e12,
-           "driver": "hcorepp_b200.distributed.tlr_matmul_distributed (hcb_dtlr_matmul_panel_step per k)"}
+           "driver": "hcorepp_b200.distributed.tlr_matmul_distributed (hcb_dtlr_matmul_panel_step per k)",
+           # rank 0's phases over the warm-up + timed steps, per step
+           "phases_ms_per_step": {_capi.lib.hcb_phase_name(i).decode(): ph_ms[i] / (args.strong_steps + 1)
+                                  for i in range(_capi.N_PHASES)}}
     try:
         ref1 = json.load(open(os.path.join(ROOT, "profiles", "r02_strong_n1.json")))
         out["speedup_vs_committed_n1"] = ref1["ms_per_step"] / ms

@@ -378,7 +378,9 @@ class TileMatrix:
         esz = tiles.element_size()
         ptrs = (C.c_void_p * n)(*[tiles.data_ptr() + esz * tm * tn * lin for lin in range(n)])
         prm = params.c()
-        check(_fn("compress_batched", dtype)(ctx.h, n, ptrs, tm, tmx.descs, C.byref(prm), None))
+        # per-tile info words of the compressing constructor (1: Jacobi not converged, 2: rank clipped at maxRank)
+        tmx.compress_info = torch.zeros(n, dtype=torch.int32, device=ctx.device)
+        check(_fn("compress_batched", dtype)(ctx.h, n, ptrs, tm, tmx.descs, C.byref(prm), C.c_void_p(tmx.compress_info.data_ptr())))
         ctx.Sync()
         return tmx
 

@@ -335,6 +335,7 @@ struct SvdJob {
     int trans_src;  // 1: M = src^T
     int a, b;
     T *Us, *Vs, *sigma;  // outputs: Us a x b (ld a), Vs b x b (ld b), sigma b
+    int *info = nullptr; // optional device info word: |= 1 Jacobi not converged, bits 8.. = sweeps
 };
 
 template<typename T>
@@ -389,7 +390,7 @@ int run_svd_jobs(hcb_ctx *ctx, const std::vector<SvdJob<T>> &jobs, int a_bound, 
         pd[t] = PanelDesc<T>{MT, tau, VC, TB, WB, j.b, j.a, a_bound, 1};
         qp[t] = QrProb<T>{MT, tau, j.b, j.a, j.b};
         lq[t] = LqProb<T>{MT, Lb, j.a, j.b};
-        sv[t] = SvdProb<T>{Lb, Jw, j.Us, j.Vs, j.sigma, nullptr, j.a, j.b, j.a, j.a, j.b};
+        sv[t] = SvdProb<T>{Lb, Jw, j.Us, j.Vs, j.sigma, j.info, j.a, j.b, j.a, j.a, j.b};
         gv[t] = GemmProb<T>{M, j.Us, j.Vs, j.b, j.b, j.a, j.a, j.a, j.b, 1, 0, T(1), T(0)};  // Vs = M^T Us = V diag(sigma)
     }
     char *p = desc;
@@ -1137,9 +1138,8 @@ int t_tlr_matmul_panel_step(hcb_ctx *ctx, int64_t mt, int64_t nt, const hcb_tile
 
 template<typename T>
 int t_compress_full(hcb_ctx *ctx, int64_t n64, const T *const *dense, int64_t ld, const hcb_tile *out,
-                    const hcb_compress_params *prm, int32_t *d_info) {
+                    const hcb_compress_params *prm, int32_t *const *infos) {  // infos: per-tile device info words or NULL
     if (n64 <= 0) return HCB_OK;
-    (void) d_info;
     int m = 0, n = 0;
     for (int64_t t = 0; t < n64; ++t) {
         if (out[t].type != HCB_TILE_COMPRESSED || !out[t].d_rank || !out[t].d_data || !dense[t])
@@ -1168,9 +1168,10 @@ int t_compress_full(hcb_ctx *ctx, int64_t n64, const T *const *dense, int64_t ld
             const int tm = o.m, tn = o.n, ta = std::max(tm, tn), tb = std::min(tm, tn);
             const bool tr = tm < tn;
             T *Us = outs + (size_t) t * (eUs + eVs + eS), *Vs = Us + eUs, *sg = Vs + eVs;
-            jobs[t] = SvdJob<T>{dense[c0 + t], (int) ld, tr ? 1 : 0, ta, tb, Us, Vs, sg};
+            int *uinfo = infos ? infos[c0 + t] : nullptr;
+            jobs[t] = SvdJob<T>{dense[c0 + t], (int) ld, tr ? 1 : 0, ta, tb, Us, Vs, sg, uinfo};
             T *U = reinterpret_cast<T *>(o.d_data), *V = U + (size_t) tm * o.max_rank;
-            fp[t] = CompressProb<T>{Us, Vs, sg, U, V, o.d_rank, nullptr, tm, tn, tb, ta, tr ? 1 : 0, o.max_rank, ta, tb, 0};
+            fp[t] = CompressProb<T>{Us, Vs, sg, U, V, o.d_rank, nullptr, tm, tn, tb, ta, tr ? 1 : 0, o.max_rank, ta, tb, 0, uinfo};
         }
         HCB_TRY(stage_array(ctx, fp, d_fp));
         HCB_TRY(run_svd_jobs<T>(ctx, jobs, a, b, ws, base));
@@ -1190,7 +1191,8 @@ constexpr int SKETCH_K = 96, SKETCH_K2 = 288, SKETCH_TAIL = 8;  // second, wider
 
 template<typename T>
 int t_compress_sketched(hcb_ctx *ctx, int cnt, const T *const *dense, int64_t ld, const hcb_tile *out,
-                        const hcb_compress_params *prm, std::vector<int> &redo, int sketch_k = SKETCH_K) {
+                        const hcb_compress_params *prm, std::vector<int> &redo, int sketch_k = SKETCH_K,
+                        int32_t *const *infos = nullptr) {
     // A ~ Qx Qx^T A, Qx = orth(A Omega) (m x k1).  B^T = A^T Qx = Qb Rb (n x k1 panel QR), Rb^T = Ub S Z^T (k1 x k1 Jacobi:
     // LEFT vectors Ub to high relative accuracy), so A ~ (Qx Ub) S (Qb Z)^T:  U = Qx Ub,  V^T = Qb [Z S ; 0].
     const int k1 = sketch_k, nblk = cdiv(k1, NBQ);
@@ -1260,11 +1262,12 @@ int t_compress_sketched(hcb_ctx *ctx, int cnt, const T *const *dense, int64_t ld
                                                    tn, tn, nc, std::min(tn, k1), nblk - 1, nblk, -1, 0};
         }
         g0[t] = SketchGlue<T>{Bt, Mr, k1, k1, tn};   // Mr = Rb^T
-        jobs[t] = SvdJob<T>{Mr, k1, 0, k1, k1, Us, Vs, sg};  // Rb^T = Ub S Z^T: Us = Ub, Vs = Z S
+        jobs[t] = SvdJob<T>{Mr, k1, 0, k1, k1, Us, Vs, sg, infos ? infos[t] : nullptr};  // Rb^T = Ub S Z^T: Us = Ub, Vs = Z S
         g1[t] = SketchGlue<T>{Vs, Vn, tn, k1, k1};   // Vn = [Z S ; 0]
         gu[t] = GemmProb<T>{Qx, Us, Uq, tm, k1, k1, tm, k1, tm, 0, 0, T(1), T(0)};                 // Uq = Qx Ub
         T *U = reinterpret_cast<T *>(o.d_data), *V = U + (size_t) tm * o.max_rank;
-        fp[t] = CompressProb<T>{Uq, Vn, sg, U, V, o.d_rank, d_flags + t, tm, tn, k1, tm, 0, o.max_rank, tm, tn, SKETCH_TAIL};
+        fp[t] = CompressProb<T>{Uq, Vn, sg, U, V, o.d_rank, d_flags + t, tm, tn, k1, tm, 0, o.max_rank, tm, tn, SKETCH_TAIL,
+                                infos ? infos[t] : nullptr};
         qx[t] = Qx;
         ms[t] = tm;
     }
@@ -1321,23 +1324,36 @@ int t_compress_batched(hcb_ctx *ctx, int64_t n64, const T *const *dense, int64_t
     // sketch when it pays (both dimensions well above the sketch width) and the strip kernels apply
     const bool sketch = std::is_same<T, double>::value && prm->fixed_rank <= 0 && mn_min >= 3 * SKETCH_K &&
                         strip_path_ok(ctx, std::max(m, n)) && !getenv("HCB_COMPRESS_FULL_SVD");
-    if (!sketch) return t_compress_full<T>(ctx, n64, dense, ld, out, prm, d_info);
+    // d_info: zeroed here, then |= 1 (Jacobi not converged) / |= 2 (rank clipped at max_rank) per tile, bits 8.. = sweeps
+    std::vector<int32_t *> ip;
+    if (d_info) {
+        HCB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t) * (size_t) n64, ctx->stream));
+        ip.resize((size_t) n64);
+        for (int64_t t = 0; t < n64; ++t) ip[t] = d_info + t;
+    }
+    int32_t *const *infos = d_info ? ip.data() : nullptr;
+    if (!sketch) return t_compress_full<T>(ctx, n64, dense, ld, out, prm, infos);
     const int64_t chunk = 512;
     for (int64_t c0 = 0; c0 < n64; c0 += chunk) {
         const int cnt = (int) std::min<int64_t>(chunk, n64 - c0);
         std::vector<int> redo;
-        HCB_TRY(t_compress_sketched<T>(ctx, cnt, dense + c0, ld, out + c0, prm, redo));
+        HCB_TRY(t_compress_sketched<T>(ctx, cnt, dense + c0, ld, out + c0, prm, redo, SKETCH_K, infos ? infos + c0 : nullptr));
         if (!redo.empty() && mn_min >= 3 * SKETCH_K2) {
             // rank beyond the first sketch (e.g. neighbouring clusters of a covariance matrix: ranks 100-200 at nb = 1024):
             // a second, 288-column sketch before giving up on sketching
             std::vector<const T *> rd(redo.size());
             std::vector<hcb_tile> ro(redo.size());
-            for (size_t i = 0; i < redo.size(); ++i) { rd[i] = dense[c0 + redo[i]]; ro[i] = out[c0 + redo[i]]; }
+            std::vector<int32_t *> ri(redo.size(), nullptr);
+            for (size_t i = 0; i < redo.size(); ++i) {
+                rd[i] = dense[c0 + redo[i]]; ro[i] = out[c0 + redo[i]];
+                if (infos) ri[i] = infos[c0 + redo[i]];
+            }
             std::vector<int> redo2, again;
             for (size_t b0 = 0; b0 < rd.size(); b0 += 128) {
                 const int bc = (int) std::min<size_t>(128, rd.size() - b0);
                 redo2.clear();
-                HCB_TRY(t_compress_sketched<T>(ctx, bc, rd.data() + b0, ld, ro.data() + b0, prm, redo2, SKETCH_K2));
+                HCB_TRY(t_compress_sketched<T>(ctx, bc, rd.data() + b0, ld, ro.data() + b0, prm, redo2, SKETCH_K2,
+                                               infos ? ri.data() + b0 : nullptr));
                 for (int r : redo2) again.push_back(redo[b0 + r]);
             }
             redo.swap(again);
@@ -1345,8 +1361,12 @@ int t_compress_batched(hcb_ctx *ctx, int64_t n64, const T *const *dense, int64_t
         if (!redo.empty()) {  // spectrum too flat for the sketches: full SVD for those tiles
             std::vector<const T *> rd(redo.size());
             std::vector<hcb_tile> ro(redo.size());
-            for (size_t i = 0; i < redo.size(); ++i) { rd[i] = dense[c0 + redo[i]]; ro[i] = out[c0 + redo[i]]; }
-            HCB_TRY(t_compress_full<T>(ctx, (int64_t) redo.size(), rd.data(), ld, ro.data(), prm, d_info));
+            std::vector<int32_t *> ri(redo.size(), nullptr);
+            for (size_t i = 0; i < redo.size(); ++i) {
+                rd[i] = dense[c0 + redo[i]]; ro[i] = out[c0 + redo[i]];
+                if (infos) ri[i] = infos[c0 + redo[i]];
+            }
+            HCB_TRY(t_compress_full<T>(ctx, (int64_t) redo.size(), rd.data(), ld, ro.data(), prm, infos ? ri.data() : nullptr));
             HCB_CUDA(cudaStreamSynchronize(ctx->stream));
         }
     }

@@ -45,7 +45,14 @@ __device__ __forceinline__ unsigned dsmem_addr(const void *smem_ptr, unsigned ra
 // also waits for this thread's outstanding global traffic -- the cp.async prefetch of the next reflector block -- so
 // every barrier exposed the full L2 / HBM latency of that prefetch.  The data crossing the barrier is shared memory
 // written by the owning SM: a CTA-scope fence (the writes are performed in this SM's shared memory) + relaxed arrive
-// + acquiring wait is enough.
+// + acquiring wait is what the hardware needs.  (Round-1 advice: in the PTX memory model a CTA-scope fence does not
+// formally order the writes for another CTA's ld.shared::cluster; the two formally sufficient forms --
+// fence.acq_rel.cluster + relaxed arrive, and barrier.cluster.arrive.release -- were compiled for sm_100a: both become
+// MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR + UCGABAR_ARV, i.e. exactly the GPU-scope fence measured above
+// (profiles/r01_cluster_barrier.txt: +1.1 k cycles per window), while this form is MEMBAR.ALL.CTA + UCGABAR_ARV.  The
+// shared-memory writes of an SM are performed in that SM's own shared memory, and the remote reads travel through the
+// cluster network AFTER the barrier wait (acquire): kept, with compute-sanitizer racecheck clean and every parity test
+// exercising it.)
 __device__ __forceinline__ void cluster_sync_pull() {
     asm volatile("fence.acq_rel.cta;\n" ::: "memory");
     asm volatile("barrier.cluster.arrive.relaxed.aligned;\n" ::: "memory");

@@ -1124,6 +1124,7 @@ struct CompressProb {
     int ld_us, ld_vs;  // leading dimensions of Us / Vs
     int tail_check;    // > 0 (sketched SVD): accept only if sigma[s - tail_check] is far below the threshold, else
                        // *info = 8 and the tile is left untouched (the caller re-does it with the full SVD)
+    int *uinfo;        // optional, the CALLER's info word of this tile: |= 2 when the rank was clipped at max_rank
 };
 
 // Uniform(-1, 1) test matrix for the range finder (counter-based: splitmix64 of the element index).
@@ -1180,7 +1181,8 @@ __global__ void __launch_bounds__(256) k_compress_finalize(const CompressProb<T>
         if (fixed_rank > 0) rk = fixed_rank < p.s ? fixed_rank : p.s;
         else rk = new_rank_rule(p.sigma, p.s, accuracy, truncated);
         if (rk < 1) rk = 1;
-        if (rk > p.max_rank) rk = p.max_rank;  // Compressed.cpp:117-119 (silent clamp)
+        const bool clipped = rk > p.max_rank;
+        if (clipped) rk = p.max_rank;  // Compressed.cpp:117-119 (silent clamp in the reference; reported here)
         if (p.tail_check > 0) {  // sketched SVD: the captured spectrum must have decayed well below the threshold
             const T thr = T(0.01) * accuracy * (truncated ? p.sigma[0] : T(1));
             const bool ok = rk + p.tail_check <= p.s && p.sigma[p.s - p.tail_check] <= thr;
@@ -1189,6 +1191,7 @@ __global__ void __launch_bounds__(256) k_compress_finalize(const CompressProb<T>
         }
         s_rk = rk;
         if (rk > 0) *p.rank_ptr = rk;
+        if (rk > 0 && clipped && p.uinfo) atomicOr(p.uinfo, 2);
     }
     __syncthreads();
     const int rk = s_rk;

@@ -175,6 +175,8 @@ typedef struct hcb_tile {
     /* Compressing constructor, batched (Compressed.cpp:75-146): dense tile t (m x n, ld) -> out[t] (U, V, *d_rank) */  \
     /* fp64 tiles >= 288 on both sides and <= 2048 rows: sketched (range finder + small SVD), tiles whose spectrum   */  \
     /* is too flat for the sketch are detected on the device and redone with the full SVD (one stream sync per call). */  \
+    /* d_info (device int32[n_tiles], may be NULL): zeroed, then |= 1 Jacobi not converged, |= 2 rank clipped at    */  \
+    /* max_rank (silent in the reference, Compressed.cpp:117-119); bits 8..15 = Jacobi sweeps.                       */  \
     int hcb_##P##compress_batched(hcb_ctx *, int64_t n_tiles, const T *const *dense_ptrs_host, int64_t ld,              \
                                   const hcb_tile *out, const hcb_compress_params *p, int32_t *d_info);                 \
     /* Multi-tile driver (examples/matrix_multiplication/omp_main.cpp:112-126) on one GPU:                           */  \

@@ -354,6 +354,10 @@ def test_sketched_compression_falls_back_on_flat_spectrum(hc, ctx):
         assert abs(g.GetTileRank() - o.rank) <= 1, (i, g.GetTileRank(), o.rank)
         # clamped tiles: both keep the leading maxRank triplets; compare the reconstructions
         assert relerr(g.to_dense(), o.to_dense()) <= (1e-6 if i != 1 else 10 * acc)
+    # the constructor's d_info is written -- bit 2 where the rank was clipped at maxRank (silent in the
+    # reference, Compressed.cpp:117-119), clean for the tile that fits, Jacobi converged everywhere
+    ci = tm.compress_info.cpu().numpy()
+    assert [int(v) & 0xff for v in ci] == [2, 0, 2], ci
 
 
 # ------------------------------------------------------------------------------------------------ live vs the oracle
