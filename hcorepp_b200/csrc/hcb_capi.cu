@@ -122,6 +122,8 @@ int launch_gemm(hcb_ctx *ctx, const GemmProb<T> *d_probs, int n_probs, int m_bou
             };
             if (m_bound <= 32) HCB_TRY(go(k_gemm_dmma<1, 4>, dg_smem_bytes<1, 4>(), cdiv(n_bound, 128)));
             else if (n_bound <= 32) HCB_TRY(go(k_gemm_dmma<4, 1>, dg_smem_bytes<4, 1>(), cdiv(m_bound, 128)));
+            else if (n_bound <= 48 && m_bound > 64)  // skinny right side (n = kp = 44): 128 x 48 tiles, all four warps along M
+                HCB_TRY(go(k_gemm_dmma<4, 1, 6>, dg_smem_bytes<4, 1, 6>(), cdiv(m_bound, 128)));
             else HCB_TRY(go(k_gemm_dmma<2, 2>, dg_smem_bytes<2, 2>(), cdiv(m_bound, 64) * cdiv(n_bound, 64)));
             HCB_LAUNCH_CHECK("k_gemm_dmma");
         } else {

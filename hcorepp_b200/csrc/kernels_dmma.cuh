@@ -51,15 +51,19 @@ __device__ __forceinline__ void cp_async_zfill_8(void *smem, const void *gmem, u
 template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 constexpr int DG_BK = 16, DG_STAGES = 3;
-template<int WM, int WN>
+template<int WM, int WN, int JT = 4>
 constexpr size_t dg_smem_bytes() {
-    constexpr int BM = 32 * WM, BN = 32 * WN;
+    constexpr int BM = 32 * WM, BN = 8 * JT * WN;
     constexpr size_t ea = (size_t) (DG_BK * (BM + 4) > BM * (DG_BK + 4) ? DG_BK * (BM + 4) : BM * (DG_BK + 4));
     constexpr size_t eb = (size_t) (DG_BK * (BN + 4) > BN * (DG_BK + 4) ? DG_BK * (BN + 4) : BN * (DG_BK + 4));
     return sizeof(double) * DG_STAGES * (ea + eb) + 8 * DG_STAGES + 16;
 }
 
-// CTA tile (32*WM) x (32*WN), WM*WN == 4 warps, each warp a 32x32 tile = 4x4 DMMA tiles (32 accumulator doubles).
+// CTA tile (32*WM) x (8*JT*WN), WM*WN == 4 warps, each warp a 32 x (8*JT) tile = 4 x JT DMMA tiles (JT = 4: 32x32, 32
+// accumulator doubles).  <4, 1, 6> is the 128 x 48 tile of the SKINNY products of the incremental recompression
+// (n = kp = 44 new columns: block Gram-Schmidt, the contraction's U_AB' / V_AB'): with 64-column tiles the second warp
+// column owns 12 of its 32 columns, so two of the four SM sub-partitions' tensor pipes idle half of the time; here the
+// four warps split M and each covers all 48 columns (92 % of the issued DMMAs are useful instead of 69 %).
 // BK = 16 per stage, THREE stages in a ring: while the tensor pipe works on stage s, the copies of stages s+1 and s+2
 // are in flight and no thread holds operand data in registers.  Every stage keeps the orientation of the GLOBAL operand,
 //     A: ta == 0 -> As[k][m] (pitch BM + 4),  ta == 1 -> As[m][k] (pitch BK + 4)
@@ -72,9 +76,9 @@ constexpr size_t dg_smem_bytes() {
 //     dimension, 8 bytes else (V factors stored with ld = rank, odd ranks) -- edges and the K tail need no special path.
 // Optional second A segment (p.A2): op(A) = [op(A) | op(A2)] along k, split at p.k1.
 // grid = (tiles_bound, n_problems), grid-stride over output tiles.
-template<int WM, int WN>
+template<int WM, int WN, int JT = 4>
 __global__ void __launch_bounds__(128, 3) k_gemm_dmma(const GemmProb<double> *__restrict__ probs) {
-    constexpr int BM = 32 * WM, BN = 32 * WN, BK = DG_BK, S = DG_STAGES;
+    constexpr int BM = 32 * WM, BN = 8 * JT * WN, WTN = 8 * JT, BK = DG_BK, S = DG_STAGES;
     constexpr int PA0 = BM + 4, PA1 = BK + 4, PB0 = BK + 4, PB1 = BN + 4;
     constexpr int EA = BK * PA0 > BM * PA1 ? BK * PA0 : BM * PA1, EB = BK * PB1 > BN * PB0 ? BK * PB1 : BN * PB0;
     static_assert(WM * WN == 4, "four warps per CTA");
@@ -107,12 +111,12 @@ __global__ void __launch_bounds__(128, 3) k_gemm_dmma(const GemmProb<double> *__
         const int mrem = min(BM, p.m - row0);
         const bool a_bulk = p.ta == 0 && a_16 && ((mrem & 1) == 0);   // whole k columns of the A tile by TMA
         const int nrem = min(BN, p.n - col0);
-        const int imax = min(4, max(0, (mrem - wm * 32 + 7) >> 3)), jmax = min(4, max(0, (nrem - wn * 32 + 7) >> 3));
-        double acc[4][4][2];
+        const int imax = min(4, max(0, (mrem - wm * 32 + 7) >> 3)), jmax = min(JT, max(0, (nrem - wn * WTN + 7) >> 3));
+        double acc[4][JT][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int j = 0; j < JT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
         // issue the copies of k-tile kt into stage st (all threads; one cp.async group per call)
         auto issue = [&](int st, int kt) {
@@ -239,10 +243,10 @@ __global__ void __launch_bounds__(128, 3) k_gemm_dmma(const GemmProb<double> *__
                     }
                     if (p.tb == 0) {
 #pragma unroll
-                        for (int j = 0; j < JM; ++j) b[j] = bs[(wn * 32 + j * 8 + g) * PB0 + ks + c];
+                        for (int j = 0; j < JM; ++j) b[j] = bs[(wn * WTN + j * 8 + g) * PB0 + ks + c];
                     } else {
 #pragma unroll
-                        for (int j = 0; j < JM; ++j) b[j] = bs[(ks + c) * PB1 + wn * 32 + j * 8 + g];
+                        for (int j = 0; j < JM; ++j) b[j] = bs[(ks + c) * PB1 + wn * WTN + j * 8 + g];
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -254,6 +258,8 @@ __global__ void __launch_bounds__(128, 3) k_gemm_dmma(const GemmProb<double> *__
                 }
             };
             switch (jmax) {
+                case 6: if constexpr (JT >= 6) mma_stage(std::integral_constant<int, 6>{}); break;
+                case 5: if constexpr (JT >= 5) mma_stage(std::integral_constant<int, 5>{}); break;
                 case 4: mma_stage(std::integral_constant<int, 4>{}); break;
                 case 3: mma_stage(std::integral_constant<int, 3>{}); break;
                 case 2: mma_stage(std::integral_constant<int, 2>{}); break;
@@ -264,10 +270,10 @@ __global__ void __launch_bounds__(128, 3) k_gemm_dmma(const GemmProb<double> *__
         cp_async_wait<0>();
         // epilogue: lane holds C[g][2c], C[g][2c+1] of every 8x8 tile
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < JT; ++j) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int gc = col0 + wn * 32 + j * 8 + 2 * c + h;
+                const int gc = col0 + wn * WTN + j * 8 + 2 * c + h;
                 if (gc >= p.n) continue;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {

@@ -313,9 +313,12 @@ class DenseTile : public Tile<T> {  // Dense.hpp:56-91
 public:
     DenseTile(size_t aNumOfRows, size_t aNumOfCols, T *aPdata, size_t aLeadingDim, blas::Layout aLayout,
               const kernels::RunContext &aContext, bool aMemoryOwnership = true) {
-        if (aLayout != blas::Layout::ColMajor) throw std::invalid_argument("DenseTile: only ColMajor tiles are supported");
+        // RowMajor (Dense.cpp:69-96 passes the tile's layout to the GEMM): an m x n row-major buffer IS the column-major
+        // n x m transpose, which is how it is held; HCore::Gemm then computes C^T = op(B)^T op(A)^T on those views.
+        const bool rm = aLayout == blas::Layout::RowMajor;
         this->mLayout = aLayout; this->mNumOfRows = aNumOfRows; this->mNumOfCols = aNumOfCols; this->mRank = 0;
-        this->mpDataArray = new dataunits::DataHolder<T>(aNumOfRows, aNumOfCols, aLeadingDim, aPdata, aContext, aMemoryOwnership);
+        this->mpDataArray = new dataunits::DataHolder<T>(rm ? aNumOfCols : aNumOfRows, rm ? aNumOfRows : aNumOfCols, aLeadingDim, aPdata,
+                                                         aContext, aMemoryOwnership);
         this->mLeadingDim = this->mpDataArray->GetLeadingDim();
     }
     DenseTile(size_t m, size_t n, T *d, size_t ld, const kernels::RunContext &c) : DenseTile(m, n, d, ld, blas::Layout::ColMajor, c) {}
@@ -334,7 +337,9 @@ public:
     int64_t GetNumOfSubMatrices() const override { return 1; }
     TileType GetTileType() override { return DENSE; }
     hcb_tile Descriptor() const override {
-        return hcb_tile{HCB_TILE_DENSE, (int32_t) this->mNumOfRows, (int32_t) this->mNumOfCols,
+        const bool rm = this->mLayout == blas::Layout::RowMajor;  // the column-major view of a row-major tile is its transpose
+        return hcb_tile{HCB_TILE_DENSE, (int32_t) (rm ? this->mNumOfCols : this->mNumOfRows),
+                        (int32_t) (rm ? this->mNumOfRows : this->mNumOfCols),
                         (int32_t) this->mpDataArray->GetLeadingDim(), 0, 0, nullptr, this->mpDataArray->GetData()};
     }
     std::pair<TileMetadata *, T *> UnPackTile(const kernels::RunContext &) override {
@@ -343,11 +348,12 @@ public:
     }
     /// Dense.cpp:137-143: adopt a DEVICE buffer (no ownership) described by the metadata
     void PackTile(TileMetadata aMetadata, T *aDataArray, const kernels::RunContext &aContext) override {
-        if (aMetadata.mLayout != blas::Layout::ColMajor) throw std::invalid_argument("DenseTile: only ColMajor tiles are supported");
         delete this->mpDataArray;
         this->mLayout = aMetadata.mLayout; this->mLeadingDim = aMetadata.mLeadingDimension;
         this->mNumOfRows = aMetadata.mNumOfRows; this->mNumOfCols = aMetadata.mNumOfCols; this->mRank = aMetadata.mMatrixRank;
-        this->mpDataArray = new dataunits::DataHolder<T>(this->mNumOfRows, this->mNumOfCols, this->mLeadingDim, aDataArray, aContext, false);
+        const bool rm = this->mLayout == blas::Layout::RowMajor;
+        this->mpDataArray = new dataunits::DataHolder<T>(rm ? this->mNumOfCols : this->mNumOfRows, rm ? this->mNumOfRows : this->mNumOfCols,
+                                                         this->mLeadingDim, aDataArray, aContext, false);
     }
 };
 
@@ -632,6 +638,17 @@ public:
             static_cast<operators::CompressedTile<T> &>(aC).EnsureCapacity(std::min(aC.GetNumOfRows(), aC.GetNumOfCols()));
         const hcb_tile a = aA.Descriptor(), b = aB.Descriptor(), c = aC.Descriptor();
         const hcb_compress_params p = aSVDArguments.ToC();
+        const bool rm = aC.GetLayout() == blas::Layout::RowMajor;
+        if (rm != (aA.GetLayout() == blas::Layout::RowMajor) || rm != (aB.GetLayout() == blas::Layout::RowMajor))
+            throw std::invalid_argument("HCore::Gemm: A, B and C must share one layout");
+        if (rm) {
+            // Row-major tiles (dense only, like the reference: Dense.cpp:69-96 hands the layout to the GEMM; compressed tiles are
+            // ColMajor, Compressed.cpp:29-34): the descriptors are the column-major TRANSPOSED views, and
+            // C^T = alpha * op(B)^T op(A)^T + beta * C^T = alpha * op_B(B^T-view) * op_A(A^T-view) + beta * C^T-view.
+            if (!(aA.isDense() && aB.isDense() && aC.isDense())) throw std::invalid_argument("HCore::Gemm: RowMajor is a dense-tile layout");
+            detail::check(detail::abi<T>::tlr_gemm_batched(aContext.Handle(), 1, &b, aBOp == blas::Op::NoTrans ? 0 : 1, &a,
+                                                           aAOp == blas::Op::NoTrans ? 0 : 1, &c, aAlpha, aBeta, &p, nullptr), "HCore::Gemm");
+        } else
         detail::check(detail::abi<T>::tlr_gemm_batched(aContext.Handle(), 1, &a, aAOp == blas::Op::NoTrans ? 0 : 1, &b,
                                                        aBOp == blas::Op::NoTrans ? 0 : 1, &c, aAlpha, aBeta, &p, nullptr), "HCore::Gemm");
         aFlops += 2 * aC.GetNumOfRows() * aC.GetNumOfCols() * (aAOp == blas::Op::NoTrans ? aA.GetNumOfCols() : aA.GetNumOfRows());

@@ -91,6 +91,22 @@ static void run(const char *type) {
         report("TestGemm 1 (DDD)", type, approx(dense_of(*C, ctx), {{60, 72, 84}, {132, 162, 192}, {204, 252, 300}}));
         delete A; delete B; delete C;
     }
+    {  // RowMajor dense tiles (Dense.cpp:69-96): the same product with every buffer row-major, ragged shapes, op(B) = B^T
+        const Mat<double> a = {{1, 2, 3}, {4, 5, 6}}, b = {{1, 0, 2}, {0, 1, 1}, {3, 1, 0}, {2, 2, 2}};  // A 2x3, B 4x3: C = A B^T (2x4)
+        auto rowmajor = [](const Mat<double> &m) { std::vector<T> o; for (auto &r : m) for (double v : r) o.push_back((T) v); return o; };
+        auto ha = rowmajor(a), hb = rowmajor(b);
+        DenseTile<T> A(2, 3, ha.data(), 3, blas::Layout::RowMajor, ctx), B(4, 3, hb.data(), 3, blas::Layout::RowMajor, ctx);
+        std::vector<T> hc = rowmajor({{1, 1, 1, 1}, {2, 2, 2, 2}});
+        DenseTile<T> C(2, 4, hc.data(), 4, blas::Layout::RowMajor, ctx);
+        HCore<T>::Gemm(2, A, blas::Op::NoTrans, B, blas::Op::Trans, 1, C, ctx, flops, unit);
+        auto got = to_host<T>(C.GetTileSubMatrix(0), 8, ctx);  // row-major 2 x 4
+        const double want[8] = {2 * 7 + 1, 2 * 5 + 1, 2 * 5 + 1, 2 * 12 + 1, 2 * 16 + 2, 2 * 11 + 2, 2 * 17 + 2, 2 * 30 + 2};
+        bool ok = true;
+        for (int i = 0; i < 8; ++i) ok = ok && std::fabs(got[i] - want[i]) < 1e-4;
+        bool mixed_throws = false;
+        try { auto *Cc = zeros_d(2, 4); try { HCore<T>::Gemm(1, A, blas::Op::NoTrans, B, blas::Op::Trans, 1, *Cc, ctx, flops, unit); } catch (const std::invalid_argument &) { mixed_throws = true; } delete Cc; } catch (...) {}
+        report("RowMajor DDD (A B^T, ragged)", type, ok && mixed_throws);
+    }
     {  // TestGemm.cpp:206 -- CDD
         auto *A = comp({{1}, {4}, {7}}, {{10, 11, 12}}); auto *B = dense({{2, 4}, {8, 10}, {14, 16}}); auto *C = zeros_d(3, 2);
         HCore<T>::Gemm(1, *A, blas::Op::NoTrans, *B, blas::Op::NoTrans, 1, *C, ctx, flops, unit);
