@@ -189,6 +189,8 @@ struct hcb_ctx {
     bool own_stream = false;
     void *ws = nullptr;  // grow-only scratch arena
     size_t ws_bytes = 0;
+    void *ws2 = nullptr;  // second grow-only arena: FP64 shadow copies of FP32 tiles (promoted fused path)
+    size_t ws2_bytes = 0;
     int *svd_sched = nullptr;  // work counters of the persistent Jacobi kernel (2 + problems ints, grow-only)
     size_t svd_sched_n = 0;
     hcb::ParamRing ring;

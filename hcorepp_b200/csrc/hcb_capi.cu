@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <type_traits>
+#include <unordered_map>
 
 namespace hcb {
 thread_local std::string g_last_error;
@@ -813,6 +814,9 @@ static int classify(const hcb_tile *A, const hcb_tile *B, const hcb_tile *C, int
     return HCB_OK;
 }
 
+int tlr_gemm_promoted(hcb_ctx *ctx, int n, const hcb_tile *A, int opA, const hcb_tile *B, int opB, const hcb_tile *C,
+                      float alpha, float beta, const hcb_compress_params *prm, int32_t *d_info, bool reset_info);
+
 template<typename T>
 int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, const hcb_tile *B, int opB,
                        const hcb_tile *C, T alpha, T beta, const hcb_compress_params *prm, int32_t *d_info,
@@ -824,6 +828,17 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     const int n = (int) n64;
     BatchShape s;
     HCB_TRY(classify(A, B, C, n, opA, opB, s));
+    if constexpr (std::is_same<T, float>::value) {
+        // FP32 tiles whose recompression is big enough for the blocked path run on the FP64 machinery (DMMA GEMMs, strip
+        // reflectors, register Jacobi, incremental recompression): the tiles are converted to FP64 shadows, the FP64 path
+        // runs on them (ranks / state words are shared), C is converted back.  The native FP32 kernels (SIMT FFMA GEMM,
+        // GEMM-blocked QR, shared-memory Jacobi) stay for small tiles and under HCB_FP32_NATIVE=1.
+        const bool native = getenv("HCB_FP32_NATIVE") && atoi(getenv("HCB_FP32_NATIVE")) != 0;  // (read per call: tests toggle it)
+        const bool recomp = (s.mix == CCC || s.mix == CDC || s.mix == DCC);
+        const int kp = (s.mix == DCC) ? s.kB : s.kA;
+        if (!native && recomp && s.kC + kp > 2 * NBQ && strip_path_ok(ctx, std::max(s.m, s.n)))
+            return tlr_gemm_promoted(ctx, n, A, opA, B, opB, C, alpha, beta, prm, d_info, reset_info);
+    }
     const Layout<T> L = make_layout<T>(s);
     const bool blocked = L.r_b > 2 * NBQ;  // compact-WY path once the stacked rank spans more than two blocks
     const int rk_bound = std::max(1, std::min(L.pq_b, s.maxrankC));
@@ -1092,6 +1107,75 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
         k_finalize<T><<<grid, dim3(32, 8), 0, ctx->stream>>>(sa.rc);
         HCB_LAUNCH_CHECK("k_finalize");
     }
+    return HCB_OK;
+}
+
+// FP32 batch on the FP64 path (see t_tlr_gemm_batched<float>).  Every distinct tile buffer of the batch gets an FP64
+// shadow in the context's second arena (a tile that appears in many triples -- A(j, k) in every C(j, :) -- is converted
+// once), element for element over its whole capacity, so offsets (V at m * max_rank, ld = rank) carry over unchanged.
+int tlr_gemm_promoted(hcb_ctx *ctx, int n, const hcb_tile *A, int opA, const hcb_tile *B, int opB, const hcb_tile *C,
+                      float alpha, float beta, const hcb_compress_params *prm, int32_t *d_info, bool reset_info) {
+    auto elems = [](const hcb_tile &t) -> size_t {
+        return t.type == HCB_TILE_COMPRESSED ? ((size_t) t.m + (size_t) t.n) * (size_t) t.max_rank : (size_t) t.ld * (size_t) t.n;
+    };
+    std::vector<hcb_tile> sh(3 * (size_t) n);
+    std::vector<ConvProb<float, double>> up;
+    std::vector<ConvProb<double, float>> down;
+    std::unordered_map<const void *, size_t> where;  // tile buffer -> shadow offset (in doubles)
+    size_t off = 0;
+    for (int side = 0; side < 3; ++side) {
+        const hcb_tile *src = side == 0 ? A : (side == 1 ? B : C);
+        for (int t = 0; t < n; ++t) {
+            const hcb_tile &x = src[t];
+            auto it = where.find(x.d_data);
+            size_t o;
+            if (it == where.end()) {
+                o = off;
+                where.emplace(x.d_data, o);
+                off += align_up(elems(x), 32);
+                up.push_back({reinterpret_cast<const float *>(x.d_data), nullptr, elems(x)});
+                up.back().dst = reinterpret_cast<double *>(o);  // patched with the arena base below
+                if (side == 2) down.push_back({reinterpret_cast<const double *>(o), reinterpret_cast<float *>(x.d_data), elems(x)});
+            } else {
+                o = it->second;
+                if (side == 2) return fail(HCB_EINVAL, "tlr_gemm_batched: a C tile appears twice in the batch (or aliases an operand)");
+            }
+            sh[(size_t) side * n + t] = x;
+            sh[(size_t) side * n + t].d_data = reinterpret_cast<void *>(o);
+        }
+    }
+    const size_t bytes = off * sizeof(double) + 256;
+    if (bytes > ctx->ws2_bytes) {
+        HCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->ws2) HCB_CUDA(cudaFree(ctx->ws2));
+        ctx->ws2 = nullptr; ctx->ws2_bytes = 0;
+        const size_t want = align_up(bytes + bytes / 8, 1 << 20);
+        cudaError_t e = cudaMalloc(&ctx->ws2, want);
+        if (e != cudaSuccess) return fail(HCB_ENOMEM, std::string("fp32 promotion arena cudaMalloc: ") + cudaGetErrorString(e));
+        ctx->ws2_bytes = want;
+    }
+    double *base = reinterpret_cast<double *>(ctx->ws2);
+    for (auto &c : up) c.dst = base + reinterpret_cast<size_t>(c.dst);
+    for (auto &c : down) c.src = base + reinterpret_cast<size_t>(c.src);
+    for (auto &t : sh) t.d_data = base + reinterpret_cast<size_t>(t.d_data);
+    size_t biggest = 0;
+    for (auto &c : up) biggest = std::max(biggest, c.n);
+    auto run = [&](auto &vec, auto kern) -> int {
+        using P = typename std::remove_reference<decltype(vec[0])>::type;
+        for (size_t o = 0; o < vec.size(); o += 4096) {
+            const size_t cnt = std::min<size_t>(4096, vec.size() - o);
+            void *d = nullptr;
+            HCB_TRY(ring_upload(ctx, vec.data() + o, sizeof(P) * cnt, &d));
+            dim3 grid((unsigned) std::max<size_t>(1, std::min<size_t>(64, (biggest + 2047) / 2048)), (unsigned) cnt);
+            kern<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const P *>(d));
+            HCB_LAUNCH_CHECK("k_convert_batched");
+        }
+        return HCB_OK;
+    };
+    HCB_TRY(run(up, k_convert_batched<float, double>));
+    HCB_TRY(t_tlr_gemm_batched<double>(ctx, n, sh.data(), opA, sh.data() + n, opB, sh.data() + 2 * (size_t) n, (double) alpha,
+                                       (double) beta, prm, d_info, reset_info));
+    HCB_TRY(run(down, k_convert_batched<double, float>));
     return HCB_OK;
 }
 
@@ -1666,6 +1750,7 @@ int hcb_ctx_destroy(hcb_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->ws) cudaFree(c->ws);
+    if (c->ws2) cudaFree(c->ws2);
     if (c->svd_sched) cudaFree(c->svd_sched);
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);

@@ -194,4 +194,14 @@ __global__ void k_expand_tri(char uplo, char diag, int n, const T *__restrict__ 
     D[(size_t) i + (size_t) j * n] = v;
 }
 
+// Element-wise precision conversion of whole buffers (FP32 tiles <-> their FP64 shadows, see t_tlr_gemm_promoted).
+// grid = (chunks, n_problems)
+template<typename S, typename D>
+struct ConvProb { const S *src; D *dst; size_t n; };
+template<typename S, typename D>
+__global__ void __launch_bounds__(256) k_convert_batched(const ConvProb<S, D> *__restrict__ probs) {
+    const ConvProb<S, D> p = probs[blockIdx.y];
+    for (size_t i = (size_t) blockIdx.x * 256 + threadIdx.x; i < p.n; i += (size_t) gridDim.x * 256) p.dst[i] = (D) p.src[i];
+}
+
 }  // namespace hcb

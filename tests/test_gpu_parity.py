@@ -942,6 +942,52 @@ def test_blocked_recompression_fp32(hc, ctx, dims):
         assert abs(c.GetTileRank() - oc.rank) <= max(1, int(0.03 * oc.rank)), (c.GetTileRank(), oc.rank)
 
 
+def test_fp32_promoted_path_vs_native_and_oracle(hc, ctx, monkeypatch):
+    """Round 2: FP32 tiles on the blocked path run on the FP64 machinery through FP64 shadows.  The same
+    4-step k-sum at nb = 512, accuracy 1e-4, three ways: promoted (default), native FP32 kernels (HCB_FP32_NATIVE=1), FP32
+    oracle.  Both GPU paths must meet the 10 * accuracy contract; a shared operand (A == B buffer) and a dense operand
+    (DCC) go through the shadow de-duplication."""
+    nb, ka, acc, dt = 512, 30, 1e-4, np.float32
+    rng = np.random.default_rng(77)
+    steps = [(lowrank(rng, nb, nb, ka, dt, 0.8), lowrank(rng, nb, nb, ka, dt, 0.8)) for _ in range(4)]
+    C0 = lowrank(rng, nb, nb, 60, dt, 0.93)
+    outs = {}
+    for mode in ("promoted", "native"):
+        if mode == "native":
+            monkeypatch.setenv("HCB_FP32_NATIVE", "1")
+        else:
+            monkeypatch.delenv("HCB_FP32_NATIVE", raising=False)
+        c = mk_tile(hc, ctx, "C", None, *C0, dt, max_rank=nb // 2)
+        for AUV, BUV in steps:
+            a, b = mk_tile(hc, ctx, "C", None, *AUV, dt), mk_tile(hc, ctx, "C", None, *BUV, dt)
+            hc.HCore.Gemm(1.0, a, False, b, False, 1.0, c, ctx, hc.CompressionParameters(acc))
+        ctx.Sync()
+        outs[mode] = (c.to_dense().astype(np.float64), c.GetTileRank())
+    monkeypatch.delenv("HCB_FP32_NATIVE", raising=False)
+    oc = oracle_tile("C", None, C0, dt)
+    oc.max_rank = nb // 2
+    for AUV, BUV in steps:
+        O.hcore_gemm(dt(1.0), oracle_tile("C", None, AUV, dt), False, oracle_tile("C", None, BUV, dt), False, dt(1.0), oc,
+                     O.CompressionParameters(acc))
+    ref = oc.to_dense().astype(np.float64)
+    for mode, (d, rk) in outs.items():
+        assert np.linalg.norm(d - ref) <= 10 * acc * np.linalg.norm(ref), mode
+        assert abs(rk - oc.rank) <= max(1, int(0.03 * oc.rank)), (mode, rk, oc.rank)
+    # X * X^T with ONE buffer for both operands, and a dense left operand (DCC): shadows are shared / dense tiles converted
+    X = mk_tile(hc, ctx, "C", None, *steps[0][0], dt)
+    c2 = mk_tile(hc, ctx, "C", None, *C0, dt, max_rank=nb // 2)
+    hc.HCore.Gemm(1.0, X, False, X, True, 1.0, c2, ctx, hc.CompressionParameters(acc))
+    xd = (steps[0][0][0].astype(np.float64) @ steps[0][0][1].astype(np.float64))
+    want = C0[0].astype(np.float64) @ C0[1].astype(np.float64) + xd @ xd.T
+    assert np.linalg.norm(c2.to_dense().astype(np.float64) - want) <= 10 * acc * np.linalg.norm(want)
+    Dn = rng.standard_normal((nb, nb)).astype(dt) / np.sqrt(nb)
+    dA = mk_tile(hc, ctx, "D", Dn, None, None, dt)
+    c3 = mk_tile(hc, ctx, "C", None, *C0, dt, max_rank=nb // 2)
+    hc.HCore.Gemm(1.0, dA, False, X, False, 1.0, c3, ctx, hc.CompressionParameters(acc))
+    want3 = C0[0].astype(np.float64) @ C0[1].astype(np.float64) + Dn.astype(np.float64) @ xd
+    assert np.linalg.norm(c3.to_dense().astype(np.float64) - want3) <= 10 * acc * np.linalg.norm(want3)
+
+
 @pytest.mark.parametrize("nb,rank,mixes", [(1024, 128, MIXES), (1024, 256, MIXES), (2048, 256, ["CCC", "CDC", "DCC", "CCD"])],
                          ids=["nb1024-r128", "nb1024-r256", "nb2048-r256"])
 def test_single_tile_sweep_large_ranks(hc, ctx, nb, rank, mixes):
