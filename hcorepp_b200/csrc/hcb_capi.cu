@@ -984,20 +984,33 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
         PhaseScope ph(ctx, 3);
         if (!blocked) HCB_TRY(launch_qr<T>(ctx, sa.qr, 2 * n));
         else {
+            // block classical Gram-Schmidt of the new U columns against the orthonormal CU and of the new V columns against
+            // W = CV^T diag(sigma)^-1 (Zv = S^-2 (CV Y), Y -= CV^T Zv): first pass of both sides, then the device decides per
+            // tile side whether the second pass is needed (k_inc_gate: "twice is enough" criterion), then the second pass
+            // (its GEMMs are no-ops where the gate switched them off)
+            static const bool gate = !(getenv("HCB_GS_ALWAYS_TWICE") && atoi(getenv("HCB_GS_ALWAYS_TWICE")) != 0);
+            dim3 gs(std::max(1, std::min(16, cdiv((long long) s.kC * L.kp_b, 256))), n);
             if (inc_enabled) {
-                // block classical Gram-Schmidt (twice) of the new U columns against the orthonormal CU
                 HCB_TRY(launch_gemm<T>(ctx, sa.gi + 0 * (size_t) n, n, s.kC, L.kp_b));
                 HCB_TRY(launch_gemm<T>(ctx, sa.gi + 1 * (size_t) n, n, s.m, L.kp_b));
-                HCB_TRY(launch_gemm<T>(ctx, sa.gi + 2 * (size_t) n, n, s.kC, L.kp_b));
-                HCB_TRY(launch_gemm<T>(ctx, sa.gi + 3 * (size_t) n, n, s.m, L.kp_b));
             }
             if (vinc_enabled) {
-                // ... and of the new V columns against W = CV^T diag(sigma)^-1 (Zv = S^-2 (CV Y), Y -= CV^T Zv, twice)
-                dim3 gs(std::max(1, std::min(16, cdiv((long long) s.kC * L.kp_b, 256))), n);
                 HCB_TRY(launch_gemm<T>(ctx, sa.giv + 0 * (size_t) n, n, s.kC, L.kp_b));
                 k_vinc_scale<T><<<gs, 256, 0, ctx->stream>>>(sa.rc, 0);
                 HCB_LAUNCH_CHECK("k_vinc_scale");
                 HCB_TRY(launch_gemm<T>(ctx, sa.giv + 1 * (size_t) n, n, s.n, L.kp_b));
+            }
+            if (inc_enabled && gate) {
+                // (HCB_GS_FORCE_ONCE=1, tests only: drop the second pass even where the criterion asks for it)
+                const int force_once = getenv("HCB_GS_FORCE_ONCE") && atoi(getenv("HCB_GS_FORCE_ONCE")) != 0;
+                k_inc_gate<T><<<2 * n, 256, 0, ctx->stream>>>(sa.rc, sa.gi, sa.giv, n, force_once);
+                HCB_LAUNCH_CHECK("k_inc_gate");
+            }
+            if (inc_enabled) {
+                HCB_TRY(launch_gemm<T>(ctx, sa.gi + 2 * (size_t) n, n, s.kC, L.kp_b));
+                HCB_TRY(launch_gemm<T>(ctx, sa.gi + 3 * (size_t) n, n, s.m, L.kp_b));
+            }
+            if (vinc_enabled) {
                 HCB_TRY(launch_gemm<T>(ctx, sa.giv + 2 * (size_t) n, n, s.kC, L.kp_b));
                 k_vinc_scale<T><<<gs, 256, 0, ctx->stream>>>(sa.rc, 1);
                 HCB_LAUNCH_CHECK("k_vinc_scale");

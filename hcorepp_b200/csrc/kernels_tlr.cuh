@@ -985,6 +985,52 @@ __global__ void __launch_bounds__(256) k_vinc_sig0(const RecompProb<T> *__restri
     }
 }
 
+// Selective re-orthogonalisation (Daniel-Gragg-Kaufman-Stewart / "twice is enough"): after the FIRST block Gram-Schmidt
+// pass  P' = P - CU G  (CU orthonormal, so |p_j|^2 = |p'_j|^2 + |g_j|^2 without cancellation), a second pass is only
+// needed for columns that lost more than half of their squared norm; when EVERY new column of a tile side kept
+//   |p'_j|^2 >= |g_j|^2     (rho^2 >= 1/2: the orthogonality of Q2 against CU is already eps / rho <= 1.5 eps)
+// the two second-pass GEMMs of that side are switched off on the device (descriptor m = 0) and their coefficient
+// buffer is zeroed.  New directions that lie mostly inside span(CU) -- the saturated tiles of smooth kernels -- fail the
+// test and take both passes; independent subspaces (the BASELINE generator's tiles: |g|^2 / |p|^2 ~ kc / nb <= 0.31) pass.
+// V side: the coefficients in the orthonormal basis W = CV^T S^-1 are S^-1 Hv, |.|^2 = sum_i Hv_ij^2 / sigma_i^2.
+// grid = 2 * n_tiles (side = blockIdx.x & 1), 256 threads; gi / giv are the [4][n_tiles] descriptor arrays.
+template<typename T>
+__global__ void __launch_bounds__(256) k_inc_gate(const RecompProb<T> *__restrict__ probs, GemmProb<T> *__restrict__ gi,
+                                                  GemmProb<T> *__restrict__ giv, int n_tiles, int force_once) {
+    const int t = blockIdx.x >> 1, side = blockIdx.x & 1;
+    const RecompProb<T> p = probs[t];
+    if (!p.active || !(side ? p.vinc : p.inc)) return;
+    const int rows = side ? p.n : p.m, kc = p.kc, kp = p.kp;
+    const T *X = side ? p.Yn : p.Pn;        // the once-orthogonalised new columns (rows x kp, ld rows)
+    const T *G = side ? p.Hv : p.Gu;        // kc x kp, ld kc
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __shared__ int s_fail;
+    if (threadIdx.x == 0) s_fail = 0;
+    __syncthreads();
+    for (int j = w; j < kp; j += nw) {
+        const T *x = X + (size_t) j * rows, *g = G + (size_t) j * kc;
+        T a0 = T(0), a1 = T(0), b = T(0);
+        int i = lane;
+        for (; i + 32 < rows; i += 64) { a0 = fma(x[i], x[i], a0); a1 = fma(x[i + 32], x[i + 32], a1); }
+        for (; i < rows; i += 32) a0 = fma(x[i], x[i], a0);
+        for (int l = lane; l < kc; l += 32) {
+            const T c = side ? g[l] / p.sig0[l] : g[l];
+            b = fma(c, c, b);
+        }
+        const T rest = warp_sum(a0 + a1), coef = warp_sum(b);
+        if (lane == 0 && !(rest >= coef)) s_fail = 1;
+    }
+    __syncthreads();
+    if (s_fail && !force_once) return;      // second pass stays on (force_once: test switch, see HCB_GS_FORCE_ONCE)
+    T *Z = side ? p.Zv : p.Gu2;             // second-pass coefficients: none
+    for (int idx = threadIdx.x; idx < kc * kp; idx += blockDim.x) Z[idx] = T(0);
+    if (threadIdx.x == 0) {
+        GemmProb<T> *arr = side ? giv : gi;
+        arr[(size_t) 2 * n_tiles + t].m = 0;
+        arr[(size_t) 3 * n_tiles + t].m = 0;
+    }
+}
+
 // Incremental V side: Zv = diag(sigma)^-2 * H of the CURRENT pass.  pass 0: H = Hv (first GEMM);  pass 1: the second
 // GEMM left H2 = CV * Y1 in Zv -- it is added to Hv (Gv = S^-1 (H + H2)) and scaled in place.  grid = (chunks, n_tiles)
 template<typename T>

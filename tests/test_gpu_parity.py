@@ -529,6 +529,65 @@ def test_incremental_u_side_ksum_vs_oracle(hc, ctx):
     assert relerr(Ct.to_dense(), o.to_dense()) <= 10 * acc and abs(Ct.GetTileRank() - o.rank) <= 1
 
 
+def test_selective_reorthogonalisation_saturated_tile(hc, ctx):
+    """Round 2: the second block Gram-Schmidt pass of the incremental recompression is switched off per tile side when
+    every new column kept more than half of its squared norm (k_inc_gate).  Here the updates are built so that it must
+    STAY ON: A_k = C_U M_k (+ a 1e-8 component outside), B_k = N_k C_V -- every new direction lies almost entirely in the
+    spans the tile already has (a saturated tile of a smooth kernel).  At accuracy 1e-12 the outside components survive the
+    truncation, and the once-projected remainder is ~1e-8 of its column: ONE Gram-Schmidt pass would leave it orthogonal
+    to C_U only to eps / 1e-8 ~ 1e-8, the second pass brings that to rounding level.  Checked: parity with the oracle, U
+    orthonormal to 1e-12 (with the second pass forced off -- HCB_GS_FORCE_ONCE, measured 1.4e-11 against 4e-14 -- the same
+    k-sum loses more than two orders of magnitude, which is asserted too), and agreement with the full Householder path."""
+    nb, kc, ka, acc, kt = 512, 60, 24, 1e-12, 4
+    rng = np.random.default_rng(4242)
+    p, po = hc.CompressionParameters(acc), O.CompressionParameters(acc)
+    c0 = O.synth_compressed_tile(nb, kc, 9100)                  # U orthonormal, V = S W^T
+    W = (c0.V / np.linalg.norm(c0.V, axis=1)[:, None]).T        # nb x kc orthonormal
+    steps = []
+    for i in range(kt):
+        qa, _ = np.linalg.qr(rng.standard_normal((nb, ka)))
+        qb, _ = np.linalg.qr(rng.standard_normal((nb, ka)))
+        M, N = rng.standard_normal((kc, ka)) / np.sqrt(kc), rng.standard_normal((kc, ka)) / np.sqrt(kc)
+        sa = 0.5 ** np.arange(ka)
+        AU = np.asfortranarray(c0.U @ M + 1e-8 * qa)            # columns inside span(CU) up to 1e-8
+        AV = np.asfortranarray((sa[:, None] * qb.T))            # ka x nb
+        BU = np.asfortranarray(qb)                              # B = qb (N^T W^T + 1e-8 qa^T): rows inside span(W)
+        BV = np.asfortranarray(N.T @ W.T + 1e-8 * qa.T)
+        steps.append((O.CompressedTile.from_uv(AU, AV), O.CompressedTile.from_uv(BU, BV)))
+    oC = O.CompressedTile.from_uv(c0.U.copy(), c0.V.copy())
+    oC.max_rank = nb // 3
+    res = {}
+    for mode in ("incremental", "full", "forced_once"):
+        if mode == "full":
+            os.environ["HCB_NO_INCREMENTAL"] = "1"
+        if mode == "forced_once":
+            os.environ["HCB_GS_FORCE_ONCE"] = "1"
+        try:
+            Ct = hc.CompressedTile.from_uv(c0.U, c0.V, ctx, max_rank=nb // 3)
+            Ct.state.fill_(3)                                   # the tile IS in SVD form (built that way above)
+            for a, b in steps:
+                A, B = hc.CompressedTile.from_uv(a.U, a.V, ctx), hc.CompressedTile.from_uv(b.U, b.V, ctx)
+                hc.HCore.Gemm(1.0, A, False, B, False, 1.0, Ct, ctx, p)
+            U = Ct.factors()[0]
+            orth = torch.linalg.norm(U.t() @ U - torch.eye(U.shape[1], dtype=torch.float64, device="cuda")).item()
+            res[mode] = (Ct.to_dense(), Ct.GetTileRank(), orth, int(Ct.state.item()))
+        finally:
+            os.environ.pop("HCB_NO_INCREMENTAL", None)
+            os.environ.pop("HCB_GS_FORCE_ONCE", None)
+    for a, b in steps:
+        O.hcore_gemm(1.0, a, False, b, False, 1.0, oC, po)
+    ref = oC.to_dense()
+    # the case really exercises the second pass: with it forced off the left factor loses orthogonality by orders of magnitude
+    forced = res.pop("forced_once")
+    assert forced[2] > 100 * res["incremental"][2] and forced[2] > 5e-12, (forced[2], res["incremental"][2])
+    for mode, (d, rk, orth, st) in res.items():
+        assert relerr(d, ref) <= 10 * acc, (mode, relerr(d, ref))
+        assert abs(rk - oC.rank) <= 1, (mode, rk, oC.rank)
+        assert orth < 1e-12, (mode, orth)
+    assert res["incremental"][3] >> 8 == kt                      # every update took the incremental path
+    assert relerr(res["incremental"][0], res["full"][0]) <= 1e-9
+
+
 def test_matmul_info_is_sticky_over_k(hc, ctx):
     """hcb_?tlr_matmul passes one d_info to every k-step -- flags are OR-ed, the sweep count is the maximum."""
     nb, T, k, acc = 128, 2, 12, 1e-8
