@@ -191,6 +191,8 @@ struct hcb_ctx {
     size_t ws_bytes = 0;
     void *ws2 = nullptr;  // second grow-only arena: FP64 shadow copies of FP32 tiles (promoted fused path)
     size_t ws2_bytes = 0;
+    void *info_tmp = nullptr;  // group-ordered info words + permutation of a mixed-mix batch (grow-only)
+    size_t info_tmp_bytes = 0;
     int *svd_sched = nullptr;  // work counters of the persistent Jacobi kernel (2 + problems ints, grow-only)
     size_t svd_sched_n = 0;
     hcb::ParamRing ring;

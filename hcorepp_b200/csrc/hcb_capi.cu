@@ -1123,6 +1123,72 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     return HCB_OK;
 }
 
+// info words of a partitioned (mixed) batch back to the caller's order: dst[perm[i]] = src[i]
+__global__ void k_scatter_info(const int32_t *__restrict__ src, const int *__restrict__ perm, int32_t *__restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[perm[i]] = src[i];
+}
+
+// Any batch: triples of DIFFERENT Dense/Compressed mixes (a Cholesky trailing update, a matrix with dense diagonal tiles)
+// are partitioned by mix on the host -- stable, so equal-mix triples keep their order -- and every group runs as one
+// homogeneous fused call; d_info comes back in the caller's order.  Homogeneous batches (the common case) pass straight
+// through with no copy.
+template<typename T>
+int t_tlr_gemm_any(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, const hcb_tile *B, int opB, const hcb_tile *C,
+                   T alpha, T beta, const hcb_compress_params *prm, int32_t *d_info) {
+    HCB_TRY(check_ctx(ctx));
+    if (n64 <= 0) return HCB_OK;
+    if (!A || !B || !C || !prm) return fail(HCB_EINVAL, "tlr_gemm_batched: null argument");
+    if (n64 > (1 << 24)) return fail(HCB_EINVAL, "tlr_gemm_batched: batch too large");
+    const int n = (int) n64;
+    auto mix_of = [&](int t) {
+        return (A[t].type == HCB_TILE_COMPRESSED ? 4 : 0) | (B[t].type == HCB_TILE_COMPRESSED ? 2 : 0) |
+               (C[t].type == HCB_TILE_COMPRESSED ? 1 : 0);
+    };
+    bool same = true;
+    for (int t = 1; t < n && same; ++t) same = mix_of(t) == mix_of(0);
+    if (same) return t_tlr_gemm_batched<T>(ctx, n, A, opA, B, opB, C, alpha, beta, prm, d_info);
+    std::vector<int> perm;
+    perm.reserve(n);
+    std::vector<hcb_tile> a, b, c;
+    a.reserve(n); b.reserve(n); c.reserve(n);
+    int group_begin[9] = {0};
+    for (int mix = 0; mix < 8; ++mix) {
+        group_begin[mix] = (int) perm.size();
+        for (int t = 0; t < n; ++t)
+            if (mix_of(t) == mix) { perm.push_back(t); a.push_back(A[t]); b.push_back(B[t]); c.push_back(C[t]); }
+    }
+    group_begin[8] = n;
+    int32_t *tmp = nullptr;
+    int *d_perm = nullptr;
+    if (d_info) {  // group-ordered info words + the permutation, in the promotion arena's neighbour (grow-only)
+        const size_t need = (size_t) n * (sizeof(int32_t) + sizeof(int)) + 256;
+        if (need > ctx->info_tmp_bytes) {
+            HCB_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (ctx->info_tmp) HCB_CUDA(cudaFree(ctx->info_tmp));
+            ctx->info_tmp = nullptr; ctx->info_tmp_bytes = 0;
+            HCB_CUDA(cudaMalloc(&ctx->info_tmp, need * 2));
+            ctx->info_tmp_bytes = need * 2;
+        }
+        tmp = reinterpret_cast<int32_t *>(ctx->info_tmp);
+        d_perm = reinterpret_cast<int *>(tmp + n);
+        void *st = nullptr;
+        HCB_TRY(ring_upload(ctx, perm.data(), sizeof(int) * (size_t) n, &st));
+        HCB_CUDA(cudaMemcpyAsync(d_perm, st, sizeof(int) * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    for (int mix = 0; mix < 8; ++mix) {
+        const int g0 = group_begin[mix], cnt = group_begin[mix + 1] - g0;
+        if (cnt <= 0) continue;
+        HCB_TRY(t_tlr_gemm_batched<T>(ctx, cnt, a.data() + g0, opA, b.data() + g0, opB, c.data() + g0, alpha, beta, prm,
+                                      tmp ? tmp + g0 : nullptr));
+    }
+    if (d_info) {
+        k_scatter_info<<<cdiv(n, 256), 256, 0, ctx->stream>>>(tmp, d_perm, d_info, n);
+        HCB_LAUNCH_CHECK("k_scatter_info");
+    }
+    return HCB_OK;
+}
+
 // FP32 batch on the FP64 path (see t_tlr_gemm_batched<float>).  Every distinct tile buffer of the batch gets an FP64
 // shadow in the context's second arena (a tile that appears in many triples -- A(j, k) in every C(j, :) -- is converted
 // once), element for element over its whole capacity, so offsets (V at m * max_rank, ld = rank) carry over unchanged.
@@ -1764,6 +1830,7 @@ int hcb_ctx_destroy(hcb_ctx *c) {
     cudaStreamSynchronize(c->stream);
     if (c->ws) cudaFree(c->ws);
     if (c->ws2) cudaFree(c->ws2);
+    if (c->info_tmp) cudaFree(c->info_tmp);
     if (c->svd_sched) cudaFree(c->svd_sched);
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
@@ -1903,7 +1970,7 @@ int hcb_memset(hcb_ctx *c, void *dst, int value, size_t bytes) {
     }                                                                                                                 \
     int hcb_##P##tlr_gemm_batched(hcb_ctx *c, int64_t n, const hcb_tile *A, int opA, const hcb_tile *B, int opB,       \
                                   const hcb_tile *C, T alpha, T beta, const hcb_compress_params *p, int32_t *info) {  \
-        return t_tlr_gemm_batched<T>(c, n, A, opA, B, opB, C, alpha, beta, p, info);                                 \
+        return t_tlr_gemm_any<T>(c, n, A, opA, B, opB, C, alpha, beta, p, info);                                     \
     }                                                                                                                 \
     int hcb_##P##compress_batched(hcb_ctx *c, int64_t n, const T *const *dense, int64_t ld, const hcb_tile *out,       \
                                   const hcb_compress_params *p, int32_t *info) {                                      \

@@ -169,7 +169,8 @@ typedef struct hcb_tile {
     /* 0 ok | 1 Jacobi not converged | 2 rank clipped to max_rank | 4 a rank exceeded its rank_bound (tile left     */  \
     /* untouched -- also reported by the next hcb_ctx_sync as HCB_EBOUND); bits 8..15 = Jacobi sweeps used.  The    */  \
     /* call zeroes d_info first; flags are OR-ed, the sweep count is a maximum.  hcb_?tlr_matmul zeroes it once and   */  \
-    /* keeps it sticky over its k loop.  Asynchronous.                                                              */  \
+    /* keeps it sticky over its k loop.  Asynchronous.  The triples of one call may have DIFFERENT Dense/Compressed  */  \
+    /* mixes: they are partitioned by mix and every group runs as one fused call (d_info in the caller's order).      */  \
     int hcb_##P##tlr_gemm_batched(hcb_ctx *, int64_t n_tiles, const hcb_tile *A, int opA, const hcb_tile *B, int opB,   \
                                   const hcb_tile *C, T alpha, T beta, const hcb_compress_params *p, int32_t *d_info);   \
     /* Compressing constructor, batched (Compressed.cpp:75-146): dense tile t (m x n, ld) -> out[t] (U, V, *d_rank) */  \

@@ -479,6 +479,43 @@ def test_batched_equals_one_by_one_and_info(hc, ctx):
     assert np.array_equal(C1[0].to_dense(), before)
 
 
+def test_mixed_mix_batch_equals_one_by_one(hc, ctx):
+    """one hcb_?tlr_gemm_batched call may hold triples of DIFFERENT Dense/Compressed mixes -- they are
+    partitioned by mix inside the library; results, ranks and the order of d_info must be those of one-by-one calls."""
+    rng = np.random.default_rng(31)
+    nb, dt = 96, np.float64
+    order = ["CCC", "DDD", "CDC", "CCD", "DCC", "CCC", "CDD", "DCD", "CCC", "DCC"]
+    p = hc.CompressionParameters(1e-8)
+
+    def build():
+        As, Bs, Cs = [], [], []
+        r2 = np.random.default_rng(77)
+        for mix in order:
+            def op(kind, k):
+                if kind == "C":
+                    return hc.CompressedTile.from_uv(*lowrank(r2, nb, nb, k, dt), ctx, max_rank=nb // 3)
+                return hc.DenseTile(np.asfortranarray(r2.standard_normal((nb, nb)) / nb), ctx)
+            As.append(op(mix[0], 7)); Bs.append(op(mix[1], 6)); Cs.append(op(mix[2], 5))
+        return As, Bs, Cs
+    A1, B1, C1 = build()
+    A2, B2, C2 = build()
+    info = torch.full((len(order),), -1, dtype=torch.int32, device="cuda")
+    hc.gemm_batched(1.0, A1, False, B1, False, 1.0, C1, ctx, p, info=info)
+    for a, b, c in zip(A2, B2, C2):
+        hc.HCore.Gemm(1.0, a, False, b, False, 1.0, c, ctx, p)
+    ctx.Sync()
+    h = info.cpu().numpy()
+    assert np.all((h & 0xff) == 0), h
+    for t, mix in enumerate(order):
+        assert relerr(C1[t].to_dense(), C2[t].to_dense()) < 1e-12, (t, mix)
+        if mix[2] == "C":
+            assert C1[t].GetTileRank() == C2[t].GetTileRank(), (t, mix)
+            assert (h[t] >> 8) >= 1, (t, mix, h)        # a recompressing triple reports its Jacobi sweeps at ITS index
+        else:
+            assert (h[t] >> 8) == 0, (t, mix, h)        # dense-output triples run no Jacobi
+    del rng
+
+
 def test_incremental_u_side_ksum_vs_oracle(hc, ctx):
     """Round 2: a C tile that carries the state bit "U orthonormal" takes the incremental U path (block Gram-Schmidt of
     the new columns against CU + a kp-column panel QR + GEMM rebuild).  An 8-step k-sum against the oracle (<= 10*acc,
