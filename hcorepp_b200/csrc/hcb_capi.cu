@@ -255,8 +255,12 @@ inline int launch_strips(hcb_ctx *ctx, const StripJob *jobs, int cnt, int rows_b
     return HCB_OK;
 }
 
+// tail_cols / tail_cnt (optional): only the FIRST tail_cnt panels can have more than tail_cols columns (the recompression
+// passes [2n stack panels | 2n kp-column panels of the incremental path] in one call): column blocks beyond tail_cols are
+// launched over those first panels only.
 template<typename T>
-int run_blocked_qr(hcb_ctx *ctx, const PanelDesc<T> *d_pds, int cnt, int rows_bound, int cols_bound, char *desc_store) {
+int run_blocked_qr(hcb_ctx *ctx, const PanelDesc<T> *d_pds, int cnt, int rows_bound, int cols_bound, char *desc_store,
+                   int tail_cols = 0, int tail_cnt = 0) {
     const int nfac = cdiv(std::min(rows_bound, cols_bound), NBQ);  // blocks that hold reflectors
     const int nblk = cdiv(cols_bound, NBQ);                         // column blocks (>= nfac for a wide panel)
     const size_t nb = (size_t) cnt * nblk;
@@ -276,8 +280,10 @@ int run_blocked_qr(hcb_ctx *ctx, const PanelDesc<T> *d_pds, int cnt, int rows_bo
     const size_t pq_smem = pr_smem_bytes<T>();
     const bool on_chip = rows_bound <= PR_MAXCS * PR_ROWS && pq_smem + 1024 <= ctx->smem_optin;
     if (on_chip) HCB_CUDA(cudaFuncSetAttribute(k_panel_qr_regs<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pq_smem));
+    const int cnt_all = cnt;
     for (int b = 0; b < nblk; ++b) {
-        const size_t o = (size_t) b * cnt;
+        const size_t o = (size_t) b * cnt_all;
+        if (tail_cnt > 0 && b * NBQ >= tail_cols) cnt = std::min(cnt_all, tail_cnt);   // only the wide panels reach this block
         // left-looking: bring column block b up to date with blocks 0..b-1 while it sits in cluster shared memory
         if (strips && b > 0) HCB_TRY(launch_strips(ctx, q.sj + o, cnt, rows_bound));
         if (b >= nfac) continue;
@@ -1017,7 +1023,8 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
                 HCB_TRY(launch_gemm<T>(ctx, sa.giv + 3 * (size_t) n, n, s.n, L.kp_b));
             }
             // one pass over 4n panels: the two stacks of every tile (inactive where incremental) + the P and Y panels
-            HCB_TRY(run_blocked_qr<T>(ctx, sa.pd_stack, inc_enabled ? 4 * n : npan, std::max(s.m, s.n), L.r_b, blk_store));
+            HCB_TRY(run_blocked_qr<T>(ctx, sa.pd_stack, inc_enabled ? 4 * n : npan, std::max(s.m, s.n), L.r_b, blk_store,
+                                      inc_enabled ? L.kp_b : 0, inc_enabled ? npan : 0));
             if (inc_enabled) {
                 dim3 ge(std::max(1, std::min(64, cdiv((long long) std::max(s.m, s.n) * L.kp_b, 2048))), 2 * n);
                 k_inc_eye<T><<<ge, 256, 0, ctx->stream>>>(sa.rc);
