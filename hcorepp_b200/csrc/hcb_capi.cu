@@ -698,7 +698,7 @@ Layout<T> make_layout(const BatchShape &s) {
         L.o_tauv = take(L.r_b);
         L.o_m = take(sq);
         L.o_j = take(sq + L.pq_b);  // rotated copy of the core with an even leading dimension
-        L.o_us = take(sq);
+        L.o_us = take(sq + L.pq_b);  // Us with an even leading dimension
         L.o_vs = take(sq);
         L.o_sig = take(L.pq_b);
         L.o_vn = take((size_t) s.n * std::min(L.pq_b, std::max(s.maxrankC, 1)));

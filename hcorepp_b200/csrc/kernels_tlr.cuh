@@ -74,6 +74,7 @@ struct RecompProb {
     T *T1b;             // Xu^T Us  (kp x b, ld kp)
     int lp, lq;         // leading dimensions of the extracted triangles MT (p x r) / Lb (q x r): p, q rounded up to even
                         // so that the core GEMM's row-contiguous operands qualify for TMA bulk copies
+    int ldus;           // leading dimension of Us: a rounded up to even, so that Us is a 16-byte-copy operand of the GEMMs
     int *state;         // C tile's device state word (may be null)
     int fixed_rank;     // per-tile fixed rank (0: batch value)
 };
@@ -284,13 +285,14 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
                 rc.a = rc.transposed ? q : p;
                 rc.b = rc.transposed ? p : q;
                 // Jacobi runs on M itself when the stacks are sorted (use_lq == 0), else on its LQ factor L
-                sv = SvdProb<T>{s.use_lq ? rc.Lb : rc.M, slab + s.o_j, rc.Us, rc.Vs, rc.sigma, rc.info, rc.a, rc.b, rc.a, rc.a, rc.b};
+                rc.ldus = (rc.a + 1) & ~1;
+                sv = SvdProb<T>{s.use_lq ? rc.Lb : rc.M, slab + s.o_j, rc.Us, rc.Vs, rc.sigma, rc.info, rc.a, rc.b, rc.a, rc.ldus, rc.b};
                 pdu = PanelDesc<T>{UW, rc.tauU, rc.VC[0], rc.TB[0], rc.WB[0], m, r, s.wcols, 1};
                 pdv = PanelDesc<T>{VW, rc.tauV, rc.VC[1], rc.TB[1], rc.WB[1], n, r, s.wcols, 1};
                 pdm = PanelDesc<T>{rc.MT, rc.tauM, slab + s.o_vcm, slab + s.o_tbm, slab + s.o_wbm, rc.b, rc.a, s.wcols, 1};
                 qm = QrProb<T>{rc.MT, rc.tauM, rc.b, rc.a, rc.b};
                 lq = LqProb<T>{rc.MT, rc.Lb, rc.a, rc.b};
-                gv = mk_gemm<T>(rc.M, rc.a, 1, rc.Us, rc.a, 0, rc.Vs, rc.b, rc.b, rc.b, rc.a, one, zero);
+                gv = mk_gemm<T>(rc.M, rc.a, 1, rc.Us, rc.ldus, 0, rc.Vs, rc.b, rc.b, rc.b, rc.a, one, zero);
                 // core from the extracted triangles RU (p x r, ld p, in MT) and RV (q x r, ld q, in Lb)
                 rc.lp = s.use_lq ? p : ((p + 1) & ~1);
                 rc.lq = s.use_lq ? q : ((q + 1) & ~1);
@@ -354,13 +356,13 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
                     pdvc = PanelDesc<T>{VW, slab + s.o_taum, slab + s.o_vcm, slab + s.o_tbm, slab + s.o_wbm, r, r, s.wcols, 1};
                     // V S' = (RV Pi) (RU Pi)^T Us  instead of  K'^T Us  (K' = K O carries the QR's orthogonal factor on the right)
                     gv.m = 0;
-                    gt1 = mk_gemm<T>(rc.MT, rc.lp, 1, rc.Us, rc.a, 0, rc.T1, r, r, rc.b, p, one, zero);
+                    gt1 = mk_gemm<T>(rc.MT, rc.lp, 1, rc.Us, rc.ldus, 0, rc.T1, r, r, rc.b, p, one, zero);
                     gx = mk_gemm<T>(rc.RVp, r, 0, rc.T1, r, 0, rc.Vs, rc.b, r, rc.b, r, one, zero);
                     if (inc) {  // both sides incremental: rank-kp forms of the core and of V S'
                         rc.both = 1;
                         rc.Xu = slab + s.o_xu; rc.Xv = slab + s.o_xv; rc.Rn = slab + s.o_rn; rc.T1b = slab + s.o_t1b;
                         gc = mk_gemm<T>(rc.Xu, r, 0, rc.Rn, r, 1, rc.M, rc.a, r, r, kp, one, one);          // K' += Xu Rn^T
-                        gt1 = mk_gemm<T>(rc.Xu, r, 1, rc.Us, rc.a, 0, rc.T1b, kp, kp, rc.b, r, one, zero);  // T1b = Xu^T Us
+                        gt1 = mk_gemm<T>(rc.Xu, r, 1, rc.Us, rc.ldus, 0, rc.T1b, kp, kp, rc.b, r, one, zero);  // T1b = Xu^T Us
                         gx = mk_gemm<T>(rc.Xv, r, 0, rc.T1b, kp, 0, rc.Vs, rc.b, r, rc.b, kp, one, zero);   // X   = Xv T1b
                     }
                 }
@@ -705,11 +707,11 @@ __global__ void k_setup_apply_strips(const RecompProb<T> *__restrict__ rcs, Stri
             int rk = *rc.rk_new;
             if (rk > rc.wcols) rk = 0;
             if (std::is_same<T, double>::value) {  // one pass: op(A) = [CU | Q2] (two-segment A of k_gemm_dmma)
-                ga = mk_gemm<T>(rc.CU, rc.m, 0, rc.Us, rc.a, 0, rc.TU, rc.m, rc.m, rk, rc.kc + rc.kp, T(1), T(0));
+                ga = mk_gemm<T>(rc.CU, rc.m, 0, rc.Us, rc.ldus, 0, rc.TU, rc.m, rc.m, rk, rc.kc + rc.kp, T(1), T(0));
                 ga.A2 = rc.Q2; ga.k1 = rc.kc; ga.lda2 = rc.m;
             } else {
-                ga = mk_gemm<T>(rc.CU, rc.m, 0, rc.Us, rc.a, 0, rc.TU, rc.m, rc.m, rk, rc.kc, T(1), T(0));
-                gb = mk_gemm<T>(rc.Q2, rc.m, 0, rc.Us + rc.kc, rc.a, 0, rc.TU, rc.m, rc.m, rk, rc.kp, T(1), T(1));
+                ga = mk_gemm<T>(rc.CU, rc.m, 0, rc.Us, rc.ldus, 0, rc.TU, rc.m, rc.m, rk, rc.kc, T(1), T(0));
+                gb = mk_gemm<T>(rc.Q2, rc.m, 0, rc.Us + rc.kc, rc.ldus, 0, rc.TU, rc.m, rc.m, rk, rc.kp, T(1), T(1));
             }
         }
         gru[idx] = ga;
@@ -879,7 +881,7 @@ __global__ void __launch_bounds__(256) k_truncate(const RecompProb<T> *__restric
         // (incremental U side: Us is consumed by the rebuild GEMMs [CU | Q2] * Us, CU must stay intact until then)
         for (int idx = threadIdx.x; idx < (p.inc ? 0 : p.m * rk); idx += blockDim.x) {
             const int i = idx % p.m, c = idx / p.m;
-            p.CU[(size_t) i + (size_t) c * p.m] = (i < p.p) ? p.Us[(size_t) i + (size_t) c * p.a] : T(0);
+            p.CU[(size_t) i + (size_t) c * p.m] = (i < p.p) ? p.Us[(size_t) i + (size_t) c * p.ldus] : T(0);
         }
         // (incremental V side: Vs = V S' in [W | Q2v] coordinates is consumed by the rebuild GEMM; its first kc rows are
         // divided by the old singular values here because the GEMM multiplies by CV^T = W diag(sigma), not by W)
@@ -888,7 +890,7 @@ __global__ void __launch_bounds__(256) k_truncate(const RecompProb<T> *__restric
                 const int i = idx % p.kc, c = idx / p.kc;
                 const size_t o = (size_t) i + (size_t) c * p.b;
                 // (rank-kp form: Vs holds Xv (Xu^T Us) only; the diagonal part beta S Us, divided by S, is beta Us)
-                p.Vs[o] = p.both ? p.Vs[o] / p.sig0[i] + p.beta_c * p.Us[(size_t) i + (size_t) c * p.a] : p.Vs[o] / p.sig0[i];
+                p.Vs[o] = p.both ? p.Vs[o] / p.sig0[i] + p.beta_c * p.Us[(size_t) i + (size_t) c * p.ldus] : p.Vs[o] / p.sig0[i];
             }
         }
         for (int idx = threadIdx.x; idx < (p.vinc ? 0 : p.n * rk); idx += blockDim.x) {
@@ -903,7 +905,7 @@ __global__ void __launch_bounds__(256) k_truncate(const RecompProb<T> *__restric
         }
         for (int idx = threadIdx.x; idx < p.n * rk; idx += blockDim.x) {
             const int i = idx % p.n, c = idx / p.n;
-            p.VN[(size_t) i + (size_t) c * p.n] = (i < p.q) ? p.sigma[c] * p.Us[(size_t) i + (size_t) c * p.a] : T(0);
+            p.VN[(size_t) i + (size_t) c * p.n] = (i < p.q) ? p.sigma[c] * p.Us[(size_t) i + (size_t) c * p.ldus] : T(0);
         }
     }
 }
