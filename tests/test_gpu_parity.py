@@ -761,6 +761,28 @@ def test_cpp_host_layer_replays_reference_tests():
 
 
 # ------------------------------------------------------------------------------------------------ TLR Cholesky (8f row 1)
+def test_example_driver_matrix_multiplication():
+    """The reference's headline example (examples/matrix_multiplication/omp_main.cpp: same command line, flow and CSV
+    lines) built on the C++ mirror: `b200-hcorepp-matrix 4 1e-4,1e-8 512` = BASELINE configs[0] shape.  The example's own
+    pass criterion (normalised error < 10, omp_main.cpp:325-327,379-381) must hold for the dense and both compressed runs,
+    compressed storage must be smaller than dense, and tighter accuracy must not give a larger error."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "examples", "matrix_multiplication", "b200-hcorepp-matrix")
+    assert os.path.exists(exe), "examples/matrix_multiplication/b200-hcorepp-matrix not built (run __graft_entry__.build())"
+    env = dict(os.environ, HCOREPP_VERBOSE="ON")
+    r = subprocess.run([exe, "4", "1e-4,1e-8", "512"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = [l for l in r.stdout.strip().splitlines() if l]
+    assert lines[0].startswith("tile_count, tile_size, matrix_size, type, error, error_normalized, memory(KB)")
+    rows = [[c.strip() for c in l.split(",")] for l in lines[1:]]
+    kinds = [row[3] for row in rows]
+    assert kinds[:2] == ["ref", "dense"] and len(rows) == 4, kinds
+    dense, c4, c8 = rows[1], rows[2], rows[3]
+    assert float(dense[5]) < 10 and float(c4[5]) < 10 and float(c8[5]) < 10, (dense, c4, c8)
+    assert int(c4[6]) < int(c8[6]) < int(dense[6]), (c4[6], c8[6], dense[6])     # memory(KB): looser accuracy, smaller tiles
+    assert float(c8[4]) <= float(c4[4])                                          # absolute error
+
+
 def _spd(rng, n, dt=np.float64):
     a = rng.standard_normal((n, n))
     return np.asfortranarray((a @ a.T / n + np.eye(n)).astype(dt))
