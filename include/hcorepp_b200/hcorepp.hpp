@@ -809,16 +809,36 @@ private:
         mRowTileCount = (mM + aTm - 1) / aTm;
         mColTileCount = (mN + aTn - 1) / aTn;
         mMatrixTiles.resize(mColTileCount);
+        // compressed: ONE device copy of the whole matrix and ONE batched compressing call over all tiles (the reference
+        // compresses tile by tile, TileMatrix.cpp:60-90; its per-tile constructor is still available on CompressedTile)
+        T *dRaw = nullptr;
+        std::vector<const T *> ptrs;
+        std::vector<hcb_tile> descs;
+        if (apParams) {
+            dRaw = memory::AllocateArray<T>(mM * mN, aContext);
+            memory::Memcpy<T>(dRaw, aRaw.GetData(), mM * mN, aContext, memory::MemoryTransfer::HOST_TO_DEVICE);
+        }
         for (size_t c = 0; c < mColTileCount; ++c) {
             mMatrixTiles[c].resize(mRowTileCount, nullptr);
             for (size_t r = 0; r < mRowTileCount; ++r) {
                 const size_t tm = std::min(aTm, mM - r * aTm), tn = std::min(aTn, mN - c * aTn);
                 T *src = const_cast<T *>(aRaw.GetData()) + r * aTm + c * aTn * mM;  // sub-matrix view, ld = M
-                if (apParams)
-                    mMatrixTiles[c][r] = new operators::CompressedTile<T>(tm, tn, src, mM, *apParams, blas::Layout::ColMajor, aContext);
-                else
+                if (apParams) {
+                    auto *t = new operators::CompressedTile<T>(tm, tn, nullptr, mM, *apParams, blas::Layout::ColMajor, aContext);
+                    mMatrixTiles[c][r] = t;
+                    ptrs.push_back(dRaw + r * aTm + c * aTn * mM);
+                    descs.push_back(t->Descriptor());
+                } else {
                     mMatrixTiles[c][r] = new operators::DenseTile<T>(tm, tn, src, mM, blas::Layout::ColMajor, aContext);
+                }
             }
+        }
+        if (apParams) {
+            const hcb_compress_params p = apParams->ToC();
+            detail::check(detail::abi<T>::compress_batched(aContext.Handle(), (int64_t) descs.size(), ptrs.data(), (int64_t) mM, descs.data(),
+                                                           &p, nullptr), "TileMatrix(compress)");
+            aContext.Sync();
+            hcb_free(aContext.Handle(), dRaw);
         }
     }
     std::vector<std::vector<operators::Tile<T> *>> mMatrixTiles;
