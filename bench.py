@@ -370,6 +370,7 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    fast_paths = ctx.stats(reset=True)  # adaptive fast paths taken over warm-up + timed passes (CholeskyQR2 panels, one-pass Gram-Schmidt)
     bad = int((info & 5).max().item())  # 1: Jacobi not converged, 4: rank bound exceeded (2 = clipped at maxRank is legal)
     sweeps = int((info >> 8).max().item())
     ms_per_step = ms / args.steps
@@ -401,7 +402,7 @@ def main():
                 2 * T * T * 2 * nb * krank * 8 / 1e6)},
         "library": _capi.lib.hcb_version().decode(),
         "gpu_launches": launches, "jacobi_or_bound_flags": bad, "jacobi_sweeps_last_step_max": sweeps,
-        "c_rank_bound": args.kc_bound,
+        "c_rank_bound": args.kc_bound, "fast_paths": fast_paths,
     }
     if world > 1 and not args.no_e2e:
         # end to end at N GPUs: every rank uploads ITS A / B tiles from pinned host memory, runs the pass (panel

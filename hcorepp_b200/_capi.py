@@ -51,6 +51,7 @@ lib.hcb_ctx_sm_count.argtypes = [vp]
 lib.hcb_ctx_reserve_workspace.argtypes = [vp, sz]
 lib.hcb_ctx_workspace_bytes.argtypes = [vp]
 lib.hcb_ctx_workspace_bytes.restype = sz
+lib.hcb_ctx_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int]
 lib.hcb_malloc.argtypes = [vp, sz, C.POINTER(vp)]
 lib.hcb_free.argtypes = [vp, vp]
 lib.hcb_memcpy.argtypes = [vp, vp, vp, sz, C.c_int]

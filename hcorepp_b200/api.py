@@ -54,6 +54,13 @@ class RunContext:
     def SupportsOMP(self) -> bool:
         return False
 
+    def stats(self, reset: bool = False) -> dict:
+        """Counters of the adaptive fast paths (include/hcore_b200.h: hcb_ctx_stats)."""
+        out = (C.c_uint64 * 8)()
+        check(lib.hcb_ctx_stats(self.h, out, 1 if reset else 0))
+        return {"cholqr_panels": int(out[0]), "cholqr_fallback_pass0": int(out[1]), "cholqr_fallback_pass1": int(out[2]),
+                "gs_second_pass_skipped": int(out[3]), "gs_second_pass_run": int(out[4]), "deflated_columns": int(out[5])}
+
     def reserve_workspace(self, nbytes: int):
         check(lib.hcb_ctx_reserve_workspace(self.h, nbytes))
 

@@ -196,6 +196,7 @@ struct hcb_ctx {
     int *svd_sched = nullptr;  // work counters of the persistent Jacobi kernel (2 + problems ints, grow-only)
     size_t svd_sched_n = 0;
     hcb::ParamRing ring;
+    unsigned long long *d_stats = nullptr;  // device counters of the adaptive fast paths (hcb_ctx_stats), 8 entries
     int *d_err = nullptr;      // device-side sticky error word of the fused path (bit 2: a rank exceeded its bound)
     int *h_err = nullptr;      // pinned mirror read by hcb_ctx_sync
     // optional per-phase device timing of the fused path (CUDA events on this stream; see hcb_ctx_phase_timing)

@@ -749,6 +749,7 @@ struct DescArrays {  // device arrays living at the front of the scratch arena
     size_t o_g1, o_g2, o_g3, o_gv, o_gc, o_cp, o_qr, o_rf, o_svd, o_rc, o_rk, o_tiles;
     size_t o_bqr = 0, o_blf = 0, o_bgw = 0, o_bgw2 = 0, o_bgup = 0, o_agw = 0, o_agw2 = 0, o_agup = 0;
     size_t o_pds = 0, o_pdc = 0, o_qrc = 0, o_lq = 0, o_pc = 0, o_asj = 0, o_gi = 0, o_isj = 0, o_gru = 0, o_giv = 0, o_pvc = 0, o_bqr2 = 0;
+    size_t o_cqf = 0;
     int nst_inc = 0;
     explicit DescArrays(int n, int nblk = 0, int qr_cols = 0, int rk_bound = 0, int kp_b = 0) {
         size_t off = 0;
@@ -771,6 +772,7 @@ struct DescArrays {  // device arrays living at the front of the scratch arena
         o_giv = take(sizeof(GemmProb<T>) * 6 * n);   // 4 Gram-Schmidt GEMMs + T1 + X of the incremental V side
         o_gru = take(sizeof(GemmProb<T>) * 3 * n);
         o_pvc = take(sizeof(PanelDesc<T>) * n);
+        o_cqf = take(sizeof(int) * 2 * n);          // CholeskyQR2 of the new-column panels: per-side fallback flags
         nst_inc = std::max(1, cdiv(std::max(kp_b, 1), NBQ));
         o_isj = take(sizeof(StripJob) * (size_t) nst_inc * 2 * n);
         o_qrc = take(sizeof(QrProb<T>) * n);
@@ -917,6 +919,11 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
     sa.gt1 = sa.giv + 4 * (size_t) n;
     sa.gx = sa.giv + 5 * (size_t) n;
     sa.pd_vcore = reinterpret_cast<PanelDesc<T> *>(base + D.o_pvc);
+    // CholeskyQR2 of the new-column panels (fp64 incremental path, kp <= 64): HCB_NO_CHOLQR=1 keeps the Householder panels
+    const bool cq_enabled = inc_enabled && L.kp_b <= CQ_KP && !(getenv("HCB_NO_CHOLQR") && atoi(getenv("HCB_NO_CHOLQR")) != 0);
+    sa.cq_fail = reinterpret_cast<int *>(base + D.o_cqf);
+    sa.cq_enabled = cq_enabled ? 1 : 0;
+    sa.stats = ctx->d_stats;
     sa.err_flag = ctx->d_err;
     if (d_info && reset_info) HCB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t) * (size_t) n, ctx->stream));
     {
@@ -1021,6 +1028,16 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
                 k_vinc_scale<T><<<gs, 256, 0, ctx->stream>>>(sa.rc, 1);
                 HCB_LAUNCH_CHECK("k_vinc_scale");
                 HCB_TRY(launch_gemm<T>(ctx, sa.giv + 3 * (size_t) n, n, s.n, L.kp_b));
+            }
+            if (cq_enabled) {
+                if constexpr (std::is_same<T, double>::value) {
+                    // CholeskyQR2 of the new columns (k_cholqr_pass, one fused kernel per pass): where it holds, Q2 / R2 are in
+                    // place afterwards and the Householder panel + explicit-Q strips below find their descriptors switched off
+                    for (int pass = 0; pass < 2; ++pass) {
+                        k_cholqr_pass<T><<<2 * n, 256, 0, ctx->stream>>>(sa.rc, sa.pd_inc, sa.inc_sj, D.nst_inc, n, pass);
+                        HCB_LAUNCH_CHECK("k_cholqr_pass");
+                    }
+                }
             }
             // one pass over 4n panels: the two stacks of every tile (inactive where incremental) + the P and Y panels
             HCB_TRY(run_blocked_qr<T>(ctx, sa.pd_stack, inc_enabled ? 4 * n : npan, std::max(s.m, s.n), L.r_b, blk_store,
@@ -1816,6 +1833,8 @@ static int ctx_init(int device, cudaStream_t stream, bool own, hcb_ctx **out) {
     c->smem_optin = prop.sharedMemPerBlockOptin;
     HCB_CUDA(cudaMalloc((void **) &c->d_err, sizeof(int)));
     HCB_CUDA(cudaMemset(c->d_err, 0, sizeof(int)));
+    HCB_CUDA(cudaMalloc((void **) &c->d_stats, 8 * sizeof(unsigned long long)));
+    HCB_CUDA(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
     HCB_CUDA(cudaMallocHost((void **) &c->h_err, sizeof(int)));
     *c->h_err = 0;
     if (own) {
@@ -1840,6 +1859,7 @@ int hcb_ctx_destroy(hcb_ctx *c) {
     if (c->info_tmp) cudaFree(c->info_tmp);
     if (c->svd_sched) cudaFree(c->svd_sched);
     if (c->d_err) cudaFree(c->d_err);
+    if (c->d_stats) cudaFree(c->d_stats);
     if (c->h_err) cudaFreeHost(c->h_err);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (auto e : c->ring.ev) if (e) cudaEventDestroy(e);
@@ -1887,6 +1907,14 @@ int hcb_ctx_sync(hcb_ctx *c) {
             return fail(HCB_EBOUND, "a tile's rank exceeded its rank_bound in a fused call since the last sync: that "
                                     "tile's update was NOT applied (raise rank_bound, or leave it 0 = max_rank)");
     }
+    return HCB_OK;
+}
+int hcb_ctx_stats(hcb_ctx *c, uint64_t *out8, int reset) {
+    HCB_TRY(check_ctx(c));
+    if (!out8) return fail(HCB_EINVAL, "ctx_stats: null output");
+    HCB_CUDA(cudaStreamSynchronize(c->stream));
+    HCB_CUDA(cudaMemcpy(out8, c->d_stats, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (reset) HCB_CUDA(cudaMemset(c->d_stats, 0, 8 * sizeof(uint64_t)));
     return HCB_OK;
 }
 void *hcb_ctx_stream(hcb_ctx *c) { return c ? (void *) c->stream : nullptr; }

@@ -9,10 +9,14 @@
 #include "kernels_strip.cuh"
 #include <type_traits>
 #include "kernels_blas.cuh"
+#include "kernels_dmma.cuh"
 #include "kernels_qr.cuh"
 #include "kernels_svd_rx.cuh"
 
 namespace hcb {
+
+// CholeskyQR2 of the new-column panels (k_cholqr_pass): up to CQ_KP = 48 columns (6 DMMA tiles), padded smem pitch
+constexpr int CQ_NT = 6, CQ_KP = 8 * CQ_NT, CQ_P = CQ_KP + 1;
 
 enum Mix { DDD = 0, DDC = 1, DCD = 2, DCC = 3, CDD = 4, CDC = 5, CCD = 6, CCC = 7 };
 
@@ -75,6 +79,13 @@ struct RecompProb {
     int lp, lq;         // leading dimensions of the extracted triangles MT (p x r) / Lb (q x r): p, q rounded up to even
                         // so that the core GEMM's row-contiguous operands qualify for TMA bulk copies
     int ldus;           // leading dimension of Us: a rounded up to even, so that Us is a 16-byte-copy operand of the GEMMs
+    // CholeskyQR2 of the kp new columns (see k_cholqr_factor): scratch (4 kp x kp matrices: G, S, R1, G2), the second Q buffer,
+    // the per-side "CholQR failed, Householder takes over" flags and "explicit Q2 is already in place"
+    T *CQw[2], *CQt[2];
+    int *cq_fail;       // [2] per tile
+    int q2_done[2];
+    unsigned long long *stats;  // context counters (hcb_ctx_stats): [0] CholQR2 sides done, [1] fell back in pass 0, [2] in pass 1,
+                                // [3] Gram-Schmidt second passes skipped, [4] run, [5] negligible new columns deflated
     int *state;         // C tile's device state word (may be null)
     int fixed_rank;     // per-tile fixed rank (0: batch value)
 };
@@ -134,6 +145,9 @@ struct SetupArgs {
     int inc_enabled;            // host: blocked fp64 strip path in use
     size_t o_gu, o_gu2, o_q2, o_tu;   // scratch offsets: Gu, Gu2 (kC_b x kp_b), [VCp | Q2] (2 m kp_b), TU (m x rank bound)
     GemmProb<T> *gi;            // 4 per tile, arrays of n: gi + q*n_tiles, q = 0..3 (G = CU^T P, P -= CU G, twice)
+    int *cq_fail;               // [2 * n_tiles] flags (zeroed here)
+    unsigned long long *stats;  // context counters
+    int cq_enabled;
     PanelDesc<T> *pd_inc;       // 1 per tile: QR of the orthogonalised P
     StripJob *inc_sj;           // nst_inc per tile: explicit Q2 = H_0 .. H_{kp-1} [I; 0]
     int nst_inc, kp_b;
@@ -390,6 +404,18 @@ __global__ void k_setup_tlr(SetupArgs<T> s) {
         // still hears about it at the next hcb_ctx_sync.
         if (s.info) atomicOr(s.info + t, 4);
         if (s.err_flag) atomicOr(s.err_flag, 4);
+    }
+    {   // CholeskyQR2 of the two new-column panels: scratch, flags
+        rc.cq_fail = s.cq_fail ? s.cq_fail + 2 * (size_t) t : nullptr;
+        rc.stats = s.stats;
+        rc.q2_done[0] = rc.q2_done[1] = 0;
+        for (int side = 0; side < 2; ++side) {
+            const bool on = s.cq_enabled && rc.active && (side ? vinc : inc) && rc.kp >= 1 && rc.kp <= CQ_KP &&
+                            rc.kp * rc.kp <= 2 * NBQ * s.wcols;
+            rc.CQw[side] = on ? rc.WB[side] : nullptr;
+            rc.CQt[side] = on ? (side ? pdiv.VC : pdi.VC) : nullptr;
+            if (rc.cq_fail) rc.cq_fail[side] = on ? 0 : 1;
+        }
     }
     for (int q = 0; q < 4; ++q) s.gi[(size_t) q * s.n_tiles + t] = q == 0 ? gi0 : (q == 1 ? gi1 : (q == 2 ? gi2 : gi3));
     for (int q = 0; q < 4; ++q) s.giv[(size_t) q * s.n_tiles + t] = q == 0 ? gv0 : (q == 1 ? gv1 : (q == 2 ? gv2 : gv3));
@@ -954,7 +980,7 @@ template<typename T>
 __global__ void __launch_bounds__(256) k_inc_eye(const RecompProb<T> *__restrict__ probs) {
     const RecompProb<T> p = probs[blockIdx.y >> 1];
     const int side = blockIdx.y & 1;
-    if (!p.active || !(side ? p.vinc : p.inc)) return;
+    if (!p.active || !(side ? p.vinc : p.inc) || p.q2_done[side]) return;   // (CholeskyQR2 already left the explicit Q2 there)
     const int rows = side ? p.n : p.m;
     T *Q = side ? p.Q2v : p.Q2;
     const size_t total = (size_t) rows * p.kp;
@@ -984,6 +1010,203 @@ __global__ void __launch_bounds__(256) k_vinc_sig0(const RecompProb<T> *__restri
             p.sig0[i] = t_sqrt(tot);
         }
         __syncthreads();
+    }
+}
+
+// CholeskyQR2 of the kp new columns X (rows x kp, after the block Gram-Schmidt against the old basis): X = Q2 R2 with
+//   pass 0:  G = X^T X,  Gs = D G D with D = diag(G)^-1/2 (column scaling: the new columns span 8 decades),
+//            Gs = Rc^T Rc (Cholesky),  Q1 = X (D Rc^-1),  R1 = Rc D^-1
+//   pass 1:  G2 = Q1^T Q1,  G2 = Rc2^T Rc2,  Q2 = Q1 Rc2^-1,  R2 = Rc2 R1
+// ONE kernel per pass, one CTA (8 warps) per tile side: every warp forms the Gram matrix of its 1/8 of the rows with DMMA
+// (m8n8k4: both fragments are the same X[r0 + c][8 t + g] loads; the 21 upper 8 x 8 tile pairs stay in registers), the
+// partial sums meet in shared memory, the kp x kp Cholesky and the triangular inverse run there, and the same warps
+// multiply their rows by S = D Rc^-1 with DMMA again.  No per-column cluster barrier, no explicit-Q strip pass: ~0.2 ms
+// per k-step of 256 tiles instead of ~2.9 ms for the register-panel Householder QR + the strips that form Q2.
+// CholeskyQR squares the condition number, so the fast path is taken only where it is provably safe: every pivot of the
+// SCALED Gram matrix must be >= 1e-6 (the column keeps at least 1e-3 of its norm after orthogonalisation against the
+// earlier ones: condition <~ 5e4, first-pass loss of orthogonality <~ 1e-7, removed by the second pass) and every pivot
+// of the second pass must lie in [1/4, 4]; otherwise the side's flag is raised and the Householder panel path -- whose
+// descriptors stay active, X untouched -- factors it as before.  Independent directions (the BASELINE generator's tiles)
+// take the fast path; nearly dependent new columns (saturated tiles) fall back.  On success pass 1 writes R2 into the top
+// triangle of X (what the core assembly reads), leaves Q2 in its buffer and switches the side's Householder panel and
+// explicit-Q strip jobs off.  kp <= 48.  grid = 2 * n_tiles (problem = side * n_tiles + tile), 256 threads.
+template<typename T>
+__global__ void __launch_bounds__(256, 2) k_cholqr_pass(RecompProb<T> *__restrict__ probs, PanelDesc<T> *__restrict__ pd_inc,
+                                                        StripJob *__restrict__ inc_sj, int nst_inc, int n_tiles, int pass) {
+    static_assert(std::is_same<T, double>::value, "FP64 tensor path");
+    const int prob = blockIdx.x, side = prob / n_tiles, t = prob % n_tiles;
+    const RecompProb<T> p = probs[t];
+    if (!p.active || !p.cq_fail || p.cq_fail[side] || !p.CQw[side]) return;
+    const int kp = p.kp, rows = side ? p.n : p.m, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, c = lane & 3;
+    T *Xg = side ? p.Yn : p.Pn;                       // the panel (its top triangle receives R2 at the end)
+    const T *In = pass == 0 ? Xg : p.CQt[side];       // pass 0 reads X, pass 1 reads Q1
+    T *Out = pass == 0 ? p.CQt[side] : (side ? p.Q2v : p.Q2);
+    T *R1 = p.CQw[side];                              // kp x kp (ld kp), kept between the passes
+    __shared__ T R[CQ_KP][CQ_P];                      // Gram matrix -> Cholesky factor (upper)
+    __shared__ T S[CQ_KP][CQ_P];                      // D Rc^-1 (upper)
+    __shared__ T sd[CQ_KP];
+    __shared__ int s_bad;
+    for (int idx = tid; idx < CQ_KP * CQ_P; idx += 256) (&R[0][0])[idx] = T(0);
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    // ---- Gram matrix: warp w takes the row chunks w, w + 8, ... of 32 rows (8 DMMA k-steps each)
+    {
+        T acc[CQ_NT * (CQ_NT + 1) / 2][2];
+#pragma unroll
+        for (int q = 0; q < CQ_NT * (CQ_NT + 1) / 2; ++q) acc[q][0] = acc[q][1] = T(0);
+        for (int r0 = w * 32; r0 < rows; r0 += 256) {
+#pragma unroll 2
+            for (int ks = 0; ks < 32; ks += 4) {
+                const int r = r0 + ks + c;
+                T v[CQ_NT];
+#pragma unroll
+                for (int tt = 0; tt < CQ_NT; ++tt) {
+                    const int col = 8 * tt + g;
+                    v[tt] = (r < rows && col < kp) ? In[(size_t) r + (size_t) col * rows] : T(0);
+                }
+                int q = 0;
+#pragma unroll
+                for (int ti = 0; ti < CQ_NT; ++ti)
+#pragma unroll
+                    for (int tj = ti; tj < CQ_NT; ++tj, ++q) dmma_m8n8k4(acc[q][0], acc[q][1], v[ti], v[tj]);
+            }
+        }
+        int q = 0;
+#pragma unroll
+        for (int ti = 0; ti < CQ_NT; ++ti)
+#pragma unroll
+            for (int tj = ti; tj < CQ_NT; ++tj, ++q) {
+                atomicAdd(&R[8 * ti + g][8 * tj + 2 * c], acc[q][0]);
+                atomicAdd(&R[8 * ti + g][8 * tj + 2 * c + 1], acc[q][1]);
+            }
+    }
+    __syncthreads();
+    // ---- scaling, Cholesky (upper, in place), checks
+    // Negligible columns are DEFLATED instead of failing the test: a new column whose norm is below 1e-13 of the largest new
+    // column (the product term's singular values reach 1e-16 of its largest; such columns are rounding noise of the
+    // contraction, often mutually parallel, and 5 decades below any accuracy the truncation can ask for) is replaced by a
+    // zero column -- Q[:, j] = 0, R[j, :] = R[:, j] = 0: the core then has an exactly zero row there, which no retained
+    // singular vector touches.  Pass 1 recognises them by their exactly zero Gram diagonal.
+    __shared__ T s_gmax;
+    if (tid < 32) {
+        T mx = T(0);
+        for (int j = tid; j < kp; j += 32) { const T v = R[j][j]; mx = (v > mx) ? v : mx; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const T other = __shfl_xor_sync(0xffffffffu, mx, o); mx = other > mx ? other : mx; }
+        if (tid == 0) s_gmax = mx;
+    }
+    __syncthreads();
+    for (int j = tid; j < kp; j += 256) {
+        const T gjj = R[j][j];
+        if (!(gjj >= T(0)) || !(gjj < T(1e300))) s_bad = 1;                  // NaN / Inf
+        const bool defl = pass == 0 ? !(gjj > T(1e-26) * s_gmax) : (gjj == T(0));
+        sd[j] = defl ? T(0) : (pass == 0 ? T(1) / t_sqrt(gjj) : T(1));
+        if (defl && pass == 0 && p.stats) atomicAdd(p.stats + 5, 1ull);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < kp * kp; idx += 256) {
+        const int i = idx % kp, j = idx / kp;
+        if (i <= j) {
+            const bool di = sd[i] == T(0), dj = sd[j] == T(0);
+            R[i][j] = (di || dj) ? ((i == j) ? T(1) : T(0)) : R[i][j] * sd[i] * sd[j];   // deflated: identity row / column
+        }
+    }
+    __syncthreads();
+    const T lo = pass == 0 ? T(1e-6) : T(0.25), hi = T(4);
+    if (!s_bad) {
+        // right-looking Cholesky with ONE barrier per step: the trailing update uses the unscaled pivot row (read-only during
+        // the step), R[i][l] -= R[j][i] R[j][l] / piv; the rows are divided by sqrt(pivot) once at the end
+        for (int j = 0; j < kp; ++j) {
+            const T piv = R[j][j];
+            if (!(piv >= lo) || !(piv <= hi)) { if (tid == 0) s_bad = 1; break; }   // (uniform: everybody reads the same value)
+            const T inv = T(1) / piv;
+            const int nt = kp - j - 1;
+            for (int idx = tid; idx < nt * nt; idx += 256) {
+                const int i = j + 1 + idx % nt, l = j + 1 + idx / nt;
+                if (i <= l) R[i][l] = fma(-R[j][i] * inv, R[j][l], R[i][l]);
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    if (!s_bad) {
+        for (int idx = tid; idx < kp * kp; idx += 256) {
+            const int i = idx % kp, j = idx / kp;
+            if (i < j) R[i][j] *= T(1) / t_sqrt(R[i][i]);       // (diagonal entries are still the pivots here)
+        }
+        __syncthreads();
+        for (int j = tid; j < kp; j += 256) R[j][j] = t_sqrt(R[j][j]);
+    }
+    __syncthreads();
+    if (s_bad) {   // not safely well conditioned: Householder takes over (X is intact)
+        if (tid == 0) {
+            p.cq_fail[side] = 1;
+            if (p.stats) atomicAdd(p.stats + 1 + pass, 1ull);
+        }
+        return;
+    }
+    // ---- S = D Rc^-1 (upper): thread j solves Rc y = e_j by back substitution, straight into shared memory
+    for (int idx = tid; idx < CQ_KP * CQ_P; idx += 256) (&S[0][0])[idx] = T(0);
+    __syncthreads();
+    for (int j = tid; j < kp; j += 256) {
+        for (int i = j; i >= 0; --i) {
+            T a = (i == j) ? T(1) : T(0);
+            for (int l = i + 1; l <= j; ++l) a = fma(-R[i][l], S[l][j], a);
+            S[i][j] = a / R[i][i];
+        }
+        for (int i = 0; i <= j; ++i) S[i][j] *= sd[i];
+    }
+    __syncthreads();
+    // ---- Out = In * S for this warp's rows: 8-row tiles, N = 48 (6 tiles), K = kp padded to a multiple of 4
+    for (int r0 = w * 8; r0 < rows; r0 += 64) {
+        T acc[CQ_NT][2];
+#pragma unroll
+        for (int tt = 0; tt < CQ_NT; ++tt) acc[tt][0] = acc[tt][1] = T(0);
+        const int r = r0 + g;
+        T a[CQ_KP / 4];                                   // all A fragments of this row tile first: 12 independent loads in flight
+#pragma unroll
+        for (int q = 0; q < CQ_KP / 4; ++q) {
+            const int kk = 4 * q + c;
+            a[q] = (r < rows && kk < kp) ? In[(size_t) r + (size_t) kk * rows] : T(0);
+        }
+#pragma unroll
+        for (int q = 0; q < CQ_KP / 4; ++q) {
+            const int kk = 4 * q + c;
+#pragma unroll
+            for (int tt = 0; tt < CQ_NT; ++tt) dmma_m8n8k4(acc[tt][0], acc[tt][1], a[q], S[kk][8 * tt + g]);
+        }
+        if (r < rows) {
+#pragma unroll
+            for (int tt = 0; tt < CQ_NT; ++tt) {
+                const int col = 8 * tt + 2 * c;
+                if (col < kp) Out[(size_t) r + (size_t) col * rows] = acc[tt][0];
+                if (col + 1 < kp) Out[(size_t) r + (size_t) (col + 1) * rows] = acc[tt][1];
+            }
+        }
+    }
+    // ---- triangular factors
+    if (pass == 0) {
+        for (int idx = tid; idx < kp * kp; idx += 256) {
+            const int i = idx % kp, j = idx / kp;
+            R1[idx] = (i <= j && sd[i] != T(0) && sd[j] != T(0)) ? R[i][j] / sd[j] : T(0);   // R1 = Rc D^-1 (zero row / column where deflated)
+        }
+    } else {
+        // (the top kp rows of X are read by nobody in this pass: pass 1 reads Q1)
+        for (int idx = tid; idx < kp * kp; idx += 256) {
+            const int i = idx % kp, j = idx / kp;
+            if (i > j) continue;
+            T a = T(0);
+            for (int l = i; l <= j; ++l) a = fma(R[i][l], R1[(size_t) l + (size_t) j * kp], a);
+            Xg[(size_t) i + (size_t) j * rows] = a;                             // R2 = Rc2 R1
+        }
+        if (tid == 0) {
+            if (p.stats) atomicAdd(p.stats + 0, 1ull);
+            probs[t].q2_done[side] = 1;
+            pd_inc[(size_t) side * n_tiles + t].active = 0;
+            for (int st = 0; st < nst_inc; ++st)
+                inc_sj[((size_t) side * n_tiles + t) * nst_inc + st] = StripJob{nullptr, nullptr, nullptr, 1, 1, 0, 0, 0, 0, 0, -1, 0};
+        }
     }
 }
 
@@ -1023,6 +1246,7 @@ __global__ void __launch_bounds__(256) k_inc_gate(const RecompProb<T> *__restric
         if (lane == 0 && !(rest >= coef)) s_fail = 1;
     }
     __syncthreads();
+    if (threadIdx.x == 0 && p.stats) atomicAdd(p.stats + ((s_fail && !force_once) ? 4 : 3), 1ull);
     if (s_fail && !force_once) return;      // second pass stays on (force_once: test switch, see HCB_GS_FORCE_ONCE)
     T *Z = side ? p.Zv : p.Gu2;             // second-pass coefficients: none
     for (int idx = threadIdx.x; idx < kc * kp; idx += blockDim.x) Z[idx] = T(0);
