@@ -625,6 +625,64 @@ def test_selective_reorthogonalisation_saturated_tile(hc, ctx):
     assert relerr(res["incremental"][0], res["full"][0]) <= 1e-9
 
 
+def test_cholqr_fast_path_fallback_and_deflation(hc):
+    """Round 2: the kp new columns of an incremental update are factored by CholeskyQR2 (k_cholqr_pass) where every pivot of
+    the scaled Gram matrix passes the safety test; otherwise that tile side falls back to the Householder panels.
+    (a) generic updates take the fast path (counters), (b) an A tile whose U columns are nearly dependent (a user-built tile,
+    condition ~1e9) must FALL BACK and still match the oracle, (c) a rank-deficient update is deflated or falls back, (d) the
+    result equals the all-Householder path (HCB_NO_CHOLQR=1) to rounding."""
+    nb, kc, ka, acc = 512, 50, 20, 1e-8
+    rng = np.random.default_rng(515)
+    c2 = hc.RunContext(0)
+    p, po = hc.CompressionParameters(acc), O.CompressionParameters(acc)
+    c0 = O.synth_compressed_tile(nb, kc, 9300)
+    good = (O.synth_compressed_tile(nb, ka, 9301), O.synth_compressed_tile(nb, ka, 9302))
+    # nearly dependent left columns: u_1 = u_0 + 1e-9 w
+    qa, _ = np.linalg.qr(rng.standard_normal((nb, ka)))
+    qa[:, 1] = qa[:, 0] + 1e-9 * qa[:, 1]
+    bad_a = O.CompressedTile.from_uv(np.asfortranarray(qa), np.asfortranarray(good[0].V.copy()))
+    # a repeated and a zero column in the right factor's row space (deflation on the V side)
+    bv = good[1].V.copy()
+    bv[3, :] = 0.0
+    defl_b = O.CompressedTile.from_uv(np.asfortranarray(good[1].U.copy()), np.asfortranarray(bv))
+    seq = [good, (bad_a, good[1]), (good[0], defl_b)]
+    outs = {}
+    for mode in ("cholqr", "householder"):
+        if mode == "householder":
+            os.environ["HCB_NO_CHOLQR"] = "1"
+        try:
+            Ct = hc.CompressedTile.from_uv(c0.U, c0.V, c2, max_rank=nb // 3)
+            Ct.state.fill_(3)
+            c2.stats(reset=True)
+            st = []
+            for a, b in seq:
+                A, B = hc.CompressedTile.from_uv(a.U, a.V, c2), hc.CompressedTile.from_uv(b.U, b.V, c2)
+                hc.HCore.Gemm(1.0, A, False, B, False, 1.0, Ct, c2, p)
+                st.append(c2.stats(reset=True))
+            U = Ct.factors()[0]
+            orth = torch.linalg.norm(U.t() @ U - torch.eye(U.shape[1], dtype=torch.float64, device="cuda")).item()
+            outs[mode] = (Ct.to_dense(), Ct.GetTileRank(), st, orth)
+        finally:
+            os.environ.pop("HCB_NO_CHOLQR", None)
+    oC = O.CompressedTile.from_uv(c0.U.copy(), c0.V.copy())
+    oC.max_rank = nb // 3
+    for a, b in seq:
+        O.hcore_gemm(1.0, a, False, b, False, 1.0, oC, po)
+    ref = oC.to_dense()
+    for mode, (d, rk, st, orth) in outs.items():
+        assert relerr(d, ref) <= 10 * acc, (mode, relerr(d, ref))
+        assert abs(rk - oC.rank) <= 1, (mode, rk, oC.rank)
+        assert orth < 0.5 * acc, (mode, orth)
+    st = outs["cholqr"][2]
+    assert st[0]["cholqr_panels"] == 2 and st[0]["cholqr_fallback_pass0"] == 0, st[0]          # generic: both sides fast
+    assert st[1]["cholqr_fallback_pass0"] + st[1]["cholqr_fallback_pass1"] >= 1, st[1]          # dependent U columns: fallback
+    # rank-deficient right factor (zero row of B.V): the degenerate new direction is either deflated or sends the side to the
+    # Householder path -- never through an unsafe CholeskyQR
+    assert st[2]["deflated_columns"] + st[2]["cholqr_fallback_pass0"] + st[2]["cholqr_fallback_pass1"] >= 1, st[2]
+    assert all(v["cholqr_panels"] == 0 for v in outs["householder"][2])
+    assert relerr(outs["cholqr"][0], outs["householder"][0]) <= 1e-9
+
+
 def test_matmul_info_is_sticky_over_k(hc, ctx):
     """hcb_?tlr_matmul passes one d_info to every k-step -- flags are OR-ed, the sweep count is the maximum."""
     nb, T, k, acc = 128, 2, 12, 1e-8
