@@ -59,7 +59,7 @@ class RunContext:
         out = (C.c_uint64 * 8)()
         check(lib.hcb_ctx_stats(self.h, out, 1 if reset else 0))
         return {"cholqr_panels": int(out[0]), "cholqr_fallback_pass0": int(out[1]), "cholqr_fallback_pass1": int(out[2]),
-                "gs_second_pass_skipped": int(out[3]), "gs_second_pass_run": int(out[4]), "deflated_columns": int(out[5])}
+                "gs_second_pass_skipped": int(out[3]), "gs_second_pass_run": int(out[4]), "deflated_columns": int(out[5]), "vcore_cholesky": int(out[6]), "vcore_fallback": int(out[7])}
 
     def reserve_workspace(self, nbytes: int):
         check(lib.hcb_ctx_reserve_workspace(self.h, nbytes))

@@ -1053,6 +1053,17 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
                 dim3 gb(std::max(1, std::min(64, cdiv((long long) L.r_b * L.r_b, 1024))), n);
                 k_vinc_build_rv<T><<<gb, 256, 0, ctx->stream>>>(sa.rc);
                 HCB_LAUNCH_CHECK("k_vinc_build_rv");
+                if constexpr (std::is_same<T, double>::value) {
+                    // the graded factor R' by a Cholesky factorisation of the assembled, column-scaled Gram matrix (k_vcore_chol);
+                    // tiles that fail its pivot test keep their Householder panel descriptor and are factored below
+                    static const bool vchol = !(getenv("HCB_NO_VCHOL") && atoi(getenv("HCB_NO_VCHOL")) != 0);
+                    const size_t vsm = vcore_chol_smem(L.r_b);
+                    if (vchol && L.kp_b <= CQ_KP && vsm + 1024 <= ctx->smem_optin) {
+                        HCB_CUDA(cudaFuncSetAttribute(k_vcore_chol<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) vsm));
+                        k_vcore_chol<T><<<n, 256, vsm, ctx->stream>>>(sa.rc, sa.pd_vcore, L.r_b);
+                        HCB_LAUNCH_CHECK("k_vcore_chol");
+                    }
+                }
                 HCB_TRY(run_blocked_qr<T>(ctx, sa.pd_vcore, n, L.r_b, L.r_b, base + D.o_bqr2));
             }
         }

@@ -52,7 +52,8 @@ size_t hcb_ctx_workspace_bytes(hcb_ctx *ctx);
 /* Counters of the adaptive fast paths of the fused recompression since the context was created (or last reset); the call
  * synchronises.  out8[0] new-column panels factored by CholeskyQR2, [1] / [2] panels that fell back to the Householder path in
  * its first / second pass, [3] block Gram-Schmidt second passes skipped by the twice-is-enough test, [4] second passes run, [5] negligible new
- * columns (norm below 1e-13 of the largest new column) deflated to zero by the CholeskyQR2 path. */
+ * columns (norm below 1e-13 of the largest new column) deflated to zero by the CholeskyQR2 path, [6] r x r graded triangular
+ * factors of the incremental V side computed by Cholesky, [7] tiles that fell back to the Householder R-only QR for it. */
 int hcb_ctx_stats(hcb_ctx *ctx, uint64_t *out8, int reset);
 int hcb_malloc(hcb_ctx *ctx, size_t bytes, void **d_out);            /* memory::AllocateArray */
 int hcb_free(hcb_ctx *ctx, void *d_ptr);                             /* memory::DestroyArray */
