@@ -1352,14 +1352,49 @@ __global__ void __launch_bounds__(256) k_vcore_chol(RecompProb<T> *__restrict__ 
         const int o = ipos[cs];
         if (o < kc) { const T v = M[(size_t) o + (size_t) cs * r]; dscale[cs] = v != T(0) ? T(1) / t_abs(v) : T(0); }
     }
-    for (int l = w; l < kp; l += 8) {
-        for (int l2 = l; l2 < kp; ++l2) {
-            const T *x = M + (size_t) p.pos[kc + l] * r, *y = M + (size_t) p.pos[kc + l2] * r;
-            T a = T(0);
-            for (int i = lane; i < r; i += 32) a = fma(x[i], y[i], a);
-            a = warp_sum(a);
-            if (lane == 0) { Nm[l * CQ_P + l2] = a; Nm[l2 * CQ_P + l] = a; }
+    // dense-dense Gram matrix N = Dn^T Dn (Dn = the kp dense columns of M, r rows) by DMMA, as in k_cholqr_pass: warp w takes
+    // the row chunks w, w + 8, ... of 32 rows; the 21 upper tile pairs stay in registers and meet in shared memory
+    for (int idx = tid; idx < CQ_KP * CQ_P; idx += 256) Nm[idx] = T(0);
+    __syncthreads();
+    {
+        T acc[CQ_NT * (CQ_NT + 1) / 2][2];
+#pragma unroll
+        for (int q = 0; q < CQ_NT * (CQ_NT + 1) / 2; ++q) acc[q][0] = acc[q][1] = T(0);
+        const T *colp[CQ_NT];
+        bool colv[CQ_NT];
+#pragma unroll
+        for (int tt = 0; tt < CQ_NT; ++tt) {
+            const int l = 8 * tt + g;
+            colv[tt] = l < kp;
+            colp[tt] = M + (size_t) (colv[tt] ? p.pos[kc + l] : 0) * r;
         }
+        for (int r0 = w * 32; r0 < r; r0 += 256) {
+#pragma unroll 2
+            for (int ks = 0; ks < 32; ks += 4) {
+                const int row = r0 + ks + c4;
+                T v[CQ_NT];
+#pragma unroll
+                for (int tt = 0; tt < CQ_NT; ++tt) v[tt] = (row < r && colv[tt]) ? colp[tt][row] : T(0);
+                int q = 0;
+#pragma unroll
+                for (int ti = 0; ti < CQ_NT; ++ti)
+#pragma unroll
+                    for (int tj = ti; tj < CQ_NT; ++tj, ++q) dmma_m8n8k4(acc[q][0], acc[q][1], v[ti], v[tj]);
+            }
+        }
+        int q = 0;
+#pragma unroll
+        for (int ti = 0; ti < CQ_NT; ++ti)
+#pragma unroll
+            for (int tj = ti; tj < CQ_NT; ++tj, ++q) {
+                atomicAdd(&Nm[(8 * ti + g) * CQ_P + 8 * tj + 2 * c4], acc[q][0]);
+                atomicAdd(&Nm[(8 * ti + g) * CQ_P + 8 * tj + 2 * c4 + 1], acc[q][1]);
+            }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < kp * kp; idx += 256) {   // mirror the upper triangle (the diagonal tiles hold both halves already)
+        const int i = idx % kp, j = idx / kp;
+        if (i > j && (i >> 3) != (j >> 3)) Nm[i * CQ_P + j] = Nm[j * CQ_P + i];
     }
     __syncthreads();
     for (int l = tid; l < kp; l += 256) { const T v = Nm[l * CQ_P + l]; dscale[p.pos[kc + l]] = v > T(0) ? T(1) / t_sqrt(v) : T(0); }
@@ -1434,22 +1469,17 @@ __global__ void __launch_bounds__(256) k_vcore_chol(RecompProb<T> *__restrict__ 
             Dk[i * (VC_NB + 1) + j] = (i <= j && j < jw) ? S[(size_t) (n0 + i) + (size_t) (n0 + j) * r] : T(0);
         }
         __syncthreads();
-        for (int j = 0; j < jw; ++j) {
-            const T piv = Dk[j * (VC_NB + 1) + j];
-            if (!(piv >= T(1e-6)) || !(piv <= T(4))) {
-                if (tid == 0) s_bad = 1;
-#ifdef HCB_DEBUG_VCHOL
-                if (tid == 0 && t < 2) printf("vchol tile %d r %d kc %d kp %d: n0 %d j %d piv %.3e (sorted col %d orig %d dscale %.3e)\n", t, r, kc, kp, n0, j, (double) piv, n0 + j, ipos[n0 + j], (double) dscale[n0 + j]);
-#endif
-                break;
+        if (w == 0) {   // 32 x 32: one warp, warp-level barriers only (lane l owns column l of the trailing block)
+            for (int j = 0; j < jw; ++j) {
+                const T piv = Dk[j * (VC_NB + 1) + j];
+                if (!(piv >= T(1e-6)) || !(piv <= T(4))) { if (lane == 0) s_bad = 1; break; }
+                const T inv = T(1) / piv;
+                if (lane > j && lane < jw) {
+                    const T f = Dk[j * (VC_NB + 1) + lane] * inv;
+                    for (int i = j + 1; i <= lane; ++i) Dk[i * (VC_NB + 1) + lane] = fma(-Dk[j * (VC_NB + 1) + i], f, Dk[i * (VC_NB + 1) + lane]);
+                }
+                __syncwarp();
             }
-            const T inv = T(1) / piv;
-            const int nt2 = jw - j - 1;
-            for (int idx = tid; idx < nt2 * nt2; idx += 256) {
-                const int i = j + 1 + idx % nt2, l = j + 1 + idx / nt2;
-                if (i <= l) Dk[i * (VC_NB + 1) + l] = fma(-Dk[j * (VC_NB + 1) + i] * inv, Dk[j * (VC_NB + 1) + l], Dk[i * (VC_NB + 1) + l]);
-            }
-            __syncthreads();
         }
         __syncthreads();
         if (s_bad) break;
