@@ -1056,7 +1056,7 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
                 if constexpr (std::is_same<T, double>::value) {
                     // the graded factor R' by a Cholesky factorisation of the assembled, column-scaled Gram matrix (k_vcore_chol);
                     // tiles that fail its pivot test keep their Householder panel descriptor and are factored below
-                    static const bool vchol = !(getenv("HCB_NO_VCHOL") && atoi(getenv("HCB_NO_VCHOL")) != 0);
+                    const bool vchol = !(getenv("HCB_NO_VCHOL") && atoi(getenv("HCB_NO_VCHOL")) != 0);   // (read per call: tests toggle it)
                     const size_t vsm = vcore_chol_smem(L.r_b);
                     if (vchol && L.kp_b <= CQ_KP && vsm + 1024 <= ctx->smem_optin) {
                         HCB_CUDA(cudaFuncSetAttribute(k_vcore_chol<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) vsm));

@@ -647,9 +647,12 @@ def test_cholqr_fast_path_fallback_and_deflation(hc):
     defl_b = O.CompressedTile.from_uv(np.asfortranarray(good[1].U.copy()), np.asfortranarray(bv))
     seq = [good, (bad_a, good[1]), (good[0], defl_b)]
     outs = {}
-    for mode in ("cholqr", "householder"):
+    for mode in ("cholqr", "householder", "no_vchol"):
         if mode == "householder":
             os.environ["HCB_NO_CHOLQR"] = "1"
+            os.environ["HCB_NO_VCHOL"] = "1"
+        if mode == "no_vchol":
+            os.environ["HCB_NO_VCHOL"] = "1"
         try:
             Ct = hc.CompressedTile.from_uv(c0.U, c0.V, c2, max_rank=nb // 3)
             Ct.state.fill_(3)
@@ -664,6 +667,7 @@ def test_cholqr_fast_path_fallback_and_deflation(hc):
             outs[mode] = (Ct.to_dense(), Ct.GetTileRank(), st, orth)
         finally:
             os.environ.pop("HCB_NO_CHOLQR", None)
+            os.environ.pop("HCB_NO_VCHOL", None)
     oC = O.CompressedTile.from_uv(c0.U.copy(), c0.V.copy())
     oC.max_rank = nb // 3
     for a, b in seq:
@@ -679,8 +683,13 @@ def test_cholqr_fast_path_fallback_and_deflation(hc):
     # rank-deficient right factor (zero row of B.V): the degenerate new direction is either deflated or sends the side to the
     # Householder path -- never through an unsafe CholeskyQR
     assert st[2]["deflated_columns"] + st[2]["cholqr_fallback_pass0"] + st[2]["cholqr_fallback_pass1"] >= 1, st[2]
-    assert all(v["cholqr_panels"] == 0 for v in outs["householder"][2])
+    assert all(v["cholqr_panels"] == 0 and v["vcore_cholesky"] == 0 for v in outs["householder"][2])
     assert relerr(outs["cholqr"][0], outs["householder"][0]) <= 1e-9
+    # the graded r x r factor of the V side: by Cholesky of the assembled scaled Gram matrix (k_vcore_chol) in the default mode,
+    # by the Householder R-only QR with HCB_NO_VCHOL=1 -- same result to rounding
+    assert all(v["vcore_cholesky"] + v["vcore_fallback"] == 1 for v in st) and st[0]["vcore_cholesky"] == 1, st
+    assert all(v["vcore_cholesky"] == 0 for v in outs["no_vchol"][2])
+    assert relerr(outs["cholqr"][0], outs["no_vchol"][0]) <= 1e-9
 
 
 def test_matmul_info_is_sticky_over_k(hc, ctx):
