@@ -956,7 +956,7 @@ int t_tlr_gemm_batched(hcb_ctx *ctx, int64_t n64, const hcb_tile *A, int opA, co
             want = align_up(want, 16);
             HCB_CUDA(cudaFuncSetAttribute(k_precond_product<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(want, 16)));
             // one warp per column pair of the round-robin (ka / 2 pairs per round)
-            const int pc_threads = std::min(1024, std::max(256, 32 * ((s.kA + 1) / 2)));
+            const int pc_threads = std::min(1024, std::max(256, 32 * ((s.kA + 3) / 4)));  // one warp per TWO column pairs: 2+ CTAs per SM, the 256 tiles of a batch run as one wave
             static const int pc_sweeps = getenv("HCB_PRECOND_SWEEPS") ? std::max(0, atoi(getenv("HCB_PRECOND_SWEEPS"))) : 8;
             k_precond_product<T><<<n, pc_threads, want, ctx->stream>>>(sa.pc, (int) (want / sizeof(T)), pc_sweeps);
             HCB_LAUNCH_CHECK("k_precond_product");
