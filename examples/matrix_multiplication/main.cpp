@@ -1,7 +1,7 @@
 // examples/matrix_multiplication/main.cpp -- the reference's headline driver (examples/matrix_multiplication/omp_main.cpp:
 // same command line, same flow, same CSV lines) on top of the C++ mirror of its API (include/hcorepp_b200/hcorepp.hpp ->
 // C ABI -> CUDA):
-//     b200-hcorepp-matrix [matrix_tiles = 2] [accuracy list = "1e-1,1e-4,1e-8"] [tile_size = 512] [per_tile_generation = 0]
+//     b200-hcorepp-matrix [nTiles = 2] [accuracy list = "1e-1,1e-4,1e-8"] [tileDim = 512] [perTileGen = 0]
 //     HCOREPP_VERBOSE=ON prints the CSV header (omp_main.cpp:173-202).
 // Flow (omp_main.cpp:219-418): generate A, B with the LATMS spectrum law, C = 0; reference dense GEMM on the device;
 // dense tile flow; per accuracy: compressed tile matrices (compression on the device), the tile GEMM (ONE batched device
@@ -71,119 +71,119 @@ static void generate(double *A, size_t n, size_t ld, std::mt19937_64 &rng, int r
         }
 }
 
-static RawMatrix<double> make_matrix(size_t tiles, size_t tile_size, bool per_tile, std::mt19937_64 &rng) {
-    const size_t n = tiles * tile_size;
+static RawMatrix<double> make_matrix(size_t tiles, size_t tileDim, bool per_tile, std::mt19937_64 &rng) {
+    const size_t n = tiles * tileDim;
     RawMatrix<double> M(n, n);
     if (!per_tile) generate(M.GetData(), n, n, rng);
     else
         for (size_t c = 0; c < tiles; ++c)
-            for (size_t r = 0; r < tiles; ++r) generate(M.GetData() + r * tile_size + c * tile_size * n, tile_size, n, rng);
+            for (size_t r = 0; r < tiles; ++r) generate(M.GetData() + r * tileDim + c * tileDim * n, tileDim, n, rng);
     return M;
 }
 
 int main(int argc, char **argv) {
-    int tile_size = 512, matrix_tiles = 2, per_tile_generation = 0;
-    std::vector<double> accuracy_list = {1e-1, 1e-4, 1e-8};
-    if (argc > 1) matrix_tiles = atoi(argv[1]);
+    int tileDim = 512, nTiles = 2, perTileGen = 0;
+    std::vector<double> accuracies = {1e-1, 1e-4, 1e-8};
+    if (argc > 1) nTiles = atoi(argv[1]);
     if (argc > 2) {
-        accuracy_list.clear();
+        accuracies.clear();
         std::stringstream ss(argv[2]);
         for (double v; ss >> v;) {
-            accuracy_list.push_back(v);
+            accuracies.push_back(v);
             if (ss.peek() == ',') ss.ignore();
         }
     }
-    if (argc > 3) tile_size = atoi(argv[3]);
-    if (argc > 4) per_tile_generation = atoi(argv[4]);
+    if (argc > 3) tileDim = atoi(argv[3]);
+    if (argc > 4) perTileGen = atoi(argv[4]);
     const char *verbose = std::getenv("HCOREPP_VERBOSE");
-    bool print_header = verbose && std::string(verbose) == "ON";
+    bool wantHeader = verbose && std::string(verbose) == "ON";
     try {
         RunContext &context = kernels::ContextManager::GetInstance().GetContext();
         double alpha = 1, beta = 1;
-        const size_t n = (size_t) matrix_tiles * tile_size;
+        const size_t n = (size_t) nTiles * tileDim;
         std::mt19937_64 rng(1);
         double t0 = now_ms();
-        RawMatrix<double> full_a = make_matrix(matrix_tiles, tile_size, per_tile_generation > 0, rng);
-        RawMatrix<double> full_b = make_matrix(matrix_tiles, tile_size, per_tile_generation > 0, rng);
-        RawMatrix<double> full_c(n, n), initial_c(n, n);
-        const double t_generation = now_ms() - t0;
+        RawMatrix<double> hostA = make_matrix(nTiles, tileDim, perTileGen > 0, rng);
+        RawMatrix<double> hostB = make_matrix(nTiles, tileDim, perTileGen > 0, rng);
+        RawMatrix<double> refC(n, n), zeroC(n, n);
+        const double msGenerate = now_ms() - t0;
         // reference solution: one dense GEMM on the device (omp_main.cpp:258-289)
-        double t_ref;
+        double msRefGemm;
         {
             double *a = memory::AllocateArray<double>(n * n, context), *b = memory::AllocateArray<double>(n * n, context),
                    *c = memory::AllocateArray<double>(n * n, context);
-            memory::Memcpy<double>(a, full_a.GetData(), n * n, context, memory::MemoryTransfer::HOST_TO_DEVICE);
-            memory::Memcpy<double>(b, full_b.GetData(), n * n, context, memory::MemoryTransfer::HOST_TO_DEVICE);
-            memory::Memcpy<double>(c, full_c.GetData(), n * n, context, memory::MemoryTransfer::HOST_TO_DEVICE);
+            memory::Memcpy<double>(a, hostA.GetData(), n * n, context, memory::MemoryTransfer::HOST_TO_DEVICE);
+            memory::Memcpy<double>(b, hostB.GetData(), n * n, context, memory::MemoryTransfer::HOST_TO_DEVICE);
+            memory::Memcpy<double>(c, refC.GetData(), n * n, context, memory::MemoryTransfer::HOST_TO_DEVICE);
             context.Sync();
             t0 = now_ms();
             kernels::HCoreKernels<double>::Gemm(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, n, n, n, alpha, a, n, b, n,
                                                 beta, c, n, context);
             context.Sync();
-            t_ref = now_ms() - t0;
-            memory::Memcpy<double>(full_c.GetData(), c, n * n, context, memory::MemoryTransfer::DEVICE_TO_HOST);
+            msRefGemm = now_ms() - t0;
+            memory::Memcpy<double>(refC.GetData(), c, n * n, context, memory::MemoryTransfer::DEVICE_TO_HOST);
             context.Sync();
             hcb_free(context.Handle(), a); hcb_free(context.Handle(), b); hcb_free(context.Handle(), c);
         }
-        const size_t ref_flops = 2 * n * n * n, ref_kb = 3 * n * n * sizeof(double) / 1024;
-        const double a_norm = full_a.Norm(), b_norm = full_b.Norm(), c_init_norm = initial_c.Norm();
-        const size_t tile_gemms = (size_t) matrix_tiles * matrix_tiles * matrix_tiles;
-        const size_t tile_flops = tile_gemms * 2 * (size_t) tile_size * tile_size * tile_size;   // what HCore::Gemm adds to aFlops
-        int failures = 0;
+        const size_t flopsRef = 2 * n * n * n, kbRef = 3 * n * n * sizeof(double) / 1024;
+        const double normA = hostA.Norm(), normB = hostB.Norm(), normC0 = zeroC.Norm();
+        const size_t nTileGemms = (size_t) nTiles * nTiles * nTiles;
+        const size_t flopsTiles = nTileGemms * 2 * (size_t) tileDim * tileDim * tileDim;   // what HCore::Gemm adds to aFlops
+        int nFailed = 0;
         // dense flow (omp_main.cpp:305-335)
-        double t_dense_creation, t_dense_gemm, dense_error, dense_error_normalized;
-        size_t dense_kb;
+        double msDenseBuild, msDenseGemm, denseErr, denseErrScaled;
+        size_t kbDense;
         {
             CompressionParameters none(1e-9);
             t0 = now_ms();
-            TileMatrix<double> a(full_a, tile_size, tile_size, context), b(full_b, tile_size, tile_size, context),
-                c(initial_c, tile_size, tile_size, context);
+            TileMatrix<double> a(hostA, tileDim, tileDim, context), b(hostB, tileDim, tileDim, context),
+                c(zeroC, tileDim, tileDim, context);
             context.Sync();
-            t_dense_creation = now_ms() - t0;
+            msDenseBuild = now_ms() - t0;
             t0 = now_ms();
             TileMatrixMultiplication<double>(a, b, c, alpha, beta, none, context);
             context.Sync();
-            t_dense_gemm = now_ms() - t0;
+            msDenseGemm = now_ms() - t0;
             RawMatrix<double> got = c.ToRawMatrix(context);
-            got.ReferenceDifference(full_c);
-            dense_error = got.Norm();
-            dense_error_normalized = dense_error / ((a_norm + b_norm + c_init_norm) * std::numeric_limits<double>::epsilon() * (double) n);
-            if (dense_error_normalized >= 10) { std::printf("Example didn't pass, dense HCore++ error > 10 \n"); ++failures; }
-            dense_kb = (a.GetMemoryFootprint() + b.GetMemoryFootprint() + c.GetMemoryFootprint()) / 1024;
+            got.ReferenceDifference(refC);
+            denseErr = got.Norm();
+            denseErrScaled = denseErr / ((normA + normB + normC0) * std::numeric_limits<double>::epsilon() * (double) n);
+            if (denseErrScaled >= 10) { std::printf("Example didn't pass, dense HCore++ error > 10 \n"); ++nFailed; }
+            kbDense = (a.GetMemoryFootprint() + b.GetMemoryFootprint() + c.GetMemoryFootprint()) / 1024;
         }
-        bool first_print = true;
-        for (double accuracy : accuracy_list) {
+        bool headerPending = true;
+        for (double accuracy : accuracies) {
             CompressionParameters prm(accuracy);
             for (int pass = 0; pass < 2; ++pass) {   // pass 0 = warm-up, like the reference (omp_main.cpp:341-348)
                 t0 = now_ms();
-                TileMatrix<double> a(full_a, tile_size, tile_size, prm, context), b(full_b, tile_size, tile_size, prm, context),
-                    c(initial_c, tile_size, tile_size, prm, context);
+                TileMatrix<double> a(hostA, tileDim, tileDim, prm, context), b(hostB, tileDim, tileDim, prm, context),
+                    c(zeroC, tileDim, tileDim, prm, context);
                 context.Sync();
-                const double t_creation = now_ms() - t0;
+                const double msBuild = now_ms() - t0;
                 t0 = now_ms();
                 TileMatrixMultiplication<double>(a, b, c, alpha, beta, prm, context);
                 context.Sync();
-                const double t_gemm = now_ms() - t0;
+                const double msGemm = now_ms() - t0;
                 if (pass == 0) continue;
                 RawMatrix<double> got = c.ToRawMatrix(context);
-                got.ReferenceDifference(full_c);
-                const double err = got.Norm(), err_n = err / ((a_norm + b_norm + c_init_norm) * accuracy * (double) n);
-                if (err_n >= 10) { std::printf("Example didn't pass, compressed HCore++ error > 10 \n"); ++failures; }
+                got.ReferenceDifference(refC);
+                const double err = got.Norm(), errScaled = err / ((normA + normB + normC0) * accuracy * (double) n);
+                if (errScaled >= 10) { std::printf("Example didn't pass, compressed HCore++ error > 10 \n"); ++nFailed; }
                 const size_t kb = (a.GetMemoryFootprint() + b.GetMemoryFootprint() + c.GetMemoryFootprint()) / 1024;
-                if (first_print) {
-                    if (print_header)
-                        std::printf("tile_count, tile_size, matrix_size, type, error, error_normalized, memory(KB), creation(ms), gemm_time(ms), flops\n");
-                    std::printf("%d, %d, %d, ref, 0, 0, %zu, %f, %f, %zu\n", matrix_tiles, tile_size, matrix_tiles * tile_size, ref_kb,
-                                t_generation, t_ref, ref_flops);
-                    std::printf("%d, %d, %d, dense, %e, %e, %zu, %f, %f, %zu\n", matrix_tiles, tile_size, matrix_tiles * tile_size,
-                                dense_error, dense_error_normalized, dense_kb, t_dense_creation, t_dense_gemm, tile_flops);
-                    first_print = false;
+                if (headerPending) {
+                    if (wantHeader)
+                        std::printf("tile_count, tileDim, matrix_size, type, error, error_normalized, memory(KB), creation(ms), gemm_time(ms), flops\n");
+                    std::printf("%d, %d, %d, ref, 0, 0, %zu, %f, %f, %zu\n", nTiles, tileDim, nTiles * tileDim, kbRef,
+                                msGenerate, msRefGemm, flopsRef);
+                    std::printf("%d, %d, %d, dense, %e, %e, %zu, %f, %f, %zu\n", nTiles, tileDim, nTiles * tileDim,
+                                denseErr, denseErrScaled, kbDense, msDenseBuild, msDenseGemm, flopsTiles);
+                    headerPending = false;
                 }
-                std::printf("%d, %d, %d, %2.1e, %e, %e, %zu, %f, %f, %zu\n", matrix_tiles, tile_size, matrix_tiles * tile_size, accuracy,
-                            err, err_n, kb, t_creation, t_gemm, tile_flops);
+                std::printf("%d, %d, %d, %2.1e, %e, %e, %zu, %f, %f, %zu\n", nTiles, tileDim, nTiles * tileDim, accuracy,
+                            err, errScaled, kb, msBuild, msGemm, flopsTiles);
             }
         }
-        return failures;
+        return nFailed;
     } catch (const std::exception &e) {
         std::printf("EXCEPTION: %s\n", e.what());
         return 100;
