@@ -1021,8 +1021,9 @@ __global__ void __launch_bounds__(256) k_vinc_sig0(const RecompProb<T> *__restri
 // ONE kernel per pass, one CTA (8 warps) per tile side: every warp forms the Gram matrix of its 1/8 of the rows with DMMA
 // (m8n8k4: both fragments are the same X[r0 + c][8 t + g] loads; the 21 upper 8 x 8 tile pairs stay in registers), the
 // partial sums meet in shared memory, the kp x kp Cholesky and the triangular inverse run there, and the same warps
-// multiply their rows by S = D Rc^-1 with DMMA again.  No per-column cluster barrier, no explicit-Q strip pass: ~0.2 ms
-// per k-step of 256 tiles instead of ~2.9 ms for the register-panel Householder QR + the strips that form Q2.
+// multiply their rows by S = D Rc^-1 with DMMA again.  No per-column cluster barrier, no explicit-Q strip pass: 2 x 0.4 ms
+// per k-step of 256 tiles (measured, ncu launch list r02) instead of ~2.9 ms for the register-panel Householder QR + the
+// strips that form Q2.
 // CholeskyQR squares the condition number, so the fast path is taken only where it is provably safe: every pivot of the
 // SCALED Gram matrix must be >= 1e-6 (the column keeps at least 1e-3 of its norm after orthogonalisation against the
 // earlier ones: condition <~ 5e4, first-pass loss of orthogonality <~ 1e-7, removed by the second pass) and every pivot
